@@ -1,0 +1,140 @@
+/* vnr_c.h -- flat C ABI of the B200-native instantvnr hot path.
+ *
+ * This is the drop-in boundary: a C-ABI shared library (libvnr_b200.so) that sits under
+ * the reference's C++ api.h surface.  Each entry point names the reference interface it
+ * replaces (paths relative to the reference repo).  INTEGRATION.md shows the api.cpp-side
+ * binding a maintainer would add.
+ *
+ * Conventions: every function returns 0 (VNR_OK) or a negative error code and never
+ * throws across the boundary; vnr_last_error() returns the message of the last failure
+ * on the calling thread.  Handles are opaque.  The caller owns every input buffer; output
+ * buffers returned by the library (mapped frames, serialized blobs) are owned by the
+ * handle and stay valid until the next call that produces the same kind of output or the
+ * handle is released.  `stream` arguments are cudaStream_t passed as void* (NULL = the
+ * handle's own stream).  Pointers named d_* are device pointers, h_* host pointers.
+ * There is no CPU fallback: without a CUDA device every compute call fails with
+ * VNR_ERR_CUDA.
+ */
+#ifndef VNR_C_H
+#define VNR_C_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VNR_OK 0
+#define VNR_ERR_INVALID (-1)     /* bad argument / bad config (api.cpp throws std::runtime_error) */
+#define VNR_ERR_CUDA (-2)        /* CUDA runtime error (reference: CUDA_CHECK throws) */
+#define VNR_ERR_UNSUPPORTED (-3) /* valid in the reference but outside this library's path */
+#define VNR_ERR_STATE (-4)       /* call sequence error (e.g. train without ground truth) */
+
+typedef struct vnr_volume vnr_volume_t;
+typedef struct vnr_renderer vnr_renderer_t;
+
+const char* vnr_last_error(void);
+/* library / device probe: number of CUDA devices visible (0 => compute calls will fail) */
+int vnr_device_count(void);
+
+/* ---- neural volume ------------------------------------------------------------------ */
+
+/* vnrCreateNeuralVolume(const vnrJson& config, vec3i dims)            api.h:123, api.cpp:190-204
+ * model_json: text of the model config (example-model.json; // comments allowed). */
+int vnr_volume_create(const char* model_json, int dx, int dy, int dz, vnr_volume_t** out);
+void vnr_volume_release(vnr_volume_t* v);                              /* vnrRelease  api.h:185 */
+
+/* sizes of the parameter blob (MLP matrices first, then grid levels;
+ * tcnn network_with_input_encoding.h:134-151) */
+int vnr_volume_model_info(const vnr_volume_t* v, uint64_t* n_params, uint64_t* n_mlp_params,
+                          int* n_levels, int* n_features_per_level, int* n_hidden_layers);
+
+/* tcnn Trainer::initialize_params (trainer.h:72-112): Xavier-uniform MLP + U(-1e-4,1e-4) grid
+ * from pcg32 seeded through std::seed_seq{seed}.  The reference seeds with time(NULL)
+ * (core/networks/tcnn_network.h:207); here the seed is explicit. Resets optimizer state. */
+int vnr_volume_init_params(vnr_volume_t* v, uint32_t seed);
+
+/* tcnn Trainer::set_params / serialize: fp16 parameter blob           trainer.h:281-311 */
+int vnr_volume_set_params_f16(vnr_volume_t* v, const uint16_t* h_params, size_t n);
+int vnr_volume_get_params_f16(const vnr_volume_t* v, uint16_t* h_params, size_t n);
+
+/* vnrNeuralVolumeSetParams / vnrCreateNeuralVolume(params) / vnrNeuralVolumeSerializeParams:
+ * the reference's params.json BSON document (core/network.cu:827-939)   api.h:124-127,142-143 */
+int vnr_volume_load_params(vnr_volume_t* v, const void* bson, size_t n);
+int vnr_volume_save_params(vnr_volume_t* v, const void** bson, size_t* n);
+/* dims / model stored in a params.json blob, to create the volume before loading it */
+int vnr_params_peek(const void* bson, size_t n, int* dx, int* dy, int* dz, const char** model_json);
+
+/* NeuralVolume::inference(len, d_input, d_output, stream)             core/network.h:102,
+ * core/network.cu:1043-1052.  d_xyz: float[3*n] (x,y,z per sample, object space [0,1]^3),
+ * d_out: float[n].  No padding requirement on n. */
+int vnr_volume_decode(vnr_volume_t* v, const float* d_xyz, float* d_out, size_t n, void* stream);
+/* same through host buffers (H2D + kernel + D2H + sync inside) */
+int vnr_volume_decode_host(vnr_volume_t* v, const float* h_xyz, float* h_out, size_t n);
+/* test tap: also returns the fp16 hash-grid features (row-major [n][enc_pad]) */
+int vnr_volume_decode_debug(vnr_volume_t* v, const float* h_xyz, float* h_out, uint16_t* h_enc, size_t n);
+
+/* vnrCreateSimpleVolume + StaticSampler ground truth (core/samplers/neural_sampler.cu:86-128):
+ * float32 volume of dims dx*dy*dz (x fastest), already normalised to [0,1]. */
+int vnr_volume_set_groundtruth_f32(vnr_volume_t* v, const float* h_volume);
+/* MacroCell::compute_everything (core/macrocell.cu:221-230): value ranges from ground truth */
+int vnr_volume_macrocell_from_groundtruth(vnr_volume_t* v);
+int vnr_volume_get_macrocell(const vnr_volume_t* v, int* mc_dims, float* h_value_range /*2*cells or NULL*/,
+                             float* h_max_opacity /*cells or NULL*/);
+int vnr_volume_set_macrocell(vnr_volume_t* v, const float* h_value_range /*2*cells, stored with -1/+1 offset*/);
+
+/* NeuralVolume::set_transfer_function (core/network.cu:743-760) + MacroCell::update_max_opacity.
+ * rgb: float[3*n_rgb]; alpha: float[n_alpha] (the .y of the reference's vec2f list). */
+int vnr_volume_set_tfn(vnr_volume_t* v, const float* rgb, int n_rgb, const float* alpha, int n_alpha, float lo, float hi);
+
+/* vnrNeuralVolumeTrain(v, steps, fast_mode)                            api.h:136, core/network.cu:769-779
+ * batch: samples per step (reference hard-codes 1<<16, core/network.cu:183; 0 = that default). */
+int vnr_volume_train(vnr_volume_t* v, int steps, int batch, int fast_mode, void* stream);
+/* One training step on caller-provided samples (AbstractNetwork::train, tcnn_network.h:223-252).
+ * d_xyz float[3*n], d_target float[n]; n must be a multiple of 128. */
+int vnr_volume_train_on(vnr_volume_t* v, const float* d_xyz, const float* d_target, size_t n, void* stream);
+/* Data-parallel split of a step: gradients only (fwd+loss+bwd), then the optimizer.  Between
+ * the two the caller all-reduces the gradient buffer (vnr_volume_grad_buffer). */
+int vnr_volume_train_grads(vnr_volume_t* v, const float* d_xyz, const float* d_target, size_t n, size_t n_global, void* stream);
+int vnr_volume_optimizer_step(vnr_volume_t* v, void* stream);
+int vnr_volume_grad_buffer(vnr_volume_t* v, void** d_grads, size_t* n_bytes, int* is_f32);
+/* StaticSampler::sample (core/samplers/neural_sampler.cu:131-164) into device buffers */
+int vnr_volume_sample(vnr_volume_t* v, float* d_xyz, float* d_target, size_t n, void* stream);
+/* advance the sampler's pcg32 stream (rank r of a data-parallel job skips r*3*n per step) */
+int vnr_volume_sampler_skip(vnr_volume_t* v, uint64_t n_floats);
+
+/* vnrNeuralVolumeGetTrainingStep / GetTrainingLoss                     api.h:132-133 */
+int vnr_volume_stats(vnr_volume_t* v, uint64_t* step, double* loss);
+
+/* ---- renderer ------------------------------------------------------------------------- */
+
+int vnr_renderer_create(vnr_volume_t* v, vnr_renderer_t** out);        /* vnrCreateRenderer api.h:168 */
+void vnr_renderer_release(vnr_renderer_t* r);
+int vnr_renderer_set_size(vnr_renderer_t* r, int width, int height);   /* SetFramebufferSize :169 */
+int vnr_renderer_set_camera(vnr_renderer_t* r, const float* from, const float* at, const float* up, float fovy); /* :171 */
+int vnr_renderer_set_mode(vnr_renderer_t* r, int mode);                /* vnrRenderMode, api.h:36-60 */
+int vnr_renderer_set_sampling_rate(vnr_renderer_t* r, float rate);     /* :174 */
+int vnr_renderer_set_density_scale(vnr_renderer_t* r, float scale);    /* :175 */
+int vnr_renderer_reset_accumulation(vnr_renderer_t* r);                /* :176 */
+/* pixel subset for tile-parallel multi-GPU rendering: this renderer handles pixel tiles
+ * (64x... row blocks) with index % world == rank.  Default (0,1) = whole frame. */
+int vnr_renderer_set_partition(vnr_renderer_t* r, int rank, int world);
+/* jitter source: 0 = gdt::LCG<16>(frame_index, pixel) as the reference, 1 = fixed 0.5 */
+int vnr_renderer_set_jitter_mode(vnr_renderer_t* r, int mode);
+int vnr_render(vnr_renderer_t* r);                                     /* vnrRender :177 (async) */
+/* vnrRendererMapFrame :178: syncs, returns host float4[w*h] valid until the second-next map */
+const float* vnr_map_frame(vnr_renderer_t* r);
+/* device frame buffer (float4[w*h]) of the last vnr_render, for on-device gathers */
+int vnr_renderer_device_frame(vnr_renderer_t* r, void** d_rgba, void* stream_out);
+/* counters of the last frame: [0] rays that hit the volume, [1] samples decoded,
+ * [2] samples composited, [3] wavefront rounds */
+int vnr_renderer_stats(vnr_renderer_t* r, uint64_t* stats4);
+
+/* vnrMemoryQuery (api.h:186): bytes of device memory held by volumes / renderers */
+int vnr_memory_query(size_t* used_by_renderer, size_t* used_by_network);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VNR_C_H */

@@ -1,0 +1,286 @@
+"""instantvnr_b200 -- B200-native (sm_100a) implementation of instantvnr's hot path.
+
+This Python package is only the harness around the product: it loads the C-ABI shared
+library (csrc -> _build/libvnr_b200.so, declared in include/vnr_c.h) through ctypes and
+offers thin object wrappers used by tests/, bench.py and the multi-GPU (torch.distributed)
+drivers.  The product itself is the CUDA/C++ library; there is no CPU or PyTorch fallback:
+importing works without a GPU (so the symbol table can be checked), every compute call
+raises VnrError if the CUDA library or a device is missing.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(_HERE)
+LIB_PATH = os.path.join(_HERE, "_build", "libvnr_b200.so")
+HEADER_PATH = os.path.join(ROOT, "include", "vnr_c.h")
+EXAMPLE_MODEL = os.path.join(_HERE, "configs", "example-model.json")
+
+VNR_OK = 0
+
+
+class VnrError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"[vnr error {code}] {msg}")
+        self.code = code
+
+
+def build(verbose=False):
+    """Compile libvnr_b200.so in-tree (nvcc, sm_100a)."""
+    subprocess.check_call(["make", "-C", os.path.join(_HERE, "csrc"), "-j8"] + ([] if verbose else ["-s"]))
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """The loaded C-ABI library.  Fails loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise VnrError(-2, f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(there is no fallback path)")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.vnr_last_error.restype = C.c_char_p
+        _lib.vnr_map_frame.restype = C.POINTER(C.c_float)
+        _lib.vnr_volume_release.restype = None
+        _lib.vnr_renderer_release.restype = None
+    return _lib
+
+
+def _check(code):
+    if code != VNR_OK:
+        raise VnrError(code, lib().vnr_last_error().decode("utf-8", "replace"))
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    if hasattr(a, "data_ptr"):          # torch tensor
+        return C.c_void_p(a.data_ptr())
+    return C.c_void_p(int(a))
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def device_count():
+    return int(lib().vnr_device_count())
+
+
+def example_model_json():
+    with open(EXAMPLE_MODEL) as f:
+        return f.read()
+
+
+def model_json(n_levels=8, n_features=8, log2_hashmap=19, base_res=16, n_hidden=4, per_level_scale=None):
+    """A model config in the reference's example-model.json schema."""
+    import json
+    cfg = json.loads("\n".join(l for l in example_model_json().splitlines() if not l.strip().startswith("//")))
+    cfg["encoding"].update(n_levels=n_levels, n_features_per_level=n_features, log2_hashmap_size=log2_hashmap,
+                           base_resolution=base_res)
+    if per_level_scale is not None:
+        cfg["encoding"]["per_level_scale"] = per_level_scale
+    cfg["network"]["n_hidden_layers"] = n_hidden
+    return json.dumps(cfg)
+
+
+class NeuralVolume:
+    """vnrVolume (neural) -- api.h:122-143."""
+
+    def __init__(self, model_json_text, dims):
+        self._h = C.c_void_p()
+        _check(lib().vnr_volume_create(model_json_text.encode(), int(dims[0]), int(dims[1]), int(dims[2]), C.byref(self._h)))
+        self.dims = tuple(int(d) for d in dims)
+        n, nm = C.c_uint64(), C.c_uint64()
+        L, F, H = C.c_int(), C.c_int(), C.c_int()
+        _check(lib().vnr_volume_model_info(self._h, C.byref(n), C.byref(nm), C.byref(L), C.byref(F), C.byref(H)))
+        self.n_params, self.n_mlp_params = n.value, nm.value
+        self.n_levels, self.n_features, self.n_hidden = L.value, F.value, H.value
+        self.enc_pad = ((self.n_levels * self.n_features + 15) // 16) * 16
+
+    def close(self):
+        if self._h:
+            lib().vnr_volume_release(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- parameters
+    def init_params(self, seed=1337):
+        _check(lib().vnr_volume_init_params(self._h, C.c_uint32(seed)))
+
+    def set_params_f16(self, params_u16):
+        p = np.ascontiguousarray(params_u16, dtype=np.uint16)
+        _check(lib().vnr_volume_set_params_f16(self._h, _ptr(p), C.c_size_t(p.size)))
+
+    def get_params_f16(self):
+        p = np.empty(self.n_params, dtype=np.uint16)
+        _check(lib().vnr_volume_get_params_f16(self._h, _ptr(p), C.c_size_t(p.size)))
+        return p
+
+    def load_params(self, blob):
+        _check(lib().vnr_volume_load_params(self._h, blob, C.c_size_t(len(blob))))
+
+    def save_params(self):
+        p, n = C.c_void_p(), C.c_size_t()
+        _check(lib().vnr_volume_save_params(self._h, C.byref(p), C.byref(n)))
+        return C.string_at(p, n.value)
+
+    # -- decode (NeuralVolume::inference)
+    def decode(self, d_xyz, d_out, n, stream=None):
+        _check(lib().vnr_volume_decode(self._h, _ptr(d_xyz), _ptr(d_out), C.c_size_t(n), _ptr(stream) if stream else None))
+
+    def decode_host(self, xyz):
+        xyz = _f32(xyz).reshape(-1, 3)
+        out = np.empty(xyz.shape[0], dtype=np.float32)
+        _check(lib().vnr_volume_decode_host(self._h, _ptr(xyz), _ptr(out), C.c_size_t(xyz.shape[0])))
+        return out
+
+    def decode_debug(self, xyz):
+        xyz = _f32(xyz).reshape(-1, 3)
+        out = np.empty(xyz.shape[0], dtype=np.float32)
+        enc = np.empty((xyz.shape[0], self.enc_pad), dtype=np.uint16)
+        _check(lib().vnr_volume_decode_debug(self._h, _ptr(xyz), _ptr(out), _ptr(enc), C.c_size_t(xyz.shape[0])))
+        return out, enc
+
+    # -- ground truth, macrocell, transfer function
+    def set_groundtruth(self, volume):
+        v = _f32(volume)
+        if v.size != self.dims[0] * self.dims[1] * self.dims[2]:
+            raise VnrError(-1, "ground-truth volume size does not match dims")
+        _check(lib().vnr_volume_set_groundtruth_f32(self._h, _ptr(v)))
+
+    def macrocell_from_groundtruth(self):
+        _check(lib().vnr_volume_macrocell_from_groundtruth(self._h))
+
+    def get_macrocell(self):
+        md = np.zeros(3, dtype=np.int32)
+        _check(lib().vnr_volume_get_macrocell(self._h, _ptr(md), None, None))
+        cells = int(md[0]) * int(md[1]) * int(md[2])
+        vr = np.empty(2 * cells, dtype=np.float32)
+        mo = np.empty(cells, dtype=np.float32)
+        _check(lib().vnr_volume_get_macrocell(self._h, _ptr(md), _ptr(vr), _ptr(mo)))
+        return tuple(int(x) for x in md), vr, mo
+
+    def set_macrocell(self, value_range):
+        vr = _f32(value_range)
+        _check(lib().vnr_volume_set_macrocell(self._h, _ptr(vr)))
+
+    def set_transfer_function(self, rgb, alpha, value_range=(0.0, 1.0)):
+        rgb = _f32(rgb).reshape(-1, 3)
+        alpha = _f32(alpha)
+        _check(lib().vnr_volume_set_tfn(self._h, _ptr(rgb), C.c_int(rgb.shape[0]), _ptr(alpha), C.c_int(alpha.size),
+                                        C.c_float(value_range[0]), C.c_float(value_range[1])))
+
+    # -- training
+    def train(self, steps, batch=0, fast_mode=True, stream=None):
+        _check(lib().vnr_volume_train(self._h, C.c_int(steps), C.c_int(batch), C.c_int(1 if fast_mode else 0), _ptr(stream) if stream else None))
+
+    def train_on(self, d_xyz, d_target, n, stream=None):
+        _check(lib().vnr_volume_train_on(self._h, _ptr(d_xyz), _ptr(d_target), C.c_size_t(n), _ptr(stream) if stream else None))
+
+    def train_grads(self, d_xyz, d_target, n, n_global=None, stream=None):
+        _check(lib().vnr_volume_train_grads(self._h, _ptr(d_xyz), _ptr(d_target), C.c_size_t(n), C.c_size_t(n_global or n),
+                                            _ptr(stream) if stream else None))
+
+    def optimizer_step(self, stream=None):
+        _check(lib().vnr_volume_optimizer_step(self._h, _ptr(stream) if stream else None))
+
+    def grad_buffer(self):
+        p, n, f = C.c_void_p(), C.c_size_t(), C.c_int()
+        _check(lib().vnr_volume_grad_buffer(self._h, C.byref(p), C.byref(n), C.byref(f)))
+        return p.value, n.value, bool(f.value)
+
+    def sample(self, d_xyz, d_target, n, stream=None):
+        _check(lib().vnr_volume_sample(self._h, _ptr(d_xyz), _ptr(d_target), C.c_size_t(n), _ptr(stream) if stream else None))
+
+    def sampler_skip(self, n_floats):
+        _check(lib().vnr_volume_sampler_skip(self._h, C.c_uint64(n_floats)))
+
+    def stats(self):
+        step, loss = C.c_uint64(), C.c_double()
+        _check(lib().vnr_volume_stats(self._h, C.byref(step), C.byref(loss)))
+        return step.value, loss.value
+
+
+class Renderer:
+    """vnrRenderer -- api.h:168-178."""
+
+    def __init__(self, volume):
+        self._h = C.c_void_p()
+        self.volume = volume           # keeps the volume alive (RendererContext, api_internal.h:41-45)
+        _check(lib().vnr_renderer_create(volume._h, C.byref(self._h)))
+        self.size = (0, 0)
+
+    def close(self):
+        if self._h:
+            lib().vnr_renderer_release(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_size(self, w, h):
+        _check(lib().vnr_renderer_set_size(self._h, int(w), int(h)))
+        self.size = (int(w), int(h))
+
+    def set_camera(self, cam_from, cam_at, cam_up, fovy=60.0):
+        _check(lib().vnr_renderer_set_camera(self._h, _ptr(_f32(cam_from)), _ptr(_f32(cam_at)), _ptr(_f32(cam_up)), C.c_float(fovy)))
+
+    def set_mode(self, mode):
+        _check(lib().vnr_renderer_set_mode(self._h, int(mode)))
+
+    def set_sampling_rate(self, r):
+        _check(lib().vnr_renderer_set_sampling_rate(self._h, C.c_float(r)))
+
+    def set_density_scale(self, s):
+        _check(lib().vnr_renderer_set_density_scale(self._h, C.c_float(s)))
+
+    def reset_accumulation(self):
+        _check(lib().vnr_renderer_reset_accumulation(self._h))
+
+    def set_partition(self, rank, world):
+        _check(lib().vnr_renderer_set_partition(self._h, int(rank), int(world)))
+
+    def set_jitter_mode(self, mode):
+        _check(lib().vnr_renderer_set_jitter_mode(self._h, int(mode)))
+
+    def render(self):
+        _check(lib().vnr_render(self._h))
+
+    def map_frame(self):
+        p = lib().vnr_map_frame(self._h)
+        if not p:
+            raise VnrError(-4, lib().vnr_last_error().decode("utf-8", "replace"))
+        w, h = self.size
+        return np.ctypeslib.as_array(p, shape=(h, w, 4)).copy()
+
+    def device_frame(self):
+        p = C.c_void_p()
+        _check(lib().vnr_renderer_device_frame(self._h, C.byref(p), None))
+        return p.value
+
+    def stats(self):
+        s = np.zeros(4, dtype=np.uint64)
+        _check(lib().vnr_renderer_stats(self._h, _ptr(s)))
+        return {"rays_hit": int(s[0]), "samples_decoded": int(s[1]), "samples_composited": int(s[2]), "rounds": int(s[3])}
+
+
+VNR_RAYMARCHING_NO_SHADING_DECODING = 4
+VNR_RAYMARCHING_NO_SHADING_SAMPLE_STREAMING = 5
+VNR_RAYMARCHING_NO_SHADING_IN_SHADER = 6

@@ -1,0 +1,129 @@
+// decode.cu -- fused neural-volume decode: coords[N] -> values[N].
+//
+// Replaces, in ONE kernel, the reference's decode boundary
+//   NeuralVolume::inference (core/network.cu:1043-1052) -> tcnn_inference
+//   (core/networks/tcnn_impl.cu:438-448) = extract_position + kernel_grid
+//   (tcnn encodings/grid.h:106-286) + kernel_mlp_fused (fully_fused_mlp.cu:495-553)
+//   + trim_and_cast (common_device.h:533-542)
+// with no intermediate round trip through global memory: each CTA (128 threads, one
+// sample row each) gathers the hash-grid features of a 128-sample tile straight into
+// the swizzled shared-memory A operand, runs the MLP chain on tcgen05 tensor cores
+// with TMEM accumulators (mlp_tile.cuh) and writes one float per sample.
+// Persistent grid: tiles are strided over gridDim.x CTAs (a multiple of the SM count).
+#include "mlp_tile.cuh"
+#include "vnr_host.h"
+
+namespace vnr {
+
+// Gather all levels of this thread's sample into row `row` of the A tile.
+template <int F>
+__device__ __forceinline__ void encode_row(uint8_t* a_smem, const DecoderDesc& d, const __half* __restrict__ grid, float x, float y, float z, uint32_t row) {
+  uint8_t* rowp = a_smem + row * 128u;
+  const uint32_t sw = (row & 7u);
+  if constexpr (F == 8) {
+#pragma unroll 2
+    for (int l = 0; l < d.n_levels; ++l) {
+      uint4 v = encode_level_f8(d.lv[l], grid, x, y, z);
+      *reinterpret_cast<uint4*>(rowp + (((uint32_t)l ^ sw) << 4)) = v;
+    }
+  } else if constexpr (F == 4) {
+#pragma unroll 2
+    for (int l = 0; l < d.n_levels; ++l) {
+      uint2 v = encode_level_f4(d.lv[l], grid, x, y, z);
+      *reinterpret_cast<uint2*>(rowp + ((((uint32_t)l >> 1) ^ sw) << 4) + ((uint32_t)l & 1u) * 8u) = v;
+    }
+  } else if constexpr (F == 2) {
+#pragma unroll 2
+    for (int l = 0; l < d.n_levels; ++l) {
+      uint32_t v = encode_level_f2(d.lv[l], grid, x, y, z);
+      *reinterpret_cast<uint32_t*>(rowp + ((((uint32_t)l >> 2) ^ sw) << 4) + ((uint32_t)l & 3u) * 4u) = v;
+    }
+  } else {
+    for (int l = 0; l < d.n_levels; ++l) {
+      __half v = encode_level_f1(d.lv[l], grid, x, y, z);
+      *reinterpret_cast<__half*>(rowp + ((((uint32_t)l >> 3) ^ sw) << 4) + ((uint32_t)l & 7u) * 2u) = v;
+    }
+  }
+  // zero the padding features up to enc_pad (tcnn pads the encoding to 16: grid.h:616-620)
+  for (int k = d.enc_dims; k < d.enc_pad; ++k)
+    *reinterpret_cast<__half*>(rowp + ((((uint32_t)k >> 3) ^ sw) << 4) + ((uint32_t)k & 7u) * 2u) = __float2half_rn(0.f);
+}
+
+template <int F>
+__global__ void __launch_bounds__(128, 4)
+decode_kernel(const DecoderDesc d, const __half* __restrict__ params, const float* __restrict__ coords, float* __restrict__ out,
+              uint32_t n, uint32_t n_tiles, __half* __restrict__ enc_out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* a_smem = smem;
+  uint8_t* w_smem = smem + MlpSmem::kATile;
+  __shared__ uint64_t mbar;
+  __shared__ uint32_t tmem_slot;
+
+  const int tid = threadIdx.x;
+  if (tid == 0) { tc05::mbar_init(&mbar, 1); tc05::fence_mbar_init(); }
+  if (tid < 32) tc05::tmem_alloc(&tmem_slot, 64);
+  stage_weights(w_smem, params, d, tid, 128);
+  tc05::fence_before_sync();
+  tc05::fence_async_smem();
+  __syncthreads();
+  tc05::fence_after_sync();
+  const uint32_t tmem_base = tmem_slot;
+  const __half* __restrict__ grid = params + d.n_mlp;
+  uint32_t phase = 0;
+
+  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const uint32_t s = tile * kTile + (uint32_t)tid;
+    const uint32_t sc = s < n ? s : n - 1;
+    const float x = coords[3 * (size_t)sc], y = coords[3 * (size_t)sc + 1], z = coords[3 * (size_t)sc + 2];
+    encode_row<F>(a_smem, d, grid, x, y, z, (uint32_t)tid);
+    if (enc_out && s < n) {   // debug / test tap of the encoded features (row-major [n][enc_pad])
+      for (int k = 0; k < d.enc_pad; ++k)
+        enc_out[(size_t)s * d.enc_pad + k] = *reinterpret_cast<__half*>(a_smem + tc05::sw128_off(tid, k >> 3) + (k & 7) * 2);
+    }
+    const float v = mlp_tile_forward(a_smem, w_smem, &mbar, phase, tmem_base, d, tid, 1);
+    if (s < n) out[s] = v;
+  }
+
+  tc05::fence_before_sync();
+  __syncthreads();
+  if (tid < 32) tc05::tmem_dealloc(tmem_base, 64);
+}
+
+static int g_num_sms = 0;
+int num_sms() {
+  if (!g_num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return g_num_sms;
+}
+
+template <int F>
+static cudaError_t launch_decode_t(const DecoderDesc& d, const __half* params, const float* coords, float* out, size_t n, __half* enc_out, cudaStream_t stream) {
+  const uint32_t n_tiles = (uint32_t)((n + kTile - 1) / kTile);
+  const size_t smem = 1024 + MlpSmem::kATile + MlpSmem::weights_bytes(d.n_hidden);
+  cudaError_t e = cudaFuncSetAttribute(decode_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  int per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_kernel<F>, 128, smem);
+  if (e != cudaSuccess) return e;
+  if (per_sm < 1) per_sm = 1;
+  const uint32_t grid = (uint32_t)std::min<size_t>(n_tiles, (size_t)num_sms() * per_sm);
+  decode_kernel<F><<<grid, 128, smem, stream>>>(d, params, coords, out, (uint32_t)n, n_tiles, enc_out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_decode(const DecoderDesc& d, const __half* params, const float* coords, float* out, size_t n, __half* enc_out, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  switch (d.n_feat) {
+    case 8: return launch_decode_t<8>(d, params, coords, out, n, enc_out, stream);
+    case 4: return launch_decode_t<4>(d, params, coords, out, n, enc_out, stream);
+    case 2: return launch_decode_t<2>(d, params, coords, out, n, enc_out, stream);
+    case 1: return launch_decode_t<1>(d, params, coords, out, n, enc_out, stream);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace vnr

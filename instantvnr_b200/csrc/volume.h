@@ -1,0 +1,65 @@
+// volume.h -- the neural volume and renderer objects behind the opaque C handles.
+#pragma once
+#include "vnr_host.h"
+
+namespace vnr {
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr; size_t n = 0;
+  DevBuf() {}
+  DevBuf(const DevBuf&) = delete; DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
+  static size_t& total() { static size_t t = 0; return t; }
+  void alloc(size_t count) {
+    if (count == n && p) return;
+    release();
+    if (count) { VNR_CUDA(cudaMalloc((void**)&p, count * sizeof(T))); n = count; total() += count * sizeof(T); }
+  }
+  void ensure(size_t count) { if (count > n) alloc(count); }
+  void zero(cudaStream_t s = 0) { if (p) VNR_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
+  void release() { if (p) { cudaFree(p); total() -= n * sizeof(T); } p = nullptr; n = 0; }
+  size_t bytes() const { return n * sizeof(T); }
+};
+
+struct Volume {
+  ModelConfig cfg;
+  int dims[3] = {0, 0, 0};
+  cudaStream_t stream = nullptr;
+
+  // parameters: fp16 working copy (MLP matrices, then grid), fp32 master, gradients, Adam state
+  DevBuf<__half> params;
+  DevBuf<float> master, m1, m2;
+  DevBuf<float> grads;             // fp32, loss-scaled (x128)
+  DevBuf<uint32_t> steps;
+  bool have_params = false, have_opt = false;
+  uint32_t opt_step = 0; float lr_factor = 1.f;
+  uint64_t train_step = 0;
+  DevBuf<double> loss_accum;       // [0] running sum of per-step losses, [1] last step
+  uint64_t loss_count = 0;
+
+  // ground truth + sampler
+  DevBuf<float> gt;                // linear [z][y][x]
+  bool have_gt = false;
+  Pcg32 sampler_rng;               // neural_sampler.cu:36  `static default_rng_t rng{1337}`
+  DevBuf<float> train_x, train_y;
+  DevBuf<__half> act_stash, dact;  // training activations / gradients
+  DevBuf<float> mlp_grad_partial;
+
+  // macrocell (core/macrocell.h): value range (offset by -1/+1) and max opacity per cell
+  int mc_dims[3] = {0, 0, 0};
+  DevBuf<float> mc_range, mc_maxop;
+
+  // transfer function (object.cpp:321-348)
+  DevBuf<float4> tfn_color; DevBuf<float> tfn_alpha;
+  int n_color = 0, n_alpha = 0; float tfn_lo = 0.f, tfn_hi = 1.f;
+
+  std::string blob;                // last serialized params.json
+  std::string peek_json;
+
+  Volume();
+  ~Volume();
+  size_t cells() const { return (size_t)mc_dims[0] * mc_dims[1] * mc_dims[2]; }
+};
+
+}  // namespace vnr
