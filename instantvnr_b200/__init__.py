@@ -71,6 +71,14 @@ def _f32(a):
     return np.ascontiguousarray(a, dtype=np.float32)
 
 
+def _stream(s):
+    """None -> NULL (the handle's own stream); 0 (torch's default stream) -> cudaStreamLegacy."""
+    if s is None:
+        return None
+    s = int(s)
+    return C.c_void_p(1 if s == 0 else s)
+
+
 def device_count():
     return int(lib().vnr_device_count())
 
@@ -140,7 +148,7 @@ class NeuralVolume:
 
     # -- decode (NeuralVolume::inference)
     def decode(self, d_xyz, d_out, n, stream=None):
-        _check(lib().vnr_volume_decode(self._h, _ptr(d_xyz), _ptr(d_out), C.c_size_t(n), _ptr(stream) if stream else None))
+        _check(lib().vnr_volume_decode(self._h, _ptr(d_xyz), _ptr(d_out), C.c_size_t(n), _stream(stream)))
 
     def decode_host(self, xyz):
         xyz = _f32(xyz).reshape(-1, 3)
@@ -186,17 +194,17 @@ class NeuralVolume:
 
     # -- training
     def train(self, steps, batch=0, fast_mode=True, stream=None):
-        _check(lib().vnr_volume_train(self._h, C.c_int(steps), C.c_int(batch), C.c_int(1 if fast_mode else 0), _ptr(stream) if stream else None))
+        _check(lib().vnr_volume_train(self._h, C.c_int(steps), C.c_int(batch), C.c_int(1 if fast_mode else 0), _stream(stream)))
 
     def train_on(self, d_xyz, d_target, n, stream=None):
-        _check(lib().vnr_volume_train_on(self._h, _ptr(d_xyz), _ptr(d_target), C.c_size_t(n), _ptr(stream) if stream else None))
+        _check(lib().vnr_volume_train_on(self._h, _ptr(d_xyz), _ptr(d_target), C.c_size_t(n), _stream(stream)))
 
     def train_grads(self, d_xyz, d_target, n, n_global=None, stream=None):
         _check(lib().vnr_volume_train_grads(self._h, _ptr(d_xyz), _ptr(d_target), C.c_size_t(n), C.c_size_t(n_global or n),
-                                            _ptr(stream) if stream else None))
+                                            _stream(stream)))
 
     def optimizer_step(self, stream=None):
-        _check(lib().vnr_volume_optimizer_step(self._h, _ptr(stream) if stream else None))
+        _check(lib().vnr_volume_optimizer_step(self._h, _stream(stream)))
 
     def grad_buffer(self):
         p, n, f = C.c_void_p(), C.c_size_t(), C.c_int()
@@ -204,7 +212,7 @@ class NeuralVolume:
         return p.value, n.value, bool(f.value)
 
     def sample(self, d_xyz, d_target, n, stream=None):
-        _check(lib().vnr_volume_sample(self._h, _ptr(d_xyz), _ptr(d_target), C.c_size_t(n), _ptr(stream) if stream else None))
+        _check(lib().vnr_volume_sample(self._h, _ptr(d_xyz), _ptr(d_target), C.c_size_t(n), _stream(stream)))
 
     def sampler_skip(self, n_floats):
         _check(lib().vnr_volume_sampler_skip(self._h, C.c_uint64(n_floats)))

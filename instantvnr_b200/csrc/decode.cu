@@ -49,10 +49,17 @@ __device__ __forceinline__ void encode_row(uint8_t* a_smem, const DecoderDesc& d
     *reinterpret_cast<__half*>(rowp + ((((uint32_t)k >> 3) ^ sw) << 4) + ((uint32_t)k & 7u) * 2u) = __float2half_rn(0.f);
 }
 
-template <int F>
+// STRIDE: floats per coordinate record (3 = xyz as NeuralVolume::inference takes them,
+// 4 = the marcher's (x, y, z, dt) sample records).  n_dev != nullptr: the sample count is
+// read from device memory (wavefront rounds are sized on the device, no host sync).
+template <int F, int STRIDE>
 __global__ void __launch_bounds__(128, 4)
 decode_kernel(const DecoderDesc d, const __half* __restrict__ params, const float* __restrict__ coords, float* __restrict__ out,
-              uint32_t n, uint32_t n_tiles, __half* __restrict__ enc_out) {
+              uint32_t n, const uint32_t* __restrict__ n_dev, __half* __restrict__ enc_out) {
+  if (n_dev) n = *n_dev;
+  if (n == 0) return;
+  const uint32_t n_tiles = (n + kTile - 1) / kTile;
+  if (blockIdx.x >= n_tiles) return;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* a_smem = smem;
@@ -75,7 +82,9 @@ decode_kernel(const DecoderDesc d, const __half* __restrict__ params, const floa
   for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const uint32_t s = tile * kTile + (uint32_t)tid;
     const uint32_t sc = s < n ? s : n - 1;
-    const float x = coords[3 * (size_t)sc], y = coords[3 * (size_t)sc + 1], z = coords[3 * (size_t)sc + 2];
+    float x, y, z;
+    if constexpr (STRIDE == 4) { const float4 c = *reinterpret_cast<const float4*>(coords + 4 * (size_t)sc); x = c.x; y = c.y; z = c.z; }
+    else { x = coords[3 * (size_t)sc]; y = coords[3 * (size_t)sc + 1]; z = coords[3 * (size_t)sc + 2]; }
     encode_row<F>(a_smem, d, grid, x, y, z, (uint32_t)tid);
     if (enc_out && s < n) {   // debug / test tap of the encoded features (row-major [n][enc_pad])
       for (int k = 0; k < d.enc_pad; ++k)
@@ -100,30 +109,47 @@ int num_sms() {
   return g_num_sms;
 }
 
-template <int F>
-static cudaError_t launch_decode_t(const DecoderDesc& d, const __half* params, const float* coords, float* out, size_t n, __half* enc_out, cudaStream_t stream) {
-  const uint32_t n_tiles = (uint32_t)((n + kTile - 1) / kTile);
+template <int F, int STRIDE>
+static cudaError_t launch_decode_t(const DecoderDesc& d, const __half* params, const float* coords, float* out, size_t n, const uint32_t* n_dev,
+                                   size_t n_max, __half* enc_out, cudaStream_t stream) {
   const size_t smem = 1024 + MlpSmem::kATile + MlpSmem::weights_bytes(d.n_hidden);
-  cudaError_t e = cudaFuncSetAttribute(decode_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  int per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_kernel<F>, 128, smem);
-  if (e != cudaSuccess) return e;
-  if (per_sm < 1) per_sm = 1;
+  static bool configured = false;
+  static int per_sm = 1;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(decode_kernel<F, STRIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_kernel<F, STRIDE>, 128, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    configured = true;
+  }
+  const size_t n_tiles = (n_max + kTile - 1) / kTile;
   const uint32_t grid = (uint32_t)std::min<size_t>(n_tiles, (size_t)num_sms() * per_sm);
-  decode_kernel<F><<<grid, 128, smem, stream>>>(d, params, coords, out, (uint32_t)n, n_tiles, enc_out);
+  decode_kernel<F, STRIDE><<<grid, 128, smem, stream>>>(d, params, coords, out, (uint32_t)n, n_dev, enc_out);
   return cudaGetLastError();
+}
+
+template <int STRIDE>
+static cudaError_t launch_decode_f(const DecoderDesc& d, const __half* params, const float* coords, float* out, size_t n, const uint32_t* n_dev,
+                                   size_t n_max, __half* enc_out, cudaStream_t stream) {
+  switch (d.n_feat) {
+    case 8: return launch_decode_t<8, STRIDE>(d, params, coords, out, n, n_dev, n_max, enc_out, stream);
+    case 4: return launch_decode_t<4, STRIDE>(d, params, coords, out, n, n_dev, n_max, enc_out, stream);
+    case 2: return launch_decode_t<2, STRIDE>(d, params, coords, out, n, n_dev, n_max, enc_out, stream);
+    case 1: return launch_decode_t<1, STRIDE>(d, params, coords, out, n, n_dev, n_max, enc_out, stream);
+    default: return cudaErrorInvalidValue;
+  }
 }
 
 cudaError_t launch_decode(const DecoderDesc& d, const __half* params, const float* coords, float* out, size_t n, __half* enc_out, cudaStream_t stream) {
   if (n == 0) return cudaSuccess;
-  switch (d.n_feat) {
-    case 8: return launch_decode_t<8>(d, params, coords, out, n, enc_out, stream);
-    case 4: return launch_decode_t<4>(d, params, coords, out, n, enc_out, stream);
-    case 2: return launch_decode_t<2>(d, params, coords, out, n, enc_out, stream);
-    case 1: return launch_decode_t<1>(d, params, coords, out, n, enc_out, stream);
-    default: return cudaErrorInvalidValue;
-  }
+  return launch_decode_f<3>(d, params, coords, out, n, nullptr, n, enc_out, stream);
+}
+
+// marcher variant: (x,y,z,dt) records, count read from *n_dev (at most n_max)
+cudaError_t launch_decode_samples(const DecoderDesc& d, const __half* params, const float4* samples, float* out, const uint32_t* n_dev, size_t n_max, cudaStream_t stream) {
+  if (n_max == 0) return cudaSuccess;
+  return launch_decode_f<4>(d, params, reinterpret_cast<const float*>(samples), out, 0, n_dev, n_max, nullptr, stream);
 }
 
 }  // namespace vnr

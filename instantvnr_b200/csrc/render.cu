@@ -1,0 +1,323 @@
+// render.cu -- the sample-streaming ray marcher (vnrRenderMode 5) as a device-driven wavefront.
+//
+// Replaces core/renderer/method_raymarching.cu:931-958 (iterative_raymarching_loop) and its
+// kernels :687-915.  Differences in structure (results are the same per ray):
+//   * no host round trip per round: the live sample count of every round lives in device
+//     memory (counters[r]) and the decode kernel reads it there; the host enqueues a bounded
+//     number of rounds (an upper bound of samples per ray / n_iters) and empty rounds exit
+//     immediately;
+//   * ONE kernel per round besides the decode: it composites the values of round r and walks
+//     the macrocell DDA for round r+1 (the reference walks the DDA twice, in the intersect
+//     and again in the compose kernel);
+//   * samples are compacted: a ray that emits k <= n_iters samples takes k slots (warp-
+//     aggregated atomic), so every 128-row tensor-core tile of the decode is full, instead of
+//     n_iters slots per live ray.
+#include <cmath>
+#include <cstring>
+
+#include "march.cuh"
+#include "render.h"
+
+namespace vnr {
+
+struct RayBuffers {
+  float4* rgba;        // colour.xyz, alpha
+  float4* tn_ncb;      // DDA t_next.xyz, next_cell_begin
+  int4* cell_base;     // DDA cell.xyz, w = first sample slot of the current round
+  uint32_t* state;     // bit 31: alive; low bits: samples in the current round
+  float* jitter;
+};
+
+__device__ __forceinline__ void write_pixel(const FrameParams& fp, float4* __restrict__ accum, float4* __restrict__ frame, uint32_t pixel, float4 c) {
+  // writePixelColor raytracing.h:196-207
+  if (fp.frame_index != 1) {
+    const float4 a = accum[pixel];
+    c = make_float4(a.x + c.x, a.y + c.y, a.z + c.z, a.w + c.w);
+  }
+  accum[pixel] = c;
+  const float fi = (float)fp.frame_index;
+  frame[pixel] = make_float4(__fdiv_rn(c.x, fi), __fdiv_rn(c.y, fi), __fdiv_rn(c.z, fi), __fdiv_rn(c.w, fi));
+}
+
+// counters: [0] rays that hit the volume, [1] samples composited, [2 + r] samples emitted for round r
+template <bool FIRST>
+__global__ void __launch_bounds__(128)
+march_round_kernel(const FrameParams fp, RayBuffers rb, const float4* __restrict__ prev_samples, const float* __restrict__ values,
+                   float4* __restrict__ next_samples, uint32_t* __restrict__ counters, int round, float4* __restrict__ accum, float4* __restrict__ frame) {
+  if (!FIRST && counters[2 + round - 1] == 0) return;      // nothing was alive in the previous round
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t lane = threadIdx.x & 31u;
+  bool active = i < fp.n_rays;
+  uint32_t pixel = 0;
+  if (active) {
+    pixel = ray_to_pixel(fp, i);
+    active = pixel < (uint32_t)fp.width * (uint32_t)fp.height;
+    if (FIRST && !active) rb.state[i] = 0;          // padding rays of a partial strip
+  }
+  uint32_t st = 0;
+  if (active && !FIRST) { st = rb.state[i]; active = (st >> 31) != 0; }
+
+  F3 org = f3(0, 0, 0), dir = f3(0, 0, 1), m_dir = dir;
+  float tmin = 0.f, tmax = VNR_FLOAT_LARGE, jitter = 0.5f;
+  float4 rgba = make_float4(0, 0, 0, 0);
+  DDAState dda; dda.tnx = dda.tny = dda.tnz = 0.f; dda.cx = dda.cy = dda.cz = 0; dda.ncb = 0.f;
+  uint32_t n_comp = 0;
+  bool hit = false;
+
+  if (active) {
+    compute_ray(fp, pixel, org, dir);
+    m_dir = f3(dir.x * fp.mc_rcp[0], dir.y * fp.mc_rcp[1], dir.z * fp.mc_rcp[2]);
+    const bool ok = intersect_box(tmin, tmax, org, dir, fp.bbox_lo, fp.bbox_hi);
+    if (FIRST) {
+      jitter = fp.jitter_mode == 0 ? jitter_lcg_tea16((uint32_t)fp.frame_index, pixel) : 0.5f;
+      if (ok) {
+        const F3 m_org = f3(org.x * fp.mc_rcp[0], org.y * fp.mc_rcp[1], org.z * fp.mc_rcp[2]);
+        dda_init(dda, m_org, m_dir, tmin, fp.mc_dims);
+        rb.jitter[i] = jitter;
+        hit = true;
+      } else {
+        write_pixel(fp, accum, frame, pixel, rgba);
+        rb.state[i] = 0;
+        active = false;
+      }
+    } else {
+      jitter = rb.jitter[i];
+      rgba = rb.rgba[i];
+      const float4 t = rb.tn_ncb[i];
+      const int4 c = rb.cell_base[i];
+      dda.tnx = t.x; dda.tny = t.y; dda.tnz = t.z; dda.ncb = t.w; dda.cx = c.x; dda.cy = c.y; dda.cz = c.z;
+      // ---- compose the samples of the previous round (iterative_compose_kernel :757-806)
+      const uint32_t cnt = st & 0xFFFFu, base = (uint32_t)c.w;
+      for (uint32_t k = 0; k < cnt; ++k) {
+        const float value = values[base + k];
+        const float dt = prev_samples[base + k].w;
+        float r, g, b, a;
+        classify(fp, fp.tfn_color, fp.tfn_alpha, value, dt, r, g, b, a);
+        const float tr = 1.f - rgba.w;
+        rgba.w = __fmaf_rn(tr, a, rgba.w);
+        rgba.x = __fmaf_rn(tr * r, a, rgba.x);
+        rgba.y = __fmaf_rn(tr * g, a, rgba.y);
+        rgba.z = __fmaf_rn(tr * b, a, rgba.z);
+        ++n_comp;
+        if (!(rgba.w < VNR_NEARLY_ONE)) break;
+      }
+      const bool resumable = dda_resumable(dda, m_dir, tmin, tmax, fp.mc_dims);
+      if (!(rgba.w < VNR_NEARLY_ONE && resumable)) {
+        write_pixel(fp, accum, frame, pixel, rgba);
+        rb.state[i] = 0;
+        active = false;
+      }
+    }
+  }
+
+  // ---- walk the DDA for the next round: up to n_iters samples (iterative_intersect_kernel :687-730)
+  float4 local[16];
+  uint32_t k = 0;
+  if (active) {
+    const uint32_t n_iters = (uint32_t)fp.n_iters;
+    march_exec(fp, dda, m_dir, tmin, tmax, [&](float tx, float ty) {
+      const float tl = __fmaf_rn(jitter, ty, (1.f - jitter) * tx);
+      const F3 c = madd(tl, dir, org);
+      local[k] = make_float4(c.x, c.y, c.z, ty - tx);
+      return (++k) < n_iters;
+    });
+  }
+  if (active && k == 0) {
+    // no sample left on this ray: the reference would carry it through one more (empty) round and
+    // then find it not resumable; finish it now.
+    write_pixel(fp, accum, frame, pixel, rgba);
+    rb.state[i] = 0;
+    active = false;
+  }
+  // ---- warp-aggregated slot reservation (compaction)
+  uint32_t incl = k;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (uint32_t)o) incl += t; }
+  const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+  uint32_t base = 0;
+  if (lane == 31 && total) base = atomicAdd(&counters[2 + round], total);
+  base = __shfl_sync(0xffffffffu, base, 31) + (incl - k);
+  if (active) {
+    for (uint32_t j = 0; j < k; ++j) next_samples[base + j] = local[j];
+    rb.rgba[i] = rgba;
+    rb.tn_ncb[i] = make_float4(dda.tnx, dda.tny, dda.tnz, dda.ncb);
+    rb.cell_base[i] = make_int4(dda.cx, dda.cy, dda.cz, (int)base);
+    rb.state[i] = 0x80000000u | k;
+  }
+  // ---- statistics
+  const uint32_t hits = __ballot_sync(0xffffffffu, hit);
+  uint32_t comp = n_comp;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) comp += __shfl_xor_sync(0xffffffffu, comp, o);
+  if (lane == 0) {
+    if (FIRST && hits) atomicAdd(&counters[0], __popc(hits));
+    if (comp) atomicAdd(&counters[1], comp);
+  }
+}
+
+// rays still alive after the last enqueued round (cannot happen when the bound holds; counted)
+__global__ void finalize_kernel(const FrameParams fp, RayBuffers rb, uint32_t* __restrict__ leftover, float4* __restrict__ accum, float4* __restrict__ frame) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= fp.n_rays) return;
+  if (rb.state[i] >> 31) {
+    const uint32_t pixel = ray_to_pixel(fp, i);
+    write_pixel(fp, accum, frame, pixel, rb.rgba[i]);
+    rb.state[i] = 0;
+    atomicAdd(leftover, 1u);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+
+Renderer::Renderer(Volume* v) : vol(v) {
+  VNR_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  VNR_CUDA(cudaEventCreateWithFlags(&frame_done[0], cudaEventDisableTiming));
+  VNR_CUDA(cudaEventCreateWithFlags(&frame_done[1], cudaEventDisableTiming));
+  VNR_CUDA(cudaEventCreateWithFlags(&vol_ready, cudaEventDisableTiming));
+  VNR_CUDA(cudaMallocHost((void**)&h_counters, sizeof(uint32_t) * (kMaxRounds + 4)));
+  memset(h_counters, 0, sizeof(uint32_t) * (kMaxRounds + 4));
+  if (const char* e = getenv("VNR_RM_N_ITERS")) {       // method_raymarching.cu:30-38
+    int n = atoi(e);
+    if (n >= 1 && n <= 16) n_iters = n;
+  }
+}
+
+Renderer::~Renderer() {
+  if (stream) cudaStreamSynchronize(stream);
+  for (int k = 0; k < 2; ++k) { if (h_frame[k]) cudaFreeHost(h_frame[k]); if (frame_done[k]) cudaEventDestroy(frame_done[k]); }
+  if (vol_ready) cudaEventDestroy(vol_ready);
+  if (h_counters) cudaFreeHost(h_counters);
+  if (stream) cudaStreamDestroy(stream);
+}
+
+uint32_t Renderer::local_rays() const {
+  if (part_world <= 1) return (uint32_t)width * (uint32_t)height;
+  const uint32_t nstrips = ((uint32_t)height + strip_rows - 1) / strip_rows;
+  const uint32_t owned = nstrips > (uint32_t)part_rank ? (nstrips - (uint32_t)part_rank + (uint32_t)part_world - 1) / (uint32_t)part_world : 0;
+  return owned * strip_rows * (uint32_t)width;
+}
+
+void Renderer::resize(int w, int h) {
+  if (w <= 0 || h <= 0) throw InvalidError("framebuffer size must be positive");
+  if (stream) VNR_CUDA(cudaStreamSynchronize(stream));
+  width = w; height = h;
+  const size_t npix = (size_t)w * h;
+  accum.alloc(npix); frame.alloc(npix);
+  accum.zero(stream); frame.zero(stream);
+  for (int k = 0; k < 2; ++k) {
+    if (h_frame[k]) { cudaFreeHost(h_frame[k]); h_frame[k] = nullptr; }
+    VNR_CUDA(cudaMallocHost((void**)&h_frame[k], npix * sizeof(float4)));
+  }
+  reset = true;
+}
+
+static void cross(const float* a, const float* b, float* o) {
+  o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0];
+}
+static void normalize3(float* v) {
+  const float d = fmaf(v[2], v[2], fmaf(v[1], v[1], v[0] * v[0]));
+  const float r = 1.0f / sqrtf(d);
+  v[0] *= r; v[1] *= r; v[2] *= r;
+}
+
+void Renderer::fill_frame_params(FrameParams& fp) {
+  memset(&fp, 0, sizeof fp);
+  fp.width = width; fp.height = height; fp.frame_index = frame_index; fp.n_iters = n_iters;
+  fp.jitter_mode = jitter_mode; fp.tex_round = 0; fp.part_rank = part_rank; fp.part_world = part_world;
+  fp.strip_rows = strip_rows; fp.n_rays = local_rays();
+  // camera basis (renderer.cpp:87-96)
+  const float t = 2.f * tanf(fovy * 0.5f * (float)M_PI / 180.f);
+  const float aspect = width / float(height);
+  float dir[3] = {cam_at[0] - cam_from[0], cam_at[1] - cam_from[1], cam_at[2] - cam_from[2]};
+  normalize3(dir);
+  float hor[3]; cross(dir, cam_up, hor); normalize3(hor);
+  const float ta = t * aspect;
+  for (int k = 0; k < 3; ++k) hor[k] = ta * hor[k];
+  float ver[3]; cross(hor, dir, ver);
+  for (int k = 0; k < 3; ++k) ver[k] = ver[k] / aspect;
+  for (int k = 0; k < 3; ++k) { fp.cam_pos[k] = cam_from[k]; fp.cam_dir[k] = dir[k]; fp.cam_hor[k] = hor[k]; fp.cam_ver[k] = ver[k]; }
+  // object -> world = translate(-dims/2) * scale(dims) (network.cu:569); world -> object = inverse
+  const float d[3] = {(float)vol->dims[0] * scale[0], (float)vol->dims[1] * scale[1], (float)vol->dims[2] * scale[2]};
+  const float det = d[0] * d[1] * d[2];
+  const float il[3] = {(d[1] * d[2]) / det, (d[0] * d[2]) / det, (d[0] * d[1]) / det};
+  fp.wto_l[0] = il[0]; fp.wto_l[4] = il[1]; fp.wto_l[8] = il[2];
+  for (int k = 0; k < 3; ++k) { const float tp = d[k] / -2.f; fp.wto_p[k] = -(il[k] * tp); }
+  for (int k = 0; k < 3; ++k) { fp.bbox_lo[k] = clip_lo[k]; fp.bbox_hi[k] = clip_hi[k]; }
+  fp.step = 1.f / sampling_rate; fp.step_rcp = sampling_rate;          // object.cpp:303-304
+  for (int k = 0; k < 3; ++k) {
+    fp.mc_dims[k] = vol->mc_dims[k];
+    const float spacing = 16.f / (float)vol->dims[k];                  // macrocell.cu:200
+    fp.mc_rcp[k] = 1.f / spacing;                                      // object.cpp:318
+  }
+  fp.mc_maxop = vol->mc_maxop.p;
+  fp.tfn_color = vol->tfn_color.p; fp.tfn_alpha = vol->tfn_alpha.p;
+  fp.n_color = vol->n_color; fp.n_alpha = vol->n_alpha;
+  fp.tfn_lo = vol->tfn_lo; fp.tfn_hi = vol->tfn_hi; fp.tfn_rcp = 1.f / (vol->tfn_hi - vol->tfn_lo);
+}
+
+int Renderer::round_bound() const {
+  // samples per ray <= world-space diagonal * sampling_rate (one per step) + one clipped sample per
+  // macrocell crossed + 2; a live ray consumes n_iters samples per round.
+  const double dx = vol->dims[0] * scale[0], dy = vol->dims[1] * scale[1], dz = vol->dims[2] * scale[2];
+  const double diag = std::sqrt(dx * dx + dy * dy + dz * dz);
+  const double max_samples = std::ceil(diag * sampling_rate) + vol->mc_dims[0] + vol->mc_dims[1] + vol->mc_dims[2] + 2;
+  return (int)std::ceil(max_samples / n_iters) + 1;
+}
+
+void Renderer::render() {
+  if (width <= 0 || height <= 0) return;                               // renderer.cpp:62
+  if (mode != 5 && mode != 6) throw UnsupportedError("rendering mode " + std::to_string(mode) + " is outside this library's path (modes 5 and 6)");
+  if (!vol->have_params) throw StateError("the neural volume has no parameters");
+  if (reset) frame_index = 0;
+  frame_index++;
+  reset = false;
+  FrameParams fp; fill_frame_params(fp);
+  const uint32_t n_rays = fp.n_rays;
+  const int rounds = round_bound();
+  // make the volume's pending work (training, tfn upload) visible to the frame stream
+  VNR_CUDA(cudaEventRecord(vol_ready, vol->stream));
+  VNR_CUDA(cudaStreamWaitEvent(stream, vol_ready, 0));
+
+  const size_t cap = (size_t)n_rays * n_iters;
+  samples[0].ensure(cap); samples[1].ensure(cap); values.ensure(cap);
+  ray_rgba.ensure(n_rays); ray_tn.ensure(n_rays); ray_cell.ensure(n_rays); ray_state.ensure(n_rays); ray_jitter.ensure(n_rays);
+  counters.ensure(kMaxRounds + 4);
+  if (rounds + 3 > kMaxRounds) throw UnsupportedError("sampling rate too high for the round bound");
+  VNR_CUDA(cudaMemsetAsync(counters.p, 0, counters.bytes(), stream));
+  RayBuffers rb{ray_rgba.p, ray_tn.p, ray_cell.p, ray_state.p, ray_jitter.p};
+  const unsigned grid = (n_rays + 127) / 128;
+  if (n_rays) {
+    march_round_kernel<true><<<grid, 128, 0, stream>>>(fp, rb, nullptr, nullptr, samples[0].p, counters.p, 0, accum.p, frame.p);
+    for (int r = 0; r < rounds; ++r) {
+      VNR_CUDA(launch_decode_samples(vol->cfg.desc, vol->params.p, samples[r & 1].p, values.p, counters.p + 2 + r, cap, stream));
+      march_round_kernel<false><<<grid, 128, 0, stream>>>(fp, rb, samples[r & 1].p, values.p, samples[(r + 1) & 1].p, counters.p, r + 1, accum.p, frame.p);
+    }
+    finalize_kernel<<<grid, 128, 0, stream>>>(fp, rb, counters.p + kMaxRounds + 3, accum.p, frame.p);
+    VNR_CUDA(cudaGetLastError());
+  }
+  last_rounds = rounds;
+  // framebuffer.download_async (renderer.cpp:133)
+  VNR_CUDA(cudaMemcpyAsync(h_frame[cur], frame.p, frame.bytes(), cudaMemcpyDeviceToHost, stream));
+  VNR_CUDA(cudaMemcpyAsync(h_counters, counters.p, sizeof(uint32_t) * (kMaxRounds + 4), cudaMemcpyDeviceToHost, stream));
+  VNR_CUDA(cudaEventRecord(frame_done[cur], stream));
+  rendered = true;
+}
+
+const float* Renderer::map_frame() {
+  if (!rendered) throw StateError("vnr_map_frame called before vnr_render");
+  VNR_CUDA(cudaEventSynchronize(frame_done[cur]));                     // renderer.h:84-94
+  const float* p = reinterpret_cast<const float*>(h_frame[cur]);
+  cur ^= 1;                                                             // double-buffer swap
+  return p;
+}
+
+void Renderer::stats(uint64_t* s4) {
+  VNR_CUDA(cudaStreamSynchronize(stream));
+  s4[0] = h_counters[0]; s4[2] = h_counters[1];
+  uint64_t dec = 0, rounds = 0;
+  for (int r = 0; r <= last_rounds && r < kMaxRounds; ++r) { dec += h_counters[2 + r]; if (h_counters[2 + r]) ++rounds; }
+  s4[1] = dec; s4[3] = rounds;
+  if (h_counters[kMaxRounds + 3]) throw StateError("round bound exceeded: " + std::to_string(h_counters[kMaxRounds + 3]) + " rays were cut short");
+}
+
+}  // namespace vnr

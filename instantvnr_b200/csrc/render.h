@@ -1,5 +1,45 @@
-// render.h -- launchers of the marcher kernels (render.cu)
+// render.h -- the renderer object behind vnr_renderer_t (MainRenderer, renderer.h:55-235)
 #pragma once
 #include "volume.h"
+
 namespace vnr {
-}
+
+struct FrameParams;
+constexpr int kMaxRounds = 1024;
+
+struct Renderer {
+  Volume* vol;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t frame_done[2] = {nullptr, nullptr};
+  cudaEvent_t vol_ready = nullptr;
+  int width = 0, height = 0;
+  int mode = 5;                         // vnrCreateRenderer default (api.cpp:456)
+  int n_iters = 16;                     // N_ITERS (method_raymarching.cu:30-40)
+  int jitter_mode = 0;
+  int part_rank = 0, part_world = 1; uint32_t strip_rows = 4;
+  float cam_from[3] = {0, 0, -1}, cam_at[3] = {0, 0, 0}, cam_up[3] = {0, 1, 0}, fovy = 60.f;   // instantvnr_types.h:74-83
+  float sampling_rate = 1.f, density_scale = 1.f;
+  float scale[3] = {1, 1, 1};
+  float clip_lo[3] = {0, 0, 0}, clip_hi[3] = {1, 1, 1};
+  int frame_index = 0; bool reset = true, rendered = false;
+  int cur = 0, last_rounds = 0;
+
+  DevBuf<float4> accum, frame, samples[2], ray_rgba, ray_tn;
+  DevBuf<int4> ray_cell;
+  DevBuf<float> values, ray_jitter;
+  DevBuf<uint32_t> ray_state, counters;
+  float4* h_frame[2] = {nullptr, nullptr};
+  uint32_t* h_counters = nullptr;
+
+  explicit Renderer(Volume* v);
+  ~Renderer();
+  uint32_t local_rays() const;
+  void resize(int w, int h);
+  void fill_frame_params(FrameParams& fp);
+  int round_bound() const;
+  void render();
+  const float* map_frame();
+  void stats(uint64_t* s4);
+};
+
+}  // namespace vnr

@@ -1,15 +1,56 @@
-// vnr_c_render.inl -- renderer entry points
-VNR_EXPORT int vnr_renderer_create(vnr_volume_t*, vnr_renderer_t**) VNR_TODO("vnr_renderer_create")
-VNR_EXPORT void vnr_renderer_release(vnr_renderer_t*) {}
-VNR_EXPORT int vnr_renderer_set_size(vnr_renderer_t*, int, int) VNR_TODO("vnr_renderer_set_size")
-VNR_EXPORT int vnr_renderer_set_camera(vnr_renderer_t*, const float*, const float*, const float*, float) VNR_TODO("vnr_renderer_set_camera")
-VNR_EXPORT int vnr_renderer_set_mode(vnr_renderer_t*, int) VNR_TODO("vnr_renderer_set_mode")
-VNR_EXPORT int vnr_renderer_set_sampling_rate(vnr_renderer_t*, float) VNR_TODO("vnr_renderer_set_sampling_rate")
-VNR_EXPORT int vnr_renderer_set_density_scale(vnr_renderer_t*, float) VNR_TODO("vnr_renderer_set_density_scale")
-VNR_EXPORT int vnr_renderer_reset_accumulation(vnr_renderer_t*) VNR_TODO("vnr_renderer_reset_accumulation")
-VNR_EXPORT int vnr_renderer_set_partition(vnr_renderer_t*, int, int) VNR_TODO("vnr_renderer_set_partition")
-VNR_EXPORT int vnr_renderer_set_jitter_mode(vnr_renderer_t*, int) VNR_TODO("vnr_renderer_set_jitter_mode")
-VNR_EXPORT int vnr_render(vnr_renderer_t*) VNR_TODO("vnr_render")
-VNR_EXPORT const float* vnr_map_frame(vnr_renderer_t*) { g_last_error = "vnr_map_frame: not implemented yet"; return nullptr; }
-VNR_EXPORT int vnr_renderer_device_frame(vnr_renderer_t*, void**, void*) VNR_TODO("vnr_renderer_device_frame")
-VNR_EXPORT int vnr_renderer_stats(vnr_renderer_t*, uint64_t*) VNR_TODO("vnr_renderer_stats")
+// vnr_c_render.inl -- renderer entry points (MainRenderer / api.cpp:419-525)
+static Renderer* R(vnr_renderer_t* r) { if (!r) throw InvalidError("null renderer handle"); return reinterpret_cast<Renderer*>(r); }
+
+VNR_EXPORT int vnr_renderer_create(vnr_volume_t* vh, vnr_renderer_t** out) {
+  return guard([&] {
+    Volume* v = V(vh);
+    if (!out) throw InvalidError("null argument");
+    *out = reinterpret_cast<vnr_renderer_t*>(new Renderer(v));
+  });
+}
+VNR_EXPORT void vnr_renderer_release(vnr_renderer_t* r) { delete reinterpret_cast<Renderer*>(r); }
+VNR_EXPORT int vnr_renderer_set_size(vnr_renderer_t* r, int w, int h) { return guard([&] { R(r)->resize(w, h); }); }
+VNR_EXPORT int vnr_renderer_set_camera(vnr_renderer_t* r, const float* from, const float* at, const float* up, float fovy) {
+  return guard([&] {
+    Renderer* s = R(r);
+    if (!from || !at || !up) throw InvalidError("null camera vector");
+    for (int k = 0; k < 3; ++k) { s->cam_from[k] = from[k]; s->cam_at[k] = at[k]; s->cam_up[k] = up[k]; }
+    if (fovy > 0.f) s->fovy = fovy;
+    s->reset = true;                                   // renderer.h set_camera -> reset_frame
+  });
+}
+VNR_EXPORT int vnr_renderer_set_mode(vnr_renderer_t* r, int mode) {
+  return guard([&] {
+    if (mode < 0 || mode >= 16) throw InvalidError("unknown rendering mode");   // api.h:85-86
+    R(r)->mode = mode; R(r)->reset = true;
+  });
+}
+VNR_EXPORT int vnr_renderer_set_sampling_rate(vnr_renderer_t* r, float rate) {
+  return guard([&] { if (!(rate > 0.f)) throw InvalidError("sampling rate must be positive"); R(r)->sampling_rate = rate; R(r)->reset = true; });
+}
+VNR_EXPORT int vnr_renderer_set_density_scale(vnr_renderer_t* r, float s) { return guard([&] { R(r)->density_scale = s; R(r)->reset = true; }); }
+VNR_EXPORT int vnr_renderer_reset_accumulation(vnr_renderer_t* r) { return guard([&] { R(r)->reset = true; }); }
+VNR_EXPORT int vnr_renderer_set_partition(vnr_renderer_t* r, int rank, int world) {
+  return guard([&] {
+    if (world < 1 || rank < 0 || rank >= world) throw InvalidError("bad partition");
+    R(r)->part_rank = rank; R(r)->part_world = world; R(r)->reset = true;
+  });
+}
+VNR_EXPORT int vnr_renderer_set_jitter_mode(vnr_renderer_t* r, int mode) {
+  return guard([&] { if (mode != 0 && mode != 1) throw InvalidError("bad jitter mode"); R(r)->jitter_mode = mode; R(r)->reset = true; });
+}
+VNR_EXPORT int vnr_render(vnr_renderer_t* r) { return guard([&] { R(r)->render(); }); }
+VNR_EXPORT const float* vnr_map_frame(vnr_renderer_t* r) {
+  const float* p = nullptr;
+  guard([&] { p = R(r)->map_frame(); });
+  return p;
+}
+VNR_EXPORT int vnr_renderer_device_frame(vnr_renderer_t* r, void** d_rgba, void* stream_out) {
+  return guard([&] {
+    Renderer* s = R(r);
+    if (!d_rgba) throw InvalidError("null argument");
+    *d_rgba = s->frame.p;
+    if (stream_out) *reinterpret_cast<cudaStream_t*>(stream_out) = s->stream;
+  });
+}
+VNR_EXPORT int vnr_renderer_stats(vnr_renderer_t* r, uint64_t* s4) { return guard([&] { if (!s4) throw InvalidError("null argument"); R(r)->stats(s4); }); }
