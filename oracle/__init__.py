@@ -36,6 +36,8 @@ def lib():
         _lib.orc_lcg_tea16_first.restype = C.c_float
         _lib.orc_grid_index.restype = C.c_uint32
         _lib.orc_hadd.restype = C.c_uint16
+        _lib.orc_hadd_exact.restype = C.c_uint16
+        _lib.orc_f16_selftest.restype = C.c_uint64
     return _lib
 
 

@@ -49,7 +49,9 @@ namespace {
 // ---------------------------------------------------------------------------
 typedef uint16_t h16;
 
-static inline float h2f(h16 h) {
+// Portable bit-level conversions (always compiled; orc_f16_selftest checks them against the
+// F16C instructions when those are used as the fast path below).
+static inline float h2f_soft(h16 h) {
   uint32_t s = (uint32_t)(h & 0x8000u) << 16;
   uint32_t e = (h >> 10) & 0x1fu;
   uint32_t m = h & 0x3ffu;
@@ -70,7 +72,7 @@ static inline float h2f(h16 h) {
   float f; std::memcpy(&f, &u, 4); return f;
 }
 
-static inline h16 f2h(float f) {
+static inline h16 f2h_soft(float f) {
   uint32_t x; std::memcpy(&x, &f, 4);
   uint32_t s = (x >> 16) & 0x8000u;
   uint32_t a = x & 0x7fffffffu;
@@ -96,7 +98,16 @@ static inline h16 f2h(float f) {
   return (h16)(s | (base + q));
 }
 
-// double -> half with a single rounding (used for the exact half + half add)
+#if defined(__F16C__)
+#include <immintrin.h>
+static inline float h2f(h16 h) { return _cvtsh_ss(h); }
+static inline h16 f2h(float f) { return (h16)_cvtss_sh(f, _MM_FROUND_TO_NEAREST_INT | _MM_FROUND_NO_EXC); }
+#else
+static inline float h2f(h16 h) { return h2f_soft(h); }
+static inline h16 f2h(float f) { return f2h_soft(f); }
+#endif
+
+// double -> half with a single rounding (reference implementation of the exact half + half add)
 static inline h16 d2h(double d) {
   // a sum of two halves is exactly representable in double; going through
   // float would round twice.  Handle by rounding the double directly.
@@ -118,8 +129,11 @@ static inline h16 d2h(double d) {
   return (h16)(s | (f2h(fv) & 0x7fffu));
 }
 
-// CUDA __hadd(a, b): exact sum rounded once to half.
-static inline h16 hadd(h16 a, h16 b) { return d2h((double)h2f(a) + (double)h2f(b)); }
+// CUDA __hadd(a, b): exact sum rounded once to half.  binary32 carries 24 >= 2*11+2 significand
+// bits, so rounding the (possibly inexact) float sum to half equals rounding the exact sum
+// (double rounding is innocuous); hadd_exact is the slow single-rounding form used by the self test.
+static inline h16 hadd_exact(h16 a, h16 b) { return d2h((double)h2f_soft(a) + (double)h2f_soft(b)); }
+static inline h16 hadd(h16 a, h16 b) { return f2h(h2f(a) + h2f(b)); }
 
 // ---------------------------------------------------------------------------
 // pcg32  (tcnn/dependencies/pcg32/pcg32.h:46-68 seed/next_uint, :107 next_float,
@@ -270,53 +284,56 @@ static void encode_one(const Model& m, const h16* grid, const float x[3], h16* o
 //   acc_mode 1: "reference-like" fp16 accumulator updated per 16-wide K chunk
 //               (wmma m16n16k16 with __half accumulator fragments, :68,:430).
 // hidden: optional [n_hidden][width] fp16 post-activation stash (training fwd :121-128)
-static float mlp_forward_one(const Model& m, const h16* w, const h16* enc, int acc_mode, h16* hidden, h16* out16 = nullptr) {
+//
+// The weights are widened to float and transposed once per call (MlpF) so that the inner loop
+// runs over the 64 independent output accumulators (vectorisable); for every output the sum
+// over k is still taken in ascending k order, so results equal the plain row-by-row loop.
+struct MlpF {
+  std::vector<float> wt;                 // per layer: [in][out] floats
+  std::vector<size_t> off; std::vector<int> in_w, out_w;
+};
+static MlpF make_mlpf(const Model& m, const h16* w) {
+  MlpF f; size_t src = 0, dst = 0;
+  for (int layer = 0; layer <= m.n_hidden; ++layer) {
+    const int in_w = layer == 0 ? m.enc_pad : m.width, out_w = layer == m.n_hidden ? m.out_pad : m.width;
+    f.off.push_back(dst); f.in_w.push_back(in_w); f.out_w.push_back(out_w);
+    f.wt.resize(dst + (size_t)in_w * out_w);
+    for (int o = 0; o < out_w; ++o) for (int k = 0; k < in_w; ++k) f.wt[dst + (size_t)k * out_w + o] = h2f(w[src + (size_t)o * in_w + k]);   // row-major [out][in] (:957-967)
+    src += (size_t)in_w * out_w; dst += (size_t)in_w * out_w;
+  }
+  return f;
+}
+static inline void mlp_layer(const MlpF& f, int layer, const float* cur, float* acc, int acc_mode) {
+  const int in_w = f.in_w[layer], out_w = f.out_w[layer];
+  const float* wt = f.wt.data() + f.off[layer];
+  for (int o = 0; o < out_w; ++o) acc[o] = 0.f;
+  if (acc_mode == 0) {
+    for (int k = 0; k < in_w; ++k) { const float c = cur[k]; const float* r = wt + (size_t)k * out_w; for (int o = 0; o < out_w; ++o) acc[o] += c * r[o]; }
+  } else {
+    for (int k0 = 0; k0 < in_w; k0 += 16) {
+      for (int k = k0; k < k0 + 16; ++k) { const float c = cur[k]; const float* r = wt + (size_t)k * out_w; for (int o = 0; o < out_w; ++o) acc[o] += c * r[o]; }
+      for (int o = 0; o < out_w; ++o) acc[o] = h2f(f2h(acc[o]));
+    }
+  }
+}
+static float mlp_forward_one(const Model& m, const MlpF& f, const h16* enc, int acc_mode, h16* hidden, h16* out16 = nullptr) {
   const int W = m.width;
-  float cur[128]; float nxt[128];
+  float cur[128]; float acc[128];
   for (int k = 0; k < m.enc_pad; ++k) cur[k] = h2f(enc[k]);
-  int in_w = m.enc_pad;
-  const h16* wl = w;
   for (int layer = 0; layer < m.n_hidden; ++layer) {
+    mlp_layer(f, layer, cur, acc, acc_mode);
     for (int o = 0; o < W; ++o) {
-      const h16* row = wl + (size_t)o * in_w;       // row-major [out][in]  (:957-967)
-      float acc;
-      if (acc_mode == 0) {
-        acc = 0.f;
-        for (int k = 0; k < in_w; ++k) acc += cur[k] * h2f(row[k]);
-      } else {
-        h16 hacc = 0;
-        for (int k0 = 0; k0 < in_w; k0 += 16) {
-          float part = h2f(hacc);
-          for (int k = k0; k < k0 + 16; ++k) part += cur[k] * h2f(row[k]);
-          hacc = f2h(part);
-        }
-        acc = h2f(hacc);
-      }
-      h16 hv = f2h(acc);
+      const h16 hv = f2h(acc[o]);
       float r = h2f(hv);
       r = r > 0.f ? r : 0.f;                        // ReLU common_device.h:71-76
-      nxt[o] = r;
+      cur[o] = r;
       if (hidden) hidden[(size_t)layer * W + o] = f2h(r);
     }
-    for (int o = 0; o < W; ++o) cur[o] = nxt[o];
-    wl += (size_t)W * in_w; in_w = W;
   }
   // output layer 64 -> 16 padded, no activation; only row 0 is meaningful
-  float y0 = 0.f;
-  for (int o = 0; o < m.out_pad; ++o) {
-    const h16* row = wl + (size_t)o * W;
-    float acc;
-    if (acc_mode == 0) { acc = 0.f; for (int k = 0; k < W; ++k) acc += cur[k] * h2f(row[k]); }
-    else {
-      h16 hacc = 0;
-      for (int k0 = 0; k0 < W; k0 += 16) { float part = h2f(hacc); for (int k = k0; k < k0 + 16; ++k) part += cur[k] * h2f(row[k]); hacc = f2h(part); }
-      acc = h2f(hacc);
-    }
-    h16 hv = f2h(acc);
-    if (out16) out16[o] = hv;
-    if (o == 0) y0 = h2f(hv);                       // trim_and_cast common_device.h:533-542
-  }
-  return y0;
+  mlp_layer(f, m.n_hidden, cur, acc, acc_mode);
+  if (out16) for (int o = 0; o < m.out_pad; ++o) out16[o] = f2h(acc[o]);
+  return h2f(f2h(acc[0]));                          // trim_and_cast common_device.h:533-542
 }
 
 // ---------------------------------------------------------------------------
@@ -567,6 +584,25 @@ ORC_API int orc_num_threads() {
 ORC_API void orc_f32_to_f16(const float* in, uint16_t* out, size_t n) { for (size_t i = 0; i < n; ++i) out[i] = f2h(in[i]); }
 ORC_API void orc_f16_to_f32(const uint16_t* in, float* out, size_t n) { for (size_t i = 0; i < n; ++i) out[i] = h2f(in[i]); }
 ORC_API uint16_t orc_hadd(uint16_t a, uint16_t b) { return hadd(a, b); }
+ORC_API uint16_t orc_hadd_exact(uint16_t a, uint16_t b) { return hadd_exact(a, b); }
+// exhaustive check of the fast conversions against the portable ones; returns mismatch count
+ORC_API uint64_t orc_f16_selftest() {
+  uint64_t bad = 0;
+  for (uint32_t h = 0; h < 65536; ++h) {
+    float a = h2f((h16)h), b = h2f_soft((h16)h);
+    uint32_t ua, ub; std::memcpy(&ua, &a, 4); std::memcpy(&ub, &b, 4);
+    bool nan = ((h >> 10) & 31) == 31 && (h & 1023);
+    if (!nan && ua != ub) ++bad;
+  }
+  uint32_t x = 0x12345678u;
+  for (int i = 0; i < 4000000; ++i) {
+    x = x * 1664525u + 1013904223u;
+    float f; std::memcpy(&f, &x, 4);
+    if (f != f) continue;
+    if (f2h(f) != f2h_soft(f)) ++bad;
+  }
+  return bad;
+}
 
 // pcg32 stream: seed(initstate, initseq), skip `advance`, emit n uint32
 ORC_API void orc_pcg32_uints(uint64_t initstate, uint64_t initseq, int64_t advance, uint32_t* out, size_t n) {
@@ -639,19 +675,21 @@ ORC_API void orc_encode(const int* cfg, float pls, const uint16_t* params_f16, c
 ORC_API void orc_decode(const int* cfg, float pls, const uint16_t* params_f16, const float* coords, size_t n, float* out, int acc_mode) {
   Model m = make_model(cfg, pls);
   const h16* grid = params_f16 + m.n_mlp;
+  const MlpF mf = make_mlpf(m, params_f16);
 #pragma omp parallel for schedule(static)
   for (long long i = 0; i < (long long)n; ++i) {
     h16 enc[128];
     encode_one(m, grid, coords + 3 * i, enc);
-    out[i] = mlp_forward_one(m, params_f16, enc, acc_mode, nullptr);
+    out[i] = mlp_forward_one(m, mf, enc, acc_mode, nullptr);
   }
 }
 
 // MLP only (encoded fp16 input given) -- used to test the tensor-core chain in isolation
 ORC_API void orc_mlp(const int* cfg, float pls, const uint16_t* params_f16, const uint16_t* enc, size_t n, float* out, int acc_mode) {
   Model m = make_model(cfg, pls);
+  const MlpF mf = make_mlpf(m, params_f16);
 #pragma omp parallel for schedule(static)
-  for (long long i = 0; i < (long long)n; ++i) out[i] = mlp_forward_one(m, params_f16, enc + (size_t)i * m.enc_pad, acc_mode, nullptr);
+  for (long long i = 0; i < (long long)n; ++i) out[i] = mlp_forward_one(m, mf, enc + (size_t)i * m.enc_pad, acc_mode, nullptr);
 }
 
 // --------------------------- sampler ---------------------------------------
@@ -792,6 +830,7 @@ ORC_API void orc_render(const int* cfg, float pls, const uint16_t* params_f16, i
                         float* accum /*w*h*4, in/out*/, float* frame /*w*h*4*/, uint64_t* stats) {
   Model m = make_model(cfg, pls);
   const h16* grid = params_f16 ? params_f16 + m.n_mlp : nullptr;
+  const MlpF mf = params_f16 ? make_mlpf(m, params_f16) : MlpF();
   Frame fr = frame_from(fparams, iparams, mc_max_opacity, colors, alphas);
   const size_t npix = (size_t)fr.width * fr.height;
   std::vector<RayState> rays(npix);
@@ -845,7 +884,7 @@ ORC_API void orc_render(const int* cfg, float pls, const uint16_t* params_f16, i
       for (int s = 0; s < k; ++s) {
         if (volume_mode == 0) {
           h16 enc[128]; encode_one(m, grid, coords + 3 * s, enc);
-          vals[s] = mlp_forward_one(m, params_f16, enc, acc_mode, nullptr);
+          vals[s] = mlp_forward_one(m, mf, enc, acc_mode, nullptr);
         } else {
           // sampleVolume: p*(1-rdims)+0.5*rdims then tex3D
           float q[3];
@@ -946,6 +985,7 @@ ORC_API double orc_train_step(void* h, const float* coords, const float* targets
   std::fill(s->grad.begin(), s->grad.end(), 0.f);
   const h16* w = s->params.data();
   const h16* grid = w + m.n_mlp;
+  const MlpF mf = make_mlpf(m, w);
   int nthreads = orc_num_threads();
   // MLP weight gradients: per-thread double accumulators, summed in thread order
   // (double makes the result independent of the thread count to float precision).
@@ -966,7 +1006,7 @@ ORC_API double orc_train_step(void* h, const float* coords, const float* targets
 #pragma omp for schedule(static)
     for (long long i = 0; i < (long long)n; ++i) {
       encode_one(m, grid, coords + 3 * i, enc);
-      float y = mlp_forward_one(m, w, enc, acc_mode, hidden.data(), out16);
+      float y = mlp_forward_one(m, mf, enc, acc_mode, hidden.data(), out16);
       // l1.h:40-76
       const float diff = y - targets[i];
       loss_terms[i] = (double)(fabsf(diff) / (float)n);
