@@ -98,14 +98,24 @@ int vnr_volume_train_on(vnr_volume_t* v, const float* d_xyz, const float* d_targ
  * the two the caller all-reduces the gradient buffer (vnr_volume_grad_buffer). */
 int vnr_volume_train_grads(vnr_volume_t* v, const float* d_xyz, const float* d_target, size_t n, size_t n_global, void* stream);
 int vnr_volume_optimizer_step(vnr_volume_t* v, void* stream);
-int vnr_volume_grad_buffer(vnr_volume_t* v, void** d_grads, size_t* n_bytes, int* is_f32);
+/* which = 0: MLP weight gradients (fp32, n_mlp elements); which = 1: hash-grid gradients (fp16,
+ * n_grid elements).  Both carry the loss scale (x128, tcnn trainer.h:234). */
+int vnr_volume_grad_buffer(vnr_volume_t* v, int which, void** d_grads, size_t* n_elems, int* is_f32);
+/* test tap: copy the current gradients to the host (either pointer may be NULL) */
+int vnr_volume_get_grads(vnr_volume_t* v, float* h_mlp /*n_mlp*/, uint16_t* h_grid /*n_grid, fp16*/);
 /* StaticSampler::sample (core/samplers/neural_sampler.cu:131-164) into device buffers */
 int vnr_volume_sample(vnr_volume_t* v, float* d_xyz, float* d_target, size_t n, void* stream);
 /* advance the sampler's pcg32 stream (rank r of a data-parallel job skips r*3*n per step) */
 int vnr_volume_sampler_skip(vnr_volume_t* v, uint64_t n_floats);
+/* test tap: trilinear ground-truth lookup at host coordinates.  hw_texture = 0: the product's
+ * software filter (1.8 fixed-point weights); 1: a real CUDA 3-D texture as the reference uses
+ * (tex3D<float>, linear filter, normalized coordinates, clamp). */
+int vnr_volume_sample_at(vnr_volume_t* v, const float* h_xyz, float* h_out, size_t n, int hw_texture);
 
 /* vnrNeuralVolumeGetTrainingStep / GetTrainingLoss                     api.h:132-133 */
 int vnr_volume_stats(vnr_volume_t* v, uint64_t* step, double* loss);
+/* loss of the most recent step (sum over the batch of |y - t| / N) */
+int vnr_volume_last_loss(vnr_volume_t* v, double* loss);
 
 /* ---- renderer ------------------------------------------------------------------------- */
 

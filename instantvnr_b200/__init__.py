@@ -206,10 +206,28 @@ class NeuralVolume:
     def optimizer_step(self, stream=None):
         _check(lib().vnr_volume_optimizer_step(self._h, _stream(stream)))
 
-    def grad_buffer(self):
+    def grad_buffer(self, which):
+        """(device pointer, n_elements, is_f32) of the MLP (which=0) or grid (which=1) gradients."""
         p, n, f = C.c_void_p(), C.c_size_t(), C.c_int()
-        _check(lib().vnr_volume_grad_buffer(self._h, C.byref(p), C.byref(n), C.byref(f)))
+        _check(lib().vnr_volume_grad_buffer(self._h, C.c_int(which), C.byref(p), C.byref(n), C.byref(f)))
         return p.value, n.value, bool(f.value)
+
+    def get_grads(self):
+        gm = np.empty(self.n_mlp_params, dtype=np.float32)
+        gg = np.empty(self.n_params - self.n_mlp_params, dtype=np.uint16)
+        _check(lib().vnr_volume_get_grads(self._h, _ptr(gm), _ptr(gg)))
+        return gm, gg
+
+    def sample_at(self, xyz, hw_texture=False):
+        xyz = _f32(xyz).reshape(-1, 3)
+        out = np.empty(xyz.shape[0], dtype=np.float32)
+        _check(lib().vnr_volume_sample_at(self._h, _ptr(xyz), _ptr(out), C.c_size_t(xyz.shape[0]), C.c_int(1 if hw_texture else 0)))
+        return out
+
+    def last_loss(self):
+        loss = C.c_double()
+        _check(lib().vnr_volume_last_loss(self._h, C.byref(loss)))
+        return loss.value
 
     def sample(self, d_xyz, d_target, n, stream=None):
         _check(lib().vnr_volume_sample(self._h, _ptr(d_xyz), _ptr(d_target), C.c_size_t(n), _stream(stream)))

@@ -1,0 +1,552 @@
+// train.cu -- the training step: sampler, fused forward + loss + backward, optimizer.
+//
+// Replaces (reference call stack):
+//   StaticSampler::sample            core/samplers/neural_sampler.cu:131-164  (pcg32 coords + tex3D target)
+//   Trainer::training_step           tcnn trainer.h:211-247                   (fwd, L1 loss x128, bwd)
+//     kernel_grid / kernel_mlp_fused / l1_loss / kernel_mlp_fused_backward /
+//     fc_multiply_split_k (x5, CUTLASS) / kernel_grid_backward (+ 46.7 MB memset)
+//   adam_step + ExponentialDecay     tcnn optimizers/adam.h:49-115, exponential_decay.h:61-72
+//
+// B200 structure: ONE persistent kernel does forward, loss and backward per 128-sample tile with
+// every activation kept in shared memory (no activation stash in HBM): hash-grid gather -> X0;
+// layer l: X_{l+1} = relu(X_l W_l^T) on tcgen05 (fp32 accumulators in TMEM); L1 gradient; then
+// walking back, for each matrix the data gradient D = d_{l+1} W_l (B operand = the same weight tile
+// read MN-major) and the weight gradient acc_l += d_{l+1}^T X_l (both operands read MN-major from the
+// activation tiles) are issued together; weight-gradient accumulators stay in TMEM for all tiles of
+// the CTA and are written once per CTA; dL/d(encoding) goes straight from TMEM to the hash table
+// with 16-byte vector fp16 reductions (red.global.add.noftz.v4.f16x2).  The optimizer sweep also
+// clears the gradients it consumes, so there is no per-step memset.
+#include <cmath>
+
+#include "mlp_tile.cuh"
+#include "train.h"
+
+namespace vnr {
+
+// ------------------------------------------------------------------------------------------
+// sampler
+// ------------------------------------------------------------------------------------------
+
+// CUDA linear filtering: weight in 1.8 fixed point (CUDA C Programming Guide, "Linear Filtering")
+__device__ __forceinline__ float tex_frac(float xb, float fl) {
+  const float fr = xb - fl;
+  return floorf(__fmaf_rn(fr, 256.f, 0.5f)) * (1.f / 256.f);
+}
+
+__device__ __forceinline__ float sample_volume_linear(const float* __restrict__ vol, int3 dims, float u, float v, float w) {
+  const float cx = __fmaf_rn(u, (float)dims.x, -0.5f), cy = __fmaf_rn(v, (float)dims.y, -0.5f), cz = __fmaf_rn(w, (float)dims.z, -0.5f);
+  const float fx = floorf(cx), fy = floorf(cy), fz = floorf(cz);
+  const float ax = tex_frac(cx, fx), ay = tex_frac(cy, fy), az = tex_frac(cz, fz);
+  const int x0 = min(max((int)fx, 0), dims.x - 1), x1 = min(max((int)fx + 1, 0), dims.x - 1);
+  const int y0 = min(max((int)fy, 0), dims.y - 1), y1 = min(max((int)fy + 1, 0), dims.y - 1);
+  const int z0 = min(max((int)fz, 0), dims.z - 1), z1 = min(max((int)fz + 1, 0), dims.z - 1);
+  const size_t sx = 1, sy = (size_t)dims.x, sz = (size_t)dims.x * dims.y;
+  auto at = [&](int x, int y, int z) { return __ldg(vol + x * sx + y * sy + z * sz); };
+  auto lerp = [](float t, float p, float q) { return __fmaf_rn(t, q, (1.f - t) * p); };
+  const float c00 = lerp(ax, at(x0, y0, z0), at(x1, y0, z0));
+  const float c10 = lerp(ax, at(x0, y1, z0), at(x1, y1, z0));
+  const float c01 = lerp(ax, at(x0, y0, z1), at(x1, y0, z1));
+  const float c11 = lerp(ax, at(x0, y1, z1), at(x1, y1, z1));
+  return lerp(az, lerp(ay, c00, c10), lerp(ay, c01, c11));
+}
+
+// Sample s draws the uniforms that generate_random_kernel (tcnn random.h:67-84) writes to
+// out[3s..3s+2]: element idx is produced by thread idx % n_threads as its (idx / n_threads)-th
+// value, i.e. stream position 4*(idx % n_threads) + idx / n_threads.
+__global__ void sampler_kernel(uint32_t n, Pcg32 base, uint32_t n_threads, const float* __restrict__ vol, int3 dims,
+                               float* __restrict__ coords, float* __restrict__ targets) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  float c[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const uint32_t idx = 3u * s + (uint32_t)d;
+    Pcg32 r = base;
+    r.advance(4ull * (idx % n_threads) + idx / n_threads);
+    c[d] = r.next_float();
+  }
+  coords[3 * (size_t)s] = c[0]; coords[3 * (size_t)s + 1] = c[1]; coords[3 * (size_t)s + 2] = c[2];
+  if (targets) targets[s] = sample_volume_linear(vol, dims, c[0], c[1], c[2]);
+}
+
+__global__ void sample_at_kernel(uint32_t n, const float* __restrict__ vol, int3 dims, const float* __restrict__ coords, float* __restrict__ out) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  out[s] = sample_volume_linear(vol, dims, coords[3 * (size_t)s], coords[3 * (size_t)s + 1], coords[3 * (size_t)s + 2]);
+}
+
+__global__ void sample_at_tex_kernel(uint32_t n, cudaTextureObject_t tex, const float* __restrict__ coords, float* __restrict__ out) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  out[s] = tex3D<float>(tex, coords[3 * (size_t)s], coords[3 * (size_t)s + 1], coords[3 * (size_t)s + 2]);
+}
+
+void sample_batch(Volume* v, float* d_xyz, float* d_target, size_t n, cudaStream_t s) {
+  if (!n) return;
+  if (d_target && !v->have_gt) throw StateError("[error]: missing a reference volume.");       // network.cu:233
+  const size_t n_floats = 3 * n, need = (n_floats + 3) / 4;
+  const uint32_t n_threads = (uint32_t)(((need + 127) / 128) * 128);
+  const int3 dims = make_int3(v->dims[0], v->dims[1], v->dims[2]);
+  sampler_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>((uint32_t)n, v->sampler_rng, n_threads, v->gt.p, dims, d_xyz, d_target);
+  VNR_CUDA(cudaGetLastError());
+  v->sampler_rng.advance(n_floats);                                    // random.h:90 rng.advance(n_elements)
+}
+
+void sample_at(Volume* v, const float* d_xyz, float* d_out, size_t n, int hw_texture, cudaStream_t s) {
+  if (!n) return;
+  if (!v->have_gt) throw StateError("no ground-truth volume set");
+  const int3 dims = make_int3(v->dims[0], v->dims[1], v->dims[2]);
+  if (!hw_texture) {
+    sample_at_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>((uint32_t)n, v->gt.p, dims, d_xyz, d_out);
+    VNR_CUDA(cudaGetLastError());
+    return;
+  }
+  // the reference's path: cudaArray + linear-filtered texture, normalized coordinates, clamp addressing
+  cudaArray_t arr = nullptr; cudaTextureObject_t tex = 0;
+  cudaChannelFormatDesc cd = cudaCreateChannelDesc<float>();
+  VNR_CUDA(cudaMalloc3DArray(&arr, &cd, make_cudaExtent(dims.x, dims.y, dims.z)));
+  cudaMemcpy3DParms cp = {};
+  cp.srcPtr = make_cudaPitchedPtr(v->gt.p, dims.x * sizeof(float), dims.x, dims.y);
+  cp.dstArray = arr; cp.extent = make_cudaExtent(dims.x, dims.y, dims.z); cp.kind = cudaMemcpyDeviceToDevice;
+  VNR_CUDA(cudaMemcpy3D(&cp));
+  cudaResourceDesc rd = {}; rd.resType = cudaResourceTypeArray; rd.res.array.array = arr;
+  cudaTextureDesc td = {};
+  td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+  td.filterMode = cudaFilterModeLinear; td.readMode = cudaReadModeElementType; td.normalizedCoords = 1;
+  VNR_CUDA(cudaCreateTextureObject(&tex, &rd, &td, nullptr));
+  sample_at_tex_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>((uint32_t)n, tex, d_xyz, d_out);
+  cudaError_t e = cudaStreamSynchronize(s);
+  cudaDestroyTextureObject(tex); cudaFreeArray(arr);
+  VNR_CUDA(e);
+}
+
+// ------------------------------------------------------------------------------------------
+// fused forward + loss + backward
+// ------------------------------------------------------------------------------------------
+
+constexpr int kTrainThreads = 256;
+
+__device__ __forceinline__ void bar_all() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__device__ __forceinline__ void red_add_f16x8(__half* addr, uint4 v) {
+  asm volatile("red.global.add.noftz.v4.f16x2 [%0], {%1, %2, %3, %4};" ::"l"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void red_add_f16x4(__half* addr, uint2 v) {
+  asm volatile("red.global.add.noftz.v2.f16x2 [%0], {%1, %2};" ::"l"(addr), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ void red_add_f16x2(__half* addr, uint32_t v) {
+  asm volatile("red.global.add.noftz.f16x2 [%0], %1;" ::"l"(addr), "r"(v) : "memory");
+}
+
+// (half)((float)grad * weight) for a packed pair  (grid.h:331)
+__device__ __forceinline__ uint32_t scale_pair(uint32_t g, float w) {
+  const float2 f = __half22float2(u32_as_h2(g));
+  return h2_as_u32(__floats2half2_rn(f.x * w, f.y * w));
+}
+
+// Scatter the gradient of one level (F halves in g[]) of one sample to its 8 corners.
+template <int F>
+__device__ __forceinline__ void scatter_level(const LevelDesc& lv, __half* __restrict__ ggrid, float x, float y, float z, const uint32_t* g) {
+  const CornerSetup c = corner_setup(lv, x, y, z);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float w = corner_weight(c, i);
+    __half* dst = ggrid + ((size_t)lv.offset + corner_index(lv, c, i)) * F;
+    if constexpr (F == 8) red_add_f16x8(dst, make_uint4(scale_pair(g[0], w), scale_pair(g[1], w), scale_pair(g[2], w), scale_pair(g[3], w)));
+    else if constexpr (F == 4) red_add_f16x4(dst, make_uint2(scale_pair(g[0], w), scale_pair(g[1], w)));
+    else if constexpr (F == 2) red_add_f16x2(dst, scale_pair(g[0], w));
+    else {
+      // F == 1: a 2-byte reduction; fp16 atomicAdd
+      const __half h = __float2half_rn(__half2float(__ushort_as_half((unsigned short)(g[0] & 0xFFFFu))) * w);
+      atomicAdd(dst, h);
+    }
+  }
+}
+
+struct TrainArgs {
+  const __half* params;
+  const float* coords;
+  const float* targets;
+  uint32_t n, n_global;
+  __half* grid_grads;          // fp16 [n_grid], loss-scaled (x128)
+  float* mlp_partial;          // fp32 [gridDim.x][n_mlp], loss-scaled
+  double* loss_accum;          // [0] running sum over steps, [1] this step
+  float loss_scale;
+};
+
+template <int F>
+__global__ void __launch_bounds__(kTrainThreads, 1)
+train_step_kernel(const DecoderDesc d, const TrainArgs a) {
+  using namespace tc05;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int NH = d.n_hidden;
+  uint8_t* xs = smem;                                         // X_0 .. X_NH : (NH+1) tiles of 16 KB
+  uint8_t* dy = xs + (size_t)(NH + 1) * MlpSmem::kATile;      // dL/dy tile (column 0 = gradient)
+  uint8_t* ws = dy + MlpSmem::kATile;                         // weight tiles
+  __shared__ uint64_t mbar;
+  __shared__ uint32_t tmem_slot;
+  __shared__ double loss_part[kTrainThreads / 32];
+
+  const int tid = threadIdx.x;
+  const uint32_t row = (uint32_t)tid & 127u;
+  const uint32_t hlf = (uint32_t)tid >> 7;                    // 0: columns 0-31, 1: columns 32-63
+  const uint32_t warp = (uint32_t)tid >> 5;
+  const uint32_t tmem_cols = (64u * (uint32_t)(NH + 2)) <= 256u ? 256u : 512u;
+
+  if (tid == 0) { mbar_init(&mbar, 1); fence_mbar_init(); }
+  if (tid < 32) tmem_alloc(&tmem_slot, tmem_cols);
+  stage_weights(ws, a.params, d, tid, kTrainThreads);
+  for (int i = tid; i < (int)(MlpSmem::kATile / 16); i += kTrainThreads) reinterpret_cast<uint4*>(dy)[i] = make_uint4(0, 0, 0, 0);
+  fence_before_sync();
+  fence_async_smem();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = tmem_slot;
+  const uint32_t t_row = tmem_base + (((warp & 3u) * 32u) << 16);      // my TMEM lane quarter
+  const uint32_t col0 = hlf * 32u;
+  const __half* __restrict__ grid = a.params + d.n_mlp;
+  __half* __restrict__ ggrid = a.grid_grads;
+  uint32_t phase = 0;
+  double loss_local = 0.0;
+
+  constexpr uint32_t idesc_fwd = make_idesc_f16(kTile, kWidth, 0, 0);       // A K-major, B K-major
+  constexpr uint32_t idesc_out = make_idesc_f16(kTile, kOutPad, 0, 0);
+  constexpr uint32_t idesc_dgrad = make_idesc_f16(kTile, kWidth, 0, 1);     // A K-major, B MN-major (W read transposed)
+  constexpr uint32_t idesc_wgrad = make_idesc_f16(64, kWidth, 1, 1);        // both MN-major: D[out][in] += d^T X
+
+  const uint32_t xs_addr = smem_u32(xs), dy_addr = smem_u32(dy), ws_addr = smem_u32(ws);
+  auto x_addr = [&](int l) { return xs_addr + (uint32_t)l * MlpSmem::kATile; };
+  auto x_ptr = [&](int l) { return xs + (size_t)l * MlpSmem::kATile; };
+  auto w_addr = [&](int m) { return ws_addr + (uint32_t)m * MlpSmem::kWHidden; };   // m == NH: output matrix
+  auto acc_col = [&](int m) { return tmem_base + 64u * (uint32_t)(m + 1); };
+
+  const uint32_t n_tiles = a.n / kTile;
+  uint32_t iter = 0;
+  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++iter) {
+    const uint32_t s = tile * kTile + row;
+    const float x = a.coords[3 * (size_t)s], y = a.coords[3 * (size_t)s + 1], z = a.coords[3 * (size_t)s + 2];
+
+    // ---- hash-grid gather: this thread's half of the feature columns of row `row` -> X_0
+    {
+      uint8_t* rowp = x_ptr(0) + row * 128u;
+      const uint32_t sw = row & 7u;
+      const int l0 = (int)(col0 / F), l1 = min(d.n_levels, (int)((col0 + 32u) / F));
+      for (int l = l0; l < l1; ++l) {
+        if constexpr (F == 8) *reinterpret_cast<uint4*>(rowp + (((uint32_t)l ^ sw) << 4)) = encode_level_f8(d.lv[l], grid, x, y, z);
+        else if constexpr (F == 4) *reinterpret_cast<uint2*>(rowp + ((((uint32_t)l >> 1) ^ sw) << 4) + ((uint32_t)l & 1u) * 8u) = encode_level_f4(d.lv[l], grid, x, y, z);
+        else if constexpr (F == 2) *reinterpret_cast<uint32_t*>(rowp + ((((uint32_t)l >> 2) ^ sw) << 4) + ((uint32_t)l & 3u) * 4u) = encode_level_f2(d.lv[l], grid, x, y, z);
+        else *reinterpret_cast<__half*>(rowp + ((((uint32_t)l >> 3) ^ sw) << 4) + ((uint32_t)l & 7u) * 2u) = encode_level_f1(d.lv[l], grid, x, y, z);
+      }
+      if (hlf == 0)
+        for (int k = d.enc_dims; k < d.enc_pad; ++k)
+          *reinterpret_cast<__half*>(rowp + ((((uint32_t)k >> 3) ^ sw) << 4) + ((uint32_t)k & 7u) * 2u) = __float2half_rn(0.f);
+    }
+    fence_async_smem();
+    bar_all();
+
+    // ---- forward: X_{l+1} = relu(X_l W_l^T)
+    for (int l = 0; l < NH; ++l) {
+      if (tid == 0) {
+        fence_after_sync();
+        const int ksteps = (l == 0 ? d.enc_pad : kWidth) >> 4;
+        const uint64_t ad = make_desc_sw128(x_addr(l)), bd = make_desc_sw128(w_addr(l));
+        for (int k = 0; k < ksteps; ++k) mma_f16_ss(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc_fwd, k > 0);
+        mma_commit(&mbar);
+      }
+      mbar_wait(&mbar, phase); phase ^= 1u;
+      fence_after_sync();
+      uint32_t r[32];
+      tmem_ld32(t_row + col0, r);
+      tmem_ld_wait();
+      uint8_t* dst = x_ptr(l + 1);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const uint4 v = make_uint4(relu_pack(r[8 * c + 0], r[8 * c + 1]), relu_pack(r[8 * c + 2], r[8 * c + 3]),
+                                   relu_pack(r[8 * c + 4], r[8 * c + 5]), relu_pack(r[8 * c + 6], r[8 * c + 7]));
+        *reinterpret_cast<uint4*>(dst + sw128_off(row, hlf * 4u + (uint32_t)c)) = v;
+      }
+      fence_before_sync();
+      fence_async_smem();
+      bar_all();
+    }
+    // ---- output layer + L1 loss (l1.h:40-76): prediction is fp16; gradient = 128 * sign / N in fp16
+    if (tid == 0) {
+      fence_after_sync();
+      const uint64_t ad = make_desc_sw128(x_addr(NH)), bd = make_desc_sw128(w_addr(NH));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) mma_f16_ss(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc_out, k > 0);
+      mma_commit(&mbar);
+    }
+    mbar_wait(&mbar, phase); phase ^= 1u;
+    fence_after_sync();
+    if (hlf == 0) {
+      const uint32_t raw = tmem_ld1(t_row);
+      tmem_ld_wait();
+      const float pred = __half2float(__float2half_rn(__uint_as_float(raw)));
+      const float diff = pred - a.targets[s];
+      loss_local += (double)__fdiv_rn(fabsf(diff), (float)a.n_global);
+      const __half g = __float2half_rn(__fdiv_rn(a.loss_scale * copysignf(1.0f, diff), (float)a.n_global));
+      *reinterpret_cast<__half*>(dy + row * 128u + ((row & 7u) << 4)) = g;          // column 0 of the swizzled row
+    }
+    fence_before_sync();
+    fence_async_smem();
+    bar_all();
+
+    // ---- backward through the output matrix and the hidden matrices NH-1 .. 1
+    for (int m = NH; m >= 1; --m) {
+      // input of matrix m is X_m; its output gradient lives in `dy` (m == NH) or X_{m+1} (in place)
+      const uint32_t dsrc = m == NH ? dy_addr : x_addr(m + 1);
+      if (tid == 0) {
+        fence_after_sync();
+        const uint64_t dmn = make_desc_sw128(dsrc), xmn = make_desc_sw128(x_addr(m)), wmn = make_desc_sw128(w_addr(m));
+        // weight gradient: acc_m[out][in] += sum_s d[s][out] * X_m[s][in]   (K = 128 samples, 8 steps of 16 rows)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) mma_f16_ss(acc_col(m), dmn + (uint64_t)(128 * k), xmn + (uint64_t)(128 * k), idesc_wgrad, (iter > 0 || k > 0));
+        // data gradient: D[s][in] = sum_out d[s][out] * W_m[out][in]
+        const int ksteps = m == NH ? 1 : 4;
+        for (int k = 0; k < ksteps; ++k) mma_f16_ss(tmem_base, dmn + (uint64_t)(2 * k), wmn + (uint64_t)(128 * k), idesc_dgrad, k > 0);
+        mma_commit(&mbar);
+      }
+      mbar_wait(&mbar, phase); phase ^= 1u;
+      fence_after_sync();
+      uint32_t r[32];
+      tmem_ld32(t_row + col0, r);
+      tmem_ld_wait();
+      uint8_t* xm = x_ptr(m);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint4* p = reinterpret_cast<uint4*>(xm + sw128_off(row, hlf * 4u + (uint32_t)c));
+        const uint4 fwd = *p;                                   // forward activations (post-ReLU) of these 8 columns
+        const uint32_t fw[4] = {fwd.x, fwd.y, fwd.z, fwd.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          __half2 g = __floats2half2_rn(__uint_as_float(r[8 * c + 2 * q]), __uint_as_float(r[8 * c + 2 * q + 1]));
+          const __half2 mask = __hgt2(u32_as_h2(fw[q]), __float2half2_rn(0.f));       // 1.0 where forward > 0
+          g = __hmul2(g, mask);
+          o[q] = h2_as_u32(g);
+        }
+        *p = make_uint4(o[0], o[1], o[2], o[3]);                // X_m := d_m (in place)
+      }
+      fence_before_sync();
+      fence_async_smem();
+      bar_all();
+    }
+    // ---- input matrix: weight gradient and dL/d(encoding), scattered straight from TMEM
+    if (tid == 0) {
+      fence_after_sync();
+      const uint64_t dmn = make_desc_sw128(x_addr(1)), xmn = make_desc_sw128(x_addr(0)), wmn = make_desc_sw128(w_addr(0));
+#pragma unroll
+      for (int k = 0; k < 8; ++k) mma_f16_ss(acc_col(0), dmn + (uint64_t)(128 * k), xmn + (uint64_t)(128 * k), idesc_wgrad, (iter > 0 || k > 0));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) mma_f16_ss(tmem_base, dmn + (uint64_t)(2 * k), wmn + (uint64_t)(128 * k), idesc_dgrad, k > 0);
+      mma_commit(&mbar);
+    }
+    mbar_wait(&mbar, phase); phase ^= 1u;
+    fence_after_sync();
+    {
+      uint32_t r[32];
+      tmem_ld32(t_row + col0, r);
+      tmem_ld_wait();
+      uint32_t gh[16];                                           // 32 columns as fp16 pairs
+#pragma unroll
+      for (int q = 0; q < 16; ++q) gh[q] = h2_as_u32(__floats2half2_rn(__uint_as_float(r[2 * q]), __uint_as_float(r[2 * q + 1])));
+      const int l0 = (int)(col0 / F), l1 = min(d.n_levels, (int)((col0 + 32u) / F));
+      for (int l = l0; l < l1; ++l) {
+        const int c = l * F - (int)col0;                         // first column of the level within my 32
+        if constexpr (F >= 2) scatter_level<F>(d.lv[l], ggrid, x, y, z, &gh[c >> 1]);
+        else { uint32_t one = (c & 1) ? (gh[c >> 1] >> 16) : (gh[c >> 1] & 0xFFFFu); scatter_level<1>(d.lv[l], ggrid, x, y, z, &one); }
+      }
+    }
+    fence_before_sync();
+    bar_all();
+  }
+
+  // ---- write this CTA's weight-gradient accumulators (TMEM, fp32) to its slice of mlp_partial.
+  // UMMA M = 64 accumulator layout: row o sits in lane 32*(o/16) + o%16 (16 lanes per quarter).
+  fence_after_sync();
+  {
+    float* part = a.mlp_partial + (size_t)blockIdx.x * d.n_mlp;
+    const uint32_t lane = (uint32_t)tid & 31u, q = warp & 3u;
+    for (int m = 0; m <= NH; ++m) {
+      const int in_w = m == 0 ? d.enc_pad : kWidth;
+      const size_t off = m == 0 ? 0 : (size_t)kWidth * d.enc_pad + (size_t)(m - 1) * kWidth * kWidth;
+      const int rows = m == NH ? kOutPad : kWidth;
+      uint32_t r[32];
+      tmem_ld32(acc_col(m) + ((q * 32u) << 16) + col0, r);
+      tmem_ld_wait();
+      const int o = (int)(q * 16u + lane);
+      if (lane < 16 && o < rows && n_tiles > 0 && blockIdx.x < n_tiles) {
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          const int col = (int)col0 + k;
+          if (col < in_w) part[off + (size_t)o * in_w + col] = __uint_as_float(r[k]);
+        }
+      }
+    }
+  }
+  // ---- loss: block reduction, one atomic per CTA
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) loss_local += __shfl_xor_sync(0xffffffffu, loss_local, o);
+  if ((tid & 31) == 0) loss_part[warp] = loss_local;
+  fence_before_sync();
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0;
+    for (int w = 0; w < kTrainThreads / 32; ++w) t += loss_part[w];
+    atomicAdd(a.loss_accum + 1, t);
+  }
+  if (tid < 32) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------
+// optimizer: Adam with per-parameter step counters, behind ExponentialDecay
+// ------------------------------------------------------------------------------------------
+
+struct AdamArgs {
+  float lr, beta1, beta2, eps, l2_reg, loss_scale;
+  float* master; __half* params; float* m1; float* m2; uint32_t* steps;
+};
+
+__device__ __forceinline__ void adam_update(const AdamArgs& a, size_t i, float gradient, bool is_matrix) {
+  const float weight_fp = a.master[i];
+  if (is_matrix) gradient = __fmaf_rn(a.l2_reg, weight_fp, gradient);        // gradient += l2_reg * w  (adam.h:87)
+  const float gradient_sq = gradient * gradient;
+  const float fm = __fmaf_rn(a.beta1, a.m1[i], (1.f - a.beta1) * gradient);
+  const float sm = __fmaf_rn(a.beta2, a.m2[i], (1.f - a.beta2) * gradient_sq);
+  a.m1[i] = fm; a.m2[i] = sm;
+  const uint32_t cs = ++a.steps[i];
+  const float lr = a.lr * __fdiv_rn(sqrtf(1.f - powf(a.beta2, (float)cs)), 1.f - powf(a.beta1, (float)cs));
+  const float eff = fminf(fmaxf(__fdiv_rn(lr, sqrtf(sm) + a.eps), 0.f), 3.402823466e+38f);
+  const float new_weight = __fmaf_rn(-eff, fm, weight_fp);
+  a.master[i] = new_weight;
+  a.params[i] = __float2half_rn(new_weight);
+}
+
+// MLP weights: reduce the per-CTA partial gradients (deterministic, no atomics), then Adam with L2.
+__global__ void adam_mlp_kernel(AdamArgs a, uint32_t n_mlp, const float* __restrict__ partial, uint32_t n_partial, float* __restrict__ mlp_grads) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_mlp) return;
+  float g = 0.f;
+  for (uint32_t c = 0; c < n_partial; ++c) g += partial[(size_t)c * n_mlp + i];
+  if (mlp_grads) mlp_grads[i] = g;
+  if (a.master) adam_update(a, i, __fdiv_rn(g, a.loss_scale), true);
+}
+
+// MLP weights from an already reduced (e.g. all-reduced across ranks) gradient vector
+__global__ void adam_mlp_from_grads_kernel(AdamArgs a, uint32_t n_mlp, const float* __restrict__ grads) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_mlp) return;
+  adam_update(a, i, __fdiv_rn(grads[i], a.loss_scale), true);
+}
+
+// Grid parameters, 8 per thread: skip parameters whose gradient is exactly zero (adam.h:76-79) and
+// clear the consumed gradients (replaces the per-step cudaMemsetAsync of grid.h:718-720).
+__global__ void adam_grid_kernel(AdamArgs a, uint32_t n_mlp, uint32_t n_grid, __half* __restrict__ grads) {
+  const size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t base = v * 8;
+  if (base >= n_grid) return;
+  uint4* gp = reinterpret_cast<uint4*>(grads + base);
+  const uint4 g = *gp;
+  if ((g.x | g.y | g.z | g.w) == 0u) return;
+  const uint32_t gw[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float2 f = __half22float2(u32_as_h2(gw[q]));
+    const float g0 = __fdiv_rn(f.x, a.loss_scale), g1 = __fdiv_rn(f.y, a.loss_scale);
+    if (g0 != 0.f) adam_update(a, (size_t)n_mlp + base + 2 * q, g0, false);
+    if (g1 != 0.f) adam_update(a, (size_t)n_mlp + base + 2 * q + 1, g1, false);
+  }
+  *gp = make_uint4(0, 0, 0, 0);
+}
+
+// ------------------------------------------------------------------------------------------
+// host
+// ------------------------------------------------------------------------------------------
+
+template <int F>
+static void launch_train_t(Volume* v, const TrainArgs& a, uint32_t grid, cudaStream_t s) {
+  const DecoderDesc& d = v->cfg.desc;
+  const size_t smem = 1024 + (size_t)(d.n_hidden + 2) * MlpSmem::kATile + MlpSmem::weights_bytes(d.n_hidden);
+  static size_t configured = 0;
+  if (smem > 226 * 1024) throw UnsupportedError("n_hidden_layers too large for the fused training kernel");
+  if (configured < smem) { VNR_CUDA(cudaFuncSetAttribute(train_step_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = smem; }
+  train_step_kernel<F><<<grid, kTrainThreads, smem, s>>>(d, a);
+  VNR_CUDA(cudaGetLastError());
+}
+
+uint32_t train_grid(const Volume* v, size_t n) { return (uint32_t)std::min<size_t>(n / kTile, (size_t)num_sms()); }
+
+void train_ensure_buffers(Volume* v) {
+  const DecoderDesc& d = v->cfg.desc;
+  if (!v->have_params) throw StateError("the neural volume has no parameters (call vnr_volume_init_params or load params)");
+  if (d.n_hidden + 2 > 8) throw UnsupportedError("training supports n_hidden_layers <= 6");
+  v->grid_grads.ensure(d.n_grid);
+  if (!v->grads_clean) { v->grid_grads.zero(v->stream); VNR_CUDA(cudaStreamSynchronize(v->stream)); v->grads_clean = true; }
+  v->mlp_partial.ensure((size_t)num_sms() * d.n_mlp);
+  v->mlp_grads.ensure(d.n_mlp);
+}
+
+// forward + loss + backward: leaves grid gradients (fp16) in grid_grads and the reduced MLP gradients
+// (fp32) in mlp_grads; n_global is the global batch size the loss is normalised by.
+void train_grads(Volume* v, const float* d_xyz, const float* d_target, size_t n, size_t n_global, cudaStream_t s) {
+  if (n == 0 || n % kTile) throw InvalidError("Batch size must be a multiple of 128.");        // fully_fused_mlp.cu:606
+  train_ensure_buffers(v);
+  const DecoderDesc& d = v->cfg.desc;
+  TrainArgs a;
+  a.params = v->params.p; a.coords = d_xyz; a.targets = d_target; a.n = (uint32_t)n; a.n_global = (uint32_t)n_global;
+  a.grid_grads = v->grid_grads.p; a.mlp_partial = v->mlp_partial.p; a.loss_accum = v->loss_accum.p; a.loss_scale = 128.f;
+  const uint32_t grid = train_grid(v, n);
+  VNR_CUDA(cudaMemsetAsync(v->loss_accum.p + 1, 0, sizeof(double), s));
+  switch (d.n_feat) {
+    case 8: launch_train_t<8>(v, a, grid, s); break;
+    case 4: launch_train_t<4>(v, a, grid, s); break;
+    case 2: launch_train_t<2>(v, a, grid, s); break;
+    default: launch_train_t<1>(v, a, grid, s); break;
+  }
+  AdamArgs none = {};
+  adam_mlp_kernel<<<(d.n_mlp + 255) / 256, 256, 0, s>>>(none, d.n_mlp, v->mlp_partial.p, grid, v->mlp_grads.p);
+  VNR_CUDA(cudaGetLastError());
+  v->grads_pending = true;
+}
+
+__global__ void loss_fold_kernel(double* acc) { acc[0] += acc[1]; }
+
+void optimizer_step(Volume* v, cudaStream_t s) {
+  if (!v->grads_pending) throw StateError("optimizer step without gradients");
+  const DecoderDesc& d = v->cfg.desc;
+  const OptimizerConfig& o = v->cfg.opt;
+  // ExponentialDecayOptimizer::step (exponential_decay.h:61-72), then AdamOptimizer::step (++m_current_step)
+  if (o.has_decay) {
+    if (v->opt_step == 0) v->lr_factor = 1.f;
+    if (v->opt_step >= o.decay_start && (v->opt_step - o.decay_start) % o.decay_interval == 0 && v->opt_step <= o.decay_end) v->lr_factor *= o.decay_base;
+  }
+  AdamArgs a;
+  a.lr = o.lr * v->lr_factor; a.beta1 = o.beta1; a.beta2 = o.beta2; a.eps = o.eps; a.l2_reg = o.l2_reg; a.loss_scale = 128.f;
+  a.master = v->master.p; a.params = v->params.p; a.m1 = v->m1.p; a.m2 = v->m2.p; a.steps = v->steps.p;
+  ++v->opt_step;
+  adam_mlp_from_grads_kernel<<<(d.n_mlp + 255) / 256, 256, 0, s>>>(a, d.n_mlp, v->mlp_grads.p);
+  const size_t vecs = ((size_t)d.n_grid + 7) / 8;
+  adam_grid_kernel<<<(unsigned)((vecs + 255) / 256), 256, 0, s>>>(a, d.n_mlp, d.n_grid, v->grid_grads.p);
+  loss_fold_kernel<<<1, 1, 0, s>>>(v->loss_accum.p);
+  VNR_CUDA(cudaGetLastError());
+  v->grads_pending = false;
+  ++v->train_step; ++v->loss_count;
+}
+
+// NeuralVolume::Impl::train (network.cu:231-259)
+void train_steps(Volume* v, int steps, size_t batch, bool update_macrocell, cudaStream_t s) {
+  if (!v->have_gt) throw StateError("[error]: missing a reference volume.");
+  if (batch == 0) batch = 1 << 16;                                       // network.cu:183
+  if (batch % kTile) throw InvalidError("Batch size must be a multiple of 128.");
+  v->train_x.ensure(3 * batch); v->train_y.ensure(batch);
+  for (int i = 0; i < steps; ++i) {
+    sample_batch(v, v->train_x.p, v->train_y.p, batch, s);
+    train_grads(v, v->train_x.p, v->train_y.p, batch, batch, s);
+    optimizer_step(v, s);
+    if (update_macrocell) macrocell_update_explicit(v, v->train_x.p, v->train_y.p, batch, s);
+  }
+}
+
+}  // namespace vnr

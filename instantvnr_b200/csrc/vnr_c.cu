@@ -91,8 +91,9 @@ static void upload_master_from_f16(Volume* v, const std::vector<__half>& h) {
 
 static void reset_optimizer(Volume* v) {
   const size_t n = v->cfg.n_params();
-  v->m1.alloc(n); v->m2.alloc(n); v->steps.alloc(n); v->grads.alloc(n);
-  v->m1.zero(v->stream); v->m2.zero(v->stream); v->steps.zero(v->stream); v->grads.zero(v->stream);
+  v->m1.alloc(n); v->m2.alloc(n); v->steps.alloc(n);
+  v->m1.zero(v->stream); v->m2.zero(v->stream); v->steps.zero(v->stream);
+  v->grads_clean = false; v->grads_pending = false;
   v->opt_step = 0; v->lr_factor = 1.f; v->train_step = 0; v->loss_count = 0;
   v->loss_accum.zero(v->stream);
   VNR_CUDA(cudaStreamSynchronize(v->stream));

@@ -22,6 +22,7 @@ VNR_EXPORT int vnr_volume_macrocell_from_groundtruth(vnr_volume_t* vh) {
     v->mc_range.zero(v->stream);
     macrocell_update_implicit(v, v->stream);
     macrocell_update_max_opacity(v, v->stream);
+    v->mc_external = true;
     VNR_CUDA(cudaStreamSynchronize(v->stream));
   });
 }
@@ -66,11 +67,101 @@ VNR_EXPORT int vnr_volume_set_tfn(vnr_volume_t* vh, const float* rgb, int n_rgb,
   });
 }
 
-VNR_EXPORT int vnr_volume_train(vnr_volume_t*, int, int, int, void*) VNR_TODO("vnr_volume_train")
-VNR_EXPORT int vnr_volume_train_on(vnr_volume_t*, const float*, const float*, size_t, void*) VNR_TODO("vnr_volume_train_on")
-VNR_EXPORT int vnr_volume_train_grads(vnr_volume_t*, const float*, const float*, size_t, size_t, void*) VNR_TODO("vnr_volume_train_grads")
-VNR_EXPORT int vnr_volume_optimizer_step(vnr_volume_t*, void*) VNR_TODO("vnr_volume_optimizer_step")
-VNR_EXPORT int vnr_volume_grad_buffer(vnr_volume_t*, void**, size_t*, int*) VNR_TODO("vnr_volume_grad_buffer")
-VNR_EXPORT int vnr_volume_sample(vnr_volume_t*, float*, float*, size_t, void*) VNR_TODO("vnr_volume_sample")
-VNR_EXPORT int vnr_volume_sampler_skip(vnr_volume_t*, uint64_t) VNR_TODO("vnr_volume_sampler_skip")
-VNR_EXPORT int vnr_volume_stats(vnr_volume_t*, uint64_t*, double*) VNR_TODO("vnr_volume_stats")
+// NeuralVolume::train (network.cu:769-779): the macrocell is updated from every batch unless
+// fast_mode with an external (ground-truth) macrocell; max opacity is refreshed when !fast_mode.
+VNR_EXPORT int vnr_volume_train(vnr_volume_t* vh, int steps, int batch, int fast_mode, void* stream) {
+  return guard([&] {
+    Volume* v = V(vh);
+    if (steps < 0 || batch < 0) throw InvalidError("negative steps / batch");
+    cudaStream_t s = S(v, stream);
+    const bool update_mc = !(fast_mode && v->mc_external);
+    train_steps(v, steps, (size_t)batch, update_mc, s);
+    if (!fast_mode) macrocell_update_max_opacity(v, s);
+  });
+}
+
+VNR_EXPORT int vnr_volume_train_on(vnr_volume_t* vh, const float* d_xyz, const float* d_target, size_t n, void* stream) {
+  return guard([&] {
+    Volume* v = V(vh);
+    if (!d_xyz || !d_target) throw InvalidError("null buffer");
+    cudaStream_t s = S(v, stream);
+    train_grads(v, d_xyz, d_target, n, n, s);
+    optimizer_step(v, s);
+  });
+}
+
+VNR_EXPORT int vnr_volume_train_grads(vnr_volume_t* vh, const float* d_xyz, const float* d_target, size_t n, size_t n_global, void* stream) {
+  return guard([&] {
+    Volume* v = V(vh);
+    if (!d_xyz || !d_target) throw InvalidError("null buffer");
+    if (n_global < n) throw InvalidError("n_global < n");
+    train_grads(v, d_xyz, d_target, n, n_global, S(v, stream));
+  });
+}
+
+VNR_EXPORT int vnr_volume_optimizer_step(vnr_volume_t* vh, void* stream) {
+  return guard([&] { Volume* v = V(vh); optimizer_step(v, S(v, stream)); });
+}
+
+VNR_EXPORT int vnr_volume_grad_buffer(vnr_volume_t* vh, int which, void** d_grads, size_t* n_elems, int* is_f32) {
+  return guard([&] {
+    Volume* v = V(vh);
+    train_ensure_buffers(v);
+    if (which == 0) { if (d_grads) *d_grads = v->mlp_grads.p; if (n_elems) *n_elems = v->cfg.desc.n_mlp; if (is_f32) *is_f32 = 1; }
+    else if (which == 1) { if (d_grads) *d_grads = v->grid_grads.p; if (n_elems) *n_elems = v->cfg.desc.n_grid; if (is_f32) *is_f32 = 0; }
+    else throw InvalidError("gradient buffer index must be 0 (MLP, fp32) or 1 (grid, fp16)");
+  });
+}
+
+VNR_EXPORT int vnr_volume_get_grads(vnr_volume_t* vh, float* h_mlp, uint16_t* h_grid) {
+  return guard([&] {
+    Volume* v = V(vh);
+    train_ensure_buffers(v);
+    VNR_CUDA(cudaStreamSynchronize(v->stream));
+    if (h_mlp) VNR_CUDA(cudaMemcpy(h_mlp, v->mlp_grads.p, v->cfg.desc.n_mlp * sizeof(float), cudaMemcpyDeviceToHost));
+    if (h_grid) VNR_CUDA(cudaMemcpy(h_grid, v->grid_grads.p, (size_t)v->cfg.desc.n_grid * sizeof(__half), cudaMemcpyDeviceToHost));
+  });
+}
+
+VNR_EXPORT int vnr_volume_sample(vnr_volume_t* vh, float* d_xyz, float* d_target, size_t n, void* stream) {
+  return guard([&] { Volume* v = V(vh); if (!d_xyz) throw InvalidError("null buffer"); sample_batch(v, d_xyz, d_target, n, S(v, stream)); });
+}
+
+VNR_EXPORT int vnr_volume_sampler_skip(vnr_volume_t* vh, uint64_t n_floats) {
+  return guard([&] { V(vh)->sampler_rng.advance(n_floats); });
+}
+
+VNR_EXPORT int vnr_volume_sample_at(vnr_volume_t* vh, const float* h_xyz, float* h_out, size_t n, int hw_texture) {
+  return guard([&] {
+    Volume* v = V(vh);
+    if (n && (!h_xyz || !h_out)) throw InvalidError("null buffer");
+    DevBuf<float> x, y; x.alloc(3 * n); y.alloc(n);
+    VNR_CUDA(cudaMemcpyAsync(x.p, h_xyz, 3 * n * sizeof(float), cudaMemcpyHostToDevice, v->stream));
+    sample_at(v, x.p, y.p, n, hw_texture, v->stream);
+    VNR_CUDA(cudaMemcpyAsync(h_out, y.p, n * sizeof(float), cudaMemcpyDeviceToHost, v->stream));
+    VNR_CUDA(cudaStreamSynchronize(v->stream));
+  });
+}
+
+// vnrNeuralVolumeGetTrainingStep / GetTrainingLoss: running mean of the per-step losses
+// (tcnn_network.h:149-153)
+VNR_EXPORT int vnr_volume_stats(vnr_volume_t* vh, uint64_t* step, double* loss) {
+  return guard([&] {
+    Volume* v = V(vh);
+    double acc[2] = {0, 0};
+    VNR_CUDA(cudaStreamSynchronize(v->stream));
+    VNR_CUDA(cudaMemcpy(acc, v->loss_accum.p, sizeof acc, cudaMemcpyDeviceToHost));
+    if (step) *step = v->train_step;
+    if (loss) *loss = v->loss_count ? acc[0] / (double)v->loss_count : 0.0;
+  });
+}
+
+VNR_EXPORT int vnr_volume_last_loss(vnr_volume_t* vh, double* loss) {
+  return guard([&] {
+    Volume* v = V(vh);
+    double acc[2] = {0, 0};
+    VNR_CUDA(cudaStreamSynchronize(v->stream));
+    VNR_CUDA(cudaMemcpy(acc, v->loss_accum.p, sizeof acc, cudaMemcpyDeviceToHost));
+    if (loss) *loss = acc[1];
+  });
+}

@@ -30,7 +30,10 @@ struct Volume {
   // parameters: fp16 working copy (MLP matrices, then grid), fp32 master, gradients, Adam state
   DevBuf<__half> params;
   DevBuf<float> master, m1, m2;
-  DevBuf<float> grads;             // fp32, loss-scaled (x128)
+  DevBuf<__half> grid_grads;       // fp16 [n_grid], loss-scaled (x128); cleared by the optimizer sweep
+  DevBuf<float> mlp_grads;         // fp32 [n_mlp], loss-scaled, reduced over CTAs
+  DevBuf<float> mlp_partial;       // fp32 [n_cta][n_mlp] per-CTA weight-gradient partials
+  bool grads_clean = false, grads_pending = false;
   DevBuf<uint32_t> steps;
   bool have_params = false, have_opt = false;
   uint32_t opt_step = 0; float lr_factor = 1.f;
@@ -43,12 +46,11 @@ struct Volume {
   bool have_gt = false;
   Pcg32 sampler_rng;               // neural_sampler.cu:36  `static default_rng_t rng{1337}`
   DevBuf<float> train_x, train_y;
-  DevBuf<__half> act_stash, dact;  // training activations / gradients
-  DevBuf<float> mlp_grad_partial;
 
   // macrocell (core/macrocell.h): value range (offset by -1/+1) and max opacity per cell
   int mc_dims[3] = {0, 0, 0};
   DevBuf<float> mc_range, mc_maxop;
+  bool mc_external = false;        // value ranges came from the ground truth (MacroCell::set_external)
 
   // transfer function (object.cpp:321-348)
   DevBuf<float4> tfn_color; DevBuf<float> tfn_alpha;

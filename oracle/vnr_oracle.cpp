@@ -1078,15 +1078,15 @@ ORC_API double orc_train_step(void* h, const float* coords, const float* targets
     const bool is_matrix = (size_t)i < m.n_mlp;
     if (!is_matrix && gradient == 0) continue;
     const float weight_fp = s->master[i];
-    if (is_matrix) gradient += s->l2_reg * weight_fp;
+    if (is_matrix) gradient = fmaf(s->l2_reg, weight_fp, gradient);
     const float gradient_sq = gradient * gradient;
-    float fm = s->m1[i] = s->beta1 * s->m1[i] + (1 - s->beta1) * gradient;
-    const float sm = s->m2[i] = s->beta2 * s->m2[i] + (1 - s->beta2) * gradient_sq;
+    float fm = s->m1[i] = fmaf(s->beta1, s->m1[i], (1 - s->beta1) * gradient);
+    const float sm = s->m2[i] = fmaf(s->beta2, s->m2[i], (1 - s->beta2) * gradient_sq);
     float learning_rate = base_lr;
     const uint32_t cs = ++s->steps[i];
     learning_rate *= sqrtf(1 - powf(s->beta2, (float)cs)) / (1 - powf(s->beta1, (float)cs));
     const float eff = fminf(fmaxf(learning_rate / (sqrtf(sm) + s->eps), 0.f), std::numeric_limits<float>::max());
-    const float new_weight = weight_fp - eff * fm;
+    const float new_weight = fmaf(-eff, fm, weight_fp);
     s->master[i] = new_weight; s->params[i] = f2h(new_weight);
   }
   return loss_sum;

@@ -1,0 +1,159 @@
+"""GPU parity of the training step: sampler, fused forward+loss+backward (tcgen05 dgrad/wgrad with
+TMEM accumulators, fp16 vector reductions into the hash table), Adam -- against the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+import instantvnr_b200 as vnr
+import oracle as O
+from instantvnr_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+SMALL = dict(n_levels=4, n_features=8, log2_hashmap=12, base_res=8, n_hidden=2)
+CFGS = [
+    SMALL,
+    dict(n_levels=8, n_features=8, log2_hashmap=14, base_res=16, n_hidden=4),
+    dict(n_levels=16, n_features=2, log2_hashmap=12, base_res=4, n_hidden=2),
+    dict(n_levels=8, n_features=4, log2_hashmap=12, base_res=4, n_hidden=3),
+    dict(n_levels=16, n_features=1, log2_hashmap=12, base_res=4, n_hidden=1),
+]
+
+
+def _model(cfg):
+    return O.ModelCfg(cfg["n_levels"], cfg["n_features"], cfg["log2_hashmap"], cfg["base_res"], 2.0, cfg["n_hidden"])
+
+
+def test_sampler_matches_oracle_bit_exact():
+    dims = (24, 16, 20)
+    gt = syn.make_volume(dims, seed=4)
+    vol = vnr.NeuralVolume(vnr.model_json(**SMALL), dims)
+    vol.set_groundtruth(gt)
+    rng = O.Rng(1337)
+    s = torch.cuda.current_stream().cuda_stream
+    for n in (1000, 128, 4096):           # consecutive batches share the pcg32 stream
+        xyz = torch.empty(n, 3, device="cuda"); tgt = torch.empty(n, device="cuda")
+        vol.sample(xyz, tgt, n, s)
+        torch.cuda.synchronize()
+        c, t = O.sample_batch(rng, n, gt, dims)
+        assert np.array_equal(xyz.cpu().numpy(), c)
+        assert np.array_equal(tgt.cpu().numpy(), t)
+
+
+def test_software_trilinear_matches_hardware_texture():
+    """The product filters the ground truth in software with 1.8 fixed-point weights; the reference
+    uses tex3D.  Difference must stay below one weight quantum times the local value range."""
+    dims = (32, 24, 16)
+    gt = syn.make_volume(dims, seed=9)
+    vol = vnr.NeuralVolume(vnr.model_json(**SMALL), dims)
+    vol.set_groundtruth(gt)
+    xyz = np.random.default_rng(0).random((20000, 3), dtype=np.float32)
+    sw = vol.sample_at(xyz, hw_texture=False)
+    hw = vol.sample_at(xyz, hw_texture=True)
+    assert np.array_equal(sw, O.tex3d(gt, dims, xyz, tex_round=0))
+    d = np.abs(sw - hw)
+    print("software vs hardware trilinear: max", d.max(), "mean", d.mean(), "exact fraction", (d == 0).mean(),
+          "| truncating variant max", np.abs(O.tex3d(gt, dims, xyz, tex_round=1) - hw).max())
+    assert d.max() <= 3.0 / 256.0 * (gt.max() - gt.min())
+
+
+@pytest.mark.parametrize("cfg", CFGS)
+def test_gradients_match_oracle(cfg):
+    m = _model(cfg)
+    dims = (16, 16, 16)
+    gt = syn.make_volume(dims, seed=3)
+    p32, _ = O.init_params(m, 5)
+    p32 = p32.copy(); p32[m.n_mlp:] *= 1000.0            # make the grid matter
+    p16 = O.f32_to_f16(p32)
+    vol = vnr.NeuralVolume(vnr.model_json(**cfg), dims)
+    vol.set_groundtruth(gt)
+    vol.set_params_f16(p16)
+    n = 128 * 20
+    rng = O.Rng(77)
+    c, t = O.sample_batch(rng, n, gt, dims)
+    dc, dt = torch.from_numpy(c).cuda(), torch.from_numpy(t).cuda()
+    vol.train_grads(dc, dt, n, n, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    gm, gg16 = vol.get_grads()
+    gg = O.f16_to_f32(gg16)
+    tr = O.Trainer(m, O.f16_to_f32(p16))
+    loss = tr.step(c, t, acc_mode=0, grad_mode=0, do_step=False)
+    want = tr.grads()
+    wm, wg = want[:m.n_mlp], want[m.n_mlp:]
+    assert abs(vol.last_loss() - loss) <= 1e-5 * max(1.0, loss)
+    # MLP weight gradients: fp32 tensor-core accumulation vs double accumulation of the same fp16 products
+    scale = np.abs(wm).max()
+    assert scale > 0
+    assert np.abs(gm - wm).max() <= 2e-3 * scale, (np.abs(gm - wm).max(), scale)
+    # padded output rows and padded input columns carry no gradient
+    W, E, NH = 64, m.enc_pad, m.n_hidden
+    out_off = W * E + (NH - 1) * W * W
+    assert np.all(gm[out_off + W:] == 0)
+    # grid gradients: fp16 reductions in arbitrary order vs sequential float sum of the same fp16 addends
+    gscale = np.abs(wg).max()
+    assert gscale > 0
+    # (entries of coarse levels collect thousands of fp16 addends: the running fp16 sum rounds at every
+    # reduction, exactly as the reference's atomicAdd(__half2) does, so the bound on single entries is loose
+    # and the tight checks are statistical)
+    err = np.abs(gg - wg)
+    assert err.max() <= 0.05 * gscale, (err.max(), gscale)
+    assert err.mean() <= 1e-4 * gscale
+    assert np.logical_xor(gg != 0, wg != 0).mean() < 1e-3
+    for l in range(m.L):
+        a, b = int(m.offsets[l]) * m.F, int(m.offsets[l + 1]) * m.F
+        assert abs(gg[a:b].sum() - wg[a:b].sum()) <= 1e-2 * np.abs(wg[a:b]).sum() + 1e-6
+
+
+def test_training_curve_matches_oracle():
+    cfg = SMALL
+    m = _model(cfg)
+    dims = (16, 16, 16)
+    gt = syn.make_volume(dims, seed=3)
+    vol = vnr.NeuralVolume(vnr.model_json(**cfg), dims)
+    vol.set_groundtruth(gt)
+    vol.init_params(21)
+    p32, _ = O.init_params(m, 21)
+    tr = O.Trainer(m, p32)
+    rng = O.Rng(1337)
+    steps, batch = 40, 2048
+    got, want = [], []
+    for _ in range(steps):
+        vol.train(1, batch=batch, fast_mode=True)
+        got.append(vol.last_loss())
+        want.append(tr.step(*O.sample_batch(rng, batch, gt, dims), acc_mode=0, grad_mode=1))
+    got, want = np.array(got), np.array(want)
+    assert got[0] == pytest.approx(want[0], rel=1e-4)            # identical init, identical first batch
+    assert np.abs(got - want).max() <= 0.02 * want.max()         # loss within 2 % of the oracle
+    assert got[-1] < 0.6 * got[0]
+    step, mean_loss = vol.stats()
+    assert step == steps and mean_loss == pytest.approx(got.mean(), rel=1e-6)
+
+
+def test_adam_skips_untouched_grid_entries_and_clears_gradients():
+    cfg = dict(n_levels=4, n_features=8, log2_hashmap=16, base_res=16, n_hidden=2)
+    m = _model(cfg)
+    dims = (16, 16, 16)
+    vol = vnr.NeuralVolume(vnr.model_json(**cfg), dims)
+    vol.set_groundtruth(syn.make_volume(dims, seed=3))
+    vol.init_params(2)
+    before = vol.get_params_f16()
+    vol.train(1, batch=128, fast_mode=True)
+    after = vol.get_params_f16()
+    changed = before[m.n_mlp:] != after[m.n_mlp:]
+    # 128 samples touch at most 128*8 corners per level: most of the table must be untouched
+    assert 0 < changed.reshape(-1, 8).any(axis=1).sum() <= 128 * 8 * cfg["n_levels"]
+    assert (before[:m.n_mlp] != after[:m.n_mlp]).mean() > 0.5     # MLP weights always step (L2 reg)
+    gm, gg = vol.get_grads()
+    assert not gg.any()                                            # consumed gradients were cleared
+
+
+def test_train_errors():
+    vol = vnr.NeuralVolume(vnr.model_json(**SMALL), (16, 16, 16))
+    vol.init_params(1)
+    with pytest.raises(vnr.VnrError) as e:
+        vol.train(1, batch=256)
+    assert e.value.code == -4 and "reference volume" in str(e.value)
+    vol.set_groundtruth(syn.make_volume((16, 16, 16)))
+    with pytest.raises(vnr.VnrError) as e:
+        vol.train(1, batch=100)
+    assert e.value.code == -1 and "multiple of 128" in str(e.value)
