@@ -141,6 +141,17 @@ int vnr_renderer_device_frame(vnr_renderer_t* r, void** d_rgba, void* stream_out
  * [2] samples composited, [3] wavefront rounds */
 int vnr_renderer_stats(vnr_renderer_t* r, uint64_t* stats4);
 
+/* MainRenderer::framebuffer_skip_download (renderer.cpp:132): 0 = keep frames on the device */
+int vnr_renderer_set_download(vnr_renderer_t* r, int on);
+/* measurement taps: CUDA events around every decode launch of the next frames; summed device time of
+ * the non-empty decode launches of the last frame, their number, and all kernels launched by it */
+int vnr_renderer_set_profiling(vnr_renderer_t* r, int on);
+int vnr_renderer_profile(vnr_renderer_t* r, float* decode_ms, int* decode_launches, uint64_t* kernel_launches);
+/* the cudaStream_t all work of this renderer is enqueued on */
+int vnr_renderer_stream(vnr_renderer_t* r, void** stream);
+/* samples per ray per wavefront round (N_ITERS, env VNR_RM_N_ITERS; method_raymarching.cu:30-40) */
+int vnr_renderer_set_n_iters(vnr_renderer_t* r, int n);
+
 /* vnrMemoryQuery (api.h:186): bytes of device memory held by volumes / renderers */
 int vnr_memory_query(size_t* used_by_renderer, size_t* used_by_network);
 

@@ -301,6 +301,25 @@ class Renderer:
         _check(lib().vnr_renderer_device_frame(self._h, C.byref(p), None))
         return p.value
 
+    def set_download(self, on):
+        _check(lib().vnr_renderer_set_download(self._h, C.c_int(1 if on else 0)))
+
+    def set_profiling(self, on):
+        _check(lib().vnr_renderer_set_profiling(self._h, C.c_int(1 if on else 0)))
+
+    def set_n_iters(self, n):
+        _check(lib().vnr_renderer_set_n_iters(self._h, C.c_int(n)))
+
+    def profile(self):
+        ms, n, k = C.c_float(), C.c_int(), C.c_uint64()
+        _check(lib().vnr_renderer_profile(self._h, C.byref(ms), C.byref(n), C.byref(k)))
+        return {"decode_ms": ms.value, "decode_launches": n.value, "kernel_launches": k.value}
+
+    def stream(self):
+        p = C.c_void_p()
+        _check(lib().vnr_renderer_stream(self._h, C.byref(p)))
+        return p.value or 0
+
     def stats(self):
         s = np.zeros(4, dtype=np.uint64)
         _check(lib().vnr_renderer_stats(self._h, _ptr(s)))

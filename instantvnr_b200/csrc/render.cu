@@ -185,6 +185,7 @@ Renderer::Renderer(Volume* v) : vol(v) {
 Renderer::~Renderer() {
   if (stream) cudaStreamSynchronize(stream);
   for (int k = 0; k < 2; ++k) { if (h_frame[k]) cudaFreeHost(h_frame[k]); if (frame_done[k]) cudaEventDestroy(frame_done[k]); }
+  for (cudaEvent_t e : prof_events) cudaEventDestroy(e);
   if (vol_ready) cudaEventDestroy(vol_ready);
   if (h_counters) cudaFreeHost(h_counters);
   if (stream) cudaStreamDestroy(stream);
@@ -286,18 +287,26 @@ void Renderer::render() {
   VNR_CUDA(cudaMemsetAsync(counters.p, 0, counters.bytes(), stream));
   RayBuffers rb{ray_rgba.p, ray_tn.p, ray_cell.p, ray_state.p, ray_jitter.p};
   const unsigned grid = (n_rays + 127) / 128;
+  launches = 0;
+  prof_used = 0;
+  if (profiling) {
+    while ((int)prof_events.size() < 2 * rounds) { cudaEvent_t e; VNR_CUDA(cudaEventCreate(&e)); prof_events.push_back(e); }
+  }
   if (n_rays) {
     march_round_kernel<true><<<grid, 128, 0, stream>>>(fp, rb, nullptr, nullptr, samples[0].p, counters.p, 0, accum.p, frame.p);
     for (int r = 0; r < rounds; ++r) {
+      if (profiling) VNR_CUDA(cudaEventRecord(prof_events[prof_used++], stream));
       VNR_CUDA(launch_decode_samples(vol->cfg.desc, vol->params.p, samples[r & 1].p, values.p, counters.p + 2 + r, cap, stream));
+      if (profiling) VNR_CUDA(cudaEventRecord(prof_events[prof_used++], stream));
       march_round_kernel<false><<<grid, 128, 0, stream>>>(fp, rb, samples[r & 1].p, values.p, samples[(r + 1) & 1].p, counters.p, r + 1, accum.p, frame.p);
     }
     finalize_kernel<<<grid, 128, 0, stream>>>(fp, rb, counters.p + kMaxRounds + 3, accum.p, frame.p);
     VNR_CUDA(cudaGetLastError());
+    launches = 2 + 2 * (uint64_t)rounds;
   }
   last_rounds = rounds;
   // framebuffer.download_async (renderer.cpp:133)
-  VNR_CUDA(cudaMemcpyAsync(h_frame[cur], frame.p, frame.bytes(), cudaMemcpyDeviceToHost, stream));
+  if (download) VNR_CUDA(cudaMemcpyAsync(h_frame[cur], frame.p, frame.bytes(), cudaMemcpyDeviceToHost, stream));
   VNR_CUDA(cudaMemcpyAsync(h_counters, counters.p, sizeof(uint32_t) * (kMaxRounds + 4), cudaMemcpyDeviceToHost, stream));
   VNR_CUDA(cudaEventRecord(frame_done[cur], stream));
   rendered = true;
@@ -305,10 +314,24 @@ void Renderer::render() {
 
 const float* Renderer::map_frame() {
   if (!rendered) throw StateError("vnr_map_frame called before vnr_render");
+  if (!download) throw StateError("frame download is disabled on this renderer");
   VNR_CUDA(cudaEventSynchronize(frame_done[cur]));                     // renderer.h:84-94
   const float* p = reinterpret_cast<const float*>(h_frame[cur]);
   cur ^= 1;                                                             // double-buffer swap
   return p;
+}
+
+void Renderer::profile(float* decode_ms, int* decode_launches) {
+  VNR_CUDA(cudaStreamSynchronize(stream));
+  float total = 0.f; int n = 0;
+  for (int k = 0; k + 1 < prof_used; k += 2) {
+    if (h_counters[2 + k / 2] == 0) continue;           // empty round: the kernel exits immediately
+    float ms = 0.f;
+    VNR_CUDA(cudaEventElapsedTime(&ms, prof_events[k], prof_events[k + 1]));
+    total += ms; ++n;
+  }
+  if (decode_ms) *decode_ms = total;
+  if (decode_launches) *decode_launches = n;
 }
 
 void Renderer::stats(uint64_t* s4) {

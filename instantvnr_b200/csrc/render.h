@@ -1,5 +1,7 @@
 // render.h -- the renderer object behind vnr_renderer_t (MainRenderer, renderer.h:55-235)
 #pragma once
+#include <vector>
+
 #include "volume.h"
 
 namespace vnr {
@@ -30,6 +32,11 @@ struct Renderer {
   DevBuf<uint32_t> ray_state, counters;
   float4* h_frame[2] = {nullptr, nullptr};
   uint32_t* h_counters = nullptr;
+  bool download = true;                 // framebuffer_skip_download (renderer.cpp:132)
+  bool profiling = false;               // CUDA events around every decode launch
+  std::vector<cudaEvent_t> prof_events;
+  int prof_used = 0;
+  uint64_t launches = 0;                // kernels launched by the last render()
 
   explicit Renderer(Volume* v);
   ~Renderer();
@@ -40,6 +47,7 @@ struct Renderer {
   void render();
   const float* map_frame();
   void stats(uint64_t* s4);
+  void profile(float* decode_ms, int* decode_launches);
 };
 
 }  // namespace vnr

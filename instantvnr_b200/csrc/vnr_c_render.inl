@@ -54,3 +54,13 @@ VNR_EXPORT int vnr_renderer_device_frame(vnr_renderer_t* r, void** d_rgba, void*
   });
 }
 VNR_EXPORT int vnr_renderer_stats(vnr_renderer_t* r, uint64_t* s4) { return guard([&] { if (!s4) throw InvalidError("null argument"); R(r)->stats(s4); }); }
+
+VNR_EXPORT int vnr_renderer_set_download(vnr_renderer_t* r, int on) { return guard([&] { R(r)->download = on != 0; }); }
+VNR_EXPORT int vnr_renderer_set_profiling(vnr_renderer_t* r, int on) { return guard([&] { R(r)->profiling = on != 0; }); }
+VNR_EXPORT int vnr_renderer_profile(vnr_renderer_t* r, float* decode_ms, int* decode_launches, uint64_t* kernel_launches) {
+  return guard([&] { Renderer* s = R(r); s->profile(decode_ms, decode_launches); if (kernel_launches) *kernel_launches = s->launches; });
+}
+VNR_EXPORT int vnr_renderer_stream(vnr_renderer_t* r, void** stream) { return guard([&] { if (!stream) throw InvalidError("null argument"); *stream = (void*)R(r)->stream; }); }
+VNR_EXPORT int vnr_renderer_set_n_iters(vnr_renderer_t* r, int n) {
+  return guard([&] { if (n < 1 || n > 16) throw InvalidError("n_iters must be in [1,16]"); R(r)->n_iters = n; R(r)->reset = true; });
+}
