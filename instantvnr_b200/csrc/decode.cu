@@ -118,8 +118,10 @@ static cudaError_t launch_decode_t(const DecoderDesc& d, const __half* params, c
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(decode_kernel<F, STRIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     if (e != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_kernel<F, STRIDE>, 128, smem);
-    if (e != cudaSuccess) return e;
+    // resident CTAs per SM: 128 threads x <=128 registers (launch bounds) allow 4; shared memory
+    // (227 KB per SM, 1 KB reserved per CTA) and TMEM (512 columns, 64 per CTA) bound it further
+    per_sm = std::min<int>(4, (int)((227 * 1024) / (smem + 1024)));
+    if (const char* env = getenv("VNR_DECODE_CTAS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(env)));
     if (per_sm < 1) per_sm = 1;
     configured = true;
   }
