@@ -75,6 +75,10 @@ int vnr_volume_decode_host(vnr_volume_t* v, const float* h_xyz, float* h_out, si
 /* test tap: also returns the fp16 hash-grid features (row-major [n][enc_pad]) */
 int vnr_volume_decode_debug(vnr_volume_t* v, const float* h_xyz, float* h_out, uint16_t* h_enc, size_t n);
 
+/* measurement tap (no reference counterpart): the hash-grid gather alone at full occupancy, one folded
+ * word per sample; bench.py times it to obtain the gather-rate ceiling of the decode roofline */
+int vnr_volume_gather_probe(vnr_volume_t* v, const float* d_xyz, uint32_t* d_out, size_t n, void* stream);
+
 /* vnrCreateSimpleVolume + StaticSampler ground truth (core/samplers/neural_sampler.cu:86-128):
  * float32 volume of dims dx*dy*dz (x fastest), already normalised to [0,1]. */
 int vnr_volume_set_groundtruth_f32(vnr_volume_t* v, const float* h_volume);
@@ -151,6 +155,19 @@ int vnr_renderer_profile(vnr_renderer_t* r, float* decode_ms, int* decode_launch
 int vnr_renderer_stream(vnr_renderer_t* r, void** stream);
 /* samples per ray per wavefront round (N_ITERS, env VNR_RM_N_ITERS; method_raymarching.cu:30-40) */
 int vnr_renderer_set_n_iters(vnr_renderer_t* r, int n);
+
+/* device-driven wavefront loop (default on): the per-round host round trip of iterative_ray_compaction
+ * (method_raymarching.cu:923-929) is replaced by a CUDA-graph WHILE node; 0 = bounded host-enqueued rounds */
+int vnr_renderer_set_graph(vnr_renderer_t* r, int on);
+
+/* multi-GPU frame gather over peer memory (no reference counterpart): finished pixels of this renderer's
+ * partition are stored to d_rgba (float4[w*h], normally rank 0's frame buffer opened with vnr_ipc_open)
+ * by the compositing kernel itself; NULL restores the local frame buffer. */
+int vnr_renderer_set_frame_target(vnr_renderer_t* r, void* d_rgba);
+/* cudaIpcMemHandle_t (64 bytes) of a device allocation of this process / mapping of a peer's allocation */
+int vnr_ipc_export(void* d_ptr, void* handle64);
+int vnr_ipc_open(const void* handle64, void** d_ptr);
+int vnr_ipc_close(void* d_ptr);
 
 /* vnrMemoryQuery (api.h:186): bytes of device memory held by volumes / renderers */
 int vnr_memory_query(size_t* used_by_renderer, size_t* used_by_network);

@@ -150,6 +150,9 @@ class NeuralVolume:
     def decode(self, d_xyz, d_out, n, stream=None):
         _check(lib().vnr_volume_decode(self._h, _ptr(d_xyz), _ptr(d_out), C.c_size_t(n), _stream(stream)))
 
+    def gather_probe(self, d_xyz, d_out, n, stream=None):
+        _check(lib().vnr_volume_gather_probe(self._h, _ptr(d_xyz), _ptr(d_out), C.c_size_t(n), _stream(stream)))
+
     def decode_host(self, xyz):
         xyz = _f32(xyz).reshape(-1, 3)
         out = np.empty(xyz.shape[0], dtype=np.float32)
@@ -289,12 +292,15 @@ class Renderer:
     def render(self):
         _check(lib().vnr_render(self._h))
 
-    def map_frame(self):
+    def map_frame(self, copy=True):
+        """vnrRendererMapFrame: syncs and returns the host frame (h, w, 4).  copy=False returns a view of the
+        library's pinned buffer, valid until the second-next map_frame (the reference's double-buffer contract)."""
         p = lib().vnr_map_frame(self._h)
         if not p:
             raise VnrError(-4, lib().vnr_last_error().decode("utf-8", "replace"))
         w, h = self.size
-        return np.ctypeslib.as_array(p, shape=(h, w, 4)).copy()
+        a = np.ctypeslib.as_array(p, shape=(h, w, 4))
+        return a.copy() if copy else a
 
     def device_frame(self):
         p = C.c_void_p()
@@ -306,6 +312,12 @@ class Renderer:
 
     def set_profiling(self, on):
         _check(lib().vnr_renderer_set_profiling(self._h, C.c_int(1 if on else 0)))
+
+    def set_graph(self, on):
+        _check(lib().vnr_renderer_set_graph(self._h, C.c_int(1 if on else 0)))
+
+    def set_frame_target(self, d_ptr):
+        _check(lib().vnr_renderer_set_frame_target(self._h, C.c_void_p(d_ptr) if d_ptr else None))
 
     def set_n_iters(self, n):
         _check(lib().vnr_renderer_set_n_iters(self._h, C.c_int(n)))
@@ -324,6 +336,22 @@ class Renderer:
         s = np.zeros(4, dtype=np.uint64)
         _check(lib().vnr_renderer_stats(self._h, _ptr(s)))
         return {"rays_hit": int(s[0]), "samples_decoded": int(s[1]), "samples_composited": int(s[2]), "rounds": int(s[3])}
+
+
+def ipc_export(d_ptr):
+    h = C.create_string_buffer(64)
+    _check(lib().vnr_ipc_export(C.c_void_p(d_ptr), h))
+    return h.raw
+
+
+def ipc_open(handle):
+    p = C.c_void_p()
+    _check(lib().vnr_ipc_open(C.c_char_p(handle), C.byref(p)))
+    return p.value
+
+
+def ipc_close(d_ptr):
+    _check(lib().vnr_ipc_close(C.c_void_p(d_ptr)))
 
 
 VNR_RAYMARCHING_NO_SHADING_DECODING = 4

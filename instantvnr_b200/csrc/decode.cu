@@ -20,30 +20,7 @@ template <int F>
 __device__ __forceinline__ void encode_row(uint8_t* a_smem, const DecoderDesc& d, const __half* __restrict__ grid, float x, float y, float z, uint32_t row) {
   uint8_t* rowp = a_smem + row * 128u;
   const uint32_t sw = (row & 7u);
-  if constexpr (F == 8) {
-#pragma unroll 2
-    for (int l = 0; l < d.n_levels; ++l) {
-      uint4 v = encode_level_f8(d.lv[l], grid, x, y, z);
-      *reinterpret_cast<uint4*>(rowp + (((uint32_t)l ^ sw) << 4)) = v;
-    }
-  } else if constexpr (F == 4) {
-#pragma unroll 2
-    for (int l = 0; l < d.n_levels; ++l) {
-      uint2 v = encode_level_f4(d.lv[l], grid, x, y, z);
-      *reinterpret_cast<uint2*>(rowp + ((((uint32_t)l >> 1) ^ sw) << 4) + ((uint32_t)l & 1u) * 8u) = v;
-    }
-  } else if constexpr (F == 2) {
-#pragma unroll 2
-    for (int l = 0; l < d.n_levels; ++l) {
-      uint32_t v = encode_level_f2(d.lv[l], grid, x, y, z);
-      *reinterpret_cast<uint32_t*>(rowp + ((((uint32_t)l >> 2) ^ sw) << 4) + ((uint32_t)l & 3u) * 4u) = v;
-    }
-  } else {
-    for (int l = 0; l < d.n_levels; ++l) {
-      __half v = encode_level_f1(d.lv[l], grid, x, y, z);
-      *reinterpret_cast<__half*>(rowp + ((((uint32_t)l >> 3) ^ sw) << 4) + ((uint32_t)l & 7u) * 2u) = v;
-    }
-  }
+  encode_levels<F>(rowp, sw, d, grid, x, y, z, 0, d.n_levels);
   // zero the padding features up to enc_pad (tcnn pads the encoding to 16: grid.h:616-620)
   for (int k = d.enc_dims; k < d.enc_pad; ++k)
     *reinterpret_cast<__half*>(rowp + ((((uint32_t)k >> 3) ^ sw) << 4) + ((uint32_t)k & 7u) * 2u) = __float2half_rn(0.f);
@@ -51,12 +28,18 @@ __device__ __forceinline__ void encode_row(uint8_t* a_smem, const DecoderDesc& d
 
 // STRIDE: floats per coordinate record (3 = xyz as NeuralVolume::inference takes them,
 // 4 = the marcher's (x, y, z, dt) sample records).  n_dev != nullptr: the sample count is
-// read from device memory (wavefront rounds are sized on the device, no host sync).
+// read from device memory (wavefront rounds are sized on the device, no host sync); with
+// round_dev the round index itself lives on the device (graph-driven wavefront): the count is
+// n_dev[round] and odd rounds read coords_alt (the marcher's ping-pong sample buffers).
 template <int F, int STRIDE>
 __global__ void __launch_bounds__(128, 4)
-decode_kernel(const DecoderDesc d, const __half* __restrict__ params, const float* __restrict__ coords, float* __restrict__ out,
-              uint32_t n, const uint32_t* __restrict__ n_dev, __half* __restrict__ enc_out) {
-  if (n_dev) n = *n_dev;
+decode_kernel(const DecoderDesc d, const __half* __restrict__ params, const float* __restrict__ coords, const float* __restrict__ coords_alt,
+              float* __restrict__ out, uint32_t n, const uint32_t* __restrict__ n_dev, const uint32_t* __restrict__ round_dev, __half* __restrict__ enc_out) {
+  if (n_dev) {
+    const uint32_t r = round_dev ? *round_dev : 0u;
+    n = n_dev[r];
+    if (r & 1u) coords = coords_alt;
+  }
   if (n == 0) return;
   const uint32_t n_tiles = (n + kTile - 1) / kTile;
   if (blockIdx.x >= n_tiles) return;
@@ -99,6 +82,43 @@ decode_kernel(const DecoderDesc d, const __half* __restrict__ params, const floa
   if (tid < 32) tc05::tmem_dealloc(tmem_base, 64);
 }
 
+// Measurement tap: the hash-grid gather alone (no MLP, no shared memory, full occupancy), one
+// thread per sample, features folded into one word.  Gives the achievable gather rate of the
+// memory system for a coordinate distribution -- the denominator of the decode roofline.
+template <int F>
+__global__ void __launch_bounds__(256)
+gather_probe_kernel(const DecoderDesc d, const __half* __restrict__ params, const float* __restrict__ coords, uint32_t* __restrict__ out, uint32_t n) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  const __half* __restrict__ grid = params + d.n_mlp;
+  const float x = coords[3 * (size_t)s], y = coords[3 * (size_t)s + 1], z = coords[3 * (size_t)s + 2];
+  typedef typename FeatVec<F>::type T;
+  uint32_t fold = 0;
+  LevelGather<F> cur, nxt;
+  cur.issue(d.lv[0], grid, x, y, z);
+  for (int l = 0; l < d.n_levels; ++l) {
+    if (l + 1 < d.n_levels) nxt.issue(d.lv[l + 1], grid, x, y, z);
+    const T r = cur.finish();
+    if constexpr (F == 8) fold ^= r.x ^ r.y ^ r.z ^ r.w;
+    else if constexpr (F == 4) fold ^= r.x ^ r.y;
+    else fold ^= (uint32_t)r;
+    cur = nxt;
+  }
+  out[s] = fold;
+}
+
+cudaError_t launch_gather_probe(const DecoderDesc& d, const __half* params, const float* coords, uint32_t* out, size_t n, cudaStream_t stream) {
+  if (!n) return cudaSuccess;
+  const unsigned grid = (unsigned)((n + 255) / 256);
+  switch (d.n_feat) {
+    case 8: gather_probe_kernel<8><<<grid, 256, 0, stream>>>(d, params, coords, out, (uint32_t)n); break;
+    case 4: gather_probe_kernel<4><<<grid, 256, 0, stream>>>(d, params, coords, out, (uint32_t)n); break;
+    case 2: gather_probe_kernel<2><<<grid, 256, 0, stream>>>(d, params, coords, out, (uint32_t)n); break;
+    default: gather_probe_kernel<1><<<grid, 256, 0, stream>>>(d, params, coords, out, (uint32_t)n); break;
+  }
+  return cudaGetLastError();
+}
+
 static int g_num_sms = 0;
 int num_sms() {
   if (!g_num_sms) {
@@ -110,8 +130,8 @@ int num_sms() {
 }
 
 template <int F, int STRIDE>
-static cudaError_t launch_decode_t(const DecoderDesc& d, const __half* params, const float* coords, float* out, size_t n, const uint32_t* n_dev,
-                                   size_t n_max, __half* enc_out, cudaStream_t stream) {
+static cudaError_t launch_decode_t(const DecoderDesc& d, const __half* params, const float* coords, const float* coords_alt, float* out, size_t n,
+                                   const uint32_t* n_dev, const uint32_t* round_dev, size_t n_max, __half* enc_out, cudaStream_t stream) {
   const size_t smem = 1024 + MlpSmem::kATile + MlpSmem::weights_bytes(d.n_hidden);
   static bool configured = false;
   static int per_sm = 1;
@@ -127,31 +147,34 @@ static cudaError_t launch_decode_t(const DecoderDesc& d, const __half* params, c
   }
   const size_t n_tiles = (n_max + kTile - 1) / kTile;
   const uint32_t grid = (uint32_t)std::min<size_t>(n_tiles, (size_t)num_sms() * per_sm);
-  decode_kernel<F, STRIDE><<<grid, 128, smem, stream>>>(d, params, coords, out, (uint32_t)n, n_dev, enc_out);
+  decode_kernel<F, STRIDE><<<grid, 128, smem, stream>>>(d, params, coords, coords_alt, out, (uint32_t)n, n_dev, round_dev, enc_out);
   return cudaGetLastError();
 }
 
 template <int STRIDE>
-static cudaError_t launch_decode_f(const DecoderDesc& d, const __half* params, const float* coords, float* out, size_t n, const uint32_t* n_dev,
-                                   size_t n_max, __half* enc_out, cudaStream_t stream) {
+static cudaError_t launch_decode_f(const DecoderDesc& d, const __half* params, const float* coords, const float* coords_alt, float* out, size_t n,
+                                   const uint32_t* n_dev, const uint32_t* round_dev, size_t n_max, __half* enc_out, cudaStream_t stream) {
   switch (d.n_feat) {
-    case 8: return launch_decode_t<8, STRIDE>(d, params, coords, out, n, n_dev, n_max, enc_out, stream);
-    case 4: return launch_decode_t<4, STRIDE>(d, params, coords, out, n, n_dev, n_max, enc_out, stream);
-    case 2: return launch_decode_t<2, STRIDE>(d, params, coords, out, n, n_dev, n_max, enc_out, stream);
-    case 1: return launch_decode_t<1, STRIDE>(d, params, coords, out, n, n_dev, n_max, enc_out, stream);
+    case 8: return launch_decode_t<8, STRIDE>(d, params, coords, coords_alt, out, n, n_dev, round_dev, n_max, enc_out, stream);
+    case 4: return launch_decode_t<4, STRIDE>(d, params, coords, coords_alt, out, n, n_dev, round_dev, n_max, enc_out, stream);
+    case 2: return launch_decode_t<2, STRIDE>(d, params, coords, coords_alt, out, n, n_dev, round_dev, n_max, enc_out, stream);
+    case 1: return launch_decode_t<1, STRIDE>(d, params, coords, coords_alt, out, n, n_dev, round_dev, n_max, enc_out, stream);
     default: return cudaErrorInvalidValue;
   }
 }
 
 cudaError_t launch_decode(const DecoderDesc& d, const __half* params, const float* coords, float* out, size_t n, __half* enc_out, cudaStream_t stream) {
   if (n == 0) return cudaSuccess;
-  return launch_decode_f<3>(d, params, coords, out, n, nullptr, n, enc_out, stream);
+  return launch_decode_f<3>(d, params, coords, nullptr, out, n, nullptr, nullptr, n, enc_out, stream);
 }
 
-// marcher variant: (x,y,z,dt) records, count read from *n_dev (at most n_max)
-cudaError_t launch_decode_samples(const DecoderDesc& d, const __half* params, const float4* samples, float* out, const uint32_t* n_dev, size_t n_max, cudaStream_t stream) {
+// marcher variant: (x,y,z,dt) records.  Host-driven rounds pass the round's buffer and counter (round_dev = nullptr,
+// samples_alt unused); graph-driven rounds pass both ping-pong buffers, the counter array and the device round index.
+cudaError_t launch_decode_samples(const DecoderDesc& d, const __half* params, const float4* samples, const float4* samples_alt, float* out,
+                                  const uint32_t* n_dev, const uint32_t* round_dev, size_t n_max, cudaStream_t stream) {
   if (n_max == 0) return cudaSuccess;
-  return launch_decode_f<4>(d, params, reinterpret_cast<const float*>(samples), out, 0, n_dev, n_max, nullptr, stream);
+  return launch_decode_f<4>(d, params, reinterpret_cast<const float*>(samples), reinterpret_cast<const float*>(samples_alt), out, 0, n_dev, round_dev, n_max,
+                            nullptr, stream);
 }
 
 }  // namespace vnr

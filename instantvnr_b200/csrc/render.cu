@@ -39,12 +39,31 @@ __device__ __forceinline__ void write_pixel(const FrameParams& fp, float4* __res
   frame[pixel] = make_float4(__fdiv_rn(c.x, fi), __fdiv_rn(c.y, fi), __fdiv_rn(c.z, fi), __fdiv_rn(c.w, fi));
 }
 
-// counters: [0] rays that hit the volume, [1] samples composited, [2 + r] samples emitted for round r
+// The frame constants live in device memory (so that a captured graph can be replayed with a new
+// camera) and are staged in shared memory by every CTA.
+__device__ __forceinline__ void stage_frame_params(FrameParams* dst, const FrameParams* __restrict__ src) {
+  static_assert(sizeof(FrameParams) % 4 == 0, "FrameParams must be word-sized");
+  for (uint32_t k = threadIdx.x; k < sizeof(FrameParams) / 4; k += blockDim.x)
+    reinterpret_cast<uint32_t*>(dst)[k] = __ldg(reinterpret_cast<const uint32_t*>(src) + k);
+  __syncthreads();
+}
+
+// counters: [0] rays that hit the volume, [1] samples composited, [2 + r] samples emitted for round r.
+// The round index comes from the host (round_dev == nullptr: bounded host-enqueued rounds) or from device
+// memory (graph-driven loop: *round_dev is the round whose values were just decoded).  Round r reads
+// samples[(r-1)&1] and writes samples[r&1].
 template <bool FIRST>
 __global__ void __launch_bounds__(128)
-march_round_kernel(const FrameParams fp, RayBuffers rb, const float4* __restrict__ prev_samples, const float* __restrict__ values,
-                   float4* __restrict__ next_samples, uint32_t* __restrict__ counters, int round, float4* __restrict__ accum, float4* __restrict__ frame) {
+march_round_kernel(const FrameParams* __restrict__ fpp, RayBuffers rb, float4* __restrict__ samples0, float4* __restrict__ samples1,
+                   const float* __restrict__ values, uint32_t* __restrict__ counters, int round_host, const uint32_t* __restrict__ round_dev,
+                   float4* __restrict__ accum, float4* __restrict__ frame) {
+  const int round = FIRST ? 0 : (round_dev ? (int)(*round_dev) + 1 : round_host);
   if (!FIRST && counters[2 + round - 1] == 0) return;      // nothing was alive in the previous round
+  __shared__ FrameParams fp_s;
+  stage_frame_params(&fp_s, fpp);
+  const FrameParams& fp = fp_s;
+  const float4* __restrict__ prev_samples = (round & 1) ? samples0 : samples1;
+  float4* __restrict__ next_samples = (round & 1) ? samples1 : samples0;
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t lane = threadIdx.x & 31u;
   bool active = i < fp.n_rays;
@@ -156,7 +175,10 @@ march_round_kernel(const FrameParams fp, RayBuffers rb, const float4* __restrict
 }
 
 // rays still alive after the last enqueued round (cannot happen when the bound holds; counted)
-__global__ void finalize_kernel(const FrameParams fp, RayBuffers rb, uint32_t* __restrict__ leftover, float4* __restrict__ accum, float4* __restrict__ frame) {
+__global__ void finalize_kernel(const FrameParams* __restrict__ fpp, RayBuffers rb, uint32_t* __restrict__ leftover, float4* __restrict__ accum, float4* __restrict__ frame) {
+  __shared__ FrameParams fp_s;
+  stage_frame_params(&fp_s, fpp);
+  const FrameParams& fp = fp_s;
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= fp.n_rays) return;
   if (rb.state[i] >> 31) {
@@ -165,6 +187,14 @@ __global__ void finalize_kernel(const FrameParams fp, RayBuffers rb, uint32_t* _
     rb.state[i] = 0;
     atomicAdd(leftover, 1u);
   }
+}
+
+// Loop control of the graph-driven wavefront: one thread advances the device round index and tells
+// the WHILE node whether the round that was just emitted holds any sample.
+__global__ void advance_round_kernel(uint32_t* __restrict__ counters, uint32_t* __restrict__ round_dev, cudaGraphConditionalHandle handle, int init, int bound) {
+  const uint32_t r = init ? 0u : *round_dev + 1u;
+  *round_dev = r;
+  cudaGraphSetConditional(handle, (counters[2 + r] > 0u && (int)r < bound) ? 1u : 0u);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -186,6 +216,7 @@ Renderer::~Renderer() {
   if (stream) cudaStreamSynchronize(stream);
   for (int k = 0; k < 2; ++k) { if (h_frame[k]) cudaFreeHost(h_frame[k]); if (frame_done[k]) cudaEventDestroy(frame_done[k]); }
   for (cudaEvent_t e : prof_events) cudaEventDestroy(e);
+  destroy_graph();
   if (vol_ready) cudaEventDestroy(vol_ready);
   if (h_counters) cudaFreeHost(h_counters);
   if (stream) cudaStreamDestroy(stream);
@@ -265,6 +296,56 @@ int Renderer::round_bound() const {
   return (int)std::ceil(max_samples / n_iters) + 1;
 }
 
+void Renderer::destroy_graph() {
+  if (loop_exec) { cudaGraphExecDestroy(loop_exec); loop_exec = nullptr; }
+  if (loop_graph) { cudaGraphDestroy(loop_graph); loop_graph = nullptr; }
+  if (capture_stream) { cudaStreamDestroy(capture_stream); capture_stream = nullptr; }
+}
+
+// (Re)build the loop graph when anything baked into its kernel nodes changed.
+void Renderer::ensure_graph(const RayBuffers& rb, unsigned grid, size_t cap, int rounds) {
+  GraphKey key;
+  memset(&key, 0, sizeof key);
+  key.desc = vol->cfg.desc; key.params = vol->params.p;
+  key.ptrs[0] = rb.rgba; key.ptrs[1] = rb.tn_ncb; key.ptrs[2] = rb.cell_base; key.ptrs[3] = rb.state; key.ptrs[4] = rb.jitter;
+  key.ptrs[5] = samples[0].p; key.ptrs[6] = samples[1].p; key.ptrs[7] = values.p; key.ptrs[8] = counters.p; key.ptrs[9] = accum.p;
+  key.ptrs[10] = frame_out(); key.ptrs[11] = fp_dev.p;
+  key.grid = grid; key.cap = cap; key.rounds = rounds;
+  if (loop_exec && !memcmp(&key, &graph_key, sizeof key)) return;
+  VNR_CUDA(cudaStreamSynchronize(stream));
+  destroy_graph();
+  VNR_CUDA(cudaGraphCreate(&loop_graph, 0));
+  cudaGraphConditionalHandle handle;
+  VNR_CUDA(cudaGraphConditionalHandleCreate(&handle, loop_graph, 0, 0));
+  uint32_t* round_dev = counters.p + kMaxRounds + 2;
+  // node 1: initialise the round index and the loop condition from round 0
+  cudaGraphNode_t init_node;
+  {
+    uint32_t* c = counters.p; int init = 1, bound = rounds;
+    void* args[] = {&c, &round_dev, &handle, &init, &bound};
+    cudaKernelNodeParams kp = {};
+    kp.func = (void*)advance_round_kernel; kp.gridDim = dim3(1); kp.blockDim = dim3(1); kp.kernelParams = args;
+    VNR_CUDA(cudaGraphAddKernelNode(&init_node, loop_graph, nullptr, 0, &kp));
+  }
+  // node 2: WHILE
+  cudaGraphNodeParams wp = {};
+  wp.type = cudaGraphNodeTypeConditional;
+  wp.conditional.handle = handle; wp.conditional.type = cudaGraphCondTypeWhile; wp.conditional.size = 1;
+  cudaGraphNode_t while_node;
+  VNR_CUDA(cudaGraphAddNode(&while_node, loop_graph, &init_node, 1, &wp));
+  cudaGraph_t body = wp.conditional.phGraph_out[0];
+  VNR_CUDA(cudaStreamCreateWithFlags(&capture_stream, cudaStreamNonBlocking));
+  VNR_CUDA(cudaStreamBeginCaptureToGraph(capture_stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
+  cudaError_t e = launch_decode_samples(vol->cfg.desc, vol->params.p, samples[0].p, samples[1].p, values.p, counters.p + 2, round_dev, cap, capture_stream);
+  march_round_kernel<false><<<grid, 128, 0, capture_stream>>>(reinterpret_cast<const FrameParams*>(fp_dev.p), rb, samples[0].p, samples[1].p, values.p, counters.p, 0, round_dev, accum.p, frame_out());
+  advance_round_kernel<<<1, 1, 0, capture_stream>>>(counters.p, round_dev, handle, 0, rounds);
+  cudaGraph_t captured = nullptr;
+  cudaError_t e2 = cudaStreamEndCapture(capture_stream, &captured);
+  VNR_CUDA(e); VNR_CUDA(e2);
+  VNR_CUDA(cudaGraphInstantiate(&loop_exec, loop_graph, 0));
+  graph_key = key;
+}
+
 void Renderer::render() {
   if (width <= 0 || height <= 0) return;                               // renderer.cpp:62
   if (mode != 5 && mode != 6) throw UnsupportedError("rendering mode " + std::to_string(mode) + " is outside this library's path (modes 5 and 6)");
@@ -292,18 +373,29 @@ void Renderer::render() {
   if (profiling) {
     while ((int)prof_events.size() < 2 * rounds) { cudaEvent_t e; VNR_CUDA(cudaEventCreate(&e)); prof_events.push_back(e); }
   }
+  fp_dev.ensure(sizeof(FrameParams));
+  // 200-odd bytes from pageable memory: staged by the driver at call time, ordered on the stream
+  VNR_CUDA(cudaMemcpyAsync(fp_dev.p, &fp, sizeof fp, cudaMemcpyHostToDevice, stream));
+  const bool graph_loop = use_graph && !profiling;
   if (n_rays) {
-    march_round_kernel<true><<<grid, 128, 0, stream>>>(fp, rb, nullptr, nullptr, samples[0].p, counters.p, 0, accum.p, frame.p);
-    for (int r = 0; r < rounds; ++r) {
-      if (profiling) VNR_CUDA(cudaEventRecord(prof_events[prof_used++], stream));
-      VNR_CUDA(launch_decode_samples(vol->cfg.desc, vol->params.p, samples[r & 1].p, values.p, counters.p + 2 + r, cap, stream));
-      if (profiling) VNR_CUDA(cudaEventRecord(prof_events[prof_used++], stream));
-      march_round_kernel<false><<<grid, 128, 0, stream>>>(fp, rb, samples[r & 1].p, values.p, samples[(r + 1) & 1].p, counters.p, r + 1, accum.p, frame.p);
+    march_round_kernel<true><<<grid, 128, 0, stream>>>(reinterpret_cast<const FrameParams*>(fp_dev.p), rb, samples[0].p, samples[1].p, nullptr, counters.p, 0, nullptr, accum.p, frame_out());
+    if (graph_loop) {
+      // device-driven loop: WHILE (round has samples) { decode; compose + march; advance }
+      ensure_graph(rb, grid, cap, rounds);
+      VNR_CUDA(cudaGraphLaunch(loop_exec, stream));
+    } else {
+      for (int r = 0; r < rounds; ++r) {
+        if (profiling) VNR_CUDA(cudaEventRecord(prof_events[prof_used++], stream));
+        VNR_CUDA(launch_decode_samples(vol->cfg.desc, vol->params.p, samples[r & 1].p, nullptr, values.p, counters.p + 2 + r, nullptr, cap, stream));
+        if (profiling) VNR_CUDA(cudaEventRecord(prof_events[prof_used++], stream));
+        march_round_kernel<false><<<grid, 128, 0, stream>>>(reinterpret_cast<const FrameParams*>(fp_dev.p), rb, samples[0].p, samples[1].p, values.p, counters.p, r + 1, nullptr, accum.p, frame_out());
+      }
     }
-    finalize_kernel<<<grid, 128, 0, stream>>>(fp, rb, counters.p + kMaxRounds + 3, accum.p, frame.p);
+    finalize_kernel<<<grid, 128, 0, stream>>>(reinterpret_cast<const FrameParams*>(fp_dev.p), rb, counters.p + kMaxRounds + 3, accum.p, frame_out());
     VNR_CUDA(cudaGetLastError());
-    launches = 2 + 2 * (uint64_t)rounds;
+    launches = graph_loop ? 0 : 2 + 2 * (uint64_t)rounds;     // graph path: counted from the device counters in stats()
   }
+  last_graph = graph_loop;
   last_rounds = rounds;
   // framebuffer.download_async (renderer.cpp:133)
   if (download) VNR_CUDA(cudaMemcpyAsync(h_frame[cur], frame.p, frame.bytes(), cudaMemcpyDeviceToHost, stream));
@@ -336,6 +428,11 @@ void Renderer::profile(float* decode_ms, int* decode_launches) {
 
 void Renderer::stats(uint64_t* s4) {
   VNR_CUDA(cudaStreamSynchronize(stream));
+  if (last_graph) {            // first round + loop init + 3 kernels per non-empty round + finalize
+    uint64_t nonempty = 0;
+    for (int r = 0; r <= last_rounds && r < kMaxRounds; ++r) if (h_counters[2 + r]) ++nonempty;
+    launches = 3 + 3 * nonempty;
+  }
   s4[0] = h_counters[0]; s4[2] = h_counters[1];
   uint64_t dec = 0, rounds = 0;
   for (int r = 0; r <= last_rounds && r < kMaxRounds; ++r) { dec += h_counters[2 + r]; if (h_counters[2 + r]) ++rounds; }

@@ -7,7 +7,16 @@
 namespace vnr {
 
 struct FrameParams;
+struct RayBuffers;
 constexpr int kMaxRounds = 1024;
+
+// everything baked into the kernel nodes of the captured wavefront loop
+struct GraphKey {
+  DecoderDesc desc;
+  const void* params;
+  const void* ptrs[12];
+  unsigned grid; size_t cap; int rounds;
+};
 
 struct Renderer {
   Volume* vol;
@@ -37,6 +46,14 @@ struct Renderer {
   std::vector<cudaEvent_t> prof_events;
   int prof_used = 0;
   uint64_t launches = 0;                // kernels launched by the last render()
+  DevBuf<uint8_t> fp_dev;               // FrameParams of the frame in flight (device copy)
+  // device-driven wavefront loop (CUDA graph with a WHILE node); off: bounded host-enqueued rounds
+  bool use_graph = true, last_graph = false;
+  cudaGraph_t loop_graph = nullptr; cudaGraphExec_t loop_exec = nullptr; cudaStream_t capture_stream = nullptr;
+  GraphKey graph_key;
+  // multi-GPU: finished pixels are stored here instead of `frame` (rank 0's frame buffer, peer-mapped)
+  float4* frame_target = nullptr;
+  float4* frame_out() { return frame_target ? frame_target : frame.p; }
 
   explicit Renderer(Volume* v);
   ~Renderer();
@@ -44,6 +61,8 @@ struct Renderer {
   void resize(int w, int h);
   void fill_frame_params(FrameParams& fp);
   int round_bound() const;
+  void destroy_graph();
+  void ensure_graph(const RayBuffers& rb, unsigned grid, size_t cap, int rounds);
   void render();
   const float* map_frame();
   void stats(uint64_t* s4);

@@ -148,10 +148,14 @@ __device__ __forceinline__ uint32_t scale_pair(uint32_t g, float w) {
 template <int F>
 __device__ __forceinline__ void scatter_level(const LevelDesc& lv, __half* __restrict__ ggrid, float x, float y, float z, const uint32_t* g) {
   const CornerSetup c = corner_setup(lv, x, y, z);
+  uint32_t idx[8];
+  float wts[8];
+  level_indices(lv, c, idx);
+  corner_weights(c.wx, c.wy, c.wz, wts);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const float w = corner_weight(c, i);
-    __half* dst = ggrid + ((size_t)lv.offset + corner_index(lv, c, i)) * F;
+    const float w = wts[i];
+    __half* dst = ggrid + ((size_t)lv.offset + idx[i]) * F;
     if constexpr (F == 8) red_add_f16x8(dst, make_uint4(scale_pair(g[0], w), scale_pair(g[1], w), scale_pair(g[2], w), scale_pair(g[3], w)));
     else if constexpr (F == 4) red_add_f16x4(dst, make_uint2(scale_pair(g[0], w), scale_pair(g[1], w)));
     else if constexpr (F == 2) red_add_f16x2(dst, scale_pair(g[0], w));
@@ -232,12 +236,7 @@ train_step_kernel(const DecoderDesc d, const TrainArgs a) {
       uint8_t* rowp = x_ptr(0) + row * 128u;
       const uint32_t sw = row & 7u;
       const int l0 = (int)(col0 / F), l1 = min(d.n_levels, (int)((col0 + 32u) / F));
-      for (int l = l0; l < l1; ++l) {
-        if constexpr (F == 8) *reinterpret_cast<uint4*>(rowp + (((uint32_t)l ^ sw) << 4)) = encode_level_f8(d.lv[l], grid, x, y, z);
-        else if constexpr (F == 4) *reinterpret_cast<uint2*>(rowp + ((((uint32_t)l >> 1) ^ sw) << 4) + ((uint32_t)l & 1u) * 8u) = encode_level_f4(d.lv[l], grid, x, y, z);
-        else if constexpr (F == 2) *reinterpret_cast<uint32_t*>(rowp + ((((uint32_t)l >> 2) ^ sw) << 4) + ((uint32_t)l & 3u) * 4u) = encode_level_f2(d.lv[l], grid, x, y, z);
-        else *reinterpret_cast<__half*>(rowp + ((((uint32_t)l >> 3) ^ sw) << 4) + ((uint32_t)l & 7u) * 2u) = encode_level_f1(d.lv[l], grid, x, y, z);
-      }
+      encode_levels<F>(rowp, sw, d, grid, x, y, z, l0, l1);
       if (hlf == 0)
         for (int k = d.enc_dims; k < d.enc_pad; ++k)
           *reinterpret_cast<__half*>(rowp + ((((uint32_t)k >> 3) ^ sw) << 4) + ((uint32_t)k & 7u) * 2u) = __float2half_rn(0.f);
@@ -407,7 +406,17 @@ train_step_kernel(const DecoderDesc d, const TrainArgs a) {
 struct AdamArgs {
   float lr, beta1, beta2, eps, l2_reg, loss_scale;
   float* master; __half* params; float* m1; float* m2; uint32_t* steps;
+  const float* bias;           // bias[t] = sqrt(1 - beta2^t) / (1 - beta1^t), t <= current optimizer step
 };
+
+// Adam's bias correction depends only on the per-parameter step count t (adam.h:97-100).  Every t a
+// parameter can have reached is <= the optimizer step, so the two powf per parameter of the reference
+// are hoisted into a table that grows with the optimizer step (same expression, same rounding).
+__global__ void adam_bias_fill_kernel(float* __restrict__ tab, uint32_t lo, uint32_t hi, float beta1, float beta2) {
+  const uint32_t t = lo + blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= hi) return;
+  tab[t] = t == 0 ? 0.f : __fdiv_rn(sqrtf(1.f - powf(beta2, (float)t)), 1.f - powf(beta1, (float)t));
+}
 
 __device__ __forceinline__ void adam_update(const AdamArgs& a, size_t i, float gradient, bool is_matrix) {
   const float weight_fp = a.master[i];
@@ -417,7 +426,7 @@ __device__ __forceinline__ void adam_update(const AdamArgs& a, size_t i, float g
   const float sm = __fmaf_rn(a.beta2, a.m2[i], (1.f - a.beta2) * gradient_sq);
   a.m1[i] = fm; a.m2[i] = sm;
   const uint32_t cs = ++a.steps[i];
-  const float lr = a.lr * __fdiv_rn(sqrtf(1.f - powf(a.beta2, (float)cs)), 1.f - powf(a.beta1, (float)cs));
+  const float lr = a.lr * __ldg(a.bias + cs);
   const float eff = fminf(fmaxf(__fdiv_rn(lr, sqrtf(sm) + a.eps), 0.f), 3.402823466e+38f);
   const float new_weight = __fmaf_rn(-eff, fm, weight_fp);
   a.master[i] = new_weight;
@@ -441,24 +450,42 @@ __global__ void adam_mlp_from_grads_kernel(AdamArgs a, uint32_t n_mlp, const flo
   adam_update(a, i, __fdiv_rn(grads[i], a.loss_scale), true);
 }
 
-// Grid parameters, 8 per thread: skip parameters whose gradient is exactly zero (adam.h:76-79) and
-// clear the consumed gradients (replaces the per-step cudaMemsetAsync of grid.h:718-720).
-__global__ void adam_grid_kernel(AdamArgs a, uint32_t n_mlp, uint32_t n_grid, __half* __restrict__ grads) {
+// Grid parameters, 4 per thread (one 16-byte vector of every fp32 state array, fully coalesced): skip
+// parameters whose gradient is exactly zero (adam.h:76-79) and clear the consumed gradients (replaces the
+// per-step cudaMemsetAsync of grid.h:718-720).  A thread whose four gradients are all zero touches nothing
+// but the 8 gradient bytes.
+__global__ void __launch_bounds__(256) adam_grid_kernel(AdamArgs a, uint32_t n_mlp, uint32_t n_grid, __half* __restrict__ grads) {
   const size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t base = v * 8;
+  const size_t base = v * 4;
   if (base >= n_grid) return;
-  uint4* gp = reinterpret_cast<uint4*>(grads + base);
-  const uint4 g = *gp;
-  if ((g.x | g.y | g.z | g.w) == 0u) return;
-  const uint32_t gw[4] = {g.x, g.y, g.z, g.w};
+  uint2* gp = reinterpret_cast<uint2*>(grads + base);
+  const uint2 g = *gp;
+  if ((g.x | g.y) == 0u) return;
+  *gp = make_uint2(0, 0);
+  const size_t i = (size_t)n_mlp + base;          // n_mlp is a multiple of 1024: the vectors stay 16-byte aligned
+  const float2 f01 = __half22float2(u32_as_h2(g.x)), f23 = __half22float2(u32_as_h2(g.y));
+  const float gr[4] = {__fdiv_rn(f01.x, a.loss_scale), __fdiv_rn(f01.y, a.loss_scale), __fdiv_rn(f23.x, a.loss_scale), __fdiv_rn(f23.y, a.loss_scale)};
+  float4 w4 = *reinterpret_cast<const float4*>(a.master + i);
+  float4 m4 = *reinterpret_cast<const float4*>(a.m1 + i);
+  float4 s4 = *reinterpret_cast<const float4*>(a.m2 + i);
+  uint4 c4 = *reinterpret_cast<const uint4*>(a.steps + i);
+  float* w = &w4.x; float* fm = &m4.x; float* sm = &s4.x; uint32_t* cs = &c4.x;
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    const float2 f = __half22float2(u32_as_h2(gw[q]));
-    const float g0 = __fdiv_rn(f.x, a.loss_scale), g1 = __fdiv_rn(f.y, a.loss_scale);
-    if (g0 != 0.f) adam_update(a, (size_t)n_mlp + base + 2 * q, g0, false);
-    if (g1 != 0.f) adam_update(a, (size_t)n_mlp + base + 2 * q + 1, g1, false);
+    const float gradient = gr[q];
+    if (gradient == 0.f) continue;
+    fm[q] = __fmaf_rn(a.beta1, fm[q], (1.f - a.beta1) * gradient);
+    sm[q] = __fmaf_rn(a.beta2, sm[q], (1.f - a.beta2) * (gradient * gradient));
+    const uint32_t t = ++cs[q];
+    const float lr = a.lr * __ldg(a.bias + t);
+    const float eff = fminf(fmaxf(__fdiv_rn(lr, sqrtf(sm[q]) + a.eps), 0.f), 3.402823466e+38f);
+    w[q] = __fmaf_rn(-eff, fm[q], w[q]);
   }
-  *gp = make_uint4(0, 0, 0, 0);
+  *reinterpret_cast<float4*>(a.master + i) = w4;
+  *reinterpret_cast<float4*>(a.m1 + i) = m4;
+  *reinterpret_cast<float4*>(a.m2 + i) = s4;
+  *reinterpret_cast<uint4*>(a.steps + i) = c4;
+  *reinterpret_cast<uint2*>(a.params + i) = make_uint2(h2_as_u32(__floats2half2_rn(w4.x, w4.y)), h2_as_u32(__floats2half2_rn(w4.z, w4.w)));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -526,8 +553,19 @@ void optimizer_step(Volume* v, cudaStream_t s) {
   a.lr = o.lr * v->lr_factor; a.beta1 = o.beta1; a.beta2 = o.beta2; a.eps = o.eps; a.l2_reg = o.l2_reg; a.loss_scale = 128.f;
   a.master = v->master.p; a.params = v->params.p; a.m1 = v->m1.p; a.m2 = v->m2.p; a.steps = v->steps.p;
   ++v->opt_step;
+  if (v->opt_step + 1 > v->bias_filled) {
+    if (v->opt_step + 1 > v->bias_tab.n) {
+      VNR_CUDA(cudaStreamSynchronize(s));
+      v->bias_tab.alloc(std::max<size_t>(1 << 16, 2 * (size_t)(v->opt_step + 1)));
+      v->bias_filled = 0;
+    }
+    const uint32_t hi = (uint32_t)std::min<size_t>(v->bias_tab.n, (size_t)v->opt_step + 1 + 4096);
+    adam_bias_fill_kernel<<<(hi - v->bias_filled + 255) / 256, 256, 0, s>>>(v->bias_tab.p, v->bias_filled, hi, o.beta1, o.beta2);
+    v->bias_filled = hi;
+  }
+  a.bias = v->bias_tab.p;
   adam_mlp_from_grads_kernel<<<(d.n_mlp + 255) / 256, 256, 0, s>>>(a, d.n_mlp, v->mlp_grads.p);
-  const size_t vecs = ((size_t)d.n_grid + 7) / 8;
+  const size_t vecs = ((size_t)d.n_grid + 3) / 4;
   adam_grid_kernel<<<(unsigned)((vecs + 255) / 256), 256, 0, s>>>(a, d.n_mlp, d.n_grid, v->grid_grads.p);
   loss_fold_kernel<<<1, 1, 0, s>>>(v->loss_accum.p);
   VNR_CUDA(cudaGetLastError());

@@ -175,6 +175,14 @@ VNR_EXPORT int vnr_volume_decode(vnr_volume_t* vh, const float* d_xyz, float* d_
   });
 }
 
+VNR_EXPORT int vnr_volume_gather_probe(vnr_volume_t* vh, const float* d_xyz, uint32_t* d_out, size_t n, void* stream) {
+  return guard([&] {
+    Volume* v = V(vh);
+    if (n && (!d_xyz || !d_out)) throw InvalidError("null buffer");
+    VNR_CUDA(launch_gather_probe(v->cfg.desc, v->params.p, d_xyz, d_out, n, S(v, stream)));
+  });
+}
+
 static void decode_host_impl(Volume* v, const float* h_xyz, float* h_out, uint16_t* h_enc, size_t n) {
   if (n == 0) return;
   if (!h_xyz || !h_out) throw InvalidError("null buffer");

@@ -64,3 +64,34 @@ VNR_EXPORT int vnr_renderer_stream(vnr_renderer_t* r, void** stream) { return gu
 VNR_EXPORT int vnr_renderer_set_n_iters(vnr_renderer_t* r, int n) {
   return guard([&] { if (n < 1 || n > 16) throw InvalidError("n_iters must be in [1,16]"); R(r)->n_iters = n; R(r)->reset = true; });
 }
+
+// device-driven wavefront loop (CUDA graph WHILE node) on/off; off = bounded host-enqueued rounds
+VNR_EXPORT int vnr_renderer_set_graph(vnr_renderer_t* r, int on) { return guard([&] { R(r)->use_graph = on != 0; }); }
+
+// ---- multi-GPU frame gather over peer memory (no reference counterpart) ---------------------------
+// Finished pixels of this renderer's partition are stored to `d_rgba` (float4[w*h]) instead of its own
+// frame buffer: pass rank 0's frame buffer opened with vnr_ipc_open so that the compositing kernel writes
+// straight into rank 0's memory over NVLink.  NULL restores the local buffer.
+VNR_EXPORT int vnr_renderer_set_frame_target(vnr_renderer_t* r, void* d_rgba) {
+  return guard([&] {
+    Renderer* s = R(r);
+    VNR_CUDA(cudaStreamSynchronize(s->stream));
+    s->frame_target = reinterpret_cast<float4*>(d_rgba);
+    s->reset = true;
+  });
+}
+VNR_EXPORT int vnr_ipc_export(void* d_ptr, void* handle64) {
+  return guard([&] {
+    if (!d_ptr || !handle64) throw InvalidError("null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    VNR_CUDA(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(handle64), d_ptr));
+  });
+}
+VNR_EXPORT int vnr_ipc_open(const void* handle64, void** d_ptr) {
+  return guard([&] {
+    if (!d_ptr || !handle64) throw InvalidError("null argument");
+    cudaIpcMemHandle_t h; memcpy(&h, handle64, sizeof h);
+    VNR_CUDA(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  });
+}
+VNR_EXPORT int vnr_ipc_close(void* d_ptr) { return guard([&] { if (d_ptr) VNR_CUDA(cudaIpcCloseMemHandle(d_ptr)); }); }

@@ -1,8 +1,154 @@
 // vnr_c_volume.inl -- ground truth, macrocell, transfer function, training, params.json
-#define VNR_TODO(name) { return guard([&] { throw UnsupportedError(name ": not implemented yet"); }); }
-VNR_EXPORT int vnr_volume_load_params(vnr_volume_t*, const void*, size_t) VNR_TODO("vnr_volume_load_params")
-VNR_EXPORT int vnr_volume_save_params(vnr_volume_t*, const void**, size_t*) VNR_TODO("vnr_volume_save_params")
-VNR_EXPORT int vnr_params_peek(const void*, size_t, int*, int*, int*, const char**) VNR_TODO("vnr_params_peek")
+// ---- params.json (BSON) --------------------------------------------------------------------
+// Layout written by NeuralVolume::save_params_to_json (core/network.cu:827-857) through
+// nlohmann::json::to_bson: objects are std::map, i.e. keys in lexicographic order; unsigned and
+// signed integers that fit int32 are BSON int32, floats are doubles, blobs are binary subtype 0.
+//   { "macrocell": { "data": <vec2f[cells]>, "dims": {x,y,z}, "groundtruth": bool, "spacings": {x,y,z} },
+//     "model": { "encoding": {...}, "loss": {...}, "network": {...} },
+//     "parameters": { "n_params": N, "params_binary": <fp16[N]> },       (tcnn trainer.h:299-311)
+//     "volume": { "dims": {x,y,z} } }
+static mj::Value sorted_copy(const mj::Value& v) {
+  if (v.type == mj::Value::ObjectT) {
+    mj::Value o = mj::Value::make_object();
+    std::vector<std::pair<std::string, mj::Value>> kv;
+    for (auto& e : *v.obj) kv.emplace_back(e.first, sorted_copy(e.second));
+    std::stable_sort(kv.begin(), kv.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+    for (auto& e : kv) o.obj->push_back(e);
+    return o;
+  }
+  if (v.type == mj::Value::ArrayT) {
+    mj::Value a = mj::Value::make_array();
+    for (auto& e : *v.arr) a.arr->push_back(sorted_copy(e));
+    return a;
+  }
+  return v;
+}
+
+static mj::Value xyz_obj_int(int x, int y, int z) {
+  mj::Value o = mj::Value::make_object();
+  o.set("x", mj::Value::from_int(x)); o.set("y", mj::Value::from_int(y)); o.set("z", mj::Value::from_int(z));
+  return o;
+}
+
+static int get_int(const mj::Value& o, const char* k) { return (int)o.at(k).num(); }
+
+VNR_EXPORT int vnr_params_peek(const void* bson, size_t n, int* dx, int* dy, int* dz, const char** model_json) {
+  static thread_local std::string model_text;
+  return guard([&] {
+    if (!bson || n < 5) throw InvalidError("empty params blob");
+    mj::Value root;
+    try { root = mj::bson::read(bson, n); } catch (const std::exception& e) { throw InvalidError(e.what()); }
+    if (!root.contains("volume")) throw InvalidError("expecting a model config with volume dims tag");      // api.cpp:215
+    const mj::Value& d = root.at("volume").at("dims");
+    if (dx) *dx = get_int(d, "x");
+    if (dy) *dy = get_int(d, "y");
+    if (dz) *dz = get_int(d, "z");
+    if (model_json) {
+      model_text.clear();
+      if (root.contains("model")) mj::dump(root.at("model"), model_text);
+      *model_json = model_text.c_str();
+    }
+  });
+}
+
+// NeuralVolume::load_params_from_json (core/network.cu:879-939)
+VNR_EXPORT int vnr_volume_load_params(vnr_volume_t* vh, const void* bson, size_t n) {
+  return guard([&] {
+    Volume* v = V(vh);
+    if (!bson || n < 5) throw InvalidError("empty params blob");
+    mj::Value root;
+    try { root = mj::bson::read(bson, n); } catch (const std::exception& e) { throw InvalidError(e.what()); }
+    if (root.contains("volume")) {
+      const mj::Value& d = root.at("volume").at("dims");
+      if (get_int(d, "x") != v->dims[0] || get_int(d, "y") != v->dims[1] || get_int(d, "z") != v->dims[2])
+        throw InvalidError("mismatch data dimension");                                                   // network.cu:892
+    }
+    if (root.contains("model")) {
+      // deserialize_model (tcnn_network.h:163-221): the network is rebuilt from the stored config; the optimizer
+      // options are not part of the file and stay as they are.
+      std::string text; mj::dump(root.at("model"), text);
+      ModelConfig c = parse_model_config(text);
+      const DecoderDesc &a = c.desc, &b = v->cfg.desc;
+      const bool same = a.n_levels == b.n_levels && a.n_feat == b.n_feat && a.n_hidden == b.n_hidden && a.n_grid == b.n_grid && a.n_mlp == b.n_mlp &&
+                        c.base_res == v->cfg.base_res && c.per_level_scale == v->cfg.per_level_scale;
+      if (!same) {
+        c.opt = v->cfg.opt;
+        v->cfg = c;
+        VNR_CUDA(cudaStreamSynchronize(v->stream));
+        v->params.alloc(c.n_params());
+        v->have_params = false; v->have_opt = false;
+      }
+    }
+    const mj::Value& P = root.contains("parameters") ? root.at("parameters") : root;                   // old format: params at the root
+    if (!P.contains("params_binary") || P.at("params_binary").type != mj::Value::Binary) throw InvalidError("params blob has no params_binary");
+    const std::string& blob = P.at("params_binary").s;
+    if (blob.size() / 2 != v->cfg.n_params()) throw InvalidError("Can't set params because CPU buffer has the wrong size.");   // trainer.h:283
+    if (root.contains("macrocell")) {
+      const mj::Value& M = root.at("macrocell");
+      const mj::Value& md = M.at("dims");
+      const int mx = get_int(md, "x"), my = get_int(md, "y"), mz = get_int(md, "z");
+      if (mx <= 0 || my <= 0 || mz <= 0) throw InvalidError("bad macrocell dims");
+      if (mx != v->mc_dims[0] || my != v->mc_dims[1] || mz != v->mc_dims[2]) {
+        // the reference re-allocates to the stored shape (network.cu:903-909); here the cell size is fixed at 16 voxels
+        throw UnsupportedError("macrocell dims of the params file do not match ceil(dims/16)");
+      }
+      const mj::Value& data = M.at("data");
+      if (data.type != mj::Value::Binary || data.s.size() != v->mc_range.bytes()) throw InvalidError("macrocell data has the wrong size");
+      VNR_CUDA(cudaMemcpyAsync(v->mc_range.p, data.s.data(), data.s.size(), cudaMemcpyHostToDevice, v->stream));
+      if (M.contains("groundtruth") && M.at("groundtruth").type == mj::Value::Bool) v->mc_external = M.at("groundtruth").b;
+      macrocell_update_max_opacity(v, v->stream);                                                        // network.cu:912
+      VNR_CUDA(cudaStreamSynchronize(v->stream));
+    }
+    std::vector<__half> h(blob.size() / 2);
+    memcpy(h.data(), blob.data(), h.size() * 2);
+    VNR_CUDA(cudaMemcpy(v->params.p, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
+    upload_master_from_f16(v, h);
+    v->have_params = true;
+    if (!v->have_opt) reset_optimizer(v);
+  });
+}
+
+// NeuralVolume::save_params_to_json (core/network.cu:827-857) + json::to_bson (:865)
+VNR_EXPORT int vnr_volume_save_params(vnr_volume_t* vh, const void** bson, size_t* n) {
+  return guard([&] {
+    Volume* v = V(vh);
+    if (!bson || !n) throw InvalidError("null argument");
+    if (!v->have_params) throw StateError("the neural volume has no parameters");
+    VNR_CUDA(cudaStreamSynchronize(v->stream));
+    mj::Value root = mj::Value::make_object();
+    {
+      mj::Value vol = mj::Value::make_object();
+      vol.set("dims", xyz_obj_int(v->dims[0], v->dims[1], v->dims[2]));
+      root.set("volume", vol);
+    }
+    {
+      mj::Value mc = mj::Value::make_object();
+      mc.set("groundtruth", mj::Value::from(v->mc_external));
+      mc.set("dims", xyz_obj_int(v->mc_dims[0], v->mc_dims[1], v->mc_dims[2]));
+      mj::Value sp = mj::Value::make_object();
+      const char* ax[3] = {"x", "y", "z"};
+      for (int k = 0; k < 3; ++k) sp.set(ax[k], mj::Value::from((double)(16.f / (float)v->dims[k])));   // macrocell.cu:200 (float -> double)
+      mc.set("spacings", sp);
+      std::vector<float> r(2 * v->cells());
+      VNR_CUDA(cudaMemcpy(r.data(), v->mc_range.p, v->mc_range.bytes(), cudaMemcpyDeviceToHost));
+      mc.set("data", mj::Value::binary(r.data(), r.size() * sizeof(float)));
+      root.set("macrocell", mc);
+    }
+    {
+      mj::Value p = mj::Value::make_object();
+      const size_t np = v->cfg.n_params();
+      p.set("n_params", mj::Value::from_int((int64_t)np));
+      std::vector<__half> h(np);
+      VNR_CUDA(cudaMemcpy(h.data(), v->params.p, np * 2, cudaMemcpyDeviceToHost));
+      p.set("params_binary", mj::Value::binary(h.data(), np * 2));
+      root.set("parameters", p);
+    }
+    root.set("model", mj::Parser::parse(v->cfg.model_json));
+    v->blob = mj::bson::write(sorted_copy(root));
+    *bson = v->blob.data();
+    *n = v->blob.size();
+  });
+}
 
 VNR_EXPORT int vnr_volume_set_groundtruth_f32(vnr_volume_t* vh, const float* h_volume) {
   return guard([&] {

@@ -83,63 +83,117 @@ __device__ __forceinline__ __half2 acc_pair(__half2 acc, uint32_t v, float w) {
   return __hadd2(acc, __floats2half2_rn(w * f.x, w * f.y));
 }
 
-// Encode one level with F = 8: returns the 8 halves as one 16-byte vector.
-__device__ __forceinline__ uint4 encode_level_f8(const LevelDesc& lv, const __half* __restrict__ grid, float x, float y, float z) {
-  const CornerSetup c = corner_setup(lv, x, y, z);
-  const uint4* __restrict__ tab = reinterpret_cast<const uint4*>(grid) + lv.offset;
-  uint4 v[8];
+// Table indices of the 8 corners of a cell.  The level descriptor is warp-uniform, so the
+// hashed/dense and power-of-two/modulo choices are real (uniform) branches, and the per-dimension
+// terms are shared between corners: (g+1)*P == g*P + P (mod 2^32).
+__device__ __forceinline__ void level_indices(const LevelDesc& lv, const CornerSetup& c, uint32_t (&idx)[8]) {
+  const uint32_t xa[2] = {c.gx, c.gx + 1u};
+  if (lv.hashed) {
+    const uint32_t y0 = c.gy * 2654435761u, z0 = c.gz * 805459861u;
+    const uint32_t yb[2] = {y0, y0 + 2654435761u}, zc[2] = {z0, z0 + 805459861u};
 #pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = __ldg(tab + corner_index(lv, c, i));
-  __half2 a0 = __float2half2_rn(0.f), a1 = a0, a2 = a0, a3 = a0;
+    for (int i = 0; i < 8; ++i) idx[i] = xa[i & 1] ^ yb[(i >> 1) & 1] ^ zc[i >> 2];
+  } else {
+    const uint32_t y0 = c.gy * lv.res, z0 = c.gz * lv.res2;
+    const uint32_t yb[2] = {y0, y0 + lv.res}, zc[2] = {z0, z0 + lv.res2};
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float w = corner_weight(c, i);
-    a0 = acc_pair(a0, v[i].x, w); a1 = acc_pair(a1, v[i].y, w);
-    a2 = acc_pair(a2, v[i].z, w); a3 = acc_pair(a3, v[i].w, w);
+    for (int i = 0; i < 8; ++i) idx[i] = xa[i & 1] + yb[(i >> 1) & 1] + zc[i >> 2];
   }
-  return make_uint4(h2_as_u32(a0), h2_as_u32(a1), h2_as_u32(a2), h2_as_u32(a3));
-}
-
-// F = 4: 8 bytes
-__device__ __forceinline__ uint2 encode_level_f4(const LevelDesc& lv, const __half* __restrict__ grid, float x, float y, float z) {
-  const CornerSetup c = corner_setup(lv, x, y, z);
-  const uint2* __restrict__ tab = reinterpret_cast<const uint2*>(grid) + lv.offset;
-  uint2 v[8];
+  if (lv.mask) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = __ldg(tab + corner_index(lv, c, i));
-  __half2 a0 = __float2half2_rn(0.f), a1 = a0;
+    for (int i = 0; i < 8; ++i) idx[i] &= lv.mask;
+  } else {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float w = corner_weight(c, i);
-    a0 = acc_pair(a0, v[i].x, w); a1 = acc_pair(a1, v[i].y, w);
+    for (int i = 0; i < 8; ++i) idx[i] %= lv.size;
   }
-  return make_uint2(h2_as_u32(a0), h2_as_u32(a1));
 }
 
-// F = 2: 4 bytes
-__device__ __forceinline__ uint32_t encode_level_f2(const LevelDesc& lv, const __half* __restrict__ grid, float x, float y, float z) {
-  const CornerSetup c = corner_setup(lv, x, y, z);
-  const uint32_t* __restrict__ tab = reinterpret_cast<const uint32_t*>(grid) + lv.offset;
-  uint32_t v[8];
+// The 8 trilinear weights, ((wx * wy) * wz) as the sequential `weight *= ...` of the reference.
+__device__ __forceinline__ void corner_weights(float wx, float wy, float wz, float (&w)[8]) {
+  const float ax[2] = {1.f - wx, wx}, ay[2] = {1.f - wy, wy}, az[2] = {1.f - wz, wz};
+  float xy[4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = __ldg(tab + corner_index(lv, c, i));
-  __half2 a0 = __float2half2_rn(0.f);
+  for (int i = 0; i < 4; ++i) xy[i] = ax[i & 1] * ay[i >> 1];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) a0 = acc_pair(a0, v[i], corner_weight(c, i));
-  return h2_as_u32(a0);
+  for (int i = 0; i < 8; ++i) w[i] = xy[i & 3] * az[i >> 2];
 }
 
-// F = 1: 2 bytes
-__device__ __forceinline__ __half encode_level_f1(const LevelDesc& lv, const __half* __restrict__ grid, float x, float y, float z) {
-  const CornerSetup c = corner_setup(lv, x, y, z);
-  const __half* __restrict__ tab = grid + lv.offset;
-  __half v[8];
+template <int F> struct FeatVec;
+template <> struct FeatVec<8> { typedef uint4 type; };
+template <> struct FeatVec<4> { typedef uint2 type; };
+template <> struct FeatVec<2> { typedef uint32_t type; };
+template <> struct FeatVec<1> { typedef unsigned short type; };
+
+// One (sample, level) gather split in two halves so that callers can keep the loads of the next
+// level in flight while the current one is reduced: issue() computes the corner indices and
+// starts the 8 vector loads, finish() does the fp16-accumulated trilinear sum.
+template <int F>
+struct LevelGather {
+  typedef typename FeatVec<F>::type T;
+  T v[8];
+  float wx, wy, wz;
+
+  __device__ __forceinline__ void issue(const LevelDesc& lv, const __half* __restrict__ grid, float x, float y, float z) {
+    const CornerSetup c = corner_setup(lv, x, y, z);
+    wx = c.wx; wy = c.wy; wz = c.wz;
+    uint32_t idx[8];
+    level_indices(lv, c, idx);
+    const T* __restrict__ tab = reinterpret_cast<const T*>(grid) + lv.offset;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = __ldg(tab + corner_index(lv, c, i));
-  __half a = __float2half_rn(0.f);
+    for (int i = 0; i < 8; ++i) v[i] = __ldg(tab + idx[i]);
+  }
+
+  __device__ __forceinline__ T finish() const {
+    float w[8];
+    corner_weights(wx, wy, wz, w);
+    if constexpr (F == 8) {
+      __half2 a0 = __float2half2_rn(0.f), a1 = a0, a2 = a0, a3 = a0;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) a = __hadd(a, __float2half_rn(corner_weight(c, i) * __half2float(v[i])));
-  return a;
+      for (int i = 0; i < 8; ++i) {
+        a0 = acc_pair(a0, v[i].x, w[i]); a1 = acc_pair(a1, v[i].y, w[i]);
+        a2 = acc_pair(a2, v[i].z, w[i]); a3 = acc_pair(a3, v[i].w, w[i]);
+      }
+      return make_uint4(h2_as_u32(a0), h2_as_u32(a1), h2_as_u32(a2), h2_as_u32(a3));
+    } else if constexpr (F == 4) {
+      __half2 a0 = __float2half2_rn(0.f), a1 = a0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { a0 = acc_pair(a0, v[i].x, w[i]); a1 = acc_pair(a1, v[i].y, w[i]); }
+      return make_uint2(h2_as_u32(a0), h2_as_u32(a1));
+    } else if constexpr (F == 2) {
+      __half2 a0 = __float2half2_rn(0.f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a0 = acc_pair(a0, v[i], w[i]);
+      return h2_as_u32(a0);
+    } else {
+      __half a = __float2half_rn(0.f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a = __hadd(a, __float2half_rn(w[i] * __half2float(__ushort_as_half(v[i]))));
+      return __half_as_ushort(a);
+    }
+  }
+};
+
+// byte offset of feature column `col` (F halves wide) inside a 128-byte swizzled tile row
+template <int F>
+__device__ __forceinline__ uint32_t feat_offset(uint32_t level, uint32_t row_sw) {
+  constexpr uint32_t per_chunk = 8u / F;                      // levels per 16-byte chunk
+  return (((level / per_chunk) ^ row_sw) << 4) + (level % per_chunk) * (2u * F);
+}
+
+// Gather levels [l0, l1) of one sample into its swizzled tile row, software-pipelined: the
+// loads of level l+1 are in flight while level l is reduced.
+template <int F>
+__device__ __forceinline__ void encode_levels(uint8_t* rowp, uint32_t row_sw, const DecoderDesc& d, const __half* __restrict__ grid,
+                                              float x, float y, float z, int l0, int l1) {
+  typedef typename FeatVec<F>::type T;
+  if (l0 >= l1) return;
+  LevelGather<F> cur, nxt;
+  cur.issue(d.lv[l0], grid, x, y, z);
+  for (int l = l0; l < l1; ++l) {
+    if (l + 1 < l1) nxt.issue(d.lv[l + 1], grid, x, y, z);
+    *reinterpret_cast<T*>(rowp + feat_offset<F>((uint32_t)l, row_sw)) = cur.finish();
+    cur = nxt;
+  }
 }
 
 }  // namespace vnr

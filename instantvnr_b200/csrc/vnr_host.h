@@ -83,6 +83,8 @@ struct Renderer;
 // ---- kernel launchers (decode.cu, render.cu, macrocell.cu, train.cu) -------------------
 int num_sms();
 cudaError_t launch_decode(const DecoderDesc& d, const __half* params, const float* coords, float* out, size_t n, __half* enc_out, cudaStream_t stream);
-cudaError_t launch_decode_samples(const DecoderDesc& d, const __half* params, const float4* samples, float* out, const uint32_t* n_dev, size_t n_max, cudaStream_t stream);
+cudaError_t launch_gather_probe(const DecoderDesc& d, const __half* params, const float* coords, uint32_t* out, size_t n, cudaStream_t stream);
+cudaError_t launch_decode_samples(const DecoderDesc& d, const __half* params, const float4* samples, const float4* samples_alt, float* out,
+                                  const uint32_t* n_dev, const uint32_t* round_dev, size_t n_max, cudaStream_t stream);
 
 }  // namespace vnr

@@ -35,6 +35,7 @@ struct Volume {
   DevBuf<float> mlp_partial;       // fp32 [n_cta][n_mlp] per-CTA weight-gradient partials
   bool grads_clean = false, grads_pending = false;
   DevBuf<uint32_t> steps;
+  DevBuf<float> bias_tab; uint32_t bias_filled = 0;   // Adam bias-correction table (train.cu)
   bool have_params = false, have_opt = false;
   uint32_t opt_step = 0; float lr_factor = 1.f;
   uint64_t train_step = 0;

@@ -115,3 +115,34 @@ def test_partition_tiles_reassemble():
         assert np.all(part[other] == 0)
         acc[rows] = part[rows]
     assert np.array_equal(acc, full)
+
+
+def test_graph_loop_equals_host_enqueued_rounds():
+    """The CUDA-graph WHILE loop and the bounded host-enqueued rounds run the same kernels: identical frames."""
+    dims, cfg = (64, 64, 64), dict(log2_hashmap=15)
+    m, p16, dec, (lo, hi) = _scene(dims, cfg)
+    rgb, alpha = syn.make_tfn(64)
+    tr = (max(lo, 0.0), min(hi, 1.0))
+    vol = vnr.NeuralVolume(vnr.model_json(**cfg), dims)
+    vol.set_params_f16(p16)
+    vol.set_transfer_function(rgb, alpha, tr)
+    vol.set_macrocell(O.macrocell_update_implicit(np.clip(dec, 0, 1), dims))
+    out = []
+    for graph in (True, False, True):
+        ren = vnr.Renderer(vol)
+        ren.set_size(80, 60)
+        ren.set_graph(graph)
+        frames = []
+        for view in (1, 5):                       # second frame replays the captured graph with a new camera
+            ren.set_camera(*syn.default_camera(dims, view))
+            ren.render()
+            frames.append(ren.map_frame())
+        ren.set_size(64, 64)                      # resize: the graph is rebuilt
+        ren.render()
+        frames.append(ren.map_frame())
+        out.append((frames, ren.stats()))
+    for k in range(3):
+        assert np.array_equal(out[0][0][k], out[1][0][k])
+        assert np.array_equal(out[0][0][k], out[2][0][k])
+    assert out[0][1] == out[1][1]
+    assert out[0][0][0][..., 3].max() > 0.3

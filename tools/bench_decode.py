@@ -36,6 +36,18 @@ def main():
             vol.decode(xs, out, n, s)
         e1.record(); torch.cuda.synchronize()
         ms2 = e0.elapsed_time(e1) / reps
+        fold = torch.empty(n, device="cuda", dtype=torch.int32)
+        res = []
+        for c in (xyz, xs):
+            for _ in range(2):
+                vol.gather_probe(c, fold, n, s)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(reps):
+                vol.gather_probe(c, fold, n, s)
+            e1.record(); torch.cuda.synchronize()
+            res.append(n / (e0.elapsed_time(e1) / reps) / 1e6)
+        print(f"{name}: gather-only probe random {res[0]:.3f} | cell-sorted {res[1]:.3f} Gsamples/s")
         print(f"{name}: random {n/ms/1e6:.3f} Gsamples/s ({ms:.3f} ms) | cell-sorted {n/ms2/1e6:.3f} Gsamples/s ({ms2:.3f} ms)", flush=True)
 
 main()
