@@ -116,6 +116,15 @@ int vnr_volume_sampler_skip(vnr_volume_t* v, uint64_t n_floats);
  * (tex3D<float>, linear filter, normalized coordinates, clamp). */
 int vnr_volume_sample_at(vnr_volume_t* v, const float* h_xyz, float* h_out, size_t n, int hw_texture);
 
+/* data-parallel hooks (no reference counterpart): the cudaStream_t the volume's own work is enqueued on;
+ * MacroCell::update_explicit (core/macrocell.cu:42-73) on caller-provided samples; the value-range buffer
+ * (float[2*cells] = (min-1, max+1) per cell, so a min / max all-reduce of the even / odd elements merges
+ * ranks); MacroCell::update_max_opacity (:232-250) after the merge */
+int vnr_volume_stream(vnr_volume_t* v, void** stream);
+int vnr_volume_macrocell_update(vnr_volume_t* v, const float* d_xyz, const float* d_values, size_t n, void* stream);
+int vnr_volume_macrocell_buffer(vnr_volume_t* v, void** d_range, size_t* n_floats);
+int vnr_volume_macrocell_refresh(vnr_volume_t* v, void* stream);
+
 /* vnrNeuralVolumeGetTrainingStep / GetTrainingLoss                     api.h:132-133 */
 int vnr_volume_stats(vnr_volume_t* v, uint64_t* step, double* loss);
 /* loss of the most recent step (sum over the batch of |y - t| / N) */
@@ -147,6 +156,9 @@ int vnr_renderer_stats(vnr_renderer_t* r, uint64_t* stats4);
 
 /* MainRenderer::framebuffer_skip_download (renderer.cpp:132): 0 = keep frames on the device */
 int vnr_renderer_set_download(vnr_renderer_t* r, int on);
+/* framebuffer.download_async (framebuffer.h:35) on demand, for callers that disabled the automatic one:
+ * enqueues the device->host copy of the current frame; vnr_map_frame then waits for it */
+int vnr_renderer_download(vnr_renderer_t* r);
 /* measurement taps: CUDA events around every decode launch of the next frames; summed device time of
  * the non-empty decode launches of the last frame, their number, and all kernels launched by it */
 int vnr_renderer_set_profiling(vnr_renderer_t* r, int on);

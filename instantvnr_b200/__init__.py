@@ -235,6 +235,22 @@ class NeuralVolume:
     def sample(self, d_xyz, d_target, n, stream=None):
         _check(lib().vnr_volume_sample(self._h, _ptr(d_xyz), _ptr(d_target), C.c_size_t(n), _stream(stream)))
 
+    def stream(self):
+        p = C.c_void_p()
+        _check(lib().vnr_volume_stream(self._h, C.byref(p)))
+        return p.value or 0
+
+    def macrocell_update(self, d_xyz, d_values, n, stream=None):
+        _check(lib().vnr_volume_macrocell_update(self._h, _ptr(d_xyz), _ptr(d_values), C.c_size_t(n), _stream(stream)))
+
+    def macrocell_buffer(self):
+        p, n = C.c_void_p(), C.c_size_t()
+        _check(lib().vnr_volume_macrocell_buffer(self._h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def macrocell_refresh(self, stream=None):
+        _check(lib().vnr_volume_macrocell_refresh(self._h, _stream(stream)))
+
     def sampler_skip(self, n_floats):
         _check(lib().vnr_volume_sampler_skip(self._h, C.c_uint64(n_floats)))
 
@@ -309,6 +325,9 @@ class Renderer:
 
     def set_download(self, on):
         _check(lib().vnr_renderer_set_download(self._h, C.c_int(1 if on else 0)))
+
+    def download(self):
+        _check(lib().vnr_renderer_download(self._h))
 
     def set_profiling(self, on):
         _check(lib().vnr_renderer_set_profiling(self._h, C.c_int(1 if on else 0)))

@@ -398,15 +398,25 @@ void Renderer::render() {
   last_graph = graph_loop;
   last_rounds = rounds;
   // framebuffer.download_async (renderer.cpp:133)
-  if (download) VNR_CUDA(cudaMemcpyAsync(h_frame[cur], frame.p, frame.bytes(), cudaMemcpyDeviceToHost, stream));
+  downloaded = false;
+  if (download) { VNR_CUDA(cudaMemcpyAsync(h_frame[cur], frame.p, frame.bytes(), cudaMemcpyDeviceToHost, stream)); downloaded = true; }
   VNR_CUDA(cudaMemcpyAsync(h_counters, counters.p, sizeof(uint32_t) * (kMaxRounds + 4), cudaMemcpyDeviceToHost, stream));
   VNR_CUDA(cudaEventRecord(frame_done[cur], stream));
   rendered = true;
 }
 
+// explicit framebuffer.download_async for callers that disabled the automatic one (multi-GPU rank 0
+// downloads after the peers' pixels have arrived)
+void Renderer::download_now() {
+  if (!rendered) throw StateError("vnr_renderer_download called before vnr_render");
+  VNR_CUDA(cudaMemcpyAsync(h_frame[cur], frame.p, frame.bytes(), cudaMemcpyDeviceToHost, stream));
+  VNR_CUDA(cudaEventRecord(frame_done[cur], stream));
+  downloaded = true;
+}
+
 const float* Renderer::map_frame() {
   if (!rendered) throw StateError("vnr_map_frame called before vnr_render");
-  if (!download) throw StateError("frame download is disabled on this renderer");
+  if (!downloaded) throw StateError("frame download is disabled on this renderer");
   VNR_CUDA(cudaEventSynchronize(frame_done[cur]));                     // renderer.h:84-94
   const float* p = reinterpret_cast<const float*>(h_frame[cur]);
   cur ^= 1;                                                             // double-buffer swap

@@ -41,6 +41,7 @@ struct Renderer {
   DevBuf<uint32_t> ray_state, counters;
   float4* h_frame[2] = {nullptr, nullptr};
   uint32_t* h_counters = nullptr;
+  bool downloaded = false;
   bool download = true;                 // framebuffer_skip_download (renderer.cpp:132)
   bool profiling = false;               // CUDA events around every decode launch
   std::vector<cudaEvent_t> prof_events;
@@ -64,6 +65,7 @@ struct Renderer {
   void destroy_graph();
   void ensure_graph(const RayBuffers& rb, unsigned grid, size_t cap, int rounds);
   void render();
+  void download_now();
   const float* map_frame();
   void stats(uint64_t* s4);
   void profile(float* decode_ms, int* decode_launches);

@@ -56,6 +56,7 @@ VNR_EXPORT int vnr_renderer_device_frame(vnr_renderer_t* r, void** d_rgba, void*
 VNR_EXPORT int vnr_renderer_stats(vnr_renderer_t* r, uint64_t* s4) { return guard([&] { if (!s4) throw InvalidError("null argument"); R(r)->stats(s4); }); }
 
 VNR_EXPORT int vnr_renderer_set_download(vnr_renderer_t* r, int on) { return guard([&] { R(r)->download = on != 0; }); }
+VNR_EXPORT int vnr_renderer_download(vnr_renderer_t* r) { return guard([&] { R(r)->download_now(); }); }
 VNR_EXPORT int vnr_renderer_set_profiling(vnr_renderer_t* r, int on) { return guard([&] { R(r)->profiling = on != 0; }); }
 VNR_EXPORT int vnr_renderer_profile(vnr_renderer_t* r, float* decode_ms, int* decode_launches, uint64_t* kernel_launches) {
   return guard([&] { Renderer* s = R(r); s->profile(decode_ms, decode_launches); if (kernel_launches) *kernel_launches = s->launches; });

@@ -311,3 +311,28 @@ VNR_EXPORT int vnr_volume_last_loss(vnr_volume_t* vh, double* loss) {
     if (loss) *loss = acc[1];
   });
 }
+
+// ---- data-parallel hooks (no reference counterpart) ------------------------------------------------
+VNR_EXPORT int vnr_volume_stream(vnr_volume_t* vh, void** stream) {
+  return guard([&] { if (!stream) throw InvalidError("null argument"); *stream = (void*)V(vh)->stream; });
+}
+// MacroCell::update_explicit (core/macrocell.cu:42-73) on caller-provided samples
+VNR_EXPORT int vnr_volume_macrocell_update(vnr_volume_t* vh, const float* d_xyz, const float* d_values, size_t n, void* stream) {
+  return guard([&] {
+    Volume* v = V(vh);
+    if (n && (!d_xyz || !d_values)) throw InvalidError("null buffer");
+    macrocell_update_explicit(v, d_xyz, d_values, n, S(v, stream));
+  });
+}
+// device buffer of the value ranges: float[2*cells], (min - 1, max + 1) interleaved
+VNR_EXPORT int vnr_volume_macrocell_buffer(vnr_volume_t* vh, void** d_range, size_t* n_floats) {
+  return guard([&] {
+    Volume* v = V(vh);
+    if (d_range) *d_range = v->mc_range.p;
+    if (n_floats) *n_floats = v->mc_range.n;
+  });
+}
+// MacroCell::update_max_opacity (core/macrocell.cu:232-250) after the ranges changed
+VNR_EXPORT int vnr_volume_macrocell_refresh(vnr_volume_t* vh, void* stream) {
+  return guard([&] { Volume* v = V(vh); macrocell_update_max_opacity(v, S(v, stream)); });
+}

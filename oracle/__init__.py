@@ -33,6 +33,9 @@ def lib():
         _lib = C.CDLL(_SO)
         _lib.orc_train_create.restype = C.c_void_p
         _lib.orc_train_step.restype = C.c_double
+        _lib.orc_train_grads.restype = C.c_double
+        _lib.orc_train_set_grads.restype = None
+        _lib.orc_train_apply.restype = None
         _lib.orc_lcg_tea16_first.restype = C.c_float
         _lib.orc_grid_index.restype = C.c_uint32
         _lib.orc_hadd.restype = C.c_uint16
@@ -274,6 +277,21 @@ class Trainer:
         targets = _f32(targets)
         return float(lib().orc_train_step(self.h, _p(coords), _p(targets), C.c_size_t(coords.shape[0]), C.c_int(acc_mode),
                                           C.c_int(grad_mode), C.c_int(1 if do_step else 0)))
+
+    def grads_only(self, coords, targets, n_global, acc_mode=0, grad_mode=0):
+        """forward + loss + backward with the loss normalised by n_global (data-parallel rank share); returns the
+        rank's share of the loss; gradients are read with grads()."""
+        coords = _f32(coords).reshape(-1, 3)
+        targets = _f32(targets)
+        return float(lib().orc_train_grads(self.h, _p(coords), _p(targets), C.c_size_t(coords.shape[0]), C.c_size_t(n_global),
+                                           C.c_int(acc_mode), C.c_int(grad_mode)))
+
+    def apply(self, grads):
+        """optimizer step (ExponentialDecay + Adam) on externally provided (e.g. all-reduced) gradients"""
+        g = _f32(grads)
+        assert g.size == self.m.n_params
+        lib().orc_train_set_grads(self.h, _p(g))
+        lib().orc_train_apply(self.h)
 
     def params(self):
         p16 = np.empty(self.m.n_params, dtype=np.uint16)

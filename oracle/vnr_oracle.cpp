@@ -977,11 +977,24 @@ ORC_API void orc_train_get_grads(void* h, float* grads) { TrainState* s = (Train
 // the accumulated weight/grid gradients to fp16 before Adam (reference storage
 // type; the reference's atomic/split-K fp16 summation order is not reproducible).
 // do_step 0: compute loss+grads only.
+// n_global: the batch size the loss is normalised by (data-parallel: the sum of all ranks' batches).
+// compute 0: skip forward/backward and apply the optimizer to the gradients already in s->grad
+// (set with orc_train_set_grads after an all-reduce).
+static double train_impl(TrainState* s, const float* coords, const float* targets, size_t n, size_t n_global, int acc_mode, int grad_mode, int compute, int do_step);
 ORC_API double orc_train_step(void* h, const float* coords, const float* targets, size_t n, int acc_mode, int grad_mode, int do_step) {
-  TrainState* s = (TrainState*)h;
+  return train_impl((TrainState*)h, coords, targets, n, n, acc_mode, grad_mode, 1, do_step);
+}
+ORC_API double orc_train_grads(void* h, const float* coords, const float* targets, size_t n, size_t n_global, int acc_mode, int grad_mode) {
+  return train_impl((TrainState*)h, coords, targets, n, n_global, acc_mode, grad_mode, 1, 0);
+}
+ORC_API void orc_train_set_grads(void* h, const float* grads) { TrainState* s = (TrainState*)h; std::memcpy(s->grad.data(), grads, s->grad.size() * 4); }
+ORC_API void orc_train_apply(void* h) { train_impl((TrainState*)h, nullptr, nullptr, 0, 0, 0, 0, 0, 1); }
+static double train_impl(TrainState* s, const float* coords, const float* targets, size_t n, size_t n_global, int acc_mode, int grad_mode, int compute, int do_step) {
   const Model& m = s->m;
   const int W = m.width, E = m.enc_pad, NH = m.n_hidden;
   const float loss_scale = 128.f;
+  double loss_sum = 0;
+  if (compute) {
   std::fill(s->grad.begin(), s->grad.end(), 0.f);
   const h16* w = s->params.data();
   const h16* grid = w + m.n_mlp;
@@ -1009,8 +1022,8 @@ ORC_API double orc_train_step(void* h, const float* coords, const float* targets
       float y = mlp_forward_one(m, mf, enc, acc_mode, hidden.data(), out16);
       // l1.h:40-76
       const float diff = y - targets[i];
-      loss_terms[i] = (double)(fabsf(diff) / (float)n);
-      const float g = h2f(f2h(loss_scale * copysignf(1.0f, diff) / (float)n));
+      loss_terms[i] = (double)(fabsf(diff) / (float)n_global);
+      const float g = h2f(f2h(loss_scale * copysignf(1.0f, diff) / (float)n_global));
       // ---- output layer: dW_out[0][k] += g * h_last[k]; d_h = g * W_out[0][k] masked by ReLU
       size_t off_out = (size_t)W * E + (size_t)(NH - 1) * W * W;
       const h16* hl = hidden.data() + (size_t)(NH - 1) * W;
@@ -1045,7 +1058,7 @@ ORC_API double orc_train_step(void* h, const float* coords, const float* targets
       for (int k = 0; k < E; ++k) denc[(size_t)i * E + k] = h2f(f2h(dnext[k]));
     }
   }
-  double loss_sum = 0; for (size_t i = 0; i < n; ++i) loss_sum += loss_terms[i];
+  for (size_t i = 0; i < n; ++i) loss_sum += loss_terms[i];
   // ---- grid backward (grid.h:288-411): scatter w_c * dL/denc (fp16) to 8 corners.
   // Serial in sample order so the oracle is deterministic (the device uses atomics).
   for (size_t i = 0; i < n; ++i) {
@@ -1066,6 +1079,7 @@ ORC_API double orc_train_step(void* h, const float* coords, const float* targets
   for (size_t k = 0; k < m.n_mlp; ++k) { double acc = 0; for (int t = 0; t < nthreads; ++t) acc += mlp_grads[t][k]; s->grad[k] = (float)acc; }
   if (grad_mode == 1) for (size_t k = 0; k < m.n_params; ++k) s->grad[k] = h2f(f2h(s->grad[k]));
   s->last_loss = loss_sum;
+  }  // compute
   if (!do_step) return loss_sum;
   // ---- ExponentialDecay::step then adam_step
   if (s->current_step == 0) s->lr_factor = 1.f;
