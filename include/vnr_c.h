@@ -130,6 +130,10 @@ int vnr_volume_stats(vnr_volume_t* v, uint64_t* step, double* loss);
 /* loss of the most recent step (sum over the batch of |y - t| / N) */
 int vnr_volume_last_loss(vnr_volume_t* v, double* loss);
 
+/* vnrNeuralVolumeGetPSNR (api.h:129; NeuralVolume::Impl::get_psnr core/network.cu:410-472): decode every voxel
+ * centre, 10 log10(range^2 / mse) against the ground truth */
+int vnr_volume_psnr(vnr_volume_t* v, double* psnr);
+
 /* ---- renderer ------------------------------------------------------------------------- */
 
 int vnr_renderer_create(vnr_volume_t* v, vnr_renderer_t** out);        /* vnrCreateRenderer api.h:168 */
@@ -140,6 +144,8 @@ int vnr_renderer_set_mode(vnr_renderer_t* r, int mode);                /* vnrRen
 int vnr_renderer_set_sampling_rate(vnr_renderer_t* r, float rate);     /* :174 */
 int vnr_renderer_set_density_scale(vnr_renderer_t* r, float scale);    /* :175 */
 int vnr_renderer_reset_accumulation(vnr_renderer_t* r);                /* :176 */
+/* vnrVolumeSetClippingBox (api.h:146, applied by vnrCreateRenderer api.cpp:454): object-space box inside [0,1]^3 */
+int vnr_renderer_set_clipping_box(vnr_renderer_t* r, const float* lower3, const float* upper3);
 /* pixel subset for tile-parallel multi-GPU rendering: this renderer handles pixel tiles
  * (64x... row blocks) with index % world == rank.  Default (0,1) = whole frame. */
 int vnr_renderer_set_partition(vnr_renderer_t* r, int rank, int world);

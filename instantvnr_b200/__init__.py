@@ -254,6 +254,11 @@ class NeuralVolume:
     def sampler_skip(self, n_floats):
         _check(lib().vnr_volume_sampler_skip(self._h, C.c_uint64(n_floats)))
 
+    def psnr(self):
+        v = C.c_double()
+        _check(lib().vnr_volume_psnr(self._h, C.byref(v)))
+        return v.value
+
     def stats(self):
         step, loss = C.c_uint64(), C.c_double()
         _check(lib().vnr_volume_stats(self._h, C.byref(step), C.byref(loss)))
@@ -295,6 +300,9 @@ class Renderer:
 
     def set_density_scale(self, s):
         _check(lib().vnr_renderer_set_density_scale(self._h, C.c_float(s)))
+
+    def set_clipping_box(self, lower, upper):
+        _check(lib().vnr_renderer_set_clipping_box(self._h, _ptr(_f32(lower)), _ptr(_f32(upper))))
 
     def reset_accumulation(self):
         _check(lib().vnr_renderer_reset_accumulation(self._h))

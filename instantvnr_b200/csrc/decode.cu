@@ -26,13 +26,24 @@ __device__ __forceinline__ void encode_row(uint8_t* a_smem, const DecoderDesc& d
     *reinterpret_cast<__half*>(rowp + ((((uint32_t)k >> 3) ^ sw) << 4) + ((uint32_t)k & 7u) * 2u) = __float2half_rn(0.f);
 }
 
+// Warp-specialised persistent decode: one CTA per SM, kGatherGroups producer groups of 128 threads
+// (one sample row each) keep the hash-grid gather running all the time and fill a ring of A tiles in
+// shared memory; one consumer group of 128 threads (warps 0-3, one TMEM lane quarter each) runs the
+// MLP chain of finished tiles on the tensor cores.  full[]/empty[] mbarriers hand the tiles over; the
+// gather of the next tiles overlaps the MLP of the current one.
+//
 // STRIDE: floats per coordinate record (3 = xyz as NeuralVolume::inference takes them,
 // 4 = the marcher's (x, y, z, dt) sample records).  n_dev != nullptr: the sample count is
 // read from device memory (wavefront rounds are sized on the device, no host sync); with
 // round_dev the round index itself lives on the device (graph-driven wavefront): the count is
 // n_dev[round] and odd rounds read coords_alt (the marcher's ping-pong sample buffers).
+constexpr int kGatherGroups = 4;                 // producer groups (128 threads each)
+constexpr int kStagesPerGroup = 2;               // A-tile ring depth per producer group
+constexpr int kStages = kGatherGroups * kStagesPerGroup;
+constexpr int kDecodeThreads = 128 * (1 + kGatherGroups);
+
 template <int F, int STRIDE>
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(kDecodeThreads, 1)
 decode_kernel(const DecoderDesc d, const __half* __restrict__ params, const float* __restrict__ coords, const float* __restrict__ coords_alt,
               float* __restrict__ out, uint32_t n, const uint32_t* __restrict__ n_dev, const uint32_t* __restrict__ round_dev, __half* __restrict__ enc_out) {
   if (n_dev) {
@@ -45,36 +56,66 @@ decode_kernel(const DecoderDesc d, const __half* __restrict__ params, const floa
   if (blockIdx.x >= n_tiles) return;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* a_smem = smem;
-  uint8_t* w_smem = smem + MlpSmem::kATile;
-  __shared__ uint64_t mbar;
+  uint8_t* a_ring = smem;                                          // kStages tiles of 16 KB
+  uint8_t* w_smem = smem + (size_t)kStages * MlpSmem::kATile;
+  __shared__ uint64_t mbar_mma;
+  __shared__ uint64_t mbar_full[kStages], mbar_empty[kStages];
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x;
-  if (tid == 0) { tc05::mbar_init(&mbar, 1); tc05::fence_mbar_init(); }
+  const int group = tid >> 7;                                      // 0: MLP consumers, 1..kGatherGroups: producers
+  const int gtid = tid & 127;
+  if (tid == 0) {
+    tc05::mbar_init(&mbar_mma, 1);
+    for (int s = 0; s < kStages; ++s) { tc05::mbar_init(&mbar_full[s], 128); tc05::mbar_init(&mbar_empty[s], 1); }
+    tc05::fence_mbar_init();
+  }
   if (tid < 32) tc05::tmem_alloc(&tmem_slot, 64);
-  stage_weights(w_smem, params, d, tid, 128);
+  stage_weights(w_smem, params, d, tid, kDecodeThreads);
   tc05::fence_before_sync();
   tc05::fence_async_smem();
   __syncthreads();
   tc05::fence_after_sync();
   const uint32_t tmem_base = tmem_slot;
-  const __half* __restrict__ grid = params + d.n_mlp;
-  uint32_t phase = 0;
+  // tiles of this CTA: blockIdx.x + j * gridDim.x, j = 0 .. my_tiles-1; tile j belongs to producer group j % G,
+  // its `it`-th tile (it = j / G) goes to ring stage g * R + it % R, use number it / R of that stage.
+  const uint32_t my_tiles = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
 
-  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const uint32_t s = tile * kTile + (uint32_t)tid;
-    const uint32_t sc = s < n ? s : n - 1;
-    float x, y, z;
-    if constexpr (STRIDE == 4) { const float4 c = *reinterpret_cast<const float4*>(coords + 4 * (size_t)sc); x = c.x; y = c.y; z = c.z; }
-    else { x = coords[3 * (size_t)sc]; y = coords[3 * (size_t)sc + 1]; z = coords[3 * (size_t)sc + 2]; }
-    encode_row<F>(a_smem, d, grid, x, y, z, (uint32_t)tid);
-    if (enc_out && s < n) {   // debug / test tap of the encoded features (row-major [n][enc_pad])
-      for (int k = 0; k < d.enc_pad; ++k)
-        enc_out[(size_t)s * d.enc_pad + k] = *reinterpret_cast<__half*>(a_smem + tc05::sw128_off(tid, k >> 3) + (k & 7) * 2);
+  if (group == 0) {
+    // ---------------- consumer: MLP on finished tiles, in tile order ----------------
+    uint32_t phase = 0;
+    for (uint32_t j = 0; j < my_tiles; ++j) {
+      const uint32_t g = j % kGatherGroups, it = j / kGatherGroups;
+      const uint32_t stage = g * kStagesPerGroup + it % kStagesPerGroup, use = it / kStagesPerGroup;
+      tc05::mbar_wait(&mbar_full[stage], use & 1u);
+      const float v = mlp_tile_forward(a_ring + (size_t)stage * MlpSmem::kATile, w_smem, &mbar_mma, phase, tmem_base, d, gtid, 1);
+      // the last MMA has been waited for: the tile can be refilled
+      if (gtid == 0) tc05::mbar_arrive(&mbar_empty[stage]);
+      const uint32_t s = (blockIdx.x + j * gridDim.x) * kTile + (uint32_t)gtid;
+      if (s < n) out[s] = v;
     }
-    const float v = mlp_tile_forward(a_smem, w_smem, &mbar, phase, tmem_base, d, tid, 1);
-    if (s < n) out[s] = v;
+  } else {
+    // ---------------- producers: hash-grid gather straight into the swizzled A tiles ----------------
+    const uint32_t g = (uint32_t)group - 1u;
+    const __half* __restrict__ grid = params + d.n_mlp;
+    uint32_t it = 0;
+    for (uint32_t j = g; j < my_tiles; j += kGatherGroups, ++it) {
+      const uint32_t stage = g * kStagesPerGroup + it % kStagesPerGroup, use = it / kStagesPerGroup;
+      const uint32_t s = (blockIdx.x + j * gridDim.x) * kTile + (uint32_t)gtid;
+      const uint32_t sc = s < n ? s : n - 1;
+      float x, y, z;
+      if constexpr (STRIDE == 4) { const float4 c = __ldg(reinterpret_cast<const float4*>(coords + 4 * (size_t)sc)); x = c.x; y = c.y; z = c.z; }
+      else { x = __ldg(coords + 3 * (size_t)sc); y = __ldg(coords + 3 * (size_t)sc + 1); z = __ldg(coords + 3 * (size_t)sc + 2); }
+      if (use > 0) tc05::mbar_wait(&mbar_empty[stage], (use - 1u) & 1u);
+      uint8_t* a_smem = a_ring + (size_t)stage * MlpSmem::kATile;
+      encode_row<F>(a_smem, d, grid, x, y, z, (uint32_t)gtid);
+      if (enc_out && s < n) {   // debug / test tap of the encoded features (row-major [n][enc_pad])
+        for (int k = 0; k < d.enc_pad; ++k)
+          enc_out[(size_t)s * d.enc_pad + k] = *reinterpret_cast<__half*>(a_smem + tc05::sw128_off(gtid, k >> 3) + (k & 7) * 2);
+      }
+      tc05::fence_async_smem();          // my generic-proxy stores -> visible to the tensor core's async-proxy reads
+      tc05::mbar_arrive(&mbar_full[stage]);
+    }
   }
 
   tc05::fence_before_sync();
@@ -132,22 +173,18 @@ int num_sms() {
 template <int F, int STRIDE>
 static cudaError_t launch_decode_t(const DecoderDesc& d, const __half* params, const float* coords, const float* coords_alt, float* out, size_t n,
                                    const uint32_t* n_dev, const uint32_t* round_dev, size_t n_max, __half* enc_out, cudaStream_t stream) {
-  const size_t smem = 1024 + MlpSmem::kATile + MlpSmem::weights_bytes(d.n_hidden);
-  static bool configured = false;
-  static int per_sm = 1;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(decode_kernel<F, STRIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  const size_t smem = 1024 + (size_t)kStages * MlpSmem::kATile + MlpSmem::weights_bytes(d.n_hidden);
+  static size_t configured = 0;
+  if (smem > 226 * 1024) return cudaErrorInvalidValue;
+  if (configured < smem) {
+    cudaError_t e = cudaFuncSetAttribute(decode_kernel<F, STRIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    // resident CTAs per SM: 128 threads x <=128 registers (launch bounds) allow 4; shared memory
-    // (227 KB per SM, 1 KB reserved per CTA) and TMEM (512 columns, 64 per CTA) bound it further
-    per_sm = std::min<int>(4, (int)((227 * 1024) / (smem + 1024)));
-    if (const char* env = getenv("VNR_DECODE_CTAS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(env)));
-    if (per_sm < 1) per_sm = 1;
-    configured = true;
+    configured = smem;
   }
+  // persistent: one CTA per SM
   const size_t n_tiles = (n_max + kTile - 1) / kTile;
-  const uint32_t grid = (uint32_t)std::min<size_t>(n_tiles, (size_t)num_sms() * per_sm);
-  decode_kernel<F, STRIDE><<<grid, 128, smem, stream>>>(d, params, coords, coords_alt, out, (uint32_t)n, n_dev, round_dev, enc_out);
+  const uint32_t grid = (uint32_t)std::min<size_t>(n_tiles, (size_t)num_sms());
+  decode_kernel<F, STRIDE><<<grid, kDecodeThreads, smem, stream>>>(d, params, coords, coords_alt, out, (uint32_t)n, n_dev, round_dev, enc_out);
   return cudaGetLastError();
 }
 

@@ -206,6 +206,7 @@ Renderer::Renderer(Volume* v) : vol(v) {
   VNR_CUDA(cudaEventCreateWithFlags(&vol_ready, cudaEventDisableTiming));
   VNR_CUDA(cudaMallocHost((void**)&h_counters, sizeof(uint32_t) * (kMaxRounds + 4)));
   memset(h_counters, 0, sizeof(uint32_t) * (kMaxRounds + 4));
+  if (const char* e = getenv("VNR_RM_GRAPH")) use_graph = atoi(e) != 0;    // 0: host-enqueued rounds (profilers do not see graph-body kernels)
   if (const char* e = getenv("VNR_RM_N_ITERS")) {       // method_raymarching.cu:30-38
     int n = atoi(e);
     if (n >= 1 && n <= 16) n_iters = n;

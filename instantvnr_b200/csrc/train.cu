@@ -573,6 +573,66 @@ void optimizer_step(Volume* v, cudaStream_t s) {
   ++v->train_step; ++v->loss_count;
 }
 
+// ------------------------------------------------------------------------------------------
+// volume PSNR (NeuralVolume::Impl::get_psnr, core/network.cu:410-472): decode every voxel centre
+// ((x+.5)/dims, generate_coords :51-68), MSE against the ground truth, 10 log10(range^2 / mse)
+// ------------------------------------------------------------------------------------------
+__global__ void voxel_coords_kernel(uint32_t n, uint64_t first, int3 dims, float* __restrict__ coords) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t idx = first + i, stride = (uint64_t)dims.x * dims.y;
+  const int x = (int)(idx % dims.x), y = (int)((idx % stride) / dims.x), z = (int)(idx / stride);
+  coords[3 * (size_t)i] = ((float)x + 0.5f) * (1.f / (float)dims.x);
+  coords[3 * (size_t)i + 1] = ((float)y + 0.5f) * (1.f / (float)dims.y);
+  coords[3 * (size_t)i + 2] = ((float)z + 0.5f) * (1.f / (float)dims.z);
+}
+
+// acc[0] += sum (pred - gt)^2 ; acc[1] = max gt ; acc[2] = -min gt (both via atomicMax on ordered doubles >= 0 shift)
+__global__ void psnr_accum_kernel(uint32_t n, const float* __restrict__ pred, const float* __restrict__ gt, double* __restrict__ acc, float* __restrict__ minmax) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  double e = 0.0; float mx = -3.4e38f, mn = 3.4e38f;
+  if (i < n) { const float d = pred[i] - gt[i]; e = (double)(d * d); mx = mn = gt[i]; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    e += __shfl_xor_sync(0xffffffffu, e, o);
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(acc, e);
+    // float atomics through integer atomics (values of a normalised volume are >= 0; handle sign anyway)
+    if (mx >= 0.f) atomicMax((int*)&minmax[1], __float_as_int(mx)); else atomicMin((unsigned*)&minmax[1], __float_as_uint(mx));
+    if (mn >= 0.f) atomicMin((int*)&minmax[0], __float_as_int(mn)); else atomicMax((unsigned*)&minmax[0], __float_as_uint(mn));
+  }
+}
+
+double volume_psnr(Volume* v, cudaStream_t s) {
+  if (!v->have_gt) throw StateError("[error]: missing a reference volume.");              // network.cu:412-414
+  if (!v->have_params) throw StateError("the neural volume has no parameters");
+  const int3 dims = make_int3(v->dims[0], v->dims[1], v->dims[2]);
+  const uint64_t total = (uint64_t)dims.x * dims.y * dims.z;
+  const uint32_t chunk = (uint32_t)std::min<uint64_t>(total, 1u << 22);
+  DevBuf<float> coords, pred, mm; DevBuf<double> acc;
+  coords.alloc(3 * (size_t)chunk); pred.alloc(chunk); mm.alloc(2); acc.alloc(1);
+  const float init[2] = {3.4e38f, -3.4e38f};
+  VNR_CUDA(cudaMemcpyAsync(mm.p, init, sizeof init, cudaMemcpyHostToDevice, s));
+  acc.zero(s);
+  for (uint64_t first = 0; first < total; first += chunk) {
+    const uint32_t n = (uint32_t)std::min<uint64_t>(chunk, total - first);
+    voxel_coords_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, first, dims, coords.p);
+    VNR_CUDA(launch_decode(v->cfg.desc, v->params.p, coords.p, pred.p, n, nullptr, s));
+    psnr_accum_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, pred.p, v->gt.p + first, acc.p, mm.p);
+  }
+  VNR_CUDA(cudaGetLastError());
+  double sum = 0; float h_mm[2];
+  VNR_CUDA(cudaMemcpyAsync(&sum, acc.p, sizeof sum, cudaMemcpyDeviceToHost, s));
+  VNR_CUDA(cudaMemcpyAsync(h_mm, mm.p, sizeof h_mm, cudaMemcpyDeviceToHost, s));
+  VNR_CUDA(cudaStreamSynchronize(s));
+  const double range = (double)h_mm[1] - (double)h_mm[0];
+  const double mse = sum / (double)total;
+  return 10.0 * std::log10(range * range / mse);
+}
+
 // NeuralVolume::Impl::train (network.cu:231-259)
 void train_steps(Volume* v, int steps, size_t batch, bool update_macrocell, cudaStream_t s) {
   if (!v->have_gt) throw StateError("[error]: missing a reference volume.");

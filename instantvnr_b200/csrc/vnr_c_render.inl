@@ -29,6 +29,15 @@ VNR_EXPORT int vnr_renderer_set_sampling_rate(vnr_renderer_t* r, float rate) {
   return guard([&] { if (!(rate > 0.f)) throw InvalidError("sampling rate must be positive"); R(r)->sampling_rate = rate; R(r)->reset = true; });
 }
 VNR_EXPORT int vnr_renderer_set_density_scale(vnr_renderer_t* r, float s) { return guard([&] { R(r)->density_scale = s; R(r)->reset = true; }); }
+// vnrVolumeSetClippingBox (api.h:146) -> MainRenderer::set_scene_clipbox (api.cpp:454): object-space box in [0,1]^3
+VNR_EXPORT int vnr_renderer_set_clipping_box(vnr_renderer_t* r, const float* lower, const float* upper) {
+  return guard([&] {
+    Renderer* s = R(r);
+    if (!lower || !upper) throw InvalidError("null clipping box");
+    for (int k = 0; k < 3; ++k) { if (!(upper[k] > lower[k])) throw InvalidError("empty clipping box"); s->clip_lo[k] = lower[k]; s->clip_hi[k] = upper[k]; }
+    s->reset = true;
+  });
+}
 VNR_EXPORT int vnr_renderer_reset_accumulation(vnr_renderer_t* r) { return guard([&] { R(r)->reset = true; }); }
 VNR_EXPORT int vnr_renderer_set_partition(vnr_renderer_t* r, int rank, int world) {
   return guard([&] {

@@ -336,3 +336,8 @@ VNR_EXPORT int vnr_volume_macrocell_buffer(vnr_volume_t* vh, void** d_range, siz
 VNR_EXPORT int vnr_volume_macrocell_refresh(vnr_volume_t* vh, void* stream) {
   return guard([&] { Volume* v = V(vh); macrocell_update_max_opacity(v, S(v, stream)); });
 }
+
+// vnrNeuralVolumeGetPSNR (api.h:129; NeuralVolume::Impl::get_psnr core/network.cu:410-472)
+VNR_EXPORT int vnr_volume_psnr(vnr_volume_t* vh, double* psnr) {
+  return guard([&] { Volume* v = V(vh); if (!psnr) throw InvalidError("null argument"); *psnr = volume_psnr(v, v->stream); });
+}
