@@ -117,9 +117,9 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dims = (args.volume,) * 3
-    W = H = args.frame
+    W, H = (args.width or args.frame), (args.height or args.frame)
     t0 = time.time()
-    vol, gt, (rgb, alpha) = build_scene(vnr, dims, args.train_steps, 1 << 16)
+    vol, gt, (rgb, alpha) = build_scene(vnr, dims, args.train_steps, 1 << 16, dict(log2_hashmap=args.log2_hashmap))
     train_step_count, train_loss = vol.stats()
     if world > 1:
         # replicate rank 0's trained model (the fp16 reductions of training are order-dependent, so independently
@@ -254,7 +254,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f16", "data": "synthetic",
-        "config": {"workload": f"render: synthetic {args.volume}^3 volume, example-model.json (8 levels x 8 features, T=2^19, 64x4 MLP), "
+        "config": {"workload": f"render: synthetic {args.volume}^3 volume, example-model.json (8 levels x 8 features, T=2^{args.log2_hashmap}, 64x4 MLP), "
                                f"{W}x{H} frame, macrocell skipping, mode 5 (sample streaming), 16-view orbit",
                    "weights": f"trained here for {train_step_count} steps (batch 2^16), mean L1 loss {train_loss:.4f}",
                    "l2_flush": "inputs larger than L2: per-frame sample/value/ray-state buffers (~500 MB) stream through the 126 MB L2 between frames",
@@ -278,7 +278,8 @@ def cpu_baseline(vol, dims, cams, rgb, alpha, args):
     m = O.ModelCfg()
     p16 = vol.get_params_f16()
     md, vr, mo = vol.get_macrocell()
-    w = h = args.frame
+    w, h = (args.width or args.frame), (args.height or args.frame)
+    m = O.ModelCfg(log2_hashmap=args.log2_hashmap)
     colors = np.concatenate([rgb, np.ones((rgb.shape[0], 1), np.float32)], 1)
     t0 = time.perf_counter()
     n = 0; views = 0
@@ -289,6 +290,112 @@ def cpu_baseline(vol, dims, cams, rgb, alpha, args):
     dt = time.perf_counter() - t0
     return {"value": n / dt, "unit": UNIT, "cores": O.lib().orc_num_threads(), "kind": "port",
             "sample": f"{views} frame(s) {w}x{h} of the same scene ({n} samples, {dt:.1f} s); fps {views / dt:.3f}"}
+
+
+def synth_volume_device(dims, seed=42):
+    """the synthetic volume of instantvnr_b200/synthetic.py, evaluated on the device slab by slab (torch is plumbing
+    here: a 1024^3 volume is 4 GiB and lives in HBM only)"""
+    import torch
+    dx, dy, dz = dims
+    rng = np.random.RandomState(seed)
+    centres = rng.uniform(0.2, 0.8, size=(8, 3)).astype(np.float32)
+    sigmas = rng.uniform(0.05, 0.15, size=8).astype(np.float32)
+    amps = rng.uniform(0.5, 1.0, size=8).astype(np.float32)
+    x = ((torch.arange(dx, device="cuda", dtype=torch.float32) + 0.5) / dx)[None, None, :]
+    y = ((torch.arange(dy, device="cuda", dtype=torch.float32) + 0.5) / dy)[None, :, None]
+    vol = torch.empty(dz, dy, dx, device="cuda", dtype=torch.float32)
+    slab = 16
+    for k0 in range(0, dz, slab):
+        z = ((torch.arange(k0, min(dz, k0 + slab), device="cuda", dtype=torch.float32) + 0.5) / dz)[:, None, None]
+        s = 0.05 * (torch.sin(2 * np.pi * x) * torch.sin(2 * np.pi * y) * torch.sin(2 * np.pi * z) + 1.0)
+        for c, sg, a in zip(centres, sigmas, amps):
+            s = s + float(a) * torch.exp(-((x - float(c[0])) ** 2 + (y - float(c[1])) ** 2 + (z - float(c[2])) ** 2) / float(2 * sg * sg))
+        vol[k0:k0 + slab] = s
+    lo, hi = vol.min(), vol.max()
+    vol.sub_(lo).div_(hi - lo)
+    return vol
+
+
+def run_train(args):
+    """BASELINE configs[2] (1 GPU) / configs[3] (N GPUs): online training steps/s -- per step and per rank: draw
+    --batch samples of the ground truth, forward + L1 + backward, (N > 1: all-reduce of hash-grid + MLP gradients),
+    Adam.  The volume lives in HBM (1024^3 float = 4 GiB).  value = optimizer steps per second; weak scaling (the
+    per-rank batch is fixed, the global batch grows with N)."""
+    import torch
+    import torch.distributed as dist
+    import instantvnr_b200 as vnr
+    from instantvnr_b200.distributed import DataParallelTrainer, GpuTrainBackend, broadcast_params
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dims = (args.volume,) * 3
+    gt = synth_volume_device(dims)
+    vol = vnr.NeuralVolume(vnr.model_json(log2_hashmap=args.log2_hashmap), dims)
+    vol.set_groundtruth_device(gt)
+    del gt
+    torch.cuda.empty_cache()
+    vol.init_params(1337)
+    if world > 1:
+        broadcast_params(vol)
+    dp = DataParallelTrainer(GpuTrainBackend(vol))
+    stream = dp.b.stream
+    n = args.batch
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        dp.step(n)
+    barrier()
+    clocks = ClockSampler(local); clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        dp.step(n)
+    ev1.record(stream)
+    stream.synchronize(); barrier()
+    ms = ev0.elapsed_time(ev1)
+    clk = clocks.stop()
+    # end to end: the same steps through the public call, with the per-step result (the loss) read back to the host
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        loss = dp.step(n, want_loss=True)
+    stream.synchronize(); barrier()
+    ms_e2e = (time.perf_counter() - t0) * 1e3
+    t = torch.tensor([ms, ms_e2e], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = t[0].item(), t[1].item()
+    step_count, mean_loss = vol.stats()
+    psnr = vol.psnr() if args.volume <= 512 else None
+    if rank == 0:
+        peak, peak_kind = measured_peaks()
+        n_grid = vol.n_params - vol.n_mlp_params
+        # algorithmic bytes per step and rank: per sample 1024 B gather + 1024 B gradient reduction + 16 B sample;
+        # optimizer sweep 38 B per touched parameter (upper bound: all) + gradient clear
+        bytes_step = n * (1024 + 1024 + 16) + n_grid * 38
+        achieved = bytes_step / (ms / args.steps * 1e-3) / 1e9
+        out = {"metric": "train_steps_per_sec", "value": args.steps / (ms * 1e-3), "unit": "steps/s", "n_gpus": world, "steps": args.steps,
+               "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "f16", "data": "synthetic",
+               "config": {"workload": f"train: synthetic {args.volume}^3 volume resident in HBM, example-model.json (T=2^{args.log2_hashmap}), "
+                                      f"{n} samples per rank per step, fwd + L1 + bwd + Adam" + (", gradient all-reduce (fp16 grid + fp32 MLP) over NCCL" if world > 1 else ""),
+                          "global_batch": n * world, "l2_flush": "per-step parameter-state sweep (~0.9 GB) exceeds L2",
+                          "parallelism": f"dp{world}"},
+               "samples_per_sec": args.steps * n * world / (ms * 1e-3), "mean_loss": mean_loss, "last_loss": loss, "volume_psnr_db": psnr,
+               "e2e": {"value": args.steps / (ms_e2e * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8,
+                       "note": "samples are drawn on the device from the HBM-resident volume (the reference's StaticSampler does the same); the loss is read back every step"},
+               "gpu_launches": args.steps * 9, "clocks": clk,
+               "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
+                            "kernel": "whole step (train_step_kernel + adam_grid_kernel)", "peak_source": peak_kind, "algorithmic_bytes_per_step": bytes_step}}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def run_reference(args):
@@ -357,6 +464,13 @@ def main():
     ap.add_argument("--volume", type=int, default=256)
     ap.add_argument("--frame", type=int, default=1024)
     ap.add_argument("--train-steps", type=int, default=600)
+    ap.add_argument("--width", type=int, default=0, help="frame width (default --frame)")
+    ap.add_argument("--height", type=int, default=0, help="frame height (default --frame)")
+    ap.add_argument("--log2-hashmap", type=int, default=19, help="hash table size per level (config 5: 22)")
+    ap.add_argument("--workload", default="render", choices=["render", "train"],
+                    help="render = BASELINE configs[1] (the headline; --width 3840 --height 2160 --log2-hashmap 22 = configs[4]); "
+                         "train = configs[2]/[3]: data-parallel training steps/s at --batch samples per rank")
+    ap.add_argument("--batch", type=int, default=1 << 18, help="train workload: samples per rank per step")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"], help="N > 1: how finished pixels reach rank 0")
     args = ap.parse_args()
@@ -364,6 +478,8 @@ def main():
         args.warmup = 3
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "train":
+        run_train(args)
     else:
         run_ours(args)
 

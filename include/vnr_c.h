@@ -82,6 +82,8 @@ int vnr_volume_gather_probe(vnr_volume_t* v, const float* d_xyz, uint32_t* d_out
 /* vnrCreateSimpleVolume + StaticSampler ground truth (core/samplers/neural_sampler.cu:86-128):
  * float32 volume of dims dx*dy*dz (x fastest), already normalised to [0,1]. */
 int vnr_volume_set_groundtruth_f32(vnr_volume_t* v, const float* h_volume);
+/* same from a device buffer (float[dx*dy*dz], copied): volumes produced / streamed on the GPU */
+int vnr_volume_set_groundtruth_device(vnr_volume_t* v, const float* d_volume);
 /* MacroCell::compute_everything (core/macrocell.cu:221-230): value ranges from ground truth */
 int vnr_volume_macrocell_from_groundtruth(vnr_volume_t* v);
 int vnr_volume_get_macrocell(const vnr_volume_t* v, int* mc_dims, float* h_value_range /*2*cells or NULL*/,

@@ -173,6 +173,9 @@ class NeuralVolume:
             raise VnrError(-1, "ground-truth volume size does not match dims")
         _check(lib().vnr_volume_set_groundtruth_f32(self._h, _ptr(v)))
 
+    def set_groundtruth_device(self, d_volume):
+        _check(lib().vnr_volume_set_groundtruth_device(self._h, _ptr(d_volume)))
+
     def macrocell_from_groundtruth(self):
         _check(lib().vnr_volume_macrocell_from_groundtruth(self._h))
 

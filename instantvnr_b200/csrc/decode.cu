@@ -58,7 +58,7 @@ decode_kernel(const DecoderDesc d, const __half* __restrict__ params, const floa
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* a_ring = smem;                                          // kStages tiles of 16 KB
   uint8_t* w_smem = smem + (size_t)kStages * MlpSmem::kATile;
-  __shared__ uint64_t mbar_mma;
+  __shared__ uint64_t mbar_mma[2];
   __shared__ uint64_t mbar_full[kStages], mbar_empty[kStages];
   __shared__ uint32_t tmem_slot;
 
@@ -66,11 +66,11 @@ decode_kernel(const DecoderDesc d, const __half* __restrict__ params, const floa
   const int group = tid >> 7;                                      // 0: MLP consumers, 1..kGatherGroups: producers
   const int gtid = tid & 127;
   if (tid == 0) {
-    tc05::mbar_init(&mbar_mma, 1);
+    tc05::mbar_init(&mbar_mma[0], 1); tc05::mbar_init(&mbar_mma[1], 1);
     for (int s = 0; s < kStages; ++s) { tc05::mbar_init(&mbar_full[s], 128); tc05::mbar_init(&mbar_empty[s], 1); }
     tc05::fence_mbar_init();
   }
-  if (tid < 32) tc05::tmem_alloc(&tmem_slot, 64);
+  if (tid < 32) tc05::tmem_alloc(&tmem_slot, 128);
   stage_weights(w_smem, params, d, tid, kDecodeThreads);
   tc05::fence_before_sync();
   tc05::fence_async_smem();
@@ -82,17 +82,32 @@ decode_kernel(const DecoderDesc d, const __half* __restrict__ params, const floa
   const uint32_t my_tiles = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
 
   if (group == 0) {
-    // ---------------- consumer: MLP on finished tiles, in tile order ----------------
-    uint32_t phase = 0;
-    for (uint32_t j = 0; j < my_tiles; ++j) {
-      const uint32_t g = j % kGatherGroups, it = j / kGatherGroups;
-      const uint32_t stage = g * kStagesPerGroup + it % kStagesPerGroup, use = it / kStagesPerGroup;
-      tc05::mbar_wait(&mbar_full[stage], use & 1u);
-      const float v = mlp_tile_forward(a_ring + (size_t)stage * MlpSmem::kATile, w_smem, &mbar_mma, phase, tmem_base, d, gtid, 1);
-      // the last MMA has been waited for: the tile can be refilled
-      if (gtid == 0) tc05::mbar_arrive(&mbar_empty[stage]);
-      const uint32_t s = (blockIdx.x + j * gridDim.x) * kTile + (uint32_t)gtid;
-      if (s < n) out[s] = v;
+    // ---------------- consumer: MLP on finished tiles, in tile order, two tiles interleaved ----------------
+    uint32_t phase[2] = {0u, 0u};
+    for (uint32_t j = 0; j < my_tiles; j += 2) {
+      uint8_t* a[2] = {nullptr, nullptr};
+      uint64_t* full[2] = {nullptr, nullptr};
+      uint32_t parity[2] = {0u, 0u}, stage[2] = {0u, 0u};
+      const int nt = j + 1 < my_tiles ? 2 : 1;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        if (q >= nt) break;
+        const uint32_t jj = j + (uint32_t)q, g = jj % kGatherGroups, it = jj / kGatherGroups;
+        stage[q] = g * kStagesPerGroup + it % kStagesPerGroup;
+        parity[q] = (it / kStagesPerGroup) & 1u;
+        a[q] = a_ring + (size_t)stage[q] * MlpSmem::kATile;
+        full[q] = &mbar_full[stage[q]];
+      }
+      float v[2];
+      mlp_forward_x2(a, full, parity, w_smem, mbar_mma, phase, tmem_base, d, gtid, 1, v);
+      // the last MMAs have been waited for: the tiles can be refilled
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        if (q >= nt) break;
+        if (gtid == 0) tc05::mbar_arrive(&mbar_empty[stage[q]]);
+        const uint32_t s = (blockIdx.x + (j + (uint32_t)q) * gridDim.x) * kTile + (uint32_t)gtid;
+        if (s < n) out[s] = v[q];
+      }
     }
   } else {
     // ---------------- producers: hash-grid gather straight into the swizzled A tiles ----------------
@@ -120,7 +135,7 @@ decode_kernel(const DecoderDesc d, const __half* __restrict__ params, const floa
 
   tc05::fence_before_sync();
   __syncthreads();
-  if (tid < 32) tc05::tmem_dealloc(tmem_base, 64);
+  if (tid < 32) tc05::tmem_dealloc(tmem_base, 128);
 }
 
 // Measurement tap: the hash-grid gather alone (no MLP, no shared memory, full occupancy), one

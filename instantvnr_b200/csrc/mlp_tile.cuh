@@ -56,74 +56,89 @@ __device__ __forceinline__ uint32_t relu_pack(uint32_t a, uint32_t b) {
   return h2_as_u32(h);
 }
 
-// Runs the whole MLP on the A tile.  Must be called by exactly 128 threads (4 warps,
-// `tid` in [0,128)) that synchronise on named barrier `bar_id`; thread `tid` owns tile
-// row `tid`.  On entry the A tile has been written by these threads (generic proxy) but
-// not yet fenced.  If `stash` != nullptr the post-activation outputs of every hidden
-// layer are also written to global memory as fp16 [layer][row][64] (training forward,
-// fully_fused_mlp.cu:121-128), `stash_stride` halves between layers.
-// Returns the network output of row `tid` (fp16-rounded, as float).
-__device__ __forceinline__ float mlp_tile_forward(uint8_t* a_smem, const uint8_t* w_smem, uint64_t* mbar, uint32_t& phase,
-                                                  uint32_t tmem_base, const DecoderDesc& d, int tid, int bar_id,
-                                                  __half* stash = nullptr, size_t stash_stride = 0) {
+// One hidden-layer epilogue of tile row `tid`: 64 fp32 accumulator columns -> fp16 -> ReLU -> the
+// row of the (same) A tile, which becomes the next layer's operand.
+__device__ __forceinline__ void mlp_epilogue_row(uint8_t* a_smem, uint32_t t_row, int tid) {
   using namespace tc05;
-  const uint32_t a_addr = smem_u32(a_smem);
-  const uint32_t w_addr = smem_u32(w_smem);
-  const uint32_t warp = (uint32_t)tid >> 5;
-  const uint32_t lane_base = (warp & 3u) * 32u;          // TMEM lane quarter this warp may touch
-  const uint32_t t_row = tmem_base + (lane_base << 16);
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    uint32_t r[32];
+    tmem_ld32(t_row + (uint32_t)half * 32u, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      uint4 v = make_uint4(relu_pack(r[8 * c + 0], r[8 * c + 1]), relu_pack(r[8 * c + 2], r[8 * c + 3]),
+                           relu_pack(r[8 * c + 4], r[8 * c + 5]), relu_pack(r[8 * c + 6], r[8 * c + 7]));
+      *reinterpret_cast<uint4*>(a_smem + sw128_off((uint32_t)tid, (uint32_t)(half * 4 + c))) = v;
+    }
+  }
+}
+
+// Issue the MMAs of one layer (layer == n_hidden: the 16-row output layer) of one tile; one thread.
+__device__ __forceinline__ void mlp_issue_layer(uint32_t a_addr, uint32_t w_addr, uint32_t tmem_acc, const DecoderDesc& d, int layer, uint64_t* mbar) {
+  using namespace tc05;
   constexpr uint32_t idesc_hidden = make_idesc_f16(kTile, kWidth, 0, 0);
   constexpr uint32_t idesc_out = make_idesc_f16(kTile, kOutPad, 0, 0);
-
-  fence_async_smem();
-  asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-
-  for (int layer = 0; layer < d.n_hidden; ++layer) {
-    if (tid == 0) {
-      fence_after_sync();
-      const int ksteps = (layer == 0 ? d.enc_pad : kWidth) >> 4;
-      const uint64_t ad = make_desc_sw128(a_addr);
-      const uint64_t bd = make_desc_sw128(w_addr + (uint32_t)layer * MlpSmem::kWHidden);
-      for (int k = 0; k < ksteps; ++k) mma_f16_ss(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc_hidden, k > 0);
-      mma_commit(mbar);
-    }
-    mbar_wait(mbar, phase);
-    phase ^= 1u;
-    fence_after_sync();
-    // epilogue: 64 fp32 columns of my row -> ReLU -> fp16 -> 8 chunks of 16 B
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      uint32_t r[32];
-      tmem_ld32(t_row + (uint32_t)half * 32u, r);
-      tmem_ld_wait();
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint4 v = make_uint4(relu_pack(r[8 * c + 0], r[8 * c + 1]), relu_pack(r[8 * c + 2], r[8 * c + 3]),
-                             relu_pack(r[8 * c + 4], r[8 * c + 5]), relu_pack(r[8 * c + 6], r[8 * c + 7]));
-        *reinterpret_cast<uint4*>(a_smem + sw128_off((uint32_t)tid, (uint32_t)(half * 4 + c))) = v;
-        if (stash) *reinterpret_cast<uint4*>(stash + (size_t)layer * stash_stride + (size_t)tid * kWidth + (half * 4 + c) * 8) = v;
-      }
-    }
-    fence_before_sync();
-    fence_async_smem();
-    asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-  }
-  // output layer: D[128 x 16] = A[128 x 64] * Wout^T
-  if (tid == 0) {
-    fence_after_sync();
-    const uint64_t ad = make_desc_sw128(a_addr);
-    const uint64_t bd = make_desc_sw128(w_addr + (uint32_t)d.n_hidden * MlpSmem::kWHidden);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) mma_f16_ss(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc_out, k > 0);
-    mma_commit(mbar);
-  }
-  mbar_wait(mbar, phase);
-  phase ^= 1u;
   fence_after_sync();
-  const uint32_t raw = tmem_ld1(t_row);
-  tmem_ld_wait();
+  const int ksteps = (layer == 0 ? d.enc_pad : kWidth) >> 4;
+  const uint64_t ad = make_desc_sw128(a_addr);
+  const uint64_t bd = make_desc_sw128(w_addr + (uint32_t)layer * MlpSmem::kWHidden);
+  const uint32_t idesc = layer == d.n_hidden ? idesc_out : idesc_hidden;
+  for (int k = 0; k < ksteps; ++k) mma_f16_ss(tmem_acc, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, k > 0);
+  mma_commit(mbar);
+}
+
+// The MLP chain on up to TWO A tiles at once, interleaved so that the tensor core works on one tile
+// while the 128 threads run the other tile's epilogue: tile q uses TMEM columns [64q, 64q+64) and
+// mbarrier mbar[q].  Called by exactly 128 threads (warps 0-3 of the CTA, `tid` in [0,128), thread
+// `tid` owns row `tid` of both tiles) that synchronise on named barrier `bar_id`.  The tiles were
+// written and proxy-fenced by other threads; `full[q]` / `full_parity[q]` is the mbarrier that says so.
+// a[1] == nullptr: single tile.  Returns the network output of row `tid` of each tile (fp16-rounded).
+__device__ __forceinline__ void mlp_forward_x2(uint8_t* const (&a)[2], uint64_t* const (&full)[2], const uint32_t (&full_parity)[2],
+                                               const uint8_t* w_smem, uint64_t* mbar /*[2]*/, uint32_t (&phase)[2], uint32_t tmem_base,
+                                               const DecoderDesc& d, int tid, int bar_id, float (&out)[2]) {
+  using namespace tc05;
+  const uint32_t w_addr = smem_u32(w_smem);
+  const uint32_t lane_base = ((uint32_t)tid >> 5 & 3u) * 32u;    // TMEM lane quarter this warp may touch
+  const int nt = a[1] ? 2 : 1;
+  uint32_t a_addr[2], t_acc[2], t_row[2];
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    a_addr[q] = a[q] ? smem_u32(a[q]) : 0u;
+    t_acc[q] = tmem_base + 64u * (uint32_t)q;
+    t_row[q] = t_acc[q] + (lane_base << 16);
+  }
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    if (q >= nt) break;
+    mbar_wait(full[q], full_parity[q]);
+    if (tid == 0) mlp_issue_layer(a_addr[q], w_addr, t_acc[q], d, 0, &mbar[q]);
+  }
+  for (int layer = 0; layer < d.n_hidden; ++layer) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      if (q >= nt) break;
+      mbar_wait(&mbar[q], phase[q]);
+      phase[q] ^= 1u;
+      fence_after_sync();
+      mlp_epilogue_row(a[q], t_row[q], tid);
+      fence_before_sync();
+      fence_async_smem();
+      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+      if (tid == 0) mlp_issue_layer(a_addr[q], w_addr, t_acc[q], d, layer + 1, &mbar[q]);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    if (q >= nt) break;
+    mbar_wait(&mbar[q], phase[q]);
+    phase[q] ^= 1u;
+    fence_after_sync();
+    const uint32_t raw = tmem_ld1(t_row[q]);
+    tmem_ld_wait();
+    out[q] = __half2float(__float2half_rn(__uint_as_float(raw)));
+  }
   fence_before_sync();
-  return __half2float(__float2half_rn(__uint_as_float(raw)));
 }
 
 }  // namespace vnr

@@ -162,6 +162,21 @@ VNR_EXPORT int vnr_volume_set_groundtruth_f32(vnr_volume_t* vh, const float* h_v
   });
 }
 
+// same from a device buffer (device-to-device copy on the volume's stream): volumes that are produced or
+// streamed on the GPU -- B200's 180 GB of HBM hold a 1024^3 float volume (4 GiB) outright, so the reference's
+// out-of-core sampler (neural_sampler.cpp:488-1191) degenerates to in-core sampling
+VNR_EXPORT int vnr_volume_set_groundtruth_device(vnr_volume_t* vh, const float* d_volume) {
+  return guard([&] {
+    Volume* v = V(vh);
+    if (!d_volume) throw InvalidError("null volume data");
+    const size_t n = (size_t)v->dims[0] * v->dims[1] * v->dims[2];
+    v->gt.alloc(n);
+    VNR_CUDA(cudaMemcpyAsync(v->gt.p, d_volume, n * sizeof(float), cudaMemcpyDeviceToDevice, v->stream));
+    VNR_CUDA(cudaStreamSynchronize(v->stream));
+    v->have_gt = true;
+  });
+}
+
 VNR_EXPORT int vnr_volume_macrocell_from_groundtruth(vnr_volume_t* vh) {
   return guard([&] {
     Volume* v = V(vh);
