@@ -248,7 +248,8 @@ def run_ours(args):
     vol.stats()
     train_ms = (time.perf_counter() - tw0) * 1e3 / 20
 
-    cpu = cpu_baseline(vol, dims, cams, rgb, alpha, args)
+    # the CPU baseline is measured at N=1 only (under torchrun the host cores are shared by the ranks)
+    cpu = cpu_baseline(vol, dims, cams, rgb, alpha, args) if world == 1 else {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "measured at N=1 only"}
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -339,7 +340,7 @@ def run_train(args):
     vol.init_params(1337)
     if world > 1:
         broadcast_params(vol)
-    dp = DataParallelTrainer(GpuTrainBackend(vol))
+    dp = DataParallelTrainer(GpuTrainBackend(vol), mode=args.dp_mode)
     stream = dp.b.stream
     n = args.batch
 
@@ -384,7 +385,8 @@ def run_train(args):
                "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "f16", "data": "synthetic",
                "config": {"workload": f"train: synthetic {args.volume}^3 volume resident in HBM, example-model.json (T=2^{args.log2_hashmap}), "
-                                      f"{n} samples per rank per step, fwd + L1 + bwd + Adam" + (", gradient all-reduce (fp16 grid + fp32 MLP) over NCCL" if world > 1 else ""),
+                                      f"{n} samples per rank per step, fwd + L1 + bwd + Adam" + ("" if world == 1 else ", gradient all-reduce (fp16 grid + fp32 MLP) over NCCL + replicated Adam" if dp.mode == "allreduce"
+                                                               else ", optimizer fused with its collectives over NVLink peer memory (reduce-scatter + Adam + all-gather in one kernel)"),
                           "global_batch": n * world, "l2_flush": "per-step parameter-state sweep (~0.9 GB) exceeds L2",
                           "parallelism": f"dp{world}"},
                "samples_per_sec": args.steps * n * world / (ms * 1e-3), "mean_loss": mean_loss, "last_loss": loss, "volume_psnr_db": psnr,
@@ -398,10 +400,60 @@ def run_train(args):
         dist.destroy_process_group()
 
 
+def run_reference_train(args):
+    """reference arm of the train workload: the reference's own Trainer::training_step (tiny-cuda-nn built unmodified from
+    /root/reference/tcnn, oracle/_ref) on the same GPU, samples drawn by the oracle-checked sampler of our library (the
+    reference's StaticSampler needs the OVR framework).  Per step: our sampler kernel + the reference's training step."""
+    import torch
+    import instantvnr_b200 as vnr
+    from oracle import tcnn_ref
+    base = {"metric": "train_steps_per_sec", "unit": "steps/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic", "impl": "reference"}
+    if not (torch.cuda.is_available() and tcnn_ref.available()):
+        base.update({"unavailable": "the reference tcnn build (oracle/_ref) or a GPU is missing; the training step has no CPU implementation in the reference"})
+        print(json.dumps(base)); return
+    dims = (args.volume,) * 3
+    gt = synth_volume_device(dims)
+    vol = vnr.NeuralVolume(vnr.model_json(log2_hashmap=args.log2_hashmap), dims)
+    vol.set_groundtruth_device(gt); del gt
+    ref = tcnn_ref.RefNetwork(vnr.model_json(log2_hashmap=args.log2_hashmap), 1337)
+    n = args.batch
+    st = torch.cuda.ExternalStream(vol.stream())
+    xyz = torch.empty(n, 3, device="cuda"); tgt = torch.empty(n, device="cuda")
+
+    def step(want_loss=False):
+        vol.sample(xyz, tgt, n)
+        return ref.training_step(xyz, tgt, n, st.cuda_stream, want_loss=want_loss)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for _ in range(args.steps):
+        step()
+    e1.record(st); st.synchronize()
+    ms = e0.elapsed_time(e1)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        loss = step(want_loss=True)
+    st.synchronize()
+    ms_e2e = (time.perf_counter() - t0) * 1e3
+    v = args.steps / (ms * 1e-3)
+    base.update({"value": v, "ms_per_step": ms / args.steps, "last_loss": loss,
+                 "config": {"workload": f"train: synthetic {args.volume}^3 volume, example-model.json (T=2^{args.log2_hashmap}), {n} samples per step, the reference's "
+                                        "Trainer::training_step (tcnn, CUDA-graph captured fwd+loss+bwd, Adam) on the same B200", "global_batch": n, "parallelism": "dp1"},
+                 "cpu_baseline": {"value": v, "unit": "steps/s", "cores": 0, "kind": "reference", "sample": f"{args.steps} steps of {n} samples on the same GPU"},
+                 "e2e": {"value": args.steps / (ms_e2e * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 4}})
+    print(json.dumps(base))
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.workload == "train":
+        return run_reference_train(args)
     import oracle as O
     from oracle import tcnn_ref
     n = 1 << 24
@@ -471,6 +523,7 @@ def main():
                     help="render = BASELINE configs[1] (the headline; --width 3840 --height 2160 --log2-hashmap 22 = configs[4]); "
                          "train = configs[2]/[3]: data-parallel training steps/s at --batch samples per rank")
     ap.add_argument("--batch", type=int, default=1 << 18, help="train workload: samples per rank per step")
+    ap.add_argument("--dp-mode", default="sharded", choices=["sharded", "allreduce"], help="train workload, N > 1: peer-memory optimizer or NCCL all-reduce")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"], help="N > 1: how finished pixels reach rank 0")
     args = ap.parse_args()

@@ -127,6 +127,18 @@ int vnr_volume_macrocell_update(vnr_volume_t* v, const float* d_xyz, const float
 int vnr_volume_macrocell_buffer(vnr_volume_t* v, void** d_range, size_t* n_floats);
 int vnr_volume_macrocell_refresh(vnr_volume_t* v, void* stream);
 
+/* Data-parallel optimizer over peer memory (no reference counterpart; one 8-GPU NVSwitch box): rank r owns an
+ * interleaved 1/world of the hash-grid parameters; ONE kernel reads every rank's gradients over NVLink, runs Adam on
+ * the owned shard and stores the new fp16 parameters into every rank's buffer (reduce-scatter + Adam + all-gather).
+ * Sequence per step on every rank: vnr_volume_train_grads -> barrier -> vnr_volume_dp_optimizer_step -> barrier ->
+ * vnr_volume_dp_finish_step.  export: 3 x 64-byte cudaIpcMemHandle_t (params, grid gradients, MLP gradients);
+ * attach: all ranks' exports concatenated rank-major. */
+int vnr_volume_dp_export(vnr_volume_t* v, void* handles192);
+int vnr_volume_dp_attach(vnr_volume_t* v, int rank, int world, const void* all_handles);
+int vnr_volume_dp_detach(vnr_volume_t* v);
+int vnr_volume_dp_optimizer_step(vnr_volume_t* v, void* stream);
+int vnr_volume_dp_finish_step(vnr_volume_t* v, void* stream);
+
 /* vnrNeuralVolumeGetTrainingStep / GetTrainingLoss                     api.h:132-133 */
 int vnr_volume_stats(vnr_volume_t* v, uint64_t* step, double* loss);
 /* loss of the most recent step (sum over the batch of |y - t| / N) */

@@ -254,6 +254,23 @@ class NeuralVolume:
     def macrocell_refresh(self, stream=None):
         _check(lib().vnr_volume_macrocell_refresh(self._h, _stream(stream)))
 
+    def dp_export(self):
+        h = C.create_string_buffer(192)
+        _check(lib().vnr_volume_dp_export(self._h, h))
+        return h.raw
+
+    def dp_attach(self, rank, world, all_handles):
+        _check(lib().vnr_volume_dp_attach(self._h, int(rank), int(world), C.c_char_p(all_handles) if all_handles else None))
+
+    def dp_detach(self):
+        _check(lib().vnr_volume_dp_detach(self._h))
+
+    def dp_optimizer_step(self, stream=None):
+        _check(lib().vnr_volume_dp_optimizer_step(self._h, _stream(stream)))
+
+    def dp_finish_step(self, stream=None):
+        _check(lib().vnr_volume_dp_finish_step(self._h, _stream(stream)))
+
     def sampler_skip(self, n_floats):
         _check(lib().vnr_volume_sampler_skip(self._h, C.c_uint64(n_floats)))
 

@@ -540,11 +540,11 @@ void train_grads(Volume* v, const float* d_xyz, const float* d_target, size_t n,
 
 __global__ void loss_fold_kernel(double* acc) { acc[0] += acc[1]; }
 
-void optimizer_step(Volume* v, cudaStream_t s) {
+// ExponentialDecayOptimizer::step (exponential_decay.h:61-72), then AdamOptimizer::step (++m_current_step):
+// hyper-parameters of this optimizer step and the bias-correction table up to it
+static AdamArgs begin_optimizer_step(Volume* v, cudaStream_t s) {
   if (!v->grads_pending) throw StateError("optimizer step without gradients");
-  const DecoderDesc& d = v->cfg.desc;
   const OptimizerConfig& o = v->cfg.opt;
-  // ExponentialDecayOptimizer::step (exponential_decay.h:61-72), then AdamOptimizer::step (++m_current_step)
   if (o.has_decay) {
     if (v->opt_step == 0) v->lr_factor = 1.f;
     if (v->opt_step >= o.decay_start && (v->opt_step - o.decay_start) % o.decay_interval == 0 && v->opt_step <= o.decay_end) v->lr_factor *= o.decay_base;
@@ -564,6 +564,12 @@ void optimizer_step(Volume* v, cudaStream_t s) {
     v->bias_filled = hi;
   }
   a.bias = v->bias_tab.p;
+  return a;
+}
+
+void optimizer_step(Volume* v, cudaStream_t s) {
+  const DecoderDesc& d = v->cfg.desc;
+  const AdamArgs a = begin_optimizer_step(v, s);
   adam_mlp_from_grads_kernel<<<(d.n_mlp + 255) / 256, 256, 0, s>>>(a, d.n_mlp, v->mlp_grads.p);
   const size_t vecs = ((size_t)d.n_grid + 3) / 4;
   adam_grid_kernel<<<(unsigned)((vecs + 255) / 256), 256, 0, s>>>(a, d.n_mlp, d.n_grid, v->grid_grads.p);
@@ -571,6 +577,103 @@ void optimizer_step(Volume* v, cudaStream_t s) {
   VNR_CUDA(cudaGetLastError());
   v->grads_pending = false;
   ++v->train_step; ++v->loss_count;
+}
+
+// ------------------------------------------------------------------------------------------
+// data-parallel optimizer over peer memory (NVLink): reduce-scatter + Adam + all-gather in ONE kernel.
+// Rank r owns the interleaved blocks {b : b % world == r} of kDpBlock 4-parameter vectors.  For its vectors
+// it reads the loss-scaled fp16 gradients of EVERY rank straight from the peers' gradient buffers (P2P
+// loads), sums them in fp32 in rank order, runs Adam on its shard of the fp32 state and stores the new fp16
+// parameters into EVERY rank's parameter buffer (P2P stores).  Versus all-reduce + replicated Adam this
+// moves half the bytes over NVLink and divides the optimizer's HBM sweep by the number of ranks.
+// The caller brackets it with two cross-rank barriers (gradients complete / parameters complete) and then
+// clears its own gradient buffer (dp_finish_step).
+// ------------------------------------------------------------------------------------------
+constexpr uint32_t kDpBlock = 1024;      // vectors per ownership block (4096 parameters, 8 KB of fp16)
+
+struct DpPtrs {
+  int rank, world;
+  const __half* grid_grads[kMaxPeers];
+  const float* mlp_grads[kMaxPeers];
+  __half* params[kMaxPeers];
+};
+
+__global__ void __launch_bounds__(256) adam_grid_sharded_kernel(AdamArgs a, DpPtrs p, uint32_t n_mlp, uint32_t n_grid, uint32_t n_my_vecs) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_my_vecs) return;
+  const uint32_t vec = ((t / kDpBlock) * (uint32_t)p.world + (uint32_t)p.rank) * kDpBlock + (t % kDpBlock);
+  const size_t base = (size_t)vec * 4;
+  if (base >= n_grid) return;
+  float gr[4] = {0.f, 0.f, 0.f, 0.f};
+  uint32_t any = 0;
+  for (int r = 0; r < p.world; ++r) {
+    const uint2 g = *reinterpret_cast<const uint2*>(p.grid_grads[r] + base);
+    any |= g.x | g.y;
+    const float2 f01 = __half22float2(u32_as_h2(g.x)), f23 = __half22float2(u32_as_h2(g.y));
+    gr[0] += f01.x; gr[1] += f01.y; gr[2] += f23.x; gr[3] += f23.y;
+  }
+  if ((any & 0x7FFF7FFFu) == 0u) return;                    // every rank's gradient is +-0: nothing to do anywhere
+  const size_t i = (size_t)n_mlp + base;
+  float4 w4 = *reinterpret_cast<const float4*>(a.master + i);
+  float4 m4 = *reinterpret_cast<const float4*>(a.m1 + i);
+  float4 s4 = *reinterpret_cast<const float4*>(a.m2 + i);
+  uint4 c4 = *reinterpret_cast<const uint4*>(a.steps + i);
+  float* w = &w4.x; float* fm = &m4.x; float* sm = &s4.x; uint32_t* cs = &c4.x;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float gradient = __fdiv_rn(gr[q], a.loss_scale);
+    if (gradient == 0.f) continue;
+    fm[q] = __fmaf_rn(a.beta1, fm[q], (1.f - a.beta1) * gradient);
+    sm[q] = __fmaf_rn(a.beta2, sm[q], (1.f - a.beta2) * (gradient * gradient));
+    const uint32_t tt = ++cs[q];
+    const float lr = a.lr * __ldg(a.bias + tt);
+    const float eff = fminf(fmaxf(__fdiv_rn(lr, sqrtf(sm[q]) + a.eps), 0.f), 3.402823466e+38f);
+    w[q] = __fmaf_rn(-eff, fm[q], w[q]);
+  }
+  *reinterpret_cast<float4*>(a.master + i) = w4;
+  *reinterpret_cast<float4*>(a.m1 + i) = m4;
+  *reinterpret_cast<float4*>(a.m2 + i) = s4;
+  *reinterpret_cast<uint4*>(a.steps + i) = c4;
+  const uint2 packed = make_uint2(h2_as_u32(__floats2half2_rn(w4.x, w4.y)), h2_as_u32(__floats2half2_rn(w4.z, w4.w)));
+  for (int r = 0; r < p.world; ++r) *reinterpret_cast<uint2*>(p.params[r] + i) = packed;
+}
+
+// MLP weights: every rank sums all ranks' (already CTA-reduced) fp32 gradients in rank order -- identical on every
+// rank -- and runs the replicated Adam; no stores to peers.
+__global__ void adam_mlp_dp_kernel(AdamArgs a, DpPtrs p, uint32_t n_mlp) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_mlp) return;
+  float g = 0.f;
+  for (int r = 0; r < p.world; ++r) g += p.mlp_grads[r][i];
+  adam_update(a, i, __fdiv_rn(g, a.loss_scale), true);
+}
+
+void dp_optimizer_step(Volume* v, cudaStream_t s) {
+  if (v->dp_world < 1) throw StateError("data-parallel peers are not attached (vnr_volume_dp_attach)");
+  const DecoderDesc& d = v->cfg.desc;
+  const AdamArgs a = begin_optimizer_step(v, s);
+  DpPtrs p;
+  p.rank = v->dp_rank; p.world = v->dp_world;
+  for (int r = 0; r < kMaxPeers; ++r) {
+    p.grid_grads[r] = r < v->dp_world ? (const __half*)v->dp_grid_grads[r] : nullptr;
+    p.mlp_grads[r] = r < v->dp_world ? (const float*)v->dp_mlp_grads[r] : nullptr;
+    p.params[r] = r < v->dp_world ? (__half*)v->dp_params[r] : nullptr;
+  }
+  adam_mlp_dp_kernel<<<(d.n_mlp + 255) / 256, 256, 0, s>>>(a, p, d.n_mlp);
+  const uint32_t vecs = (uint32_t)(((size_t)d.n_grid + 3) / 4);
+  const uint32_t blocks = (vecs + kDpBlock - 1) / kDpBlock;
+  const uint32_t my_blocks = blocks > (uint32_t)v->dp_rank ? (blocks - (uint32_t)v->dp_rank + (uint32_t)v->dp_world - 1) / (uint32_t)v->dp_world : 0;
+  const uint32_t my_vecs = my_blocks * kDpBlock;
+  if (my_vecs) adam_grid_sharded_kernel<<<(my_vecs + 255) / 256, 256, 0, s>>>(a, p, d.n_mlp, d.n_grid, my_vecs);
+  loss_fold_kernel<<<1, 1, 0, s>>>(v->loss_accum.p);
+  VNR_CUDA(cudaGetLastError());
+  v->grads_pending = false;
+  ++v->train_step; ++v->loss_count;
+}
+
+// after the second barrier: nobody reads this rank's gradients any more
+void dp_finish_step(Volume* v, cudaStream_t s) {
+  v->grid_grads.zero(s);
 }
 
 // ------------------------------------------------------------------------------------------

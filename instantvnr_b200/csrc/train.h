@@ -10,6 +10,8 @@ void sample_at(Volume* v, const float* d_xyz, float* d_out, size_t n, int hw_tex
 void train_ensure_buffers(Volume* v);
 void train_grads(Volume* v, const float* d_xyz, const float* d_target, size_t n, size_t n_global, cudaStream_t s);
 void optimizer_step(Volume* v, cudaStream_t s);
+void dp_optimizer_step(Volume* v, cudaStream_t s);
+void dp_finish_step(Volume* v, cudaStream_t s);
 double volume_psnr(Volume* v, cudaStream_t s);
 void train_steps(Volume* v, int steps, size_t batch, bool update_macrocell, cudaStream_t s);
 }

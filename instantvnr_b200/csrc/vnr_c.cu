@@ -33,7 +33,16 @@ static void require_device() {
 }
 
 Volume::Volume() { sampler_rng.seed(1337); }
-Volume::~Volume() { if (stream) cudaStreamDestroy(stream); }
+Volume::~Volume() {
+  if (stream) cudaStreamSynchronize(stream);
+  for (int r = 0; r < dp_world; ++r) {          // mappings of the peers' buffers (vnr_volume_dp_attach)
+    if (r == dp_rank) continue;
+    if (dp_params[r]) cudaIpcCloseMemHandle(dp_params[r]);
+    if (dp_grid_grads[r]) cudaIpcCloseMemHandle(dp_grid_grads[r]);
+    if (dp_mlp_grads[r]) cudaIpcCloseMemHandle(dp_mlp_grads[r]);
+  }
+  if (stream) cudaStreamDestroy(stream);
+}
 
 static Volume* V(vnr_volume_t* v) { if (!v) throw InvalidError("null volume handle"); return reinterpret_cast<Volume*>(v); }
 static const Volume* V(const vnr_volume_t* v) { if (!v) throw InvalidError("null volume handle"); return reinterpret_cast<const Volume*>(v); }

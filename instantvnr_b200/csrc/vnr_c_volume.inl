@@ -356,3 +356,52 @@ VNR_EXPORT int vnr_volume_macrocell_refresh(vnr_volume_t* vh, void* stream) {
 VNR_EXPORT int vnr_volume_psnr(vnr_volume_t* vh, double* psnr) {
   return guard([&] { Volume* v = V(vh); if (!psnr) throw InvalidError("null argument"); *psnr = volume_psnr(v, v->stream); });
 }
+
+// ---- data-parallel optimizer over peer memory (train.cu) ---------------------------------------------
+// handles192: three cudaIpcMemHandle_t (64 bytes each): parameters (fp16), hash-grid gradients (fp16), MLP gradients (fp32)
+VNR_EXPORT int vnr_volume_dp_export(vnr_volume_t* vh, void* handles192) {
+  return guard([&] {
+    Volume* v = V(vh);
+    if (!handles192) throw InvalidError("null argument");
+    train_ensure_buffers(v);
+    cudaIpcMemHandle_t* h = reinterpret_cast<cudaIpcMemHandle_t*>(handles192);
+    VNR_CUDA(cudaIpcGetMemHandle(&h[0], v->params.p));
+    VNR_CUDA(cudaIpcGetMemHandle(&h[1], v->grid_grads.p));
+    VNR_CUDA(cudaIpcGetMemHandle(&h[2], v->mlp_grads.p));
+  });
+}
+static void dp_detach_impl(Volume* v) {
+  for (int r = 0; r < v->dp_world; ++r) {
+    if (r == v->dp_rank) continue;
+    if (v->dp_params[r]) cudaIpcCloseMemHandle(v->dp_params[r]);
+    if (v->dp_grid_grads[r]) cudaIpcCloseMemHandle(v->dp_grid_grads[r]);
+    if (v->dp_mlp_grads[r]) cudaIpcCloseMemHandle(v->dp_mlp_grads[r]);
+  }
+  for (int r = 0; r < kMaxPeers; ++r) v->dp_params[r] = v->dp_grid_grads[r] = v->dp_mlp_grads[r] = nullptr;
+  v->dp_world = 0; v->dp_rank = 0;
+}
+// all_handles: world x 192 bytes, rank-major (what every rank's vnr_volume_dp_export wrote); maps the peers' buffers
+VNR_EXPORT int vnr_volume_dp_attach(vnr_volume_t* vh, int rank, int world, const void* all_handles) {
+  return guard([&] {
+    Volume* v = V(vh);
+    if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world) throw InvalidError("bad data-parallel rank / world (at most 8 ranks)");
+    if (world > 1 && !all_handles) throw InvalidError("null argument");
+    train_ensure_buffers(v);
+    VNR_CUDA(cudaStreamSynchronize(v->stream));
+    dp_detach_impl(v);
+    v->dp_rank = rank; v->dp_world = world;
+    for (int r = 0; r < world; ++r) {
+      if (r == rank) { v->dp_params[r] = v->params.p; v->dp_grid_grads[r] = v->grid_grads.p; v->dp_mlp_grads[r] = v->mlp_grads.p; continue; }
+      cudaIpcMemHandle_t h[3];
+      memcpy(h, reinterpret_cast<const char*>(all_handles) + (size_t)r * sizeof h, sizeof h);
+      VNR_CUDA(cudaIpcOpenMemHandle(&v->dp_params[r], h[0], cudaIpcMemLazyEnablePeerAccess));
+      VNR_CUDA(cudaIpcOpenMemHandle(&v->dp_grid_grads[r], h[1], cudaIpcMemLazyEnablePeerAccess));
+      VNR_CUDA(cudaIpcOpenMemHandle(&v->dp_mlp_grads[r], h[2], cudaIpcMemLazyEnablePeerAccess));
+    }
+  });
+}
+VNR_EXPORT int vnr_volume_dp_detach(vnr_volume_t* vh) { return guard([&] { Volume* v = V(vh); VNR_CUDA(cudaStreamSynchronize(v->stream)); dp_detach_impl(v); }); }
+// the fused reduce-scatter + Adam + all-gather; the caller places a cross-rank barrier before (all gradients complete)
+// and after (all parameters complete), then calls vnr_volume_dp_finish_step (local gradient clear)
+VNR_EXPORT int vnr_volume_dp_optimizer_step(vnr_volume_t* vh, void* stream) { return guard([&] { Volume* v = V(vh); dp_optimizer_step(v, S(v, stream)); }); }
+VNR_EXPORT int vnr_volume_dp_finish_step(vnr_volume_t* vh, void* stream) { return guard([&] { Volume* v = V(vh); dp_finish_step(v, S(v, stream)); }); }

@@ -57,6 +57,10 @@ struct Volume {
   DevBuf<float4> tfn_color; DevBuf<float> tfn_alpha;
   int n_color = 0, n_alpha = 0; float tfn_lo = 0.f, tfn_hi = 1.f;
 
+  // data-parallel peers (train.cu dp_optimizer_step): every rank's parameter / gradient buffers, own ones included
+  int dp_rank = 0, dp_world = 0;
+  void* dp_params[kMaxPeers] = {}; void* dp_grid_grads[kMaxPeers] = {}; void* dp_mlp_grads[kMaxPeers] = {};
+
   std::string blob;                // last serialized params.json
   std::string peek_json;
 

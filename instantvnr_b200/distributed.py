@@ -75,16 +75,36 @@ class GpuTrainBackend:
         self.vol.macrocell_update(xyz, tgt, n)
         return self.mc
 
+    # -- peer-memory optimizer (vnr_volume_dp_*): reduce-scatter + Adam + all-gather in one kernel
+    def attach_peers(self, group=None):
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        handles = [None] * world
+        dist.all_gather_object(handles, self.vol.dp_export(), group=group)
+        self.vol.dp_attach(rank, world, b"".join(handles))
+        self._flag = torch.zeros(1, device="cuda")
+
+    def apply_sharded(self, group=None):
+        """every rank: barrier (all gradients complete) -> fused kernel -> barrier (all parameters complete) -> clear"""
+        dist.all_reduce(self._flag, group=group)
+        self.vol.dp_optimizer_step()
+        dist.all_reduce(self._flag, group=group)
+        self.vol.dp_finish_step()
+
 
 class DataParallelTrainer:
     """vnrNeuralVolumeTrain across ranks: per-rank batches, one gradient all-reduce per step."""
 
-    def __init__(self, backend, group=None):
+    def __init__(self, backend, group=None, mode="allreduce"):
+        """mode "allreduce": NCCL all-reduce of the gradient buffers + replicated optimizer; mode "sharded": the
+        optimizer runs over peer memory (NVLink P2P), each rank owning 1/world of the hash-grid parameters."""
         self.b = backend
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.last_loss = None
+        self.mode = mode if self.world > 1 else "allreduce"
+        if self.mode == "sharded":
+            self.b.attach_peers(group)
 
     def _stream_ctx(self):
         st = getattr(self.b, "stream", None)
@@ -97,10 +117,13 @@ class DataParallelTrainer:
             xyz, tgt = self.b.sample(n_per_rank)
             self.b.sampler_skip(after)
             bufs = self.b.grads(xyz, tgt, n_per_rank, n_per_rank * self.world)
-            if self.world > 1:
-                for g in bufs:
-                    dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group)
-            self.b.apply()
+            if self.mode == "sharded":
+                self.b.apply_sharded(self.group)
+            else:
+                if self.world > 1:
+                    for g in bufs:
+                        dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group)
+                self.b.apply()
             if not fast_mode:
                 # online macrocell value ranges (core/network.cu:249-257): merge the ranks' (min-1, max+1) pairs
                 mc = self.b.macrocell(xyz, tgt, n_per_rank)

@@ -38,7 +38,7 @@ def _init(rank, world, port):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
 
 
-def _dp_worker(rank, world, port, out_dir):
+def _dp_worker(rank, world, port, out_dir, mode):
     _init(rank, world, port)
     try:
         vol = vnr.NeuralVolume(vnr.model_json(**CFG), DIMS)
@@ -47,7 +47,8 @@ def _dp_worker(rank, world, port, out_dir):
         broadcast_params(vol)
         rgb, alpha = syn.make_tfn(32)
         vol.set_transfer_function(rgb, alpha)
-        dp = DataParallelTrainer(GpuTrainBackend(vol))
+        dp = DataParallelTrainer(GpuTrainBackend(vol), mode=mode)
+        assert dp.mode == mode
         losses = [dp.step(N, fast_mode=False, want_loss=True) for _ in range(STEPS)]
         torch.cuda.synchronize()
         md, vr, mo = vol.get_macrocell()
@@ -56,10 +57,11 @@ def _dp_worker(rank, world, port, out_dir):
         dist.destroy_process_group()
 
 
-def test_data_parallel_training_two_gpus(tmp_path):
+@pytest.mark.parametrize("mode", ["allreduce", "sharded"])
+def test_data_parallel_training_two_gpus(tmp_path, mode):
     _need_two_gpus()
     world = 2
-    mp.spawn(_dp_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_dp_worker, args=(world, _free_port(), str(tmp_path), mode), nprocs=world, join=True)
     r = [np.load(tmp_path / f"rank{k}.npz") for k in range(world)]
     assert np.array_equal(r[0]["p16"], r[1]["p16"])                 # replicas stay bit-identical
     assert np.array_equal(r[0]["vr"], r[1]["vr"])                   # merged macrocell value ranges

@@ -157,3 +157,47 @@ def test_train_errors():
     with pytest.raises(vnr.VnrError) as e:
         vol.train(1, batch=100)
     assert e.value.code == -1 and "multiple of 128" in str(e.value)
+
+
+@pytest.mark.parametrize("sharded", [False, True])
+def test_first_optimizer_step_matches_the_adam_formula(sharded):
+    """One optimizer step from a known state on the gradients the device actually produced (read back before the
+    step), for the plain kernel and for the peer-memory kernel with world = 1: parameters must equal the Adam
+    formula of adam.h:49-115 evaluated in numpy (t = 1), untouched grid entries must not move."""
+    cfg = dict(n_levels=4, n_features=8, log2_hashmap=12, base_res=8, n_hidden=2)
+    m = _model(cfg)
+    dims = (16, 16, 16)
+    gt = syn.make_volume(dims, seed=3)
+    c, t = O.sample_batch(O.Rng(5), 1024, gt, dims)
+    vol = vnr.NeuralVolume(vnr.model_json(**cfg), dims)
+    vol.set_groundtruth(gt)
+    vol.init_params(4)
+    w0, _ = O.init_params(m, 4)                      # fp32 master == the device's (test_decode_fresh_init_params...)
+    if sharded:
+        vol.dp_attach(0, 1, None)
+    dc, dt = torch.from_numpy(c).cuda(), torch.from_numpy(t).cuda()
+    vol.train_grads(dc, dt, 1024, 1024, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    gm, gg = vol.get_grads()
+    if sharded:
+        vol.dp_optimizer_step(); vol.dp_finish_step()
+    else:
+        vol.optimizer_step()
+    got = vol.get_params_f16()
+    assert not vol.get_grads()[1].any()              # consumed gradients were cleared
+    f = np.float32
+    h = O.DEFAULT_HYPER
+    lr, b1, b2, eps, l2 = f(h["lr"]), f(h["beta1"]), f(h["beta2"]), f(h["eps"]), f(h["l2_reg"])
+    g = np.concatenate([gm, O.f16_to_f32(gg)]).astype(f) / f(128.0)
+    g[:m.n_mlp] = (g[:m.n_mlp].astype(np.float64) + np.float64(l2) * w0[:m.n_mlp].astype(np.float64)).astype(f)
+    upd = np.ones(m.n_params, bool); upd[m.n_mlp:] = g[m.n_mlp:] != 0
+    fm = (f(1) - b1) * g
+    sm = (f(1) - b2) * (g * g)
+    lr_t = lr * (np.sqrt(f(1) - b2) / (f(1) - b1))
+    eff = lr_t / (np.sqrt(sm) + eps)
+    w1 = (w0.astype(np.float64) - eff.astype(np.float64) * fm.astype(np.float64)).astype(f)
+    want = O.f32_to_f16(np.where(upd, w1, w0))
+    assert upd[m.n_mlp:].mean() < 0.9                 # part of the table is untouched and must stay put
+    assert np.array_equal(got[~upd], want[~upd])
+    d = np.abs(got.astype(np.int32) - want.astype(np.int32))
+    assert d.max() <= 1 and (d != 0).mean() < 2e-3    # fp16 ulp: fused vs double-rounded arithmetic
