@@ -15,17 +15,6 @@
 
 namespace vnr {
 
-// Gather all levels of this thread's sample into row `row` of the A tile.
-template <int F>
-__device__ __forceinline__ void encode_row(uint8_t* a_smem, const DecoderDesc& d, const __half* __restrict__ grid, float x, float y, float z, uint32_t row) {
-  uint8_t* rowp = a_smem + row * 128u;
-  const uint32_t sw = (row & 7u);
-  encode_levels<F>(rowp, sw, d, grid, x, y, z, 0, d.n_levels);
-  // zero the padding features up to enc_pad (tcnn pads the encoding to 16: grid.h:616-620)
-  for (int k = d.enc_dims; k < d.enc_pad; ++k)
-    *reinterpret_cast<__half*>(rowp + ((((uint32_t)k >> 3) ^ sw) << 4) + ((uint32_t)k & 7u) * 2u) = __float2half_rn(0.f);
-}
-
 // Warp-specialised persistent decode: one CTA per SM, kGatherGroups producer groups of 128 threads
 // (one sample row each) keep the hash-grid gather running all the time and fill a ring of A tiles in
 // shared memory; one consumer group of 128 threads (warps 0-3, one TMEM lane quarter each) runs the

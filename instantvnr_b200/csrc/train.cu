@@ -124,9 +124,20 @@ void sample_at(Volume* v, const float* d_xyz, float* d_out, size_t n, int hw_tex
 // fused forward + loss + backward
 // ------------------------------------------------------------------------------------------
 
-constexpr int kTrainThreads = 256;
+// Thread roles of the training CTA (one persistent CTA per SM):
+//   warps 0-7   compute group (256 threads): forward, loss, backward on the tensor cores; thread (row, hlf) owns
+//               columns [32*hlf, 32*hlf+32) of tile row `row`; warp & 3 = its TMEM lane quarter
+//   warps 8-15  two gather groups (128 threads each, one sample row each): hash-grid features of the NEXT tiles
+//               into a ring of X0 tiles
+//   warps 16-23 two scatter groups (128 threads each): dL/d(encoding) of the PREVIOUS tiles from a ring of
+//               gradient tiles to the hash table (16-byte vector fp16 reductions)
+// so the gather, the MMA chain and the scatter of three different tiles overlap.
+constexpr int kComputeThreads = 256;
+constexpr int kGatherGroupsT = 2, kScatterGroupsT = 2;
+constexpr int kTrainThreads = kComputeThreads + 128 * (kGatherGroupsT + kScatterGroupsT);
+constexpr int kX0Stages = 3, kDxStages = 2;
 
-__device__ __forceinline__ void bar_all() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 __device__ __forceinline__ void red_add_f16x8(__half* addr, uint4 v) {
   asm volatile("red.global.add.noftz.v4.f16x2 [%0], {%1, %2, %3, %4};" ::"l"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
@@ -185,20 +196,24 @@ train_step_kernel(const DecoderDesc d, const TrainArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int NH = d.n_hidden;
-  uint8_t* xs = smem;                                         // X_0 .. X_NH : (NH+1) tiles of 16 KB
-  uint8_t* dy = xs + (size_t)(NH + 1) * MlpSmem::kATile;      // dL/dy tile (column 0 = gradient)
-  uint8_t* ws = dy + MlpSmem::kATile;                         // weight tiles
+  uint8_t* x0_ring = smem;                                              // kX0Stages tiles: X_0 of the tiles in flight
+  uint8_t* xs = x0_ring + (size_t)kX0Stages * MlpSmem::kATile;          // X_1 .. X_NH of the tile being computed
+  uint8_t* dy = xs + (size_t)NH * MlpSmem::kATile;                      // dL/dy tile (column 0 = gradient)
+  uint8_t* dx_ring = dy + MlpSmem::kATile;                              // kDxStages tiles: dL/dX_0 (fp16) waiting for the scatter
+  uint8_t* ws = dx_ring + (size_t)kDxStages * MlpSmem::kATile;          // weight tiles
   __shared__ uint64_t mbar;
+  __shared__ uint64_t x0_full[kX0Stages], x0_empty[kX0Stages], dx_full[kDxStages], dx_empty[kDxStages];
   __shared__ uint32_t tmem_slot;
-  __shared__ double loss_part[kTrainThreads / 32];
+  __shared__ double loss_part[kComputeThreads / 32];
 
   const int tid = threadIdx.x;
-  const uint32_t row = (uint32_t)tid & 127u;
-  const uint32_t hlf = (uint32_t)tid >> 7;                    // 0: columns 0-31, 1: columns 32-63
-  const uint32_t warp = (uint32_t)tid >> 5;
   const uint32_t tmem_cols = (64u * (uint32_t)(NH + 2)) <= 256u ? 256u : 512u;
-
-  if (tid == 0) { mbar_init(&mbar, 1); fence_mbar_init(); }
+  if (tid == 0) {
+    mbar_init(&mbar, 1);
+    for (int s = 0; s < kX0Stages; ++s) { mbar_init(&x0_full[s], 128); mbar_init(&x0_empty[s], 1); }
+    for (int s = 0; s < kDxStages; ++s) { mbar_init(&dx_full[s], kComputeThreads); mbar_init(&dx_empty[s], 128); }
+    fence_mbar_init();
+  }
   if (tid < 32) tmem_alloc(&tmem_slot, tmem_cols);
   stage_weights(ws, a.params, d, tid, kTrainThreads);
   for (int i = tid; i < (int)(MlpSmem::kATile / 16); i += kTrainThreads) reinterpret_cast<uint4*>(dy)[i] = make_uint4(0, 0, 0, 0);
@@ -207,193 +222,225 @@ train_step_kernel(const DecoderDesc d, const TrainArgs a) {
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_base = tmem_slot;
-  const uint32_t t_row = tmem_base + (((warp & 3u) * 32u) << 16);      // my TMEM lane quarter
-  const uint32_t col0 = hlf * 32u;
-  const __half* __restrict__ grid = a.params + d.n_mlp;
-  __half* __restrict__ ggrid = a.grid_grads;
-  uint32_t phase = 0;
-  double loss_local = 0.0;
-
-  constexpr uint32_t idesc_fwd = make_idesc_f16(kTile, kWidth, 0, 0);       // A K-major, B K-major
-  constexpr uint32_t idesc_out = make_idesc_f16(kTile, kOutPad, 0, 0);
-  constexpr uint32_t idesc_dgrad = make_idesc_f16(kTile, kWidth, 0, 1);     // A K-major, B MN-major (W read transposed)
-  constexpr uint32_t idesc_wgrad = make_idesc_f16(64, kWidth, 1, 1);        // both MN-major: D[out][in] += d^T X
-
-  const uint32_t xs_addr = smem_u32(xs), dy_addr = smem_u32(dy), ws_addr = smem_u32(ws);
-  auto x_addr = [&](int l) { return xs_addr + (uint32_t)l * MlpSmem::kATile; };
-  auto x_ptr = [&](int l) { return xs + (size_t)l * MlpSmem::kATile; };
-  auto w_addr = [&](int m) { return ws_addr + (uint32_t)m * MlpSmem::kWHidden; };   // m == NH: output matrix
-  auto acc_col = [&](int m) { return tmem_base + 64u * (uint32_t)(m + 1); };
-
   const uint32_t n_tiles = a.n / kTile;
-  uint32_t iter = 0;
-  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++iter) {
-    const uint32_t s = tile * kTile + row;
-    const float x = a.coords[3 * (size_t)s], y = a.coords[3 * (size_t)s + 1], z = a.coords[3 * (size_t)s + 2];
+  const uint32_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;   // tile j = blockIdx.x + j * gridDim.x
 
-    // ---- hash-grid gather: this thread's half of the feature columns of row `row` -> X_0
-    {
-      uint8_t* rowp = x_ptr(0) + row * 128u;
+  if (tid >= kComputeThreads + 128 * kGatherGroupsT) {
+    // ---------------- scatter groups: dL/dX_0 rows -> hash-table gradient reductions ----------------
+    const uint32_t sg = (uint32_t)(tid - kComputeThreads - 128 * kGatherGroupsT) >> 7, row = (uint32_t)tid & 127u;
+    __half* __restrict__ ggrid = a.grid_grads;
+    for (uint32_t j = sg; j < my_tiles; j += kScatterGroupsT) {
+      const uint32_t stage = j % kDxStages, use = j / kDxStages;
+      const uint32_t s = (blockIdx.x + j * gridDim.x) * kTile + row;
+      const float x = __ldg(a.coords + 3 * (size_t)s), y = __ldg(a.coords + 3 * (size_t)s + 1), z = __ldg(a.coords + 3 * (size_t)s + 2);
+      mbar_wait(&dx_full[stage], use & 1u);
+      const uint8_t* rowp = dx_ring + (size_t)stage * MlpSmem::kATile + row * 128u;
       const uint32_t sw = row & 7u;
-      const int l0 = (int)(col0 / F), l1 = min(d.n_levels, (int)((col0 + 32u) / F));
-      encode_levels<F>(rowp, sw, d, grid, x, y, z, l0, l1);
-      if (hlf == 0)
-        for (int k = d.enc_dims; k < d.enc_pad; ++k)
-          *reinterpret_cast<__half*>(rowp + ((((uint32_t)k >> 3) ^ sw) << 4) + ((uint32_t)k & 7u) * 2u) = __float2half_rn(0.f);
+      for (int l = 0; l < d.n_levels; ++l) {
+        const uint8_t* src = rowp + feat_offset<F>((uint32_t)l, sw);
+        if constexpr (F == 8) { const uint4 g = *reinterpret_cast<const uint4*>(src); const uint32_t gg[4] = {g.x, g.y, g.z, g.w}; scatter_level<8>(d.lv[l], ggrid, x, y, z, gg); }
+        else if constexpr (F == 4) { const uint2 g = *reinterpret_cast<const uint2*>(src); const uint32_t gg[2] = {g.x, g.y}; scatter_level<4>(d.lv[l], ggrid, x, y, z, gg); }
+        else if constexpr (F == 2) { const uint32_t gg[1] = {*reinterpret_cast<const uint32_t*>(src)}; scatter_level<2>(d.lv[l], ggrid, x, y, z, gg); }
+        else { const uint32_t gg[1] = {(uint32_t)*reinterpret_cast<const unsigned short*>(src)}; scatter_level<1>(d.lv[l], ggrid, x, y, z, gg); }
+      }
+      mbar_arrive(&dx_empty[stage]);
     }
-    fence_async_smem();
-    bar_all();
-
-    // ---- forward: X_{l+1} = relu(X_l W_l^T)
-    for (int l = 0; l < NH; ++l) {
-      if (tid == 0) {
-        fence_after_sync();
-        const int ksteps = (l == 0 ? d.enc_pad : kWidth) >> 4;
-        const uint64_t ad = make_desc_sw128(x_addr(l)), bd = make_desc_sw128(w_addr(l));
-        for (int k = 0; k < ksteps; ++k) mma_f16_ss(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc_fwd, k > 0);
-        mma_commit(&mbar);
-      }
-      mbar_wait(&mbar, phase); phase ^= 1u;
-      fence_after_sync();
-      uint32_t r[32];
-      tmem_ld32(t_row + col0, r);
-      tmem_ld_wait();
-      uint8_t* dst = x_ptr(l + 1);
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const uint4 v = make_uint4(relu_pack(r[8 * c + 0], r[8 * c + 1]), relu_pack(r[8 * c + 2], r[8 * c + 3]),
-                                   relu_pack(r[8 * c + 4], r[8 * c + 5]), relu_pack(r[8 * c + 6], r[8 * c + 7]));
-        *reinterpret_cast<uint4*>(dst + sw128_off(row, hlf * 4u + (uint32_t)c)) = v;
-      }
-      fence_before_sync();
+  } else if (tid >= kComputeThreads) {
+    // ---------------- gather groups: hash-grid features -> X_0 ring ----------------
+    const uint32_t gg = (uint32_t)(tid - kComputeThreads) >> 7, row = (uint32_t)tid & 127u;
+    const __half* __restrict__ grid = a.params + d.n_mlp;
+    for (uint32_t j = gg; j < my_tiles; j += kGatherGroupsT) {
+      const uint32_t stage = j % kX0Stages, use = j / kX0Stages;
+      const uint32_t s = (blockIdx.x + j * gridDim.x) * kTile + row;
+      const float x = __ldg(a.coords + 3 * (size_t)s), y = __ldg(a.coords + 3 * (size_t)s + 1), z = __ldg(a.coords + 3 * (size_t)s + 2);
+      if (use > 0) mbar_wait(&x0_empty[stage], (use - 1u) & 1u);
+      encode_row<F, false>(x0_ring + (size_t)stage * MlpSmem::kATile, d, grid, x, y, z, row);
       fence_async_smem();
-      bar_all();
+      mbar_arrive(&x0_full[stage]);
     }
-    // ---- output layer + L1 loss (l1.h:40-76): prediction is fp16; gradient = 128 * sign / N in fp16
-    if (tid == 0) {
-      fence_after_sync();
-      const uint64_t ad = make_desc_sw128(x_addr(NH)), bd = make_desc_sw128(w_addr(NH));
-#pragma unroll
-      for (int k = 0; k < 4; ++k) mma_f16_ss(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc_out, k > 0);
-      mma_commit(&mbar);
-    }
-    mbar_wait(&mbar, phase); phase ^= 1u;
-    fence_after_sync();
-    if (hlf == 0) {
-      const uint32_t raw = tmem_ld1(t_row);
-      tmem_ld_wait();
-      const float pred = __half2float(__float2half_rn(__uint_as_float(raw)));
-      const float diff = pred - a.targets[s];
-      loss_local += (double)__fdiv_rn(fabsf(diff), (float)a.n_global);
-      const __half g = __float2half_rn(__fdiv_rn(a.loss_scale * copysignf(1.0f, diff), (float)a.n_global));
-      *reinterpret_cast<__half*>(dy + row * 128u + ((row & 7u) << 4)) = g;          // column 0 of the swizzled row
-    }
-    fence_before_sync();
-    fence_async_smem();
-    bar_all();
+  } else {
+    // ---------------- compute group ----------------
+    const uint32_t row = (uint32_t)tid & 127u;
+    const uint32_t hlf = (uint32_t)tid >> 7;                    // 0: columns 0-31, 1: columns 32-63
+    const uint32_t warp = (uint32_t)tid >> 5;
+    const uint32_t t_row = tmem_base + (((warp & 3u) * 32u) << 16);      // my TMEM lane quarter
+    const uint32_t col0 = hlf * 32u;
+    uint32_t phase = 0;
+    double loss_local = 0.0;
 
-    // ---- backward through the output matrix and the hidden matrices NH-1 .. 1
-    for (int m = NH; m >= 1; --m) {
-      // input of matrix m is X_m; its output gradient lives in `dy` (m == NH) or X_{m+1} (in place)
-      const uint32_t dsrc = m == NH ? dy_addr : x_addr(m + 1);
-      if (tid == 0) {
-        fence_after_sync();
-        const uint64_t dmn = make_desc_sw128(dsrc), xmn = make_desc_sw128(x_addr(m)), wmn = make_desc_sw128(w_addr(m));
-        // weight gradient: acc_m[out][in] += sum_s d[s][out] * X_m[s][in]   (K = 128 samples, 8 steps of 16 rows)
-#pragma unroll
-        for (int k = 0; k < 8; ++k) mma_f16_ss(acc_col(m), dmn + (uint64_t)(128 * k), xmn + (uint64_t)(128 * k), idesc_wgrad, (iter > 0 || k > 0));
-        // data gradient: D[s][in] = sum_out d[s][out] * W_m[out][in]
-        const int ksteps = m == NH ? 1 : 4;
-        for (int k = 0; k < ksteps; ++k) mma_f16_ss(tmem_base, dmn + (uint64_t)(2 * k), wmn + (uint64_t)(128 * k), idesc_dgrad, k > 0);
-        mma_commit(&mbar);
-      }
-      mbar_wait(&mbar, phase); phase ^= 1u;
-      fence_after_sync();
-      uint32_t r[32];
-      tmem_ld32(t_row + col0, r);
-      tmem_ld_wait();
-      uint8_t* xm = x_ptr(m);
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint4* p = reinterpret_cast<uint4*>(xm + sw128_off(row, hlf * 4u + (uint32_t)c));
-        const uint4 fwd = *p;                                   // forward activations (post-ReLU) of these 8 columns
-        const uint32_t fw[4] = {fwd.x, fwd.y, fwd.z, fwd.w};
-        uint32_t o[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          __half2 g = __floats2half2_rn(__uint_as_float(r[8 * c + 2 * q]), __uint_as_float(r[8 * c + 2 * q + 1]));
-          const __half2 mask = __hgt2(u32_as_h2(fw[q]), __float2half2_rn(0.f));       // 1.0 where forward > 0
-          g = __hmul2(g, mask);
-          o[q] = h2_as_u32(g);
+    constexpr uint32_t idesc_fwd = make_idesc_f16(kTile, kWidth, 0, 0);       // A K-major, B K-major
+    constexpr uint32_t idesc_out = make_idesc_f16(kTile, kOutPad, 0, 0);
+    constexpr uint32_t idesc_dgrad = make_idesc_f16(kTile, kWidth, 0, 1);     // A K-major, B MN-major (W read transposed)
+    constexpr uint32_t idesc_wgrad = make_idesc_f16(64, kWidth, 1, 1);        // both MN-major: D[out][in] += d^T X
+
+    const uint32_t x0_addr = smem_u32(x0_ring), xs_addr = smem_u32(xs), dy_addr = smem_u32(dy), ws_addr = smem_u32(ws);
+    auto w_addr = [&](int m) { return ws_addr + (uint32_t)m * MlpSmem::kWHidden; };   // m == NH: output matrix
+    auto acc_col = [&](int m) { return tmem_base + 64u * (uint32_t)(m + 1); };
+
+    for (uint32_t j = 0; j < my_tiles; ++j) {
+      const uint32_t s = (blockIdx.x + j * gridDim.x) * kTile + row;
+      const uint32_t xstage = j % kX0Stages;
+      const uint32_t x0a = x0_addr + xstage * MlpSmem::kATile;
+      auto x_addr = [&](int l) { return l == 0 ? x0a : xs_addr + (uint32_t)(l - 1) * MlpSmem::kATile; };
+      auto x_ptr = [&](int l) { return l == 0 ? x0_ring + (size_t)xstage * MlpSmem::kATile : xs + (size_t)(l - 1) * MlpSmem::kATile; };
+      mbar_wait(&x0_full[xstage], (j / kX0Stages) & 1u);
+
+      // ---- forward: X_{l+1} = relu(X_l W_l^T)
+      for (int l = 0; l < NH; ++l) {
+        if (tid == 0) {
+          fence_after_sync();
+          const int ksteps = (l == 0 ? d.enc_pad : kWidth) >> 4;
+          const uint64_t ad = make_desc_sw128(x_addr(l)), bd = make_desc_sw128(w_addr(l));
+          for (int k = 0; k < ksteps; ++k) mma_f16_ss(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc_fwd, k > 0);
+          mma_commit(&mbar);
         }
-        *p = make_uint4(o[0], o[1], o[2], o[3]);                // X_m := d_m (in place)
+        mbar_wait(&mbar, phase); phase ^= 1u;
+        fence_after_sync();
+        uint32_t r[32];
+        tmem_ld32(t_row + col0, r);
+        tmem_ld_wait();
+        uint8_t* dst = x_ptr(l + 1);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint4 v = make_uint4(relu_pack(r[8 * c + 0], r[8 * c + 1]), relu_pack(r[8 * c + 2], r[8 * c + 3]),
+                                     relu_pack(r[8 * c + 4], r[8 * c + 5]), relu_pack(r[8 * c + 6], r[8 * c + 7]));
+          *reinterpret_cast<uint4*>(dst + sw128_off(row, hlf * 4u + (uint32_t)c)) = v;
+        }
+        fence_before_sync();
+        fence_async_smem();
+        bar_compute();
+      }
+      // ---- output layer + L1 loss (l1.h:40-76): prediction is fp16; gradient = 128 * sign / N in fp16
+      if (tid == 0) {
+        fence_after_sync();
+        const uint64_t ad = make_desc_sw128(x_addr(NH)), bd = make_desc_sw128(w_addr(NH));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) mma_f16_ss(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc_out, k > 0);
+        mma_commit(&mbar);
+      }
+      mbar_wait(&mbar, phase); phase ^= 1u;
+      fence_after_sync();
+      if (hlf == 0) {
+        const uint32_t raw = tmem_ld1(t_row);
+        tmem_ld_wait();
+        const float pred = __half2float(__float2half_rn(__uint_as_float(raw)));
+        const float diff = pred - a.targets[s];
+        loss_local += (double)__fdiv_rn(fabsf(diff), (float)a.n_global);
+        const __half g = __float2half_rn(__fdiv_rn(a.loss_scale * copysignf(1.0f, diff), (float)a.n_global));
+        *reinterpret_cast<__half*>(dy + row * 128u + ((row & 7u) << 4)) = g;          // column 0 of the swizzled row
       }
       fence_before_sync();
       fence_async_smem();
-      bar_all();
-    }
-    // ---- input matrix: weight gradient and dL/d(encoding), scattered straight from TMEM
-    if (tid == 0) {
+      bar_compute();
+
+      // ---- backward through the output matrix and the hidden matrices NH-1 .. 1
+      for (int m = NH; m >= 1; --m) {
+        // input of matrix m is X_m; its output gradient lives in `dy` (m == NH) or X_{m+1} (in place)
+        const uint32_t dsrc = m == NH ? dy_addr : x_addr(m + 1);
+        if (tid == 0) {
+          fence_after_sync();
+          const uint64_t dmn = make_desc_sw128(dsrc), xmn = make_desc_sw128(x_addr(m)), wmn = make_desc_sw128(w_addr(m));
+          // weight gradient: acc_m[out][in] += sum_s d[s][out] * X_m[s][in]   (K = 128 samples, 8 steps of 16 rows)
+#pragma unroll
+          for (int k = 0; k < 8; ++k) mma_f16_ss(acc_col(m), dmn + (uint64_t)(128 * k), xmn + (uint64_t)(128 * k), idesc_wgrad, (j > 0 || k > 0));
+          // data gradient: D[s][in] = sum_out d[s][out] * W_m[out][in]
+          const int ksteps = m == NH ? 1 : 4;
+          for (int k = 0; k < ksteps; ++k) mma_f16_ss(tmem_base, dmn + (uint64_t)(2 * k), wmn + (uint64_t)(128 * k), idesc_dgrad, k > 0);
+          mma_commit(&mbar);
+        }
+        mbar_wait(&mbar, phase); phase ^= 1u;
+        fence_after_sync();
+        uint32_t r[32];
+        tmem_ld32(t_row + col0, r);
+        tmem_ld_wait();
+        uint8_t* xm = x_ptr(m);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint4* p = reinterpret_cast<uint4*>(xm + sw128_off(row, hlf * 4u + (uint32_t)c));
+          const uint4 fwd = *p;                                   // forward activations (post-ReLU) of these 8 columns
+          const uint32_t fw[4] = {fwd.x, fwd.y, fwd.z, fwd.w};
+          uint32_t o[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            __half2 g = __floats2half2_rn(__uint_as_float(r[8 * c + 2 * q]), __uint_as_float(r[8 * c + 2 * q + 1]));
+            const __half2 mask = __hgt2(u32_as_h2(fw[q]), __float2half2_rn(0.f));       // 1.0 where forward > 0
+            g = __hmul2(g, mask);
+            o[q] = h2_as_u32(g);
+          }
+          *p = make_uint4(o[0], o[1], o[2], o[3]);                // X_m := d_m (in place)
+        }
+        fence_before_sync();
+        fence_async_smem();
+        bar_compute();
+      }
+      // ---- input matrix: weight gradient, and dL/d(encoding) handed to the scatter groups
+      if (tid == 0) {
+        fence_after_sync();
+        const uint64_t dmn = make_desc_sw128(x_addr(1)), xmn = make_desc_sw128(x_addr(0)), wmn = make_desc_sw128(w_addr(0));
+#pragma unroll
+        for (int k = 0; k < 8; ++k) mma_f16_ss(acc_col(0), dmn + (uint64_t)(128 * k), xmn + (uint64_t)(128 * k), idesc_wgrad, (j > 0 || k > 0));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) mma_f16_ss(tmem_base, dmn + (uint64_t)(2 * k), wmn + (uint64_t)(128 * k), idesc_dgrad, k > 0);
+        mma_commit(&mbar);
+      }
+      mbar_wait(&mbar, phase); phase ^= 1u;
       fence_after_sync();
-      const uint64_t dmn = make_desc_sw128(x_addr(1)), xmn = make_desc_sw128(x_addr(0)), wmn = make_desc_sw128(w_addr(0));
+      if (tid == 0) mbar_arrive(&x0_empty[xstage]);               // every MMA that reads X_0 has completed
+      {
+        const uint32_t dstage = j % kDxStages, duse = j / kDxStages;
+        if (duse > 0) mbar_wait(&dx_empty[dstage], (duse - 1u) & 1u);
+        uint32_t r[32];
+        tmem_ld32(t_row + col0, r);
+        tmem_ld_wait();
+        uint8_t* dst = dx_ring + (size_t)dstage * MlpSmem::kATile;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) mma_f16_ss(acc_col(0), dmn + (uint64_t)(128 * k), xmn + (uint64_t)(128 * k), idesc_wgrad, (iter > 0 || k > 0));
-#pragma unroll
-      for (int k = 0; k < 4; ++k) mma_f16_ss(tmem_base, dmn + (uint64_t)(2 * k), wmn + (uint64_t)(128 * k), idesc_dgrad, k > 0);
-      mma_commit(&mbar);
+        for (int c = 0; c < 4; ++c) {
+          const uint4 v = make_uint4(h2_as_u32(__floats2half2_rn(__uint_as_float(r[8 * c + 0]), __uint_as_float(r[8 * c + 1]))),
+                                     h2_as_u32(__floats2half2_rn(__uint_as_float(r[8 * c + 2]), __uint_as_float(r[8 * c + 3]))),
+                                     h2_as_u32(__floats2half2_rn(__uint_as_float(r[8 * c + 4]), __uint_as_float(r[8 * c + 5]))),
+                                     h2_as_u32(__floats2half2_rn(__uint_as_float(r[8 * c + 6]), __uint_as_float(r[8 * c + 7]))));
+          *reinterpret_cast<uint4*>(dst + sw128_off(row, hlf * 4u + (uint32_t)c)) = v;
+        }
+        mbar_arrive(&dx_full[dstage]);                             // release: the scatter group acquires through the mbarrier
+      }
+      fence_before_sync();
+      bar_compute();                                               // TMEM column 0..63 is rewritten by the next tile's first MMA
     }
-    mbar_wait(&mbar, phase); phase ^= 1u;
+
+    // ---- write this CTA's weight-gradient accumulators (TMEM, fp32) to its slice of mlp_partial.
+    // UMMA M = 64 accumulator layout: row o sits in lane 32*(o/16) + o%16 (16 lanes per quarter).
     fence_after_sync();
     {
-      uint32_t r[32];
-      tmem_ld32(t_row + col0, r);
-      tmem_ld_wait();
-      uint32_t gh[16];                                           // 32 columns as fp16 pairs
+      float* part = a.mlp_partial + (size_t)blockIdx.x * d.n_mlp;
+      const uint32_t lane = (uint32_t)tid & 31u, q = warp & 3u;
+      for (int m = 0; m <= NH; ++m) {
+        const int in_w = m == 0 ? d.enc_pad : kWidth;
+        const size_t off = m == 0 ? 0 : (size_t)kWidth * d.enc_pad + (size_t)(m - 1) * kWidth * kWidth;
+        const int rows = m == NH ? kOutPad : kWidth;
+        uint32_t r[32];
+        tmem_ld32(acc_col(m) + ((q * 32u) << 16) + col0, r);
+        tmem_ld_wait();
+        const int o = (int)(q * 16u + lane);
+        if (lane < 16 && o < rows && my_tiles > 0) {
 #pragma unroll
-      for (int q = 0; q < 16; ++q) gh[q] = h2_as_u32(__floats2half2_rn(__uint_as_float(r[2 * q]), __uint_as_float(r[2 * q + 1])));
-      const int l0 = (int)(col0 / F), l1 = min(d.n_levels, (int)((col0 + 32u) / F));
-      for (int l = l0; l < l1; ++l) {
-        const int c = l * F - (int)col0;                         // first column of the level within my 32
-        if constexpr (F >= 2) scatter_level<F>(d.lv[l], ggrid, x, y, z, &gh[c >> 1]);
-        else { uint32_t one = (c & 1) ? (gh[c >> 1] >> 16) : (gh[c >> 1] & 0xFFFFu); scatter_level<1>(d.lv[l], ggrid, x, y, z, &one); }
-      }
-    }
-    fence_before_sync();
-    bar_all();
-  }
-
-  // ---- write this CTA's weight-gradient accumulators (TMEM, fp32) to its slice of mlp_partial.
-  // UMMA M = 64 accumulator layout: row o sits in lane 32*(o/16) + o%16 (16 lanes per quarter).
-  fence_after_sync();
-  {
-    float* part = a.mlp_partial + (size_t)blockIdx.x * d.n_mlp;
-    const uint32_t lane = (uint32_t)tid & 31u, q = warp & 3u;
-    for (int m = 0; m <= NH; ++m) {
-      const int in_w = m == 0 ? d.enc_pad : kWidth;
-      const size_t off = m == 0 ? 0 : (size_t)kWidth * d.enc_pad + (size_t)(m - 1) * kWidth * kWidth;
-      const int rows = m == NH ? kOutPad : kWidth;
-      uint32_t r[32];
-      tmem_ld32(acc_col(m) + ((q * 32u) << 16) + col0, r);
-      tmem_ld_wait();
-      const int o = (int)(q * 16u + lane);
-      if (lane < 16 && o < rows && n_tiles > 0 && blockIdx.x < n_tiles) {
-#pragma unroll
-        for (int k = 0; k < 32; ++k) {
-          const int col = (int)col0 + k;
-          if (col < in_w) part[off + (size_t)o * in_w + col] = __uint_as_float(r[k]);
+          for (int k = 0; k < 32; ++k) {
+            const int col = (int)col0 + k;
+            if (col < in_w) part[off + (size_t)o * in_w + col] = __uint_as_float(r[k]);
+          }
         }
       }
     }
-  }
-  // ---- loss: block reduction, one atomic per CTA
+    // ---- loss: warp reduction
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) loss_local += __shfl_xor_sync(0xffffffffu, loss_local, o);
-  if ((tid & 31) == 0) loss_part[warp] = loss_local;
+    for (int o = 16; o > 0; o >>= 1) loss_local += __shfl_xor_sync(0xffffffffu, loss_local, o);
+    if ((tid & 31) == 0) loss_part[warp] = loss_local;
+  }
+
   fence_before_sync();
   __syncthreads();
   if (tid == 0) {
     double t = 0;
-    for (int w = 0; w < kTrainThreads / 32; ++w) t += loss_part[w];
+    for (int w = 0; w < kComputeThreads / 32; ++w) t += loss_part[w];
     atomicAdd(a.loss_accum + 1, t);
   }
   if (tid < 32) tmem_dealloc(tmem_base, tmem_cols);
@@ -495,7 +542,7 @@ __global__ void __launch_bounds__(256) adam_grid_kernel(AdamArgs a, uint32_t n_m
 template <int F>
 static void launch_train_t(Volume* v, const TrainArgs& a, uint32_t grid, cudaStream_t s) {
   const DecoderDesc& d = v->cfg.desc;
-  const size_t smem = 1024 + (size_t)(d.n_hidden + 2) * MlpSmem::kATile + MlpSmem::weights_bytes(d.n_hidden);
+  const size_t smem = 1024 + (size_t)(kX0Stages + d.n_hidden + 1 + kDxStages) * MlpSmem::kATile + MlpSmem::weights_bytes(d.n_hidden);
   static size_t configured = 0;
   if (smem > 226 * 1024) throw UnsupportedError("n_hidden_layers too large for the fused training kernel");
   if (configured < smem) { VNR_CUDA(cudaFuncSetAttribute(train_step_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = smem; }
@@ -508,7 +555,8 @@ uint32_t train_grid(const Volume* v, size_t n) { return (uint32_t)std::min<size_
 void train_ensure_buffers(Volume* v) {
   const DecoderDesc& d = v->cfg.desc;
   if (!v->have_params) throw StateError("the neural volume has no parameters (call vnr_volume_init_params or load params)");
-  if (d.n_hidden + 2 > 8) throw UnsupportedError("training supports n_hidden_layers <= 6");
+  if (d.n_hidden + 2 > 8 || 1024 + (size_t)(kX0Stages + d.n_hidden + 1 + kDxStages) * MlpSmem::kATile + MlpSmem::weights_bytes(d.n_hidden) > 226 * 1024)
+    throw UnsupportedError("training supports n_hidden_layers <= 5 (shared-memory budget of the fused kernel)");
   v->grid_grads.ensure(d.n_grid);
   if (!v->grads_clean) { v->grid_grads.zero(v->stream); VNR_CUDA(cudaStreamSynchronize(v->stream)); v->grads_clean = true; }
   v->mlp_partial.ensure((size_t)num_sms() * d.n_mlp);

@@ -197,4 +197,29 @@ __device__ __forceinline__ void encode_levels(uint8_t* rowp, uint32_t row_sw, co
   }
 }
 
+// Same without the cross-level software pipeline (one level's 8 loads in flight): fewer live registers, for
+// kernels whose gather threads are capped low and whose gather is not the bound (training).
+template <int F>
+__device__ __forceinline__ void encode_levels_lean(uint8_t* rowp, uint32_t row_sw, const DecoderDesc& d, const __half* __restrict__ grid,
+                                                   float x, float y, float z, int l0, int l1) {
+  typedef typename FeatVec<F>::type T;
+  for (int l = l0; l < l1; ++l) {
+    LevelGather<F> g;
+    g.issue(d.lv[l], grid, x, y, z);
+    *reinterpret_cast<T*>(rowp + feat_offset<F>((uint32_t)l, row_sw)) = g.finish();
+  }
+}
+
+// Gather all levels of one sample into row `row` of a 128B-swizzled A tile (128 rows of 64 halves) and zero the
+// padding features up to enc_pad (tcnn pads the encoding to a multiple of 16: grid.h:616-620).
+template <int F, bool PIPELINED = true>
+__device__ __forceinline__ void encode_row(uint8_t* a_smem, const DecoderDesc& d, const __half* __restrict__ grid, float x, float y, float z, uint32_t row) {
+  uint8_t* rowp = a_smem + row * 128u;
+  const uint32_t sw = (row & 7u);
+  if constexpr (PIPELINED) encode_levels<F>(rowp, sw, d, grid, x, y, z, 0, d.n_levels);
+  else encode_levels_lean<F>(rowp, sw, d, grid, x, y, z, 0, d.n_levels);
+  for (int k = d.enc_dims; k < d.enc_pad; ++k)
+    *reinterpret_cast<__half*>(rowp + ((((uint32_t)k >> 3) ^ sw) << 4) + ((uint32_t)k & 7u) * 2u) = __float2half_rn(0.f);
+}
+
 }  // namespace vnr
