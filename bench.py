@@ -38,6 +38,25 @@ UNIT = "samples/s"
 BYTES_PER_SAMPLE = 1024 + 16 + 4          # gather (8 levels x 8 corners x 16 B) + sample record + value
 
 
+_REAL_STDOUT = None
+
+
+def isolate_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version banner): route fd 1 to
+    stderr for the whole run and keep the original stdout for the result line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(obj) + "\n")
+    out.flush()
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -267,7 +286,7 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "setup_seconds": round(time.time() - t0, 1),
     }
-    print(json.dumps(out))
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
 
@@ -395,7 +414,7 @@ def run_train(args):
                "gpu_launches": args.steps * 9, "clocks": clk,
                "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
                             "kernel": "whole step (train_step_kernel + adam_grid_kernel)", "peak_source": peak_kind, "algorithmic_bytes_per_step": bytes_step}}
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 
@@ -411,7 +430,7 @@ def run_reference_train(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic", "impl": "reference"}
     if not (torch.cuda.is_available() and tcnn_ref.available()):
         base.update({"unavailable": "the reference tcnn build (oracle/_ref) or a GPU is missing; the training step has no CPU implementation in the reference"})
-        print(json.dumps(base)); return
+        emit(base); return
     dims = (args.volume,) * 3
     gt = synth_volume_device(dims)
     vol = vnr.NeuralVolume(vnr.model_json(log2_hashmap=args.log2_hashmap), dims)
@@ -445,7 +464,7 @@ def run_reference_train(args):
                                         "Trainer::training_step (tcnn, CUDA-graph captured fwd+loss+bwd, Adam) on the same B200", "global_batch": n, "parallelism": "dp1"},
                  "cpu_baseline": {"value": v, "unit": "steps/s", "cores": 0, "kind": "reference", "sample": f"{args.steps} steps of {n} samples on the same GPU"},
                  "e2e": {"value": args.steps / (ms_e2e * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 4}})
-    print(json.dumps(base))
+    emit(base)
 
 
 def run_reference(args):
@@ -488,7 +507,7 @@ def run_reference(args):
                                             "its frame rate is bounded above by this rate / samples per frame"},
                      "cpu_baseline": {"value": v, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "2^24 uniform samples per step on the same GPU"},
                      "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
-        print(json.dumps(base))
+        emit(base)
         return
     # CPU port of the decode on the host cores
     m = O.ModelCfg()
@@ -504,7 +523,7 @@ def run_reference(args):
     base.update({"value": v, "ms_per_step": dt * 1e3, "config": {"workload": "CPU oracle port of the decode, 2^20 uniform samples per step"},
                  "cpu_baseline": {"value": v, "unit": UNIT, "cores": O.lib().orc_num_threads(), "kind": "port", "sample": "2^20 uniform samples per step"},
                  "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
-    print(json.dumps(base))
+    emit(base)
 
 
 def main():
@@ -529,6 +548,7 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    isolate_stdout()
     if args.impl == "reference":
         run_reference(args)
     elif args.workload == "train":

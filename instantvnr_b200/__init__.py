@@ -49,6 +49,7 @@ def lib():
         _lib.vnr_map_frame.restype = C.POINTER(C.c_float)
         _lib.vnr_volume_release.restype = None
         _lib.vnr_renderer_release.restype = None
+        _lib.vnr_peer_barrier_release.restype = None
     return _lib
 
 
@@ -399,6 +400,38 @@ def ipc_open(handle):
 
 def ipc_close(d_ptr):
     _check(lib().vnr_ipc_close(C.c_void_p(d_ptr)))
+
+
+class PeerBarrier:
+    """vnr_peer_barrier_*: stream-ordered cross-rank barrier over NVLink peer memory."""
+
+    def __init__(self):
+        self._h = C.c_void_p()
+        h = C.create_string_buffer(64)
+        _check(lib().vnr_peer_barrier_create(C.byref(self._h), h))
+        self.handle = h.raw
+
+    def attach(self, rank, world, all_handles):
+        _check(lib().vnr_peer_barrier_attach(self._h, int(rank), int(world), C.c_char_p(all_handles) if all_handles else None))
+
+    def sync(self, stream):
+        _check(lib().vnr_peer_barrier_sync(self._h, _stream(stream)))
+
+    def timed_out(self):
+        v = C.c_uint64()
+        _check(lib().vnr_peer_barrier_check(self._h, C.byref(v)))
+        return v.value
+
+    def close(self):
+        if self._h:
+            lib().vnr_peer_barrier_release(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 VNR_RAYMARCHING_NO_SHADING_DECODING = 4

@@ -29,6 +29,20 @@ def sampler_schedule(rank, world, n):
     return rank * 3 * n, (world - 1 - rank) * 3 * n
 
 
+def make_peer_barrier(group=None):
+    """a vnr.PeerBarrier attached to every rank of `group` (None when the group has one rank)"""
+    import instantvnr_b200 as vnr
+    world = dist.get_world_size(group)
+    if world == 1:
+        return None
+    b = vnr.PeerBarrier()
+    handles = [None] * world
+    dist.all_gather_object(handles, b.handle, group=group)
+    b.attach(dist.get_rank(group), world, b"".join(handles))
+    dist.barrier(group=group)          # every rank has mapped every flag array before the first sync
+    return b
+
+
 def _wrap_device(ptr, n, dtype):
     """zero-copy torch view of a device buffer owned by the library (CUDA array interface)"""
     typestr = {torch.float32: "<f4", torch.float16: "<f2"}[dtype]
@@ -81,13 +95,14 @@ class GpuTrainBackend:
         handles = [None] * world
         dist.all_gather_object(handles, self.vol.dp_export(), group=group)
         self.vol.dp_attach(rank, world, b"".join(handles))
-        self._flag = torch.zeros(1, device="cuda")
+        self.barrier = make_peer_barrier(group)
 
     def apply_sharded(self, group=None):
         """every rank: barrier (all gradients complete) -> fused kernel -> barrier (all parameters complete) -> clear"""
-        dist.all_reduce(self._flag, group=group)
+        s = self.vol.stream()
+        self.barrier.sync(s)
         self.vol.dp_optimizer_step()
-        dist.all_reduce(self._flag, group=group)
+        self.barrier.sync(s)
         self.vol.dp_finish_step()
 
 
@@ -202,20 +217,27 @@ class TileParallelRenderer:
         elif self.world > 1:
             self.rows = [torch.tensor(strip_rows(self.h, r, self.world), device="cuda", dtype=torch.long) for r in range(self.world)]
         self.download = True
+        self.barrier = None
         if self.world > 1:
             renderer.set_download(False)          # rank 0 downloads after the peers' pixels have arrived
-            self._flag = torch.zeros(1, device="cuda")
+            if mode == "p2p":
+                self.barrier = make_peer_barrier(group)
 
     def render(self):
         """one frame; on return (all ranks) the frame in rank 0's device buffer is complete on rank 0's stream"""
+        if self.barrier is not None and self.download:
+            # rank 0's download of the previous frame (enqueued on its stream) must finish before a peer's
+            # ray-generation kernel starts storing pixels of this frame into the same buffer
+            self.barrier.sync(self.ren.stream())
         self.ren.render()
         if self.world == 1:
             return
         with torch.cuda.stream(self.stream):
             if self.mode == "p2p":
-                # every rank's stores must have completed before rank 0 reads / downloads the frame: a 4-byte
-                # all-reduce on the renderer streams is the frame barrier (stream-ordered, no host sync)
-                dist.all_reduce(self._flag, group=self.group)
+                # every rank's stores must have completed before rank 0 reads / downloads the frame, and rank 0 must
+                # have consumed the previous frame before anybody overwrites it: one peer-memory barrier kernel on
+                # the renderer streams (stream-ordered, no host sync, no collective call)
+                self.barrier.sync(self.ren.stream())
             else:
                 gather_strips(self.frame, self.rows, self.rank, self.world, self.group)
         if self.rank == 0 and self.download:
