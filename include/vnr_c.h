@@ -82,6 +82,15 @@ int vnr_volume_gather_probe(vnr_volume_t* v, const float* d_xyz, uint32_t* d_out
 /* vnrCreateSimpleVolume + StaticSampler ground truth (core/samplers/neural_sampler.cu:86-128):
  * float32 volume of dims dx*dy*dz (x fastest), already normalised to [0,1]. */
 int vnr_volume_set_groundtruth_f32(vnr_volume_t* v, const float* h_volume);
+/* StaticSampler::load (core/samplers/neural_sampler.cpp:223-288) and the out-of-core samplers (:488-1191): a raw
+ * structured volume file (x fastest) of scalar type `value_type` (the reference's ValueType, core/mathdef.h:51-65:
+ * 0 uint8, 1 int8, 2 uint16, 3 int16, 4 uint32, 5 int32, 8 float, 12 double) starting at byte `offset`, streamed
+ * into HBM through pinned double buffers and normalised on the device: clamp((v - vmin) / (vmax - vmin), 0, 1)
+ * (convert_volume :176-210).  vmin >= vmax: the range is computed from the data (one extra pass over the file).
+ * range_out2 (optional) receives the unnormalised range used.  The volume then lives in HBM; training samples it
+ * in-core (a 1024^3 float volume is 4 GiB of the 180 GB). */
+int vnr_volume_set_groundtruth_file(vnr_volume_t* v, const char* path, int value_type, uint64_t offset, int big_endian,
+                                    float vmin, float vmax, float* range_out2);
 /* same from a device buffer (float[dx*dy*dz], copied): volumes produced / streamed on the GPU */
 int vnr_volume_set_groundtruth_device(vnr_volume_t* v, const float* d_volume);
 /* MacroCell::compute_everything (core/macrocell.cu:221-230): value ranges from ground truth */

@@ -174,6 +174,16 @@ class NeuralVolume:
             raise VnrError(-1, "ground-truth volume size does not match dims")
         _check(lib().vnr_volume_set_groundtruth_f32(self._h, _ptr(v)))
 
+    VALUE_TYPES = {"uint8": 0, "int8": 1, "uint16": 2, "int16": 3, "uint32": 4, "int32": 5, "float32": 8, "float64": 12}
+
+    def set_groundtruth_file(self, path, dtype, offset=0, big_endian=False, value_range=None):
+        """raw structured volume file -> HBM, normalised to [0,1]; returns the unnormalised (min, max) used"""
+        lo, hi = value_range if value_range else (1.0, 0.0)
+        r = (C.c_float * 2)()
+        _check(lib().vnr_volume_set_groundtruth_file(self._h, str(path).encode(), C.c_int(self.VALUE_TYPES[str(np.dtype(dtype))]), C.c_uint64(offset),
+                                                     C.c_int(1 if big_endian else 0), C.c_float(lo), C.c_float(hi), r))
+        return float(r[0]), float(r[1])
+
     def set_groundtruth_device(self, d_volume):
         _check(lib().vnr_volume_set_groundtruth_device(self._h, _ptr(d_volume)))
 

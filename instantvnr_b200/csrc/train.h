@@ -12,6 +12,7 @@ void train_grads(Volume* v, const float* d_xyz, const float* d_target, size_t n,
 void optimizer_step(Volume* v, cudaStream_t s);
 void dp_optimizer_step(Volume* v, cudaStream_t s);
 void dp_finish_step(Volume* v, cudaStream_t s);
+void load_groundtruth_file(Volume* v, const char* path, int type, uint64_t offset, bool big_endian, float vmin, float vmax, float* range_out);
 double volume_psnr(Volume* v, cudaStream_t s);
 void train_steps(Volume* v, int steps, size_t batch, bool update_macrocell, cudaStream_t s);
 }

@@ -177,6 +177,17 @@ VNR_EXPORT int vnr_volume_set_groundtruth_device(vnr_volume_t* vh, const float* 
   });
 }
 
+// StaticSampler::load (core/samplers/neural_sampler.cpp:223-288) / OutOfCoreSampler (:488-1191): a raw structured
+// volume file of any scalar type, streamed into HBM and normalised on the device (ingest.cu)
+VNR_EXPORT int vnr_volume_set_groundtruth_file(vnr_volume_t* vh, const char* path, int value_type, uint64_t offset, int big_endian,
+                                               float vmin, float vmax, float* range_out2) {
+  return guard([&] {
+    Volume* v = V(vh);
+    if (!path) throw InvalidError("null path");
+    load_groundtruth_file(v, path, value_type, offset, big_endian != 0, vmin, vmax, range_out2);
+  });
+}
+
 VNR_EXPORT int vnr_volume_macrocell_from_groundtruth(vnr_volume_t* vh) {
   return guard([&] {
     Volume* v = V(vh);

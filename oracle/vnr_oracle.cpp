@@ -1,5 +1,6 @@
 // ============================================================================
-// vnr_oracle.cpp -- CPU ORACLE for the instantvnr hot path.   PARITY UNPINNED.
+// vnr_oracle.cpp -- CPU ORACLE for the instantvnr hot path.
+// PARITY: decode + training pinned to the reference's own tiny-cuda-nn build; MARCHER UNPINNED.
 //
 // THIS FILE IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only tests/, the
 // smoke() check in __graft_entry__.py and bench.py's cpu_baseline / --impl
@@ -13,12 +14,19 @@
 // compositing.  Every function cites the reference file:line it follows
 // (paths relative to /root/reference).
 //
-// "Parity unpinned": the reference ships no tests, golden vectors or fixtures
-// for this path and the instantvnr library cannot be
-// built offline, so the oracle is pinned only by (a) published known-answer
-// vectors of the third-party algorithms it restates (pcg32 demo vector), (b)
-// closed-form constants of the reference (level offset table, hash primes) and
-// (c) where it runs, the reference's own tcnn build (oracle/_ref).
+// What pins it: the reference ships no tests, golden vectors or fixtures for
+// this path and the instantvnr library cannot be
+// built offline, so
+//  (a) decode, parameter initialisation and the training step are pinned by
+//      tests/golden/tcnn_ref_*.npz, generated on a B200 from the reference's OWN
+//      tiny-cuda-nn sources compiled in place (oracle/ref_driver -> oracle/_ref,
+//      tools/make_golden_tcnn.py);
+//  (b) pcg32 by its published demo vector, the level tables / hash by the
+//      closed-form constants of the reference;
+//  (c) the marcher (DDA, adaptive step, classification, compositing) has NO
+//      reference output to compare with -- "parity unpinned" for that part: it
+//      is checked only on closed-form scenes (constant volume, empty macrocells,
+//      early termination).
 //
 // Third-party arithmetic not vendored in /root/reference and restated from the
 // published algorithm:  gdt::LCG<16> (TEA-initialised LCG, OVR/owl

@@ -146,3 +146,48 @@ def test_graph_loop_equals_host_enqueued_rounds():
         assert np.array_equal(out[0][0][k], out[2][0][k])
     assert out[0][1] == out[1][1]
     assert out[0][0][0][..., 3].max() > 0.3
+
+
+def test_full_size_frame_is_invariant_under_rescheduling():
+    """BASELINE configs[1] size (256^3 volume, 1024^2 frame, example model): the frame is a per-ray function of the
+    samples, so it must not depend on how the wavefront is scheduled: device-driven graph loop vs host-enqueued
+    rounds and one renderer vs the union of three pixel partitions give the SAME bits; a different number of samples
+    per ray per round (n_iters) resumes the DDA at round boundaries through next_cell_begin = t - t_min
+    (dda.h:20-138), which re-rounds t by an ulp, so those frames agree to rounding only."""
+    dims = (256, 256, 256)
+    m = O.ModelCfg()
+    p32, _ = O.init_params(m, 7)
+    p32 = p32.copy(); p32[m.n_mlp:] *= 3000.0
+    vol = vnr.NeuralVolume(vnr.example_model_json(), dims)
+    vol.set_params_f16(O.f32_to_f16(p32))
+    dec = np.clip(vol.decode_host(np.random.default_rng(1).random((100000, 3), dtype=np.float32)), 0.0, 1.0)
+    assert dec.max() > dec.min()
+    rgb, alpha = syn.make_tfn(256)
+    vol.set_transfer_function(rgb, alpha, (float(dec.min()), float(dec.max())))
+    vol.set_macrocell(np.tile(np.array([-1.0, 2.0], np.float32), 16 ** 3))        # value range [0,1] everywhere
+
+    def frame(n_iters=16, graph=True, partition=None):
+        ren = vnr.Renderer(vol)
+        ren.set_size(1024, 1024)
+        ren.set_camera(*syn.default_camera(dims, 3))
+        ren.set_n_iters(n_iters); ren.set_graph(graph)
+        if partition:
+            ren.set_partition(*partition)
+        ren.render()
+        return ren.map_frame(), ren.stats()
+
+    ref, st = frame()
+    assert ref[..., 3].max() > 0.9 and st["rays_hit"] > 500000 and st["samples_composited"] > 5e6
+    assert np.all(ref[..., 3] <= 1.0) and np.all(ref >= 0.0)
+    img, st2 = frame(16, False)
+    assert np.array_equal(img, ref) and st2 == st
+    for n_iters, graph in ((8, True), (5, False)):
+        img, st2 = frame(n_iters, graph)
+        assert np.abs(img - ref).max() <= 2e-3 and syn.psnr(img, ref) >= 70.0
+        assert abs(st2["samples_composited"] - st["samples_composited"]) <= 1e-4 * st["samples_composited"] and st2["rays_hit"] == st["rays_hit"]
+    acc = np.zeros_like(ref)
+    for rank in range(3):
+        part, _ = frame(partition=(rank, 3))
+        rows = [y for y in range(1024) if (y // 4) % 3 == rank]
+        acc[rows] = part[rows]
+    assert np.array_equal(acc, ref)
