@@ -8,7 +8,7 @@
 //   * vnrJson is a small value type (JSON text | file name | BSON blob), not nlohmann::json;
 //   * vnrCreateSimpleVolume takes an in-memory normalised float volume: the reference's scene-file
 //     ingest (serializer.cpp, OVR volume readers) is outside the path;
-//   * rendering modes other than 5/6 throw "unsupported".
+//   * rendering modes other than 4/5/6 throw "unsupported".
 // apps/vnr_cmd_train.cpp and apps/vnr_cmd_render.cpp are the reference's two headless drivers
 // (apps/batch_trainer.cpp:72-141, apps/batch_renderer.cpp:156-239) written against this header.
 #pragma once
@@ -163,6 +163,8 @@ inline void vnrNeuralVolumeTrain(vnrVolume v, int steps, bool fast_mode) { vnr::
 inline int vnrNeuralVolumeGetTrainingStep(vnrVolume v) { uint64_t s; double l; vnr::check(vnr_volume_stats(castNeuralVolume(v)->h, &s, &l)); return (int)s; }
 inline double vnrNeuralVolumeGetTrainingLoss(vnrVolume v) { uint64_t s; double l; vnr::check(vnr_volume_stats(castNeuralVolume(v)->h, &s, &l)); return l; }
 inline double vnrNeuralVolumeGetPSNR(vnrVolume v, bool /*verbose*/) { double p; vnr::check(vnr_volume_psnr(castNeuralVolume(v)->h, &p)); return p; }
+inline void vnrNeuralVolumeDecodeProgressive(vnrVolume v) { vnr::check(vnr_volume_decode_progressive(castNeuralVolume(v)->h, nullptr)); }   // api.cpp:228-232
+inline int vnrNeuralVolumeGetNumberOfBlobs(vnrVolume v) { int n; vnr::check(vnr_volume_num_blobs(castNeuralVolume(v)->h, &n)); return n; }    // api.cpp:314-318
 inline void vnrNeuralVolumeSerializeParams(vnrVolume v, vnrJson& params) {                          // api.cpp:292-298
   const void* p; size_t n;
   vnr::check(vnr_volume_save_params(castNeuralVolume(v)->h, &p, &n));

@@ -157,13 +157,24 @@ int vnr_volume_last_loss(vnr_volume_t* v, double* loss);
  * centre, 10 log10(range^2 / mse) against the ground truth */
 int vnr_volume_psnr(vnr_volume_t* v, double* psnr);
 
+/* vnrNeuralVolumeDecodeProgressive (api.h:137; infer_progressively_decode_volume core/network.cu:290-326): decode the
+ * next blob of 16 z-slices of voxel centres into the decoded volume that the "decoding" rendering modes march;
+ * vnrNeuralVolumeGetNumberOfBlobs (api.h:134) calls cover the volume once; get_decoded copies it out (test tap). */
+int vnr_volume_decode_progressive(vnr_volume_t* v, void* stream);
+int vnr_volume_num_blobs(const vnr_volume_t* v, int* n);
+int vnr_volume_get_decoded(vnr_volume_t* v, float* h_out);
+
 /* ---- renderer ------------------------------------------------------------------------- */
 
 int vnr_renderer_create(vnr_volume_t* v, vnr_renderer_t** out);        /* vnrCreateRenderer api.h:168 */
 void vnr_renderer_release(vnr_renderer_t* r);
 int vnr_renderer_set_size(vnr_renderer_t* r, int width, int height);   /* SetFramebufferSize :169 */
 int vnr_renderer_set_camera(vnr_renderer_t* r, const float* from, const float* at, const float* up, float fovy); /* :171 */
-int vnr_renderer_set_mode(vnr_renderer_t* r, int mode);                /* vnrRenderMode, api.h:36-60 */
+int vnr_renderer_set_mode(vnr_renderer_t* r, int mode);                /* vnrRenderMode, api.h:36-60: 4 (march the decoded
+                                                                          volume), 5 / 6 (decode the network per sample) */
+/* what a SimpleVolume renderer marches (vnrCreateRenderer on a simple volume, api.cpp:441-452): 1 = the ground-truth
+ * volume of `v` through the same wavefront (the "GT render" frames are compared against); 0 = per mode */
+int vnr_renderer_set_groundtruth_source(vnr_renderer_t* r, int on);
 int vnr_renderer_set_sampling_rate(vnr_renderer_t* r, float rate);     /* :174 */
 int vnr_renderer_set_density_scale(vnr_renderer_t* r, float scale);    /* :175 */
 int vnr_renderer_reset_accumulation(vnr_renderer_t* r);                /* :176 */

@@ -285,6 +285,19 @@ class NeuralVolume:
     def sampler_skip(self, n_floats):
         _check(lib().vnr_volume_sampler_skip(self._h, C.c_uint64(n_floats)))
 
+    def decode_progressive(self, stream=None):
+        _check(lib().vnr_volume_decode_progressive(self._h, _stream(stream)))
+
+    def num_blobs(self):
+        n = C.c_int()
+        _check(lib().vnr_volume_num_blobs(self._h, C.byref(n)))
+        return n.value
+
+    def get_decoded(self):
+        out = np.empty(self.dims[2] * self.dims[1] * self.dims[0], dtype=np.float32)
+        _check(lib().vnr_volume_get_decoded(self._h, _ptr(out)))
+        return out.reshape(self.dims[2], self.dims[1], self.dims[0])
+
     def psnr(self):
         v = C.c_double()
         _check(lib().vnr_volume_psnr(self._h, C.byref(v)))
@@ -325,6 +338,9 @@ class Renderer:
 
     def set_mode(self, mode):
         _check(lib().vnr_renderer_set_mode(self._h, int(mode)))
+
+    def set_groundtruth_source(self, on):
+        _check(lib().vnr_renderer_set_groundtruth_source(self._h, C.c_int(1 if on else 0)))
 
     def set_sampling_rate(self, r):
         _check(lib().vnr_renderer_set_sampling_rate(self._h, C.c_float(r)))

@@ -17,6 +17,7 @@
 
 #include "march.cuh"
 #include "render.h"
+#include "train.h"
 
 namespace vnr {
 
@@ -304,14 +305,14 @@ void Renderer::destroy_graph() {
 }
 
 // (Re)build the loop graph when anything baked into its kernel nodes changed.
-void Renderer::ensure_graph(const RayBuffers& rb, unsigned grid, size_t cap, int rounds) {
+void Renderer::ensure_graph(const RayBuffers& rb, unsigned grid, size_t cap, int rounds, const float* volume_src) {
   GraphKey key;
   memset(&key, 0, sizeof key);
   key.desc = vol->cfg.desc; key.params = vol->params.p;
   key.ptrs[0] = rb.rgba; key.ptrs[1] = rb.tn_ncb; key.ptrs[2] = rb.cell_base; key.ptrs[3] = rb.state; key.ptrs[4] = rb.jitter;
   key.ptrs[5] = samples[0].p; key.ptrs[6] = samples[1].p; key.ptrs[7] = values.p; key.ptrs[8] = counters.p; key.ptrs[9] = accum.p;
   key.ptrs[10] = frame_out(); key.ptrs[11] = fp_dev.p;
-  key.grid = grid; key.cap = cap; key.rounds = rounds;
+  key.grid = grid; key.cap = cap; key.rounds = rounds; key.volume_src = volume_src;
   if (loop_exec && !memcmp(&key, &graph_key, sizeof key)) return;
   VNR_CUDA(cudaStreamSynchronize(stream));
   destroy_graph();
@@ -337,7 +338,8 @@ void Renderer::ensure_graph(const RayBuffers& rb, unsigned grid, size_t cap, int
   cudaGraph_t body = wp.conditional.phGraph_out[0];
   VNR_CUDA(cudaStreamCreateWithFlags(&capture_stream, cudaStreamNonBlocking));
   VNR_CUDA(cudaStreamBeginCaptureToGraph(capture_stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
-  cudaError_t e = launch_decode_samples(vol->cfg.desc, vol->params.p, samples[0].p, samples[1].p, values.p, counters.p + 2, round_dev, cap, capture_stream);
+  cudaError_t e = volume_src ? launch_volume_samples(volume_src, vol->dims, samples[0].p, samples[1].p, values.p, counters.p + 2, round_dev, cap, capture_stream)
+                             : launch_decode_samples(vol->cfg.desc, vol->params.p, samples[0].p, samples[1].p, values.p, counters.p + 2, round_dev, cap, capture_stream);
   march_round_kernel<false><<<grid, 128, 0, capture_stream>>>(reinterpret_cast<const FrameParams*>(fp_dev.p), rb, samples[0].p, samples[1].p, values.p, counters.p, 0, round_dev, accum.p, frame_out());
   advance_round_kernel<<<1, 1, 0, capture_stream>>>(counters.p, round_dev, handle, 0, rounds);
   cudaGraph_t captured = nullptr;
@@ -349,8 +351,17 @@ void Renderer::ensure_graph(const RayBuffers& rb, unsigned grid, size_t cap, int
 
 void Renderer::render() {
   if (width <= 0 || height <= 0) return;                               // renderer.cpp:62
-  if (mode != 5 && mode != 6) throw UnsupportedError("rendering mode " + std::to_string(mode) + " is outside this library's path (modes 5 and 6)");
-  if (!vol->have_params) throw StateError("the neural volume has no parameters");
+  if (mode != 4 && mode != 5 && mode != 6) throw UnsupportedError("rendering mode " + std::to_string(mode) + " is outside this library's path (modes 4, 5 and 6)");
+  // value source of the wavefront: the network (modes 5 / 6), the progressively decoded volume (mode 4: the reference
+  // marches neural.texture(), api.cpp:429-438) or the ground truth (SimpleVolume renderer)
+  const float* volume_src = nullptr;
+  if (gt_source) {
+    if (!vol->have_gt) throw StateError("no ground-truth volume set");
+    volume_src = vol->gt.p;
+  } else if (mode == 4) {
+    if (!vol->decoded.p) { vol->decoded.alloc((size_t)vol->dims[0] * vol->dims[1] * vol->dims[2]); vol->decoded.zero(vol->stream); vol->decode_blob = 0; }
+    volume_src = vol->decoded.p;
+  } else if (!vol->have_params) throw StateError("the neural volume has no parameters");
   if (reset) frame_index = 0;
   frame_index++;
   reset = false;
@@ -382,12 +393,13 @@ void Renderer::render() {
     march_round_kernel<true><<<grid, 128, 0, stream>>>(reinterpret_cast<const FrameParams*>(fp_dev.p), rb, samples[0].p, samples[1].p, nullptr, counters.p, 0, nullptr, accum.p, frame_out());
     if (graph_loop) {
       // device-driven loop: WHILE (round has samples) { decode; compose + march; advance }
-      ensure_graph(rb, grid, cap, rounds);
+      ensure_graph(rb, grid, cap, rounds, volume_src);
       VNR_CUDA(cudaGraphLaunch(loop_exec, stream));
     } else {
       for (int r = 0; r < rounds; ++r) {
         if (profiling) VNR_CUDA(cudaEventRecord(prof_events[prof_used++], stream));
-        VNR_CUDA(launch_decode_samples(vol->cfg.desc, vol->params.p, samples[r & 1].p, nullptr, values.p, counters.p + 2 + r, nullptr, cap, stream));
+        if (volume_src) VNR_CUDA(launch_volume_samples(volume_src, vol->dims, samples[r & 1].p, nullptr, values.p, counters.p + 2 + r, nullptr, cap, stream));
+        else VNR_CUDA(launch_decode_samples(vol->cfg.desc, vol->params.p, samples[r & 1].p, nullptr, values.p, counters.p + 2 + r, nullptr, cap, stream));
         if (profiling) VNR_CUDA(cudaEventRecord(prof_events[prof_used++], stream));
         march_round_kernel<false><<<grid, 128, 0, stream>>>(reinterpret_cast<const FrameParams*>(fp_dev.p), rb, samples[0].p, samples[1].p, values.p, counters.p, r + 1, nullptr, accum.p, frame_out());
       }

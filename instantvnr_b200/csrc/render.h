@@ -15,6 +15,7 @@ struct GraphKey {
   DecoderDesc desc;
   const void* params;
   const void* ptrs[12];
+  const void* volume_src;               // non-null: trilinear volume lookup instead of the network decode
   unsigned grid; size_t cap; int rounds;
 };
 
@@ -25,6 +26,7 @@ struct Renderer {
   cudaEvent_t vol_ready = nullptr;
   int width = 0, height = 0;
   int mode = 5;                         // vnrCreateRenderer default (api.cpp:456)
+  bool gt_source = false;               // march the ground-truth volume (SimpleVolume renderer)
   int n_iters = 16;                     // N_ITERS (method_raymarching.cu:30-40)
   int jitter_mode = 0;
   int part_rank = 0, part_world = 1; uint32_t strip_rows = 4;
@@ -63,7 +65,7 @@ struct Renderer {
   void fill_frame_params(FrameParams& fp);
   int round_bound() const;
   void destroy_graph();
-  void ensure_graph(const RayBuffers& rb, unsigned grid, size_t cap, int rounds);
+  void ensure_graph(const RayBuffers& rb, unsigned grid, size_t cap, int rounds, const float* volume_src);
   void render();
   void download_now();
   const float* map_frame();

@@ -81,6 +81,51 @@ __global__ void sample_at_tex_kernel(uint32_t n, cudaTextureObject_t tex, const 
   out[s] = tex3D<float>(tex, coords[3 * (size_t)s], coords[3 * (size_t)s + 1], coords[3 * (size_t)s + 2]);
 }
 
+__global__ void voxel_coords_kernel(uint32_t n, uint64_t first, int3 dims, float* __restrict__ coords);
+
+// Wavefront variant of the volume lookup (rendering modes that march a decoded / ground-truth volume instead of the
+// network: raymarching_kernel + sampleVolume, core/renderer/method_raymarching.cu:400-530): (x,y,z,dt) sample records
+// in, one value out; sample count and round index live on the device like in the decode kernel.
+__global__ void volume_samples_kernel(const float* __restrict__ vol, int3 dims, const float4* __restrict__ s0, const float4* __restrict__ s1,
+                                      float* __restrict__ out, const uint32_t* __restrict__ n_dev, const uint32_t* __restrict__ round_dev) {
+  const uint32_t r = round_dev ? *round_dev : 0u;
+  const uint32_t n = n_dev[r];
+  const float4* __restrict__ samples = (r & 1u) ? s1 : s0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 c = samples[i];
+    // sampleVolume (raytracing.h:105-110): p * (1 - rdims) + 0.5 * rdims, then tex3D
+    const float rx = 1.f / (float)dims.x, ry = 1.f / (float)dims.y, rz = 1.f / (float)dims.z;
+    out[i] = sample_volume_linear(vol, dims, __fmaf_rn(c.x, 1.f - rx, 0.5f * rx), __fmaf_rn(c.y, 1.f - ry, 0.5f * ry), __fmaf_rn(c.z, 1.f - rz, 0.5f * rz));
+  }
+}
+
+cudaError_t launch_volume_samples(const float* vol, const int* dims3, const float4* samples, const float4* samples_alt, float* out,
+                                  const uint32_t* n_dev, const uint32_t* round_dev, size_t n_max, cudaStream_t stream) {
+  if (!n_max) return cudaSuccess;
+  const unsigned grid = (unsigned)std::min<size_t>((n_max + 255) / 256, (size_t)num_sms() * 8);
+  volume_samples_kernel<<<grid, 256, 0, stream>>>(vol, make_int3(dims3[0], dims3[1], dims3[2]), samples, samples_alt, out, n_dev, round_dev);
+  return cudaGetLastError();
+}
+
+// NeuralVolume::Impl::infer_progressively_decode_volume (core/network.cu:290-326): decode the next blob of 16
+// z-slices (m_num_slices_per_blob :171) of voxel centres into the decoded volume; the cursor wraps.
+void decode_progressive(Volume* v, cudaStream_t s) {
+  if (!v->have_params) throw StateError("the neural volume has no parameters");
+  const int3 dims = make_int3(v->dims[0], v->dims[1], v->dims[2]);
+  const size_t total = (size_t)dims.x * dims.y * dims.z;
+  if (v->decoded.n != total) { v->decoded.alloc(total); v->decoded.zero(s); v->decode_blob = 0; }
+  const int z0 = v->decode_blob * kSlicesPerBlob;
+  const int nz = std::min(kSlicesPerBlob, dims.z - z0);
+  const uint32_t n = (uint32_t)((size_t)dims.x * dims.y * nz);
+  v->train_x.ensure(3 * (size_t)n);
+  const uint64_t first = (uint64_t)z0 * dims.x * dims.y;
+  voxel_coords_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, first, dims, v->train_x.p);
+  VNR_CUDA(cudaGetLastError());
+  VNR_CUDA(launch_decode(v->cfg.desc, v->params.p, v->train_x.p, v->decoded.p + first, n, nullptr, s));
+  ++v->decode_blob;
+  if (v->decode_blob * kSlicesPerBlob >= dims.z) v->decode_blob = 0;
+}
+
 void sample_batch(Volume* v, float* d_xyz, float* d_target, size_t n, cudaStream_t s) {
   if (!n) return;
   if (d_target && !v->have_gt) throw StateError("[error]: missing a reference volume.");       // network.cu:233

@@ -13,6 +13,10 @@ void optimizer_step(Volume* v, cudaStream_t s);
 void dp_optimizer_step(Volume* v, cudaStream_t s);
 void dp_finish_step(Volume* v, cudaStream_t s);
 void load_groundtruth_file(Volume* v, const char* path, int type, uint64_t offset, bool big_endian, float vmin, float vmax, float* range_out);
+constexpr int kSlicesPerBlob = 16;
+void decode_progressive(Volume* v, cudaStream_t s);
+cudaError_t launch_volume_samples(const float* vol, const int* dims3, const float4* samples, const float4* samples_alt, float* out,
+                                  const uint32_t* n_dev, const uint32_t* round_dev, size_t n_max, cudaStream_t stream);
 double volume_psnr(Volume* v, cudaStream_t s);
 void train_steps(Volume* v, int steps, size_t batch, bool update_macrocell, cudaStream_t s);
 }

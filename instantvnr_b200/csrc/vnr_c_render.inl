@@ -25,6 +25,7 @@ VNR_EXPORT int vnr_renderer_set_mode(vnr_renderer_t* r, int mode) {
     R(r)->mode = mode; R(r)->reset = true;
   });
 }
+VNR_EXPORT int vnr_renderer_set_groundtruth_source(vnr_renderer_t* r, int on) { return guard([&] { R(r)->gt_source = on != 0; R(r)->reset = true; }); }
 VNR_EXPORT int vnr_renderer_set_sampling_rate(vnr_renderer_t* r, float rate) {
   return guard([&] { if (!(rate > 0.f)) throw InvalidError("sampling rate must be positive"); R(r)->sampling_rate = rate; R(r)->reset = true; });
 }

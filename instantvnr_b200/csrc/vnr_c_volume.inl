@@ -416,3 +416,21 @@ VNR_EXPORT int vnr_volume_dp_detach(vnr_volume_t* vh) { return guard([&] { Volum
 // and after (all parameters complete), then calls vnr_volume_dp_finish_step (local gradient clear)
 VNR_EXPORT int vnr_volume_dp_optimizer_step(vnr_volume_t* vh, void* stream) { return guard([&] { Volume* v = V(vh); dp_optimizer_step(v, S(v, stream)); }); }
 VNR_EXPORT int vnr_volume_dp_finish_step(vnr_volume_t* vh, void* stream) { return guard([&] { Volume* v = V(vh); dp_finish_step(v, S(v, stream)); }); }
+
+// vnrNeuralVolumeDecodeProgressive / GetNumberOfBlobs (api.h:134,137; core/network.cu:290-326)
+VNR_EXPORT int vnr_volume_decode_progressive(vnr_volume_t* vh, void* stream) {
+  return guard([&] { Volume* v = V(vh); decode_progressive(v, S(v, stream)); });
+}
+VNR_EXPORT int vnr_volume_num_blobs(const vnr_volume_t* vh, int* n) {
+  return guard([&] { const Volume* v = V(vh); if (!n) throw InvalidError("null argument"); *n = (v->dims[2] + kSlicesPerBlob - 1) / kSlicesPerBlob; });
+}
+// test / export tap: the decoded volume (float[dx*dy*dz]); slices not decoded yet are zero
+VNR_EXPORT int vnr_volume_get_decoded(vnr_volume_t* vh, float* h_out) {
+  return guard([&] {
+    Volume* v = V(vh);
+    if (!h_out) throw InvalidError("null argument");
+    if (!v->decoded.p) throw StateError("nothing has been decoded yet");
+    VNR_CUDA(cudaStreamSynchronize(v->stream));
+    VNR_CUDA(cudaMemcpy(h_out, v->decoded.p, v->decoded.bytes(), cudaMemcpyDeviceToHost));
+  });
+}

@@ -48,6 +48,9 @@ struct Volume {
   Pcg32 sampler_rng;               // neural_sampler.cu:36  `static default_rng_t rng{1337}`
   DevBuf<float> train_x, train_y;
 
+  // progressively decoded volume (network.cu:290-326): what the "decoding" rendering modes march
+  DevBuf<float> decoded; int decode_blob = 0;
+
   // macrocell (core/macrocell.h): value range (offset by -1/+1) and max opacity per cell
   int mc_dims[3] = {0, 0, 0};
   DevBuf<float> mc_range, mc_maxop;
