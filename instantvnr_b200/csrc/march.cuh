@@ -37,6 +37,11 @@ struct FrameParams {
   const float* tfn_alpha;
   int n_color, n_alpha;
   float tfn_lo, tfn_hi, tfn_rcp;
+  // shaded modes (method_raymarching.cu:773-833): 0 none, 1 gradient shading, 2 single-shade heuristic, 3 its shadow pass
+  int shade_mode;
+  float light_dir[3];                // world space, sign-corrected against the camera (renderer.cpp:98-101)
+  float otw_diag[3];                 // object->world linear part (network.cu:569)
+  float grad_step[3];                // object.cpp:305
 };
 
 struct F3 { float x, y, z; };
@@ -68,6 +73,20 @@ __device__ __forceinline__ float jitter_lcg_tea16(uint32_t val0, uint32_t val1) 
   }
   const uint32_t state = 1664525u * v0 + 1013904223u;
   return (float)(state & 0x00FFFFFFu) / (float)0x01000000u;
+}
+// first and second float of the same generator (get_floats(): camera-ray jitter, shadow-ray jitter :851-852,870)
+__device__ __forceinline__ void jitter_lcg_tea16_pair(uint32_t val0, uint32_t val1, float& j0, float& j1) {
+  uint32_t v0 = val0, v1 = val1, s0 = 0;
+#pragma unroll
+  for (int n = 0; n < 16; ++n) {
+    s0 += 0x9e3779b9u;
+    v0 += ((v1 << 4) + 0xa341316cu) ^ (v1 + s0) ^ ((v1 >> 5) + 0xc8013ea4u);
+    v1 += ((v0 << 4) + 0xad90777du) ^ (v0 + s0) ^ ((v0 >> 5) + 0x7e95761eu);
+  }
+  uint32_t state = 1664525u * v0 + 1013904223u;
+  j0 = (float)(state & 0x00FFFFFFu) / (float)0x01000000u;
+  state = 1664525u * state + 1013904223u;
+  j1 = (float)(state & 0x00FFFFFFu) / (float)0x01000000u;
 }
 
 __device__ __forceinline__ void compute_ray(const FrameParams& fp, uint32_t pixel, F3& org, F3& dir) {
@@ -210,6 +229,57 @@ __device__ __forceinline__ void classify(const FrameParams& fp, const float4* __
     a = lerp_tex(w, alphas[i0], alphas[i1]);
   }
   a = 1.f - powf(1.f - a, fp.step_rcp * dt);
+}
+
+// ---- shading (all vectors world space; raytracing.h:209-246, constants instantvnr_types.h:137-148)
+#define VNR_SHADING_SCALE 0.95f
+__device__ __forceinline__ float lerp1(float f, float a, float b) { return __fmaf_rn(f, b, (1.f - f) * a); }
+__device__ __forceinline__ F3 normalize3(F3 a) { const float r = __fdiv_rn(1.0f, __fsqrt_rn(dot3(a, a))); return f3(r * a.x, r * a.y, r * a.z); }
+
+__device__ __forceinline__ F3 shade_simple_light(F3 ray_dir, F3 normal, F3 albedo) {
+  if (dot3(normal, normal) > 1.0e-6f) {
+    const F3 n = normalize3(normal);
+    const float s = __fmaf_rn(.8f, fabsf(dot3(f3(-ray_dir.x, -ray_dir.y, -ray_dir.z), n)), 0.2f);
+    return f3(s * albedo.x, s * albedo.y, s * albedo.z);
+  }
+  return f3(0.f, 0.f, 0.f);
+}
+
+// mat = {ambient, diffuse, specular, shininess}; light_diffuse = light_directional_rgb = 1
+__device__ __forceinline__ F3 shade_scivis_light(F3 ray_dir, F3 normal, F3 albedo, float m_amb, float m_dif, float m_spec, float m_shin, F3 light_dir) {
+  F3 color = f3(0.f, 0.f, 0.f);
+  if (dot3(normal, normal) > 1.0e-6f) {
+    const F3 L = normalize3(light_dir), N = normalize3(normal), V = f3(-ray_dir.x, -ray_dir.y, -ray_dir.z);
+    color = f3(color.x + m_amb * albedo.x, color.y + m_amb * albedo.y, color.z + m_amb * albedo.z);
+    const float cosNL = fmaxf(dot3(N, L), 0.f);
+    if (cosNL > 0.f) {
+      const float dc = m_dif * cosNL;
+      color = f3(color.x + dc * albedo.x, color.y + dc * albedo.y, color.z + dc * albedo.z);
+      const F3 H = normalize3(f3(L.x + V.x, L.y + V.y, L.z + V.z));
+      const float cosNH = fmaxf(dot3(N, H), 0.f);
+      const float sp = m_spec * powf(cosNH, m_shin);
+      color = f3(color.x + sp, color.y + sp, color.z + sp);
+    }
+  }
+  const F3 s2 = shade_simple_light(ray_dir, normal, albedo);
+  return f3(lerp1(0.5f, s2.x, color.x), lerp1(0.5f, s2.y, color.y), lerp1(0.5f, s2.z, color.z));
+}
+
+// GRADIENT_SHADING (method_raymarching.cu:773-788): g = forward differences / grad_step (= -No), dir_obj = object-space ray direction
+__device__ __forceinline__ void shade_gradient(const FrameParams& fp, F3 dir_obj, F3 g, float& r, float& gg, float& b) {
+  const F3 Nw = f3(-g.x * fp.wto_l[0], -g.y * fp.wto_l[4], -g.z * fp.wto_l[8]);          // xfmNormal(otw, No)
+  const F3 dirw = f3(dir_obj.x * fp.otw_diag[0], dir_obj.y * fp.otw_diag[1], dir_obj.z * fp.otw_diag[2]);
+  const F3 sc = shade_scivis_light(dirw, Nw, f3(r, gg, b), .6f, .9f, .4f, 40.f, f3(fp.light_dir));   // mat_gradient_shading
+  r = lerp1(VNR_SHADING_SCALE, r, sc.x); gg = lerp1(VNR_SHADING_SCALE, gg, sc.y); b = lerp1(VNR_SHADING_SCALE, b, sc.z);
+}
+
+// shadow ray direction in object space: xfmVector(wto, normalize(light_directional_dir)) (compute_ray<SHADOW> :640-654)
+__device__ __forceinline__ F3 shadow_dir(const FrameParams& fp) {
+  const F3 d = normalize3(f3(fp.light_dir));
+  const float* l = fp.wto_l;
+  return f3(__fmaf_rn(d.x, l[0], __fmaf_rn(d.y, l[3], d.z * l[6])),
+            __fmaf_rn(d.x, l[1], __fmaf_rn(d.y, l[4], d.z * l[7])),
+            __fmaf_rn(d.x, l[2], __fmaf_rn(d.y, l[5], d.z * l[8])));
 }
 
 }  // namespace vnr

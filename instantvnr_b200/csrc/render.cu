@@ -27,6 +27,12 @@ struct RayBuffers {
   int4* cell_base;     // DDA cell.xyz, w = first sample slot of the current round
   uint32_t* state;     // bit 31: alive; low bits: samples in the current round
   float* jitter;
+  // single-shade heuristic (SingleShotPayload + final_highest_* + shading_color + jitter_ssh, method_raymarching.cu:156-162,
+  // 243-255).  Rays keep their index for the whole frame here, so the in-flight and the final copies are the same arrays.
+  float4* ssh_org;     // highest_org.xyz, highest_alpha
+  float4* ssh_col;     // highest_color.xyz
+  float4* ssh_rgba;    // shading_color: the camera pass' composited colour
+  float* ssh_jitter;   // second float of the pixel's generator: the shadow ray's jitter
 };
 
 __device__ __forceinline__ void write_pixel(const FrameParams& fp, float4* __restrict__ accum, float4* __restrict__ frame, uint32_t pixel, float4 c) {
@@ -40,6 +46,22 @@ __device__ __forceinline__ void write_pixel(const FrameParams& fp, float4* __res
   frame[pixel] = make_float4(__fdiv_rn(c.x, fi), __fdiv_rn(c.y, fi), __fdiv_rn(c.z, fi), __fdiv_rn(c.w, fi));
 }
 
+// what a finished ray leaves behind (iterative_compose_kernel :813-833)
+template <int SHADE>
+__device__ __forceinline__ void finish_ray(const FrameParams& fp, const RayBuffers& rb, float4* __restrict__ accum, float4* __restrict__ frame,
+                                           uint32_t i, uint32_t pixel, float4 rgba, float4 hi_org, float4 hi_col) {
+  if (SHADE == 2) {                 // camera pass of the single-shade heuristic: park the result for the shadow pass
+    rb.ssh_org[i] = hi_org; rb.ssh_col[i] = hi_col; rb.ssh_rgba[i] = rgba;
+  } else if (SHADE == 3) {          // shadow pass: blend the single shade in
+    const float tr = 1.f - rgba.w;
+    const float4 sc = rb.ssh_rgba[i], hc = rb.ssh_col[i];
+    write_pixel(fp, accum, frame, pixel, make_float4(lerp1(VNR_SHADING_SCALE, sc.x, (hc.x * sc.w) * tr), lerp1(VNR_SHADING_SCALE, sc.y, (hc.y * sc.w) * tr),
+                                                     lerp1(VNR_SHADING_SCALE, sc.z, (hc.z * sc.w) * tr), sc.w));
+  } else {
+    write_pixel(fp, accum, frame, pixel, rgba);
+  }
+}
+
 // The frame constants live in device memory (so that a captured graph can be replayed with a new
 // camera) and are staged in shared memory by every CTA.
 __device__ __forceinline__ void stage_frame_params(FrameParams* dst, const FrameParams* __restrict__ src) {
@@ -49,15 +71,19 @@ __device__ __forceinline__ void stage_frame_params(FrameParams* dst, const Frame
   __syncthreads();
 }
 
-// counters: [0] rays that hit the volume, [1] samples composited, [2 + r] samples emitted for round r.
+// counters: [0] rays that hit the volume, [1] samples composited, [2 + r] decode entries emitted for round r.
 // The round index comes from the host (round_dev == nullptr: bounded host-enqueued rounds) or from device
 // memory (graph-driven loop: *round_dev is the round whose values were just decoded).  Round r reads
 // samples[(r-1)&1] and writes samples[r&1].
-template <bool FIRST>
+// SHADE 0: no shading; 1: gradient shading (every sample is 4 consecutive decode entries: the position and its three
+// forward-difference neighbours, :719-726); 2: single-shade heuristic, camera pass; 3: its shadow pass (rays start at the
+// highest-contribution point of pass 2 and run along the light direction; alpha only).
+template <bool FIRST, int SHADE>
 __global__ void __launch_bounds__(128)
 march_round_kernel(const FrameParams* __restrict__ fpp, RayBuffers rb, float4* __restrict__ samples0, float4* __restrict__ samples1,
                    const float* __restrict__ values, uint32_t* __restrict__ counters, int round_host, const uint32_t* __restrict__ round_dev,
                    float4* __restrict__ accum, float4* __restrict__ frame) {
+  constexpr uint32_t EPS = SHADE == 1 ? 4u : 1u;             // decode entries per sample
   const int round = FIRST ? 0 : (round_dev ? (int)(*round_dev) + 1 : round_host);
   if (!FIRST && counters[2 + round - 1] == 0) return;      // nothing was alive in the previous round
   __shared__ FrameParams fp_s;
@@ -72,7 +98,7 @@ march_round_kernel(const FrameParams* __restrict__ fpp, RayBuffers rb, float4* _
   if (active) {
     pixel = ray_to_pixel(fp, i);
     active = pixel < (uint32_t)fp.width * (uint32_t)fp.height;
-    if (FIRST && !active) rb.state[i] = 0;          // padding rays of a partial strip
+    if (FIRST && !active && SHADE != 3) rb.state[i] = 0;          // padding rays of a partial strip
   }
   uint32_t st = 0;
   if (active && !FIRST) { st = rb.state[i]; active = (st >> 31) != 0; }
@@ -80,50 +106,69 @@ march_round_kernel(const FrameParams* __restrict__ fpp, RayBuffers rb, float4* _
   F3 org = f3(0, 0, 0), dir = f3(0, 0, 1), m_dir = dir;
   float tmin = 0.f, tmax = VNR_FLOAT_LARGE, jitter = 0.5f;
   float4 rgba = make_float4(0, 0, 0, 0);
+  float4 hi_org = make_float4(0, 0, 0, 0), hi_col = make_float4(0, 0, 0, 0);
   DDAState dda; dda.tnx = dda.tny = dda.tnz = 0.f; dda.cx = dda.cy = dda.cz = 0; dda.ncb = 0.f;
   uint32_t n_comp = 0;
   bool hit = false;
 
   if (active) {
-    compute_ray(fp, pixel, org, dir);
+    if (SHADE == 3) { const float4 o = rb.ssh_org[i]; org = f3(o.x, o.y, o.z); hi_org = o; dir = shadow_dir(fp); }
+    else compute_ray(fp, pixel, org, dir);
     m_dir = f3(dir.x * fp.mc_rcp[0], dir.y * fp.mc_rcp[1], dir.z * fp.mc_rcp[2]);
-    const bool ok = intersect_box(tmin, tmax, org, dir, fp.bbox_lo, fp.bbox_hi);
+    bool ok = intersect_box(tmin, tmax, org, dir, fp.bbox_lo, fp.bbox_hi);
     if (FIRST) {
-      jitter = fp.jitter_mode == 0 ? jitter_lcg_tea16((uint32_t)fp.frame_index, pixel) : 0.5f;
+      if (SHADE == 3) { jitter = rb.ssh_jitter[i]; ok = ok && hi_org.w > 0.f; }          // iterative_raygen_kernel_shadow :877-900
+      else if (SHADE == 2) {
+        float j1 = 0.5f;
+        if (fp.jitter_mode == 0) jitter_lcg_tea16_pair((uint32_t)fp.frame_index, pixel, jitter, j1);
+        rb.ssh_jitter[i] = j1;
+      } else jitter = fp.jitter_mode == 0 ? jitter_lcg_tea16((uint32_t)fp.frame_index, pixel) : 0.5f;
       if (ok) {
         const F3 m_org = f3(org.x * fp.mc_rcp[0], org.y * fp.mc_rcp[1], org.z * fp.mc_rcp[2]);
         dda_init(dda, m_org, m_dir, tmin, fp.mc_dims);
         rb.jitter[i] = jitter;
         hit = true;
       } else {
-        write_pixel(fp, accum, frame, pixel, rgba);
+        if (SHADE == 3) write_pixel(fp, accum, frame, pixel, rb.ssh_rgba[i]);
+        else finish_ray<SHADE>(fp, rb, accum, frame, i, pixel, rgba, hi_org, hi_col);     // SHADE 2: zeros for the shadow pass (the reference memsets)
         rb.state[i] = 0;
         active = false;
       }
     } else {
       jitter = rb.jitter[i];
       rgba = rb.rgba[i];
+      if (SHADE == 2) { hi_org = rb.ssh_org[i]; hi_col = rb.ssh_col[i]; }
       const float4 t = rb.tn_ncb[i];
       const int4 c = rb.cell_base[i];
       dda.tnx = t.x; dda.tny = t.y; dda.tnz = t.z; dda.ncb = t.w; dda.cx = c.x; dda.cy = c.y; dda.cz = c.z;
       // ---- compose the samples of the previous round (iterative_compose_kernel :757-806)
       const uint32_t cnt = st & 0xFFFFu, base = (uint32_t)c.w;
       for (uint32_t k = 0; k < cnt; ++k) {
-        const float value = values[base + k];
-        const float dt = prev_samples[base + k].w;
+        const float value = values[base + EPS * k];
+        const float4 smp = prev_samples[base + EPS * k];
         float r, g, b, a;
-        classify(fp, fp.tfn_color, fp.tfn_alpha, value, dt, r, g, b, a);
+        classify(fp, fp.tfn_color, fp.tfn_alpha, value, smp.w, r, g, b, a);
+        if (SHADE == 1) {
+          const F3 grad = f3(__fdiv_rn(values[base + 4 * k + 1] - value, fp.grad_step[0]), __fdiv_rn(values[base + 4 * k + 2] - value, fp.grad_step[1]),
+                             __fdiv_rn(values[base + 4 * k + 3] - value, fp.grad_step[2]));
+          shade_gradient(fp, dir, grad, r, g, b);
+        } else if (SHADE == 2) {
+          const float contrib = (1.f - rgba.w) * a;
+          if (hi_org.w < contrib) { hi_org = make_float4(smp.x, smp.y, smp.z, contrib); hi_col = make_float4(r, g, b, 0.f); }
+        }
         const float tr = 1.f - rgba.w;
         rgba.w = __fmaf_rn(tr, a, rgba.w);
-        rgba.x = __fmaf_rn(tr * r, a, rgba.x);
-        rgba.y = __fmaf_rn(tr * g, a, rgba.y);
-        rgba.z = __fmaf_rn(tr * b, a, rgba.z);
+        if (SHADE != 3) {
+          rgba.x = __fmaf_rn(tr * r, a, rgba.x);
+          rgba.y = __fmaf_rn(tr * g, a, rgba.y);
+          rgba.z = __fmaf_rn(tr * b, a, rgba.z);
+        }
         ++n_comp;
         if (!(rgba.w < VNR_NEARLY_ONE)) break;
       }
       const bool resumable = dda_resumable(dda, m_dir, tmin, tmax, fp.mc_dims);
       if (!(rgba.w < VNR_NEARLY_ONE && resumable)) {
-        write_pixel(fp, accum, frame, pixel, rgba);
+        finish_ray<SHADE>(fp, rb, accum, frame, i, pixel, rgba, hi_org, hi_col);
         rb.state[i] = 0;
         active = false;
       }
@@ -145,7 +190,7 @@ march_round_kernel(const FrameParams* __restrict__ fpp, RayBuffers rb, float4* _
   if (active && k == 0) {
     // no sample left on this ray: the reference would carry it through one more (empty) round and
     // then find it not resumable; finish it now.
-    write_pixel(fp, accum, frame, pixel, rgba);
+    finish_ray<SHADE>(fp, rb, accum, frame, i, pixel, rgba, hi_org, hi_col);
     rb.state[i] = 0;
     active = false;
   }
@@ -155,11 +200,20 @@ march_round_kernel(const FrameParams* __restrict__ fpp, RayBuffers rb, float4* _
   for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (uint32_t)o) incl += t; }
   const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
   uint32_t base = 0;
-  if (lane == 31 && total) base = atomicAdd(&counters[2 + round], total);
-  base = __shfl_sync(0xffffffffu, base, 31) + (incl - k);
+  if (lane == 31 && total) base = atomicAdd(&counters[2 + round], EPS * total);
+  base = __shfl_sync(0xffffffffu, base, 31) + EPS * (incl - k);
   if (active) {
-    for (uint32_t j = 0; j < k; ++j) next_samples[base + j] = local[j];
+    for (uint32_t j = 0; j < k; ++j) {
+      const float4 c = local[j];
+      next_samples[base + EPS * j] = c;
+      if (SHADE == 1) {
+        next_samples[base + 4 * j + 1] = make_float4(c.x + fp.grad_step[0], c.y, c.z, 0.f);
+        next_samples[base + 4 * j + 2] = make_float4(c.x, c.y + fp.grad_step[1], c.z, 0.f);
+        next_samples[base + 4 * j + 3] = make_float4(c.x, c.y, c.z + fp.grad_step[2], 0.f);
+      }
+    }
     rb.rgba[i] = rgba;
+    if (SHADE == 2) { rb.ssh_org[i] = hi_org; rb.ssh_col[i] = hi_col; }
     rb.tn_ncb[i] = make_float4(dda.tnx, dda.tny, dda.tnz, dda.ncb);
     rb.cell_base[i] = make_int4(dda.cx, dda.cy, dda.cz, (int)base);
     rb.state[i] = 0x80000000u | k;
@@ -184,7 +238,10 @@ __global__ void finalize_kernel(const FrameParams* __restrict__ fpp, RayBuffers 
   if (i >= fp.n_rays) return;
   if (rb.state[i] >> 31) {
     const uint32_t pixel = ray_to_pixel(fp, i);
-    write_pixel(fp, accum, frame, pixel, rb.rgba[i]);
+    const float4 rgba = rb.rgba[i];
+    if (fp.shade_mode == 2) finish_ray<2>(fp, rb, accum, frame, i, pixel, rgba, rb.ssh_org[i], rb.ssh_col[i]);
+    else if (fp.shade_mode == 3) finish_ray<3>(fp, rb, accum, frame, i, pixel, rgba, rb.ssh_org[i], rb.ssh_col[i]);
+    else write_pixel(fp, accum, frame, pixel, rgba);
     rb.state[i] = 0;
     atomicAdd(leftover, 1u);
   }
@@ -205,8 +262,8 @@ Renderer::Renderer(Volume* v) : vol(v) {
   VNR_CUDA(cudaEventCreateWithFlags(&frame_done[0], cudaEventDisableTiming));
   VNR_CUDA(cudaEventCreateWithFlags(&frame_done[1], cudaEventDisableTiming));
   VNR_CUDA(cudaEventCreateWithFlags(&vol_ready, cudaEventDisableTiming));
-  VNR_CUDA(cudaMallocHost((void**)&h_counters, sizeof(uint32_t) * (kMaxRounds + 4)));
-  memset(h_counters, 0, sizeof(uint32_t) * (kMaxRounds + 4));
+  VNR_CUDA(cudaMallocHost((void**)&h_counters, sizeof(uint32_t) * 2 * (kMaxRounds + 4)));
+  memset(h_counters, 0, sizeof(uint32_t) * 2 * (kMaxRounds + 4));
   if (const char* e = getenv("VNR_RM_GRAPH")) use_graph = atoi(e) != 0;    // 0: host-enqueued rounds (profilers do not see graph-body kernels)
   if (const char* e = getenv("VNR_RM_N_ITERS")) {       // method_raymarching.cu:30-38
     int n = atoi(e);
@@ -287,6 +344,14 @@ void Renderer::fill_frame_params(FrameParams& fp) {
   fp.tfn_color = vol->tfn_color.p; fp.tfn_alpha = vol->tfn_alpha.p;
   fp.n_color = vol->n_color; fp.n_alpha = vol->n_alpha;
   fp.tfn_lo = vol->tfn_lo; fp.tfn_hi = vol->tfn_hi; fp.tfn_rcp = 1.f / (vol->tfn_hi - vol->tfn_lo);
+  // correct the light direction (renderer.cpp:98-101): the flip persists in the renderer's parameters
+  if (fmaf(dir[2], light_dir[2], fmaf(dir[1], light_dir[1], dir[0] * light_dir[0])) > 0.f)
+    for (int k = 0; k < 3; ++k) light_dir[k] = -light_dir[k];
+  for (int k = 0; k < 3; ++k) {
+    fp.light_dir[k] = light_dir[k];
+    fp.otw_diag[k] = d[k];
+    fp.grad_step[k] = 1.f / (float)vol->dims[k];                       // object.cpp:305
+  }
 }
 
 int Renderer::round_bound() const {
@@ -299,121 +364,149 @@ int Renderer::round_bound() const {
 }
 
 void Renderer::destroy_graph() {
-  if (loop_exec) { cudaGraphExecDestroy(loop_exec); loop_exec = nullptr; }
-  if (loop_graph) { cudaGraphDestroy(loop_graph); loop_graph = nullptr; }
+  for (int k = 0; k < 2; ++k) {
+    if (loop_exec[k]) { cudaGraphExecDestroy(loop_exec[k]); loop_exec[k] = nullptr; }
+    if (loop_graph[k]) { cudaGraphDestroy(loop_graph[k]); loop_graph[k] = nullptr; }
+  }
   if (capture_stream) { cudaStreamDestroy(capture_stream); capture_stream = nullptr; }
 }
 
-// (Re)build the loop graph when anything baked into its kernel nodes changed.
-void Renderer::ensure_graph(const RayBuffers& rb, unsigned grid, size_t cap, int rounds, const float* volume_src) {
+typedef void (*march_kernel_t)(const FrameParams*, RayBuffers, float4*, float4*, const float*, uint32_t*, int, const uint32_t*, float4*, float4*);
+static march_kernel_t march_kernel(bool first, int shade) {
+  switch (shade) {
+    case 1: return first ? march_round_kernel<true, 1> : march_round_kernel<false, 1>;
+    case 2: return first ? march_round_kernel<true, 2> : march_round_kernel<false, 2>;
+    case 3: return first ? march_round_kernel<true, 3> : march_round_kernel<false, 3>;
+    default: return first ? march_round_kernel<true, 0> : march_round_kernel<false, 0>;
+  }
+}
+
+// (Re)build the loop graph of one pass when anything baked into its kernel nodes changed.
+void Renderer::ensure_graph(int pass, int shade, const RayBuffers& rb, unsigned grid, size_t cap, int rounds, const float* volume_src) {
+  uint32_t* cnt = counters.p + (size_t)pass * (kMaxRounds + 4);
+  const FrameParams* fpd = reinterpret_cast<const FrameParams*>(fp_dev.p) + pass;
   GraphKey key;
   memset(&key, 0, sizeof key);
   key.desc = vol->cfg.desc; key.params = vol->params.p;
   key.ptrs[0] = rb.rgba; key.ptrs[1] = rb.tn_ncb; key.ptrs[2] = rb.cell_base; key.ptrs[3] = rb.state; key.ptrs[4] = rb.jitter;
-  key.ptrs[5] = samples[0].p; key.ptrs[6] = samples[1].p; key.ptrs[7] = values.p; key.ptrs[8] = counters.p; key.ptrs[9] = accum.p;
-  key.ptrs[10] = frame_out(); key.ptrs[11] = fp_dev.p;
-  key.grid = grid; key.cap = cap; key.rounds = rounds; key.volume_src = volume_src;
-  if (loop_exec && !memcmp(&key, &graph_key, sizeof key)) return;
+  key.ptrs[5] = samples[0].p; key.ptrs[6] = samples[1].p; key.ptrs[7] = values.p; key.ptrs[8] = cnt; key.ptrs[9] = accum.p;
+  key.ptrs[10] = frame_out(); key.ptrs[11] = fpd; key.ptrs[12] = rb.ssh_org; key.ptrs[13] = rb.ssh_col; key.ptrs[14] = rb.ssh_rgba; key.ptrs[15] = rb.ssh_jitter;
+  key.grid = grid; key.cap = cap; key.rounds = rounds; key.volume_src = volume_src; key.shade = shade;
+  if (loop_exec[pass] && !memcmp(&key, &graph_key[pass], sizeof key)) return;
   VNR_CUDA(cudaStreamSynchronize(stream));
-  destroy_graph();
-  VNR_CUDA(cudaGraphCreate(&loop_graph, 0));
+  if (loop_exec[pass]) { cudaGraphExecDestroy(loop_exec[pass]); loop_exec[pass] = nullptr; }
+  if (loop_graph[pass]) { cudaGraphDestroy(loop_graph[pass]); loop_graph[pass] = nullptr; }
+  VNR_CUDA(cudaGraphCreate(&loop_graph[pass], 0));
   cudaGraphConditionalHandle handle;
-  VNR_CUDA(cudaGraphConditionalHandleCreate(&handle, loop_graph, 0, 0));
-  uint32_t* round_dev = counters.p + kMaxRounds + 2;
+  VNR_CUDA(cudaGraphConditionalHandleCreate(&handle, loop_graph[pass], 0, 0));
+  uint32_t* round_dev = cnt + kMaxRounds + 2;
   // node 1: initialise the round index and the loop condition from round 0
   cudaGraphNode_t init_node;
   {
-    uint32_t* c = counters.p; int init = 1, bound = rounds;
+    uint32_t* c = cnt; int init = 1, bound = rounds;
     void* args[] = {&c, &round_dev, &handle, &init, &bound};
     cudaKernelNodeParams kp = {};
     kp.func = (void*)advance_round_kernel; kp.gridDim = dim3(1); kp.blockDim = dim3(1); kp.kernelParams = args;
-    VNR_CUDA(cudaGraphAddKernelNode(&init_node, loop_graph, nullptr, 0, &kp));
+    VNR_CUDA(cudaGraphAddKernelNode(&init_node, loop_graph[pass], nullptr, 0, &kp));
   }
   // node 2: WHILE
   cudaGraphNodeParams wp = {};
   wp.type = cudaGraphNodeTypeConditional;
   wp.conditional.handle = handle; wp.conditional.type = cudaGraphCondTypeWhile; wp.conditional.size = 1;
   cudaGraphNode_t while_node;
-  VNR_CUDA(cudaGraphAddNode(&while_node, loop_graph, &init_node, 1, &wp));
+  VNR_CUDA(cudaGraphAddNode(&while_node, loop_graph[pass], &init_node, 1, &wp));
   cudaGraph_t body = wp.conditional.phGraph_out[0];
-  VNR_CUDA(cudaStreamCreateWithFlags(&capture_stream, cudaStreamNonBlocking));
+  if (!capture_stream) VNR_CUDA(cudaStreamCreateWithFlags(&capture_stream, cudaStreamNonBlocking));
   VNR_CUDA(cudaStreamBeginCaptureToGraph(capture_stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
-  cudaError_t e = volume_src ? launch_volume_samples(volume_src, vol->dims, samples[0].p, samples[1].p, values.p, counters.p + 2, round_dev, cap, capture_stream)
-                             : launch_decode_samples(vol->cfg.desc, vol->params.p, samples[0].p, samples[1].p, values.p, counters.p + 2, round_dev, cap, capture_stream);
-  march_round_kernel<false><<<grid, 128, 0, capture_stream>>>(reinterpret_cast<const FrameParams*>(fp_dev.p), rb, samples[0].p, samples[1].p, values.p, counters.p, 0, round_dev, accum.p, frame_out());
-  advance_round_kernel<<<1, 1, 0, capture_stream>>>(counters.p, round_dev, handle, 0, rounds);
+  cudaError_t e = volume_src ? launch_volume_samples(volume_src, vol->dims, samples[0].p, samples[1].p, values.p, cnt + 2, round_dev, cap, capture_stream)
+                             : launch_decode_samples(vol->cfg.desc, vol->params.p, samples[0].p, samples[1].p, values.p, cnt + 2, round_dev, cap, capture_stream);
+  march_kernel(false, shade)<<<grid, 128, 0, capture_stream>>>(fpd, rb, samples[0].p, samples[1].p, values.p, cnt, 0, round_dev, accum.p, frame_out());
+  advance_round_kernel<<<1, 1, 0, capture_stream>>>(cnt, round_dev, handle, 0, rounds);
   cudaGraph_t captured = nullptr;
   cudaError_t e2 = cudaStreamEndCapture(capture_stream, &captured);
   VNR_CUDA(e); VNR_CUDA(e2);
-  VNR_CUDA(cudaGraphInstantiate(&loop_exec, loop_graph, 0));
-  graph_key = key;
+  VNR_CUDA(cudaGraphInstantiate(&loop_exec[pass], loop_graph[pass], 0));
+  graph_key[pass] = key;
 }
+
+// vnrRenderMode -> shading of the marcher (renderer.cpp:152-225): 4-6 none, 7-9 gradient shading, 10-12 single-shade heuristic
+static int shade_of_mode(int mode) { return mode >= 10 ? 2 : (mode >= 7 ? 1 : 0); }
 
 void Renderer::render() {
   if (width <= 0 || height <= 0) return;                               // renderer.cpp:62
-  if (mode != 4 && mode != 5 && mode != 6) throw UnsupportedError("rendering mode " + std::to_string(mode) + " is outside this library's path (modes 4, 5 and 6)");
-  // value source of the wavefront: the network (modes 5 / 6), the progressively decoded volume (mode 4: the reference
-  // marches neural.texture(), api.cpp:429-438) or the ground truth (SimpleVolume renderer)
+  if (mode < 4 || mode > 12) throw UnsupportedError("rendering mode " + std::to_string(mode) + " is outside this library's path (ray-marching modes 4-12)");
+  // value source of the wavefront: the network (sample streaming / in-shader modes), the progressively decoded volume
+  // (decoding modes 4 / 7 / 10: the reference marches neural.texture(), api.cpp:429-438) or the ground truth (SimpleVolume renderer)
+  const bool decoding = mode == 4 || mode == 7 || mode == 10;
+  const int shade = shade_of_mode(mode);
   const float* volume_src = nullptr;
   if (gt_source) {
     if (!vol->have_gt) throw StateError("no ground-truth volume set");
     volume_src = vol->gt.p;
-  } else if (mode == 4) {
+  } else if (decoding) {
     if (!vol->decoded.p) { vol->decoded.alloc((size_t)vol->dims[0] * vol->dims[1] * vol->dims[2]); vol->decoded.zero(vol->stream); vol->decode_blob = 0; }
     volume_src = vol->decoded.p;
   } else if (!vol->have_params) throw StateError("the neural volume has no parameters");
   if (reset) frame_index = 0;
   frame_index++;
   reset = false;
-  FrameParams fp; fill_frame_params(fp);
-  const uint32_t n_rays = fp.n_rays;
+  FrameParams fp[2]; fill_frame_params(fp[0]);
+  fp[0].shade_mode = shade; fp[1] = fp[0]; fp[1].shade_mode = 3;
+  const uint32_t n_rays = fp[0].n_rays;
   const int rounds = round_bound();
+  const int n_pass = shade == 2 ? 2 : 1;
   // make the volume's pending work (training, tfn upload) visible to the frame stream
   VNR_CUDA(cudaEventRecord(vol_ready, vol->stream));
   VNR_CUDA(cudaStreamWaitEvent(stream, vol_ready, 0));
 
-  const size_t cap = (size_t)n_rays * n_iters;
+  const size_t cap = (size_t)n_rays * n_iters * (shade == 1 ? 4 : 1);
   samples[0].ensure(cap); samples[1].ensure(cap); values.ensure(cap);
   ray_rgba.ensure(n_rays); ray_tn.ensure(n_rays); ray_cell.ensure(n_rays); ray_state.ensure(n_rays); ray_jitter.ensure(n_rays);
-  counters.ensure(kMaxRounds + 4);
+  if (shade == 2) { ssh_org.ensure(n_rays); ssh_col.ensure(n_rays); ssh_rgba.ensure(n_rays); ssh_jitter.ensure(n_rays); }
+  const size_t cstride = kMaxRounds + 4;
+  counters.ensure(2 * cstride);
   if (rounds + 3 > kMaxRounds) throw UnsupportedError("sampling rate too high for the round bound");
   VNR_CUDA(cudaMemsetAsync(counters.p, 0, counters.bytes(), stream));
-  RayBuffers rb{ray_rgba.p, ray_tn.p, ray_cell.p, ray_state.p, ray_jitter.p};
+  RayBuffers rb{ray_rgba.p, ray_tn.p, ray_cell.p, ray_state.p, ray_jitter.p, ssh_org.p, ssh_col.p, ssh_rgba.p, ssh_jitter.p};
   const unsigned grid = (n_rays + 127) / 128;
   launches = 0;
   prof_used = 0;
   if (profiling) {
-    while ((int)prof_events.size() < 2 * rounds) { cudaEvent_t e; VNR_CUDA(cudaEventCreate(&e)); prof_events.push_back(e); }
+    while ((int)prof_events.size() < 2 * rounds * n_pass) { cudaEvent_t e; VNR_CUDA(cudaEventCreate(&e)); prof_events.push_back(e); }
   }
-  fp_dev.ensure(sizeof(FrameParams));
-  // 200-odd bytes from pageable memory: staged by the driver at call time, ordered on the stream
-  VNR_CUDA(cudaMemcpyAsync(fp_dev.p, &fp, sizeof fp, cudaMemcpyHostToDevice, stream));
+  fp_dev.ensure(2 * sizeof(FrameParams));
+  // a few hundred bytes from pageable memory: staged by the driver at call time, ordered on the stream
+  VNR_CUDA(cudaMemcpyAsync(fp_dev.p, fp, sizeof fp, cudaMemcpyHostToDevice, stream));
   const bool graph_loop = use_graph && !profiling;
-  if (n_rays) {
-    march_round_kernel<true><<<grid, 128, 0, stream>>>(reinterpret_cast<const FrameParams*>(fp_dev.p), rb, samples[0].p, samples[1].p, nullptr, counters.p, 0, nullptr, accum.p, frame_out());
+  for (int pass = 0; pass < n_pass && n_rays; ++pass) {
+    const int sh = pass == 1 ? 3 : shade;
+    uint32_t* cnt = counters.p + (size_t)pass * cstride;
+    const FrameParams* fpd = reinterpret_cast<const FrameParams*>(fp_dev.p) + pass;
+    march_kernel(true, sh)<<<grid, 128, 0, stream>>>(fpd, rb, samples[0].p, samples[1].p, nullptr, cnt, 0, nullptr, accum.p, frame_out());
     if (graph_loop) {
       // device-driven loop: WHILE (round has samples) { decode; compose + march; advance }
-      ensure_graph(rb, grid, cap, rounds, volume_src);
-      VNR_CUDA(cudaGraphLaunch(loop_exec, stream));
+      ensure_graph(pass, sh, rb, grid, cap, rounds, volume_src);
+      VNR_CUDA(cudaGraphLaunch(loop_exec[pass], stream));
     } else {
       for (int r = 0; r < rounds; ++r) {
         if (profiling) VNR_CUDA(cudaEventRecord(prof_events[prof_used++], stream));
-        if (volume_src) VNR_CUDA(launch_volume_samples(volume_src, vol->dims, samples[r & 1].p, nullptr, values.p, counters.p + 2 + r, nullptr, cap, stream));
-        else VNR_CUDA(launch_decode_samples(vol->cfg.desc, vol->params.p, samples[r & 1].p, nullptr, values.p, counters.p + 2 + r, nullptr, cap, stream));
+        if (volume_src) VNR_CUDA(launch_volume_samples(volume_src, vol->dims, samples[r & 1].p, nullptr, values.p, cnt + 2 + r, nullptr, cap, stream));
+        else VNR_CUDA(launch_decode_samples(vol->cfg.desc, vol->params.p, samples[r & 1].p, nullptr, values.p, cnt + 2 + r, nullptr, cap, stream));
         if (profiling) VNR_CUDA(cudaEventRecord(prof_events[prof_used++], stream));
-        march_round_kernel<false><<<grid, 128, 0, stream>>>(reinterpret_cast<const FrameParams*>(fp_dev.p), rb, samples[0].p, samples[1].p, values.p, counters.p, r + 1, nullptr, accum.p, frame_out());
+        march_kernel(false, sh)<<<grid, 128, 0, stream>>>(fpd, rb, samples[0].p, samples[1].p, values.p, cnt, r + 1, nullptr, accum.p, frame_out());
       }
     }
-    finalize_kernel<<<grid, 128, 0, stream>>>(reinterpret_cast<const FrameParams*>(fp_dev.p), rb, counters.p + kMaxRounds + 3, accum.p, frame_out());
+    finalize_kernel<<<grid, 128, 0, stream>>>(fpd, rb, cnt + kMaxRounds + 3, accum.p, frame_out());
     VNR_CUDA(cudaGetLastError());
-    launches = graph_loop ? 0 : 2 + 2 * (uint64_t)rounds;     // graph path: counted from the device counters in stats()
+    if (!graph_loop) launches += 2 + 2 * (uint64_t)rounds;     // graph path: counted from the device counters in stats()
   }
   last_graph = graph_loop;
   last_rounds = rounds;
+  last_passes = n_pass;
   // framebuffer.download_async (renderer.cpp:133)
   downloaded = false;
   if (download) { VNR_CUDA(cudaMemcpyAsync(h_frame[cur], frame.p, frame.bytes(), cudaMemcpyDeviceToHost, stream)); downloaded = true; }
-  VNR_CUDA(cudaMemcpyAsync(h_counters, counters.p, sizeof(uint32_t) * (kMaxRounds + 4), cudaMemcpyDeviceToHost, stream));
+  VNR_CUDA(cudaMemcpyAsync(h_counters, counters.p, sizeof(uint32_t) * 2 * cstride, cudaMemcpyDeviceToHost, stream));
   VNR_CUDA(cudaEventRecord(frame_done[cur], stream));
   rendered = true;
 }
@@ -440,7 +533,8 @@ void Renderer::profile(float* decode_ms, int* decode_launches) {
   VNR_CUDA(cudaStreamSynchronize(stream));
   float total = 0.f; int n = 0;
   for (int k = 0; k + 1 < prof_used; k += 2) {
-    if (h_counters[2 + k / 2] == 0) continue;           // empty round: the kernel exits immediately
+    const int pass = (k / 2) / last_rounds, r = (k / 2) % last_rounds;
+    if (h_counters[(size_t)pass * (kMaxRounds + 4) + 2 + r] == 0) continue;           // empty round: the kernel exits immediately
     float ms = 0.f;
     VNR_CUDA(cudaEventElapsedTime(&ms, prof_events[k], prof_events[k + 1]));
     total += ms; ++n;
@@ -451,16 +545,16 @@ void Renderer::profile(float* decode_ms, int* decode_launches) {
 
 void Renderer::stats(uint64_t* s4) {
   VNR_CUDA(cudaStreamSynchronize(stream));
-  if (last_graph) {            // first round + loop init + 3 kernels per non-empty round + finalize
-    uint64_t nonempty = 0;
-    for (int r = 0; r <= last_rounds && r < kMaxRounds; ++r) if (h_counters[2 + r]) ++nonempty;
-    launches = 3 + 3 * nonempty;
+  uint64_t dec = 0, rounds = 0, comp = 0, leftover = 0;
+  for (int pass = 0; pass < last_passes; ++pass) {
+    const uint32_t* c = h_counters + (size_t)pass * (kMaxRounds + 4);
+    for (int r = 0; r <= last_rounds && r < kMaxRounds; ++r) { dec += c[2 + r]; if (c[2 + r]) ++rounds; }
+    comp += c[1]; leftover += c[kMaxRounds + 3];
   }
-  s4[0] = h_counters[0]; s4[2] = h_counters[1];
-  uint64_t dec = 0, rounds = 0;
-  for (int r = 0; r <= last_rounds && r < kMaxRounds; ++r) { dec += h_counters[2 + r]; if (h_counters[2 + r]) ++rounds; }
-  s4[1] = dec; s4[3] = rounds;
-  if (h_counters[kMaxRounds + 3]) throw StateError("round bound exceeded: " + std::to_string(h_counters[kMaxRounds + 3]) + " rays were cut short");
+  // graph path: first round + loop init + 3 kernels per non-empty round + finalize, per pass
+  if (last_graph) launches = 3 * (uint64_t)last_passes + 3 * rounds;
+  s4[0] = h_counters[0]; s4[1] = dec; s4[2] = comp; s4[3] = rounds;
+  if (leftover) throw StateError("round bound exceeded: " + std::to_string(leftover) + " rays were cut short");
 }
 
 }  // namespace vnr

@@ -14,9 +14,9 @@ constexpr int kMaxRounds = 1024;
 struct GraphKey {
   DecoderDesc desc;
   const void* params;
-  const void* ptrs[12];
+  const void* ptrs[16];
   const void* volume_src;               // non-null: trilinear volume lookup instead of the network decode
-  unsigned grid; size_t cap; int rounds;
+  unsigned grid; size_t cap; int rounds; int shade;
 };
 
 struct Renderer {
@@ -35,11 +35,12 @@ struct Renderer {
   float scale[3] = {1, 1, 1};
   float clip_lo[3] = {0, 0, 0}, clip_hi[3] = {1, 1, 1};
   int frame_index = 0; bool reset = true, rendered = false;
-  int cur = 0, last_rounds = 0;
+  int cur = 0, last_rounds = 1, last_passes = 1;
+  float light_dir[3] = {0.7f, 0.9f, 0.4f};                                // light_directional_dir, instantvnr_types.h:148 (persistent sign flips)
 
-  DevBuf<float4> accum, frame, samples[2], ray_rgba, ray_tn;
+  DevBuf<float4> accum, frame, samples[2], ray_rgba, ray_tn, ssh_org, ssh_col, ssh_rgba;
   DevBuf<int4> ray_cell;
-  DevBuf<float> values, ray_jitter;
+  DevBuf<float> values, ray_jitter, ssh_jitter;
   DevBuf<uint32_t> ray_state, counters;
   float4* h_frame[2] = {nullptr, nullptr};
   uint32_t* h_counters = nullptr;
@@ -52,8 +53,8 @@ struct Renderer {
   DevBuf<uint8_t> fp_dev;               // FrameParams of the frame in flight (device copy)
   // device-driven wavefront loop (CUDA graph with a WHILE node); off: bounded host-enqueued rounds
   bool use_graph = true, last_graph = false;
-  cudaGraph_t loop_graph = nullptr; cudaGraphExec_t loop_exec = nullptr; cudaStream_t capture_stream = nullptr;
-  GraphKey graph_key;
+  cudaGraph_t loop_graph[2] = {nullptr, nullptr}; cudaGraphExec_t loop_exec[2] = {nullptr, nullptr}; cudaStream_t capture_stream = nullptr;
+  GraphKey graph_key[2];                // [1]: the shadow pass of the single-shade heuristic
   // multi-GPU: finished pixels are stored here instead of `frame` (rank 0's frame buffer, peer-mapped)
   float4* frame_target = nullptr;
   float4* frame_out() { return frame_target ? frame_target : frame.p; }
@@ -65,7 +66,7 @@ struct Renderer {
   void fill_frame_params(FrameParams& fp);
   int round_bound() const;
   void destroy_graph();
-  void ensure_graph(const RayBuffers& rb, unsigned grid, size_t cap, int rounds, const float* volume_src);
+  void ensure_graph(int pass, int shade, const RayBuffers& rb, unsigned grid, size_t cap, int rounds, const float* volume_src);
   void render();
   void download_now();
   const float* map_frame();

@@ -203,7 +203,7 @@ class Frame:
     """Per-frame constants (LaunchParams / DeviceVolume subset, instantvnr_types.h:89-149)."""
 
     def __init__(self, dims, width, height, cam_from, cam_at, cam_up, fovy=60.0, sampling_rate=1.0,
-                 tfn_range=(0.0, 1.0), frame_index=1, n_iters=16, tex_round=0):
+                 tfn_range=(0.0, 1.0), frame_index=1, n_iters=16, tex_round=0, shade_mode=0, light_dir=None):
         self.f = np.zeros(FRAME_FLOATS, dtype=np.float32)
         self.i = np.zeros(FRAME_INTS, dtype=np.int32)
         d = np.array(dims, dtype=np.int32)
@@ -213,6 +213,11 @@ class Frame:
         self.i[:10] = [width, height, frame_index, n_iters, tex_round, md[0], md[1], md[2], 0, 0]
         self.dims = tuple(int(x) for x in dims)
         self.width, self.height = width, height
+        # shaded modes (0 none, 1 gradient shading, 2 single-shade heuristic + shadow pass); light_dir is the renderer's
+        # persistent light direction before this frame's sign correction (renderer.cpp:98-101)
+        self.light_dir = np.zeros(3, dtype=np.float32)
+        lib().orc_frame_shading(_p(self.f), _p(self.i), C.c_int(shade_mode), _p(d), _p(_f32(light_dir)) if light_dir is not None else None,
+                                _p(self.light_dir))
 
     def set_tfn_sizes(self, n_color, n_alpha):
         self.i[8], self.i[9] = n_color, n_alpha

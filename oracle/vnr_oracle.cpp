@@ -821,21 +821,83 @@ ORC_API void orc_frame_setup(const float* from, const float* at, const float* up
   p[35] = tfn_range[0]; p[36] = tfn_range[1]; p[37] = 1.f / (tfn_range[1] - tfn_range[0]);
 }
 
-typedef void (*orc_decode_cb)(const float* coords, size_t n, float* out, void* user);
+// Shaded modes: fills the light / transform entries of the frame block.  light_dir_in is the renderer's persistent
+// light direction (default {0.7, 0.9, 0.4}, instantvnr_types.h:148); it is flipped when it points along the camera
+// direction (renderer.cpp:98-101) and the corrected vector is also returned through light_dir_out.
+ORC_API void orc_frame_shading(float* p /*64*/, int* ip /*16*/, int shade_mode, const int* dims, const float* light_dir_in, float* light_dir_out) {
+  V3 L = light_dir_in ? v3(light_dir_in[0], light_dir_in[1], light_dir_in[2]) : v3(0.7f, 0.9f, 0.4f);
+  if (dot(v3(p[3], p[4], p[5]), L) > 0.f) L = v3(-L.x, -L.y, -L.z);
+  p[38] = L.x; p[39] = L.y; p[40] = L.z;
+  for (int k = 0; k < 3; ++k) { p[41 + k] = (float)dims[k]; p[44 + k] = 1.f / (float)dims[k]; }
+  ip[10] = shade_mode;
+  if (light_dir_out) { light_dir_out[0] = L.x; light_dir_out[1] = L.y; light_dir_out[2] = L.z; }
+}
 
-struct RayState { uint32_t pixel; float jitter, alpha; float color[3]; DDAIter it; bool alive; V3 org, dir; float tmin, tmax; };
+// Shading constants of LaunchParams (instantvnr_types.h:137-148) and the per-frame vectors the shaded modes need.
+struct Shading {
+  int mode;                  // 0 NO_SHADING, 1 GRADIENT_SHADING, 2 SINGLE_SHADE_HEURISTIC (+ SHADOW pass)
+  V3 light_dir;              // world space, already sign-corrected against the camera (renderer.cpp:98-101)
+  V3 otw_diag;               // object->world linear part (network.cu:569: diag(dims * scaling))
+  V3 grad_step;              // object.cpp:305: 1 / dims
+};
+static const float kShadingScale = 0.95f;                                 // scivis_shading_scale :140
+static const float kMatGradient[4] = {.6f, .9f, .4f, 40.f};               // mat_gradient_shading :142 (ambient, diffuse, specular, shininess)
+static const float kShadowSamplingScale = 2.f;                            // raymarching_shadow_sampling_scale :137
 
-// The sample-streaming marcher (method_raymarching.cu:931-958): raygen (:840-875),
+static inline float lerp1(float f, float a, float b) { return fmaf(f, b, (1.f - f) * a); }   // gdt lerp(f,a,b) = (1-f)*a + f*b
+
+// raytracing.h:214-221
+static inline V3 shade_simple_light(V3 ray_dir, V3 normal, V3 albedo) {
+  if (dot(normal, normal) > 1.0e-6f) {
+    const V3 n = normalize(normal);
+    const float s = fmaf(.8f, fabsf(dot(v3(-ray_dir.x, -ray_dir.y, -ray_dir.z), n)), 0.2f);
+    return s * albedo;
+  }
+  return v3(0, 0, 0);
+}
+// raytracing.h:223-246 (light_diffuse = light_directional_rgb = 1; light_ambient is not used by the function body)
+static inline V3 shade_scivis_light(V3 ray_dir, V3 normal, V3 albedo, const float* mat, V3 light_dir) {
+  V3 color = v3(0, 0, 0);
+  if (dot(normal, normal) > 1.0e-6f) {
+    const V3 L = normalize(light_dir), N = normalize(normal), V = v3(-ray_dir.x, -ray_dir.y, -ray_dir.z);
+    color = color + mat[0] * albedo;
+    const float cosNL = fmaxf(dot(N, L), 0.f);
+    if (cosNL > 0.f) {
+      color = color + (mat[1] * cosNL) * albedo;
+      const V3 H = normalize(L + V);
+      const float cosNH = fmaxf(dot(N, H), 0.f);
+      const float sp = mat[2] * powf(cosNH, mat[3]);
+      color = color + v3(sp, sp, sp);
+    }
+  }
+  const V3 s2 = shade_simple_light(ray_dir, normal, albedo);
+  return v3(lerp1(0.5f, s2.x, color.x), lerp1(0.5f, s2.y, color.y), lerp1(0.5f, s2.z, color.z));
+}
+// GRADIENT_SHADING body of the compose kernel (method_raymarching.cu:773-788) and of raymarching_traceray (:436-455):
+// `g` = forward differences already divided by the step (= -No)
+static inline void shade_gradient(const Frame& fr, const Shading& sh, V3 dir_obj, V3 g, float rgb[3]) {
+  const V3 No = v3(-g.x, -g.y, -g.z);
+  const V3 Nw = v3(No.x * fr.wto_l[0], No.y * fr.wto_l[4], No.z * fr.wto_l[8]);      // xfmNormal(otw, No): inverse-transpose of a diagonal
+  const V3 dirw = dir_obj * sh.otw_diag;                                              // xfmVector(otw, ray.dir)
+  const V3 sc = shade_scivis_light(dirw, Nw, v3(rgb[0], rgb[1], rgb[2]), kMatGradient, sh.light_dir);
+  rgb[0] = lerp1(kShadingScale, rgb[0], sc.x); rgb[1] = lerp1(kShadingScale, rgb[1], sc.y); rgb[2] = lerp1(kShadingScale, rgb[2], sc.z);
+}
+
+struct RayState { uint32_t pixel; float jitter, alpha; float color[3]; DDAIter it; bool alive; V3 org, dir; float tmin, tmax;
+                  V3 hi_org; float hi_color[3]; float hi_alpha; };
+
+// The sample-streaming marcher (method_raymarching.cu:931-958): raygen (:840-900),
 // then rounds of [intersect (:687-730) -> batch decode -> compose (:732-838)].
 // `volume_mode` 0: decode through the network (params); 1: sample the ground-truth
 // volume (iterative_sampling_groundtruth_kernel :902-915 / sampleVolume raytracing.h:107-112).
-// jitter_mode 0: gdt::LCG<16>(frame_index, pixel) first float; 1: fixed 0.5.
-// stats: [0]=rays hit, [1]=samples decoded, [2]=samples composited, [3]=rounds
-ORC_API void orc_render(const int* cfg, float pls, const uint16_t* params_f16, int acc_mode,
-                        const float* fparams, const int* iparams, const float* mc_max_opacity,
-                        const float* colors, const float* alphas,
-                        int volume_mode, const float* gt_volume, const int* gt_dims, int jitter_mode,
-                        float* accum /*w*h*4, in/out*/, float* frame /*w*h*4*/, uint64_t* stats) {
+// jitter_mode 0: gdt::LCG<16>(frame_index, pixel) floats (first: camera ray, second: shadow ray); 1: fixed 0.5.
+// shade mode 2 runs the camera pass and then the SHADOW pass (do_raymarching_iterative :960-973).
+// stats: [0]=rays hit, [1]=samples decoded (network / volume evaluations), [2]=samples composited, [3]=rounds
+static void render_wavefront(const int* cfg, float pls, const uint16_t* params_f16, int acc_mode,
+                             const float* fparams, const int* iparams, const float* mc_max_opacity,
+                             const float* colors, const float* alphas,
+                             int volume_mode, const float* gt_volume, const int* gt_dims, int jitter_mode, const Shading& sh,
+                             float* accum /*w*h*4, in/out*/, float* frame /*w*h*4*/, uint64_t* stats) {
   Model m = make_model(cfg, pls);
   const h16* grid = params_f16 ? params_f16 + m.n_mlp : nullptr;
   const MlpF mf = params_f16 ? make_mlpf(m, params_f16) : MlpF();
@@ -850,81 +912,153 @@ ORC_API void orc_render(const int* cfg, float pls, const uint16_t* params_f16, i
       frame[4 * (size_t)pidx + c] = v[c] / (float)fr.frame_index;
     }
   };
-  uint64_t n_hit = 0, n_dec = 0, n_comp = 0, n_rounds = 0;
-#pragma omp parallel for schedule(static) reduction(+ : n_hit)
-  for (long long i = 0; i < (long long)npix; ++i) {
-    RayState& r = rays[i];
-    r.pixel = (uint32_t)i; r.alpha = 0.f; r.color[0] = r.color[1] = r.color[2] = 0.f;
-    if (jitter_mode == 0) { LcgTea16 rng((uint32_t)fr.frame_index, (uint32_t)i); r.jitter = rng.next(); } else r.jitter = 0.5f;
-    compute_ray(fr, r.pixel, r.org, r.dir);
-    r.tmin = 0.f; r.tmax = FLOAT_LARGE;
-    r.alive = intersect_box(r.tmin, r.tmax, r.org, r.dir, fr.bbox_lo, fr.bbox_hi);
-    if (r.alive) {
-      V3 mo = r.org * fr.mc_spacing_rcp, md = r.dir * fr.mc_spacing_rcp;
-      r.it.init(mo, md, r.tmin, r.tmax, fr.mc_dims);
-      ++n_hit;
-    } else {
-      float rgba[4] = {0, 0, 0, 0};
-      write_pixel(r.pixel, rgba);
+  auto sample_value = [&](const float* c) -> float {
+    if (volume_mode == 0) {
+      h16 enc[128]; encode_one(m, grid, c, enc);
+      return mlp_forward_one(m, mf, enc, acc_mode, nullptr);
     }
-  }
+    // sampleVolume: p*(1-rdims)+0.5*rdims then tex3D
+    float q[3];
+    for (int d = 0; d < 3; ++d) { float rd = 1.f / (float)gt_dims[d]; q[d] = fmaf(c[d], (1.f - rd), 0.5f * rd); }
+    return tex3d_linear(gt_volume, gt_dims, q[0], q[1], q[2], fr.tex_round);
+  };
+  // per-pixel outputs of the SINGLE_SHADE_HEURISTIC camera pass (final_highest_*, shading_color, jitter_ssh)
+  std::vector<float> fin_org, fin_color, fin_alpha, shading_color, jitter_ssh;
+  if (sh.mode == 2) { fin_org.assign(3 * npix, 0.f); fin_color.assign(3 * npix, 0.f); fin_alpha.assign(npix, 0.f); shading_color.assign(4 * npix, 0.f); jitter_ssh.assign(npix, 0.5f); }
+  uint64_t n_hit = 0, n_dec = 0, n_comp = 0, n_rounds = 0;
   const int NI = fr.n_iters;
-  bool any = n_hit > 0;
-  while (any) {
-    ++n_rounds;
-    uint64_t dec = 0, comp = 0, alive = 0;
-#pragma omp parallel for schedule(dynamic, 64) reduction(+ : dec, comp, alive)
+  const int n_pass = sh.mode == 2 ? 2 : 1;
+  for (int pass = 0; pass < n_pass; ++pass) {
+    const bool shadow = pass == 1;
+    const int mode = shadow ? 3 : sh.mode;
+    uint64_t hit = 0;
+    // ---- raygen: iterative_raygen_kernel_camera :840-875 / iterative_raygen_kernel_shadow :877-900
+#pragma omp parallel for schedule(static) reduction(+ : hit)
     for (long long i = 0; i < (long long)npix; ++i) {
       RayState& r = rays[i];
-      if (!r.alive) continue;
-      // --- intersect: replay the iterator to emit <= NI sample coordinates
-      float coords[64 * 3]; float tt[64 * 2]; int k = 0;
-      DDAIter it = r.it;
-      march_exec(fr, it, r.org, r.dir, r.tmin, r.tmax, [&](float tx, float ty) {
-        const float tl = fmaf(r.jitter, ty, (1 - r.jitter) * tx);   // lerp(jitter, t.x, t.y) instantvnr_types.h:162-166
-        V3 c = madd(tl, r.dir, r.org);
-        coords[3 * k] = c.x; coords[3 * k + 1] = c.y; coords[3 * k + 2] = c.z;
-        tt[2 * k] = tx; tt[2 * k + 1] = ty;
-        return (++k) < NI;
-      });
-      // --- decode
-      float vals[64];
-      for (int s = 0; s < k; ++s) {
-        if (volume_mode == 0) {
-          h16 enc[128]; encode_one(m, grid, coords + 3 * s, enc);
-          vals[s] = mlp_forward_one(m, mf, enc, acc_mode, nullptr);
-        } else {
-          // sampleVolume: p*(1-rdims)+0.5*rdims then tex3D
-          float q[3];
-          for (int d = 0; d < 3; ++d) { float rd = 1.f / (float)gt_dims[d]; q[d] = fmaf(coords[3 * s + d], (1.f - rd), 0.5f * rd); }
-          vals[s] = tex3d_linear(gt_volume, gt_dims, q[0], q[1], q[2], fr.tex_round);
-        }
+      r.pixel = (uint32_t)i; r.alpha = 0.f; r.color[0] = r.color[1] = r.color[2] = 0.f;
+      r.hi_org = v3(0, 0, 0); r.hi_color[0] = r.hi_color[1] = r.hi_color[2] = 0.f; r.hi_alpha = 0.f;
+      if (!shadow) {
+        if (jitter_mode == 0) { LcgTea16 rng((uint32_t)fr.frame_index, (uint32_t)i); r.jitter = rng.next(); if (sh.mode == 2) jitter_ssh[i] = rng.next(); }
+        else r.jitter = 0.5f;
+        compute_ray(fr, r.pixel, r.org, r.dir);
+      } else {
+        r.jitter = jitter_ssh[i];
+        r.org = v3(fin_org[3 * i], fin_org[3 * i + 1], fin_org[3 * i + 2]);           // compute_ray<SHADOW> :640-654
+        r.dir = xfm_vec(fr.wto_l, normalize(sh.light_dir));
       }
-      dec += (uint64_t)k;
-      // --- compose: replay again, consuming values (the iterator state saved is this one)
-      int kk = 0;
-      march_exec(fr, r.it, r.org, r.dir, r.tmin, r.tmax, [&](float tx, float ty) {
-        float rgb[3], a;
-        classify(fr, vals[kk], ty - tx, rgb, a);
-        const float tr = 1.f - r.alpha;
-        r.alpha = fmaf(tr, a, r.alpha);
-        for (int c = 0; c < 3; ++c) r.color[c] = fmaf(tr * rgb[c], a, r.color[c]);
-        ++comp;
-        return ((++kk) < NI) && (r.alpha < NEARLY_ONE);
-      });
-      V3 md = r.dir * fr.mc_spacing_rcp;
-      const bool resumable = r.it.resumable(md, r.tmin, r.tmax, fr.mc_dims);
-      if (r.alpha < NEARLY_ONE && resumable) { ++alive; }
-      else {
-        r.alive = false;
-        float rgba[4] = {r.color[0], r.color[1], r.color[2], r.alpha};
-#pragma omp critical
+      r.tmin = 0.f; r.tmax = FLOAT_LARGE;
+      r.alive = intersect_box(r.tmin, r.tmax, r.org, r.dir, fr.bbox_lo, fr.bbox_hi);
+      if (shadow) r.alive = r.alive && fin_alpha[i] > 0.f;
+      if (r.alive) {
+        V3 mo = r.org * fr.mc_spacing_rcp, md = r.dir * fr.mc_spacing_rcp;
+        r.it.init(mo, md, r.tmin, r.tmax, fr.mc_dims);
+        ++hit;
+      } else if (shadow) {
+        write_pixel(r.pixel, &shading_color[4 * i]);
+      } else if (sh.mode != 2) {
+        float rgba[4] = {0, 0, 0, 0};
         write_pixel(r.pixel, rgba);
       }
     }
-    n_dec += dec; n_comp += comp; any = alive > 0;
+    if (!shadow) n_hit = hit;
+    bool any = hit > 0;
+    while (any) {
+      ++n_rounds;
+      uint64_t dec = 0, comp = 0, alive = 0;
+#pragma omp parallel for schedule(dynamic, 64) reduction(+ : dec, comp, alive)
+      for (long long i = 0; i < (long long)npix; ++i) {
+        RayState& r = rays[i];
+        if (!r.alive) continue;
+        // --- intersect: replay the iterator to emit <= NI sample coordinates
+        float coords[64 * 3]; int k = 0;
+        DDAIter it = r.it;
+        march_exec(fr, it, r.org, r.dir, r.tmin, r.tmax, [&](float tx, float ty) {
+          const float tl = fmaf(r.jitter, ty, (1 - r.jitter) * tx);   // lerp(jitter, t.x, t.y) instantvnr_types.h:162-166
+          V3 c = madd(tl, r.dir, r.org);
+          coords[3 * k] = c.x; coords[3 * k + 1] = c.y; coords[3 * k + 2] = c.z;
+          return (++k) < NI;
+        });
+        // --- decode (GRADIENT_SHADING: + three forward-difference positions per sample, :719-726)
+        float vals[64], gvals[64 * 3];
+        for (int s = 0; s < k; ++s) {
+          vals[s] = sample_value(coords + 3 * s);
+          if (mode == 1) {
+            const float gs[3] = {sh.grad_step.x, sh.grad_step.y, sh.grad_step.z};
+            for (int d = 0; d < 3; ++d) {
+              float q[3] = {coords[3 * s], coords[3 * s + 1], coords[3 * s + 2]};
+              q[d] = q[d] + gs[d];
+              gvals[3 * s + d] = sample_value(q);
+            }
+          }
+        }
+        dec += (uint64_t)k * (mode == 1 ? 4 : 1);
+        // --- compose: replay again, consuming values (the iterator state saved is this one)
+        int kk = 0;
+        march_exec(fr, r.it, r.org, r.dir, r.tmin, r.tmax, [&](float tx, float ty) {
+          float rgb[3], a;
+          classify(fr, vals[kk], ty - tx, rgb, a);
+          if (mode == 1) {
+            const V3 g = v3((gvals[3 * kk] - vals[kk]) / sh.grad_step.x, (gvals[3 * kk + 1] - vals[kk]) / sh.grad_step.y, (gvals[3 * kk + 2] - vals[kk]) / sh.grad_step.z);
+            shade_gradient(fr, sh, r.dir, g, rgb);
+          } else if (mode == 2) {
+            const float contrib = (1.f - r.alpha) * a;
+            if (r.hi_alpha < contrib) {
+              r.hi_org = v3(coords[3 * kk], coords[3 * kk + 1], coords[3 * kk + 2]);
+              r.hi_color[0] = rgb[0]; r.hi_color[1] = rgb[1]; r.hi_color[2] = rgb[2];
+              r.hi_alpha = contrib;
+            }
+          }
+          const float tr = 1.f - r.alpha;
+          r.alpha = fmaf(tr, a, r.alpha);
+          if (mode != 3) for (int c = 0; c < 3; ++c) r.color[c] = fmaf(tr * rgb[c], a, r.color[c]);
+          ++comp;
+          return ((++kk) < NI) && (r.alpha < NEARLY_ONE);
+        });
+        V3 md = r.dir * fr.mc_spacing_rcp;
+        const bool resumable = r.it.resumable(md, r.tmin, r.tmax, fr.mc_dims);
+        if (r.alpha < NEARLY_ONE && resumable) { ++alive; }
+        else {
+          r.alive = false;
+          if (mode == 3) {                                   // :813-819
+            const float tr = 1.f - r.alpha;
+            const float* sc = &shading_color[4 * i];
+            float rgba[4];
+            for (int c = 0; c < 3; ++c) rgba[c] = lerp1(kShadingScale, sc[c], (fin_color[3 * i + c] * sc[3]) * tr);
+            rgba[3] = sc[3];
+#pragma omp critical
+            write_pixel(r.pixel, rgba);
+          } else if (mode == 2) {                            // :820-826
+            fin_org[3 * i] = r.hi_org.x; fin_org[3 * i + 1] = r.hi_org.y; fin_org[3 * i + 2] = r.hi_org.z;
+            for (int c = 0; c < 3; ++c) { fin_color[3 * i + c] = r.hi_color[c]; shading_color[4 * i + c] = r.color[c]; }
+            fin_alpha[i] = r.hi_alpha; shading_color[4 * i + 3] = r.alpha;
+          } else {
+            float rgba[4] = {r.color[0], r.color[1], r.color[2], r.alpha};
+#pragma omp critical
+            write_pixel(r.pixel, rgba);
+          }
+        }
+      }
+      n_dec += dec; n_comp += comp; any = alive > 0;
+    }
   }
   if (stats) { stats[0] = n_hit; stats[1] = n_dec; stats[2] = n_comp; stats[3] = n_rounds; }
+}
+
+static Shading shading_from(const float* p, const int* ip) {
+  Shading sh;
+  sh.mode = ip[10];
+  sh.light_dir = v3(p[38], p[39], p[40]); sh.otw_diag = v3(p[41], p[42], p[43]); sh.grad_step = v3(p[44], p[45], p[46]);
+  return sh;
+}
+
+ORC_API void orc_render(const int* cfg, float pls, const uint16_t* params_f16, int acc_mode,
+                        const float* fparams, const int* iparams, const float* mc_max_opacity,
+                        const float* colors, const float* alphas,
+                        int volume_mode, const float* gt_volume, const int* gt_dims, int jitter_mode,
+                        float* accum /*w*h*4, in/out*/, float* frame /*w*h*4*/, uint64_t* stats) {
+  render_wavefront(cfg, pls, params_f16, acc_mode, fparams, iparams, mc_max_opacity, colors, alphas, volume_mode, gt_volume, gt_dims,
+                   jitter_mode, shading_from(fparams, iparams), accum, frame, stats);
 }
 
 // expose pieces for unit tests

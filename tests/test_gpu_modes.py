@@ -97,3 +97,45 @@ def test_neural_frame_psnr_within_a_tenth_of_a_db_of_the_reference_arithmetic():
         deltas.append(abs(a - b))
     print("PSNR deltas (dB):", deltas)
     assert max(deltas) <= 0.1
+
+
+@pytest.mark.parametrize("mode,shade", [(8, 1), (11, 2)])
+def test_shaded_sample_streaming_modes_match_the_oracle(mode, shade):
+    """Modes 8 (gradient shading: 4 decodes per sample, Phong-style scivis light, method_raymarching.cu:719-726,773-788)
+    and 11 (single-shade heuristic: camera pass + shadow pass, :789-795,813-833,877-900) on the same wavefront, for the
+    network and for the ground-truth volume.  Tolerance: PSNR >= 50 dB and max-abs <= 4/255 vs the oracle frame."""
+    vol, gt, rgb, alpha = _trained_volume(200)
+    m = O.ModelCfg(CFG["n_levels"], CFG["n_features"], CFG["log2_hashmap"], CFG["base_res"], 2.0, CFG["n_hidden"])
+    p16 = vol.get_params_f16()
+    _, _, mo = vol.get_macrocell()
+    colors = np.concatenate([rgb, np.ones((rgb.shape[0], 1), np.float32)], 1)
+    plain, _ = _frame(vol, mode=5)
+    for view in (2, 9):
+        fr = O.Frame(DIMS, 72, 56, *syn.default_camera(DIMS, view), shade_mode=shade)
+        got, st = _frame(vol, mode=mode, view=view)
+        want, _, ost = O.render(m, p16, fr, mo, colors, alpha)
+        assert want[..., 3].max() > 0.3
+        assert st["rays_hit"] == ost["rays_hit"]
+        assert abs(st["samples_decoded"] - ost["samples_decoded"]) <= 0.002 * ost["samples_decoded"]
+        assert syn.psnr(got, want) >= 50.0 and np.abs(got - want).max() <= 4.0 / 255.0
+        # ground-truth source through the same shaded wavefront (render_normal, renderer.cpp:143-180)
+        got_gt, _ = _frame(vol, mode=mode, gt_source=True, view=view)
+        want_gt, _, _ = O.render(m, p16, fr, mo, colors, alpha, volume=gt)
+        assert syn.psnr(got_gt, want_gt) >= 50.0 and np.abs(got_gt - want_gt).max() <= 4.0 / 255.0
+    # shading changes colours, never the alpha channel
+    got, _ = _frame(vol, mode=mode, view=2)
+    assert np.array_equal(got[..., 3], plain[..., 3]) and not np.allclose(got[..., :3], plain[..., :3], atol=1e-3)
+
+
+def test_shaded_modes_graph_and_host_enqueued_frames_are_identical_and_accumulate():
+    vol, _, _, _ = _trained_volume(100)
+    for mode in (8, 11):
+        frames = []
+        for graph in (True, False):
+            ren = vnr.Renderer(vol)
+            ren.set_size(64, 48); ren.set_camera(*syn.default_camera(DIMS, 4)); ren.set_mode(mode); ren.set_graph(graph)
+            ren.render(); a = ren.map_frame().copy()
+            ren.render(); b = ren.map_frame().copy()         # frame_index 2: accumulation with a new jitter
+            frames.append((a, b))
+        assert np.array_equal(frames[0][0], frames[1][0]) and np.array_equal(frames[0][1], frames[1][1])
+        assert not np.array_equal(frames[0][0], frames[0][1])

@@ -241,6 +241,61 @@ def test_marcher_skips_empty_macrocells_and_terminates_early():
     assert img[..., 3].max() > 0.5
 
 
+def test_shaded_marcher_closed_forms():
+    """Gradient shading and the single-shade heuristic (method_raymarching.cu:773-833) on cases with a known answer."""
+    dims = (32, 32, 32)
+    n = 16
+    rgb = np.tile(np.array([[1.0, 0.5, 0.25]], np.float32), (n, 1))
+    alpha = np.full(n, 0.02, np.float32)
+    colors = np.concatenate([rgb, np.ones((n, 1), np.float32)], 1)
+    cam = (np.array([0, 0, -100], np.float32), np.zeros(3, np.float32), np.array([0, 1, 0], np.float32))
+    m = O.ModelCfg(2, 2, 8, 4, 2.0, 1)
+    # (1) constant volume: zero gradient -> shade_scivis_light returns 0 -> colour = (1 - 0.95) * unshaded colour
+    vol = np.full(dims[::-1], 0.5, np.float32)
+    mo = O.macrocell_max_opacity(O.macrocell_update_implicit(vol, dims), alpha)
+    plain, _, st0 = O.render(m, None, O.Frame(dims, 33, 33, *cam, fovy=10.0), mo, colors, alpha, volume=vol, jitter_mode=1)
+    shaded, _, st1 = O.render(m, None, O.Frame(dims, 33, 33, *cam, fovy=10.0, shade_mode=1), mo, colors, alpha, volume=vol, jitter_mode=1)
+    assert np.array_equal(shaded[..., 3], plain[..., 3]) and st1["samples_decoded"] == 4 * st0["samples_decoded"]
+    assert np.allclose(shaded[..., :3], 0.05 * plain[..., :3], atol=1e-6)
+    # (2) a linear ramp along x lit head-on: the forward difference is exact, so every sample gets the same factor
+    #     0.05 + 0.95 * 0.5 * (simple + scivis) with N = -x in world space
+    x = ((np.arange(32, dtype=np.float32) + 0.5) / 32)
+    ramp = np.broadcast_to(x[None, None, :], dims[::-1]).astype(np.float32).copy()
+    mo = O.macrocell_max_opacity(O.macrocell_update_implicit(ramp, dims), alpha)
+    fr = O.Frame(dims, 9, 9, *cam, fovy=2.0, shade_mode=1)
+    plain, _, _ = O.render(m, None, O.Frame(dims, 9, 9, *cam, fovy=2.0), mo, colors, alpha, volume=ramp, jitter_mode=1)
+    shaded, _, _ = O.render(m, None, fr, mo, colors, alpha, volume=ramp, jitter_mode=1)
+    L = fr.light_dir / np.linalg.norm(fr.light_dir)
+    assert np.dot(L, [0, 0, 1]) < 0                                   # flipped to face the camera (renderer.cpp:98-101)
+    N, V = np.array([-1.0, 0, 0]), np.array([0, 0, -1.0])
+    cosNL = max(float(N @ L), 0.0)
+    H = (L + V) / np.linalg.norm(L + V)
+    scivis = 0.6 + (0.9 * cosNL if cosNL > 0 else 0.0)
+    spec = 0.4 * max(float(N @ H), 0.0) ** 40 if cosNL > 0 else 0.0
+    simple = 0.2 + 0.8 * abs(float(-V @ N))
+    c = plain[4, 4, :3]
+    want = 0.05 * c + 0.95 * 0.5 * (simple * c + scivis * c + spec * plain[4, 4, 3])
+    assert np.allclose(shaded[4, 4, :3], want, rtol=2e-3, atol=1e-5)
+    # (3) single-shade heuristic: alpha untouched; colour = 0.05 c + 0.95 * highest_colour * alpha * T with 0 <= T <= 1;
+    #     rays that miss the box stay exactly zero
+    vol = syn.make_volume(dims, seed=3)
+    rgb2, alpha2 = syn.make_tfn(64)
+    colors2 = np.concatenate([rgb2, np.ones((64, 1), np.float32)], 1)
+    mo = O.macrocell_max_opacity(O.macrocell_update_implicit(vol, dims), alpha2)
+    cam2 = syn.default_camera(dims, 3)
+    plain, _, _ = O.render(m, None, O.Frame(dims, 40, 40, *cam2), mo, colors2, alpha2, volume=vol)
+    ssh, _, st = O.render(m, None, O.Frame(dims, 40, 40, *cam2, shade_mode=2), mo, colors2, alpha2, volume=vol)
+    assert np.array_equal(ssh[..., 3], plain[..., 3]) and plain[..., 3].max() > 0.3
+    lo = 0.05 * plain[..., :3]
+    hi = lo + 0.95 * rgb2.max() * plain[..., 3:4]
+    assert (ssh[..., :3] >= lo - 1e-6).all() and (ssh[..., :3] <= hi + 1e-6).all()
+    assert (ssh[..., :3] > lo + 1e-4).any()                            # some light gets through
+    assert not ssh[plain[..., 3] == 0].any()
+    # the light never shines from behind the camera: a second frame with the already-corrected direction keeps it
+    fr3 = O.Frame(dims, 8, 8, *cam2, shade_mode=2, light_dir=fr.light_dir)
+    assert float(np.dot(fr3.light_dir, fr3.f[3:6])) <= 0
+
+
 def test_training_reduces_loss_small_model():
     m = O.ModelCfg(4, 2, 10, 4, 2.0, 2)
     dims = (16, 16, 16)
