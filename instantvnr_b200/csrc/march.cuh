@@ -62,8 +62,10 @@ __device__ __forceinline__ uint32_t ray_to_pixel(const FrameParams& fp, uint32_t
   return y * w + x;
 }
 
-// gdt::LCG<16> (TEA-initialised LCG; OVR gdt/random/random.h, un-vendored): first float
-__device__ __forceinline__ float jitter_lcg_tea16(uint32_t val0, uint32_t val1) {
+// gdt::LCG<16> (TEA-initialised LCG; OVR gdt/random/random.h, un-vendored).  The fork's get_floats() is taken to
+// draw two consecutive floats per call: the streaming raygen uses .x for the camera ray and .y for the shadow ray
+// (method_raymarching.cu:851-852,870), the single-kernel marcher .x of the first call and .x of the second (:378,420).
+__device__ __forceinline__ uint32_t tea16(uint32_t val0, uint32_t val1) {
   uint32_t v0 = val0, v1 = val1, s0 = 0;
 #pragma unroll
   for (int n = 0; n < 16; ++n) {
@@ -71,22 +73,18 @@ __device__ __forceinline__ float jitter_lcg_tea16(uint32_t val0, uint32_t val1) 
     v0 += ((v1 << 4) + 0xa341316cu) ^ (v1 + s0) ^ ((v1 >> 5) + 0xc8013ea4u);
     v1 += ((v0 << 4) + 0xad90777du) ^ (v0 + s0) ^ ((v0 >> 5) + 0x7e95761eu);
   }
-  const uint32_t state = 1664525u * v0 + 1013904223u;
+  return v0;
+}
+__device__ __forceinline__ float lcg_next(uint32_t& state) {
+  state = 1664525u * state + 1013904223u;
   return (float)(state & 0x00FFFFFFu) / (float)0x01000000u;
 }
-// first and second float of the same generator (get_floats(): camera-ray jitter, shadow-ray jitter :851-852,870)
+__device__ __forceinline__ float jitter_lcg_tea16(uint32_t val0, uint32_t val1) { uint32_t s = tea16(val0, val1); return lcg_next(s); }
 __device__ __forceinline__ void jitter_lcg_tea16_pair(uint32_t val0, uint32_t val1, float& j0, float& j1) {
-  uint32_t v0 = val0, v1 = val1, s0 = 0;
-#pragma unroll
-  for (int n = 0; n < 16; ++n) {
-    s0 += 0x9e3779b9u;
-    v0 += ((v1 << 4) + 0xa341316cu) ^ (v1 + s0) ^ ((v1 >> 5) + 0xc8013ea4u);
-    v1 += ((v0 << 4) + 0xad90777du) ^ (v0 + s0) ^ ((v0 >> 5) + 0x7e95761eu);
-  }
-  uint32_t state = 1664525u * v0 + 1013904223u;
-  j0 = (float)(state & 0x00FFFFFFu) / (float)0x01000000u;
-  state = 1664525u * state + 1013904223u;
-  j1 = (float)(state & 0x00FFFFFFu) / (float)0x01000000u;
+  uint32_t s = tea16(val0, val1); j0 = lcg_next(s); j1 = lcg_next(s);
+}
+__device__ __forceinline__ void jitter_lcg_tea16_triple(uint32_t val0, uint32_t val1, float& j0, float& j2) {
+  uint32_t s = tea16(val0, val1); j0 = lcg_next(s); (void)lcg_next(s); j2 = lcg_next(s);
 }
 
 __device__ __forceinline__ void compute_ray(const FrameParams& fp, uint32_t pixel, F3& org, F3& dir) {
@@ -160,8 +158,10 @@ __device__ __forceinline__ float adaptive_sampling_rate(float base, float max_op
 // Walk the macrocell DDA from state `s`, calling body(t0, t1) for every sample interval until
 // body returns false or the ray leaves the grid.  Equivalent to
 // `while (DDAIter::next(..., lambda)) {}` with the lambda of RayMarchingIter::exec.
-template <typename Body>
-__device__ __forceinline__ void march_exec(const FrameParams& fp, DDAState& s, F3 m_dir, float tMin, float tMax, Body&& body) {
+// UNIFORM: the single-kernel marcher's raymarching_iterator (method_raymarching.cu:269-297) -- same traversal (dda3,
+// dda.h:140-288), but every cell is divided into equal steps (sample_size_scaler :262-267) and `step` may be scaled.
+template <bool UNIFORM = false, typename Body>
+__device__ __forceinline__ void march_exec(const FrameParams& fp, DDAState& s, F3 m_dir, float tMin, float tMax, Body&& body, float step_scale = 1.f) {
   const int stopx = m_dir.x > 0.f ? fp.mc_dims[0] : -1, stopy = m_dir.y > 0.f ? fp.mc_dims[1] : -1, stopz = m_dir.z > 0.f ? fp.mc_dims[2] : -1;
   const float tsx = fabsf(__frcp_rn(m_dir.x)), tsy = fabsf(__frcp_rn(m_dir.y)), tsz = fabsf(__frcp_rn(m_dir.z));
   const int dx = m_dir.x > 0.f ? 1 : -1, dy = m_dir.y > 0.f ? 1 : -1, dz = m_dir.z > 0.f ? 1 : -1;
@@ -177,7 +177,11 @@ __device__ __forceinline__ void march_exec(const FrameParams& fp, DDAState& s, F
       const uint32_t idx = (uint32_t)s.cx + (uint32_t)s.cy * (uint32_t)fp.mc_dims[0] + (uint32_t)s.cz * (uint32_t)fp.mc_dims[0] * (uint32_t)fp.mc_dims[1];
       const float r = __ldg(fp.mc_maxop + idx);
       if (!(fabsf(r) <= FLT_EPSILON)) {
-        const float ss = adaptive_sampling_rate(fp.step, r);
+        float ss = adaptive_sampling_rate(UNIFORM ? step_scale * fp.step : fp.step, r);
+        if (UNIFORM) {
+          const int n = (int)(__fdiv_rn(cell_t1 - cell_t0, ss) + 1.f);
+          ss = __fdiv_rn(cell_t1 - cell_t0, (float)n);
+        }
         float tx = cell_t0, ty = fminf(cell_t1, cell_t0 + ss);
         while (ty > tx) {
           s.ncb = ty - tMin;

@@ -18,6 +18,7 @@
 #include "march.cuh"
 #include "render.h"
 #include "train.h"
+#include "volume_tex.cuh"
 
 namespace vnr {
 
@@ -247,6 +248,105 @@ __global__ void finalize_kernel(const FrameParams* __restrict__ fpp, RayBuffers 
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// The single-kernel marcher (raymarching_kernel + raymarching_traceray, method_raymarching.cu:400-545): one thread walks
+// one ray to the end against a resident volume.  The reference uses it for the "decoding" modes 4 / 7 / 10 (the
+// progressively decoded network, api.cpp:429-438) and, on a SimpleVolume, for those and the in-shader modes 6 / 9 / 12
+// (renderer.cpp:143-180).  Differences to the wavefront: cells are divided into equal steps (sample_size_scaler), the
+// gradient flips to a backward difference at the upper volume faces (sampleGradient raytracing.h:113-127), and the
+// single shade's shadow ray is marched inline with twice the step (raymarching_transmittance :365-398).
+// SHADE 0 none, 1 gradient shading, 2 single-shade heuristic.
+template <int SHADE>
+__global__ void __launch_bounds__(128)
+march_volume_kernel(const FrameParams* __restrict__ fpp, const float* __restrict__ vol, int3 dims, uint32_t* __restrict__ counters,
+                    float4* __restrict__ accum, float4* __restrict__ frame) {
+  __shared__ FrameParams fp_s;
+  stage_frame_params(&fp_s, fpp);
+  const FrameParams& fp = fp_s;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t lane = threadIdx.x & 31u;
+  bool active = i < fp.n_rays;
+  uint32_t pixel = 0;
+  if (active) { pixel = ray_to_pixel(fp, i); active = pixel < (uint32_t)fp.width * (uint32_t)fp.height; }
+  uint32_t n_samples = 0;
+  bool hit = false;
+  if (active) {
+    F3 org, dir;
+    compute_ray(fp, pixel, org, dir);
+    float tmin = 0.f, tmax = VNR_FLOAT_LARGE;
+    float4 rgba = make_float4(0, 0, 0, 0);
+    if (intersect_box(tmin, tmax, org, dir, fp.bbox_lo, fp.bbox_hi)) {
+      hit = true;
+      // RandomTEA rng(frame_index, pixel): get_floats() draws two floats per call; the camera ray takes the first of the
+      // first call (:420), the shadow ray the first of the second call (:378)
+      float jitter = 0.5f, j_shadow = 0.5f;
+      if (fp.jitter_mode == 0) jitter_lcg_tea16_triple((uint32_t)fp.frame_index, pixel, jitter, j_shadow);
+      F3 hi_org = f3(0, 0, 0), hi_col = f3(0, 0, 0);
+      float hi_alpha = 0.f;
+      DDAState dda;
+      F3 m_dir = f3(dir.x * fp.mc_rcp[0], dir.y * fp.mc_rcp[1], dir.z * fp.mc_rcp[2]);
+      dda_init(dda, f3(org.x * fp.mc_rcp[0], org.y * fp.mc_rcp[1], org.z * fp.mc_rcp[2]), m_dir, tmin, fp.mc_dims);
+      march_exec<true>(fp, dda, m_dir, tmin, tmax, [&](float tx, float ty) {
+        const float tl = __fmaf_rn(jitter, ty, (1.f - jitter) * tx);
+        const F3 p = madd(tl, dir, org);
+        const float value = sample_volume(vol, dims, p.x, p.y, p.z);
+        float r, g, b, a;
+        classify(fp, fp.tfn_color, fp.tfn_alpha, value, ty - tx, r, g, b, a);
+        ++n_samples;
+        if (SHADE == 1) {
+          float sx = fp.grad_step[0], sy = fp.grad_step[1], sz = fp.grad_step[2];
+          if (p.x + sx > 1.f - FLT_EPSILON) sx = -sx;
+          if (p.y + sy > 1.f - FLT_EPSILON) sy = -sy;
+          if (p.z + sz > 1.f - FLT_EPSILON) sz = -sz;
+          const F3 grad = f3(__fdiv_rn(sample_volume(vol, dims, p.x + sx, p.y, p.z) - value, sx), __fdiv_rn(sample_volume(vol, dims, p.x, p.y + sy, p.z) - value, sy),
+                             __fdiv_rn(sample_volume(vol, dims, p.x, p.y, p.z + sz) - value, sz));
+          n_samples += 3;
+          shade_gradient(fp, dir, grad, r, g, b);
+        } else if (SHADE == 2) {
+          const float contrib = (1.f - rgba.w) * a;
+          if (hi_alpha < contrib) { hi_org = p; hi_col = f3(r, g, b); hi_alpha = contrib; }
+        }
+        const float tr = 1.f - rgba.w;
+        rgba.x = __fmaf_rn(tr * r, a, rgba.x);
+        rgba.y = __fmaf_rn(tr * g, a, rgba.y);
+        rgba.z = __fmaf_rn(tr * b, a, rgba.z);
+        rgba.w = __fmaf_rn(tr, a, rgba.w);
+        return rgba.w < VNR_NEARLY_ONE;
+      });
+      if (SHADE == 2 && hi_alpha > 0.f) {
+        // raymarching_transmittance from the highest-contribution point towards the light
+        const F3 ldir = shadow_dir(fp);
+        float t0 = 0.f, t1 = VNR_FLOAT_LARGE, alpha = 0.f;
+        if (intersect_box(t0, t1, hi_org, ldir, fp.bbox_lo, fp.bbox_hi)) {
+          const F3 lm_dir = f3(ldir.x * fp.mc_rcp[0], ldir.y * fp.mc_rcp[1], ldir.z * fp.mc_rcp[2]);
+          dda_init(dda, f3(hi_org.x * fp.mc_rcp[0], hi_org.y * fp.mc_rcp[1], hi_org.z * fp.mc_rcp[2]), lm_dir, t0, fp.mc_dims);
+          march_exec<true>(fp, dda, lm_dir, t0, t1, [&](float tx, float ty) {
+            const float tl = __fmaf_rn(j_shadow, ty, (1.f - j_shadow) * tx);
+            const F3 p = madd(tl, ldir, hi_org);
+            float r, g, b, a;
+            classify(fp, fp.tfn_color, fp.tfn_alpha, sample_volume(vol, dims, p.x, p.y, p.z), ty - tx, r, g, b, a);
+            ++n_samples;
+            alpha = __fmaf_rn(1.f - alpha, a, alpha);
+            return alpha < VNR_NEARLY_ONE;
+          }, 2.f /* raymarching_shadow_sampling_scale, instantvnr_types.h:137 */);
+        }
+        const float tr = 1.f - alpha;
+        rgba.x = lerp1(VNR_SHADING_SCALE, rgba.x, (hi_col.x * rgba.w) * tr);
+        rgba.y = lerp1(VNR_SHADING_SCALE, rgba.y, (hi_col.y * rgba.w) * tr);
+        rgba.z = lerp1(VNR_SHADING_SCALE, rgba.z, (hi_col.z * rgba.w) * tr);
+      }
+    }
+    write_pixel(fp, accum, frame, pixel, rgba);
+  }
+  const uint32_t hits = __ballot_sync(0xffffffffu, hit);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) n_samples += __shfl_xor_sync(0xffffffffu, n_samples, o);
+  if (lane == 0) {
+    if (hits) atomicAdd(&counters[0], __popc(hits));
+    if (n_samples) { atomicAdd(&counters[1], n_samples); atomicAdd(&counters[2], n_samples); }
+  }
+}
+
 // Loop control of the graph-driven wavefront: one thread advances the device round index and tells
 // the WHILE node whether the round that was just emitted holds any sample.
 __global__ void advance_round_kernel(uint32_t* __restrict__ counters, uint32_t* __restrict__ round_dev, cudaGraphConditionalHandle handle, int init, int bound) {
@@ -459,10 +559,14 @@ void Renderer::render() {
   VNR_CUDA(cudaEventRecord(vol_ready, vol->stream));
   VNR_CUDA(cudaStreamWaitEvent(stream, vol_ready, 0));
 
+  // decoding modes, and a SimpleVolume in every mode but the sample-streaming ones, run the single-kernel marcher
+  const bool single_kernel = decoding || (gt_source && mode != 5 && mode != 8 && mode != 11);
   const size_t cap = (size_t)n_rays * n_iters * (shade == 1 ? 4 : 1);
-  samples[0].ensure(cap); samples[1].ensure(cap); values.ensure(cap);
-  ray_rgba.ensure(n_rays); ray_tn.ensure(n_rays); ray_cell.ensure(n_rays); ray_state.ensure(n_rays); ray_jitter.ensure(n_rays);
-  if (shade == 2) { ssh_org.ensure(n_rays); ssh_col.ensure(n_rays); ssh_rgba.ensure(n_rays); ssh_jitter.ensure(n_rays); }
+  if (!single_kernel) {
+    samples[0].ensure(cap); samples[1].ensure(cap); values.ensure(cap);
+    ray_rgba.ensure(n_rays); ray_tn.ensure(n_rays); ray_cell.ensure(n_rays); ray_state.ensure(n_rays); ray_jitter.ensure(n_rays);
+    if (shade == 2) { ssh_org.ensure(n_rays); ssh_col.ensure(n_rays); ssh_rgba.ensure(n_rays); ssh_jitter.ensure(n_rays); }
+  }
   const size_t cstride = kMaxRounds + 4;
   counters.ensure(2 * cstride);
   if (rounds + 3 > kMaxRounds) throw UnsupportedError("sampling rate too high for the round bound");
@@ -478,7 +582,16 @@ void Renderer::render() {
   // a few hundred bytes from pageable memory: staged by the driver at call time, ordered on the stream
   VNR_CUDA(cudaMemcpyAsync(fp_dev.p, fp, sizeof fp, cudaMemcpyHostToDevice, stream));
   const bool graph_loop = use_graph && !profiling;
-  for (int pass = 0; pass < n_pass && n_rays; ++pass) {
+  if (single_kernel && n_rays) {
+    const int3 d3 = make_int3(vol->dims[0], vol->dims[1], vol->dims[2]);
+    const FrameParams* fpd = reinterpret_cast<const FrameParams*>(fp_dev.p);
+    if (shade == 1) march_volume_kernel<1><<<grid, 128, 0, stream>>>(fpd, volume_src, d3, counters.p, accum.p, frame_out());
+    else if (shade == 2) march_volume_kernel<2><<<grid, 128, 0, stream>>>(fpd, volume_src, d3, counters.p, accum.p, frame_out());
+    else march_volume_kernel<0><<<grid, 128, 0, stream>>>(fpd, volume_src, d3, counters.p, accum.p, frame_out());
+    VNR_CUDA(cudaGetLastError());
+    launches = 1;
+  }
+  for (int pass = 0; pass < n_pass && n_rays && !single_kernel; ++pass) {
     const int sh = pass == 1 ? 3 : shade;
     uint32_t* cnt = counters.p + (size_t)pass * cstride;
     const FrameParams* fpd = reinterpret_cast<const FrameParams*>(fp_dev.p) + pass;
@@ -500,9 +613,9 @@ void Renderer::render() {
     VNR_CUDA(cudaGetLastError());
     if (!graph_loop) launches += 2 + 2 * (uint64_t)rounds;     // graph path: counted from the device counters in stats()
   }
-  last_graph = graph_loop;
+  last_graph = graph_loop && !single_kernel;
   last_rounds = rounds;
-  last_passes = n_pass;
+  last_passes = single_kernel ? 1 : n_pass;
   // framebuffer.download_async (renderer.cpp:133)
   downloaded = false;
   if (download) { VNR_CUDA(cudaMemcpyAsync(h_frame[cur], frame.p, frame.bytes(), cudaMemcpyDeviceToHost, stream)); downloaded = true; }

@@ -20,35 +20,13 @@
 
 #include "mlp_tile.cuh"
 #include "train.h"
+#include "volume_tex.cuh"
 
 namespace vnr {
 
 // ------------------------------------------------------------------------------------------
 // sampler
 // ------------------------------------------------------------------------------------------
-
-// CUDA linear filtering: weight in 1.8 fixed point (CUDA C Programming Guide, "Linear Filtering")
-__device__ __forceinline__ float tex_frac(float xb, float fl) {
-  const float fr = xb - fl;
-  return floorf(__fmaf_rn(fr, 256.f, 0.5f)) * (1.f / 256.f);
-}
-
-__device__ __forceinline__ float sample_volume_linear(const float* __restrict__ vol, int3 dims, float u, float v, float w) {
-  const float cx = __fmaf_rn(u, (float)dims.x, -0.5f), cy = __fmaf_rn(v, (float)dims.y, -0.5f), cz = __fmaf_rn(w, (float)dims.z, -0.5f);
-  const float fx = floorf(cx), fy = floorf(cy), fz = floorf(cz);
-  const float ax = tex_frac(cx, fx), ay = tex_frac(cy, fy), az = tex_frac(cz, fz);
-  const int x0 = min(max((int)fx, 0), dims.x - 1), x1 = min(max((int)fx + 1, 0), dims.x - 1);
-  const int y0 = min(max((int)fy, 0), dims.y - 1), y1 = min(max((int)fy + 1, 0), dims.y - 1);
-  const int z0 = min(max((int)fz, 0), dims.z - 1), z1 = min(max((int)fz + 1, 0), dims.z - 1);
-  const size_t sx = 1, sy = (size_t)dims.x, sz = (size_t)dims.x * dims.y;
-  auto at = [&](int x, int y, int z) { return __ldg(vol + x * sx + y * sy + z * sz); };
-  auto lerp = [](float t, float p, float q) { return __fmaf_rn(t, q, (1.f - t) * p); };
-  const float c00 = lerp(ax, at(x0, y0, z0), at(x1, y0, z0));
-  const float c10 = lerp(ax, at(x0, y1, z0), at(x1, y1, z0));
-  const float c01 = lerp(ax, at(x0, y0, z1), at(x1, y0, z1));
-  const float c11 = lerp(ax, at(x0, y1, z1), at(x1, y1, z1));
-  return lerp(az, lerp(ay, c00, c10), lerp(ay, c01, c11));
-}
 
 // Sample s draws the uniforms that generate_random_kernel (tcnn random.h:67-84) writes to
 // out[3s..3s+2]: element idx is produced by thread idx % n_threads as its (idx / n_threads)-th
@@ -93,9 +71,7 @@ __global__ void volume_samples_kernel(const float* __restrict__ vol, int3 dims, 
   const float4* __restrict__ samples = (r & 1u) ? s1 : s0;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const float4 c = samples[i];
-    // sampleVolume (raytracing.h:105-110): p * (1 - rdims) + 0.5 * rdims, then tex3D
-    const float rx = 1.f / (float)dims.x, ry = 1.f / (float)dims.y, rz = 1.f / (float)dims.z;
-    out[i] = sample_volume_linear(vol, dims, __fmaf_rn(c.x, 1.f - rx, 0.5f * rx), __fmaf_rn(c.y, 1.f - ry, 0.5f * ry), __fmaf_rn(c.z, 1.f - rz, 0.5f * rz));
+    out[i] = sample_volume(vol, dims, c.x, c.y, c.z);
   }
 }
 

@@ -244,6 +244,25 @@ def render(m, params_f16, frame, mc_max_opacity, colors_rgba, alphas, acc_mode=0
                                                               "samples_composited": int(stats[2]), "rounds": int(stats[3])}
 
 
+def render_single_kernel(frame, mc_max_opacity, colors_rgba, alphas, volume, jitter_mode=0, accum=None):
+    """The single-kernel marcher of the decoding / SimpleVolume in-shader modes (method_raymarching.cu:400-545)."""
+    colors_rgba = _f32(colors_rgba).reshape(-1, 4)
+    alphas = _f32(alphas)
+    frame.set_tfn_sizes(colors_rgba.shape[0], alphas.size)
+    npix = frame.width * frame.height
+    if accum is None:
+        accum = np.zeros((npix, 4), dtype=np.float32)
+    out = np.zeros((npix, 4), dtype=np.float32)
+    stats = np.zeros(4, dtype=np.uint64)
+    mc_max_opacity = _f32(mc_max_opacity)
+    vol = _f32(volume)
+    gd = np.array(frame.dims, dtype=np.int32)
+    lib().orc_render_single_kernel(_p(frame.f), _p(frame.i), _p(mc_max_opacity), _p(colors_rgba), _p(alphas), _p(vol), _p(gd),
+                                   C.c_int(jitter_mode), _p(accum), _p(out), _p(stats))
+    return out.reshape(frame.height, frame.width, 4), accum, {"rays_hit": int(stats[0]), "samples_decoded": int(stats[1]),
+                                                              "samples_composited": int(stats[2]), "rounds": int(stats[3])}
+
+
 def rays(frame):
     out = np.empty((frame.width * frame.height, 8), dtype=np.float32)
     lib().orc_rays(_p(frame.f), _p(frame.i), _p(out))

@@ -540,15 +540,18 @@ static inline float adaptive_sampling_rate(float base, float max_opacity) {
 }
 
 // method_raymarching.cu:555-600 RayMarchingIter::exec (ADAPTIVE_SAMPLING=1)
+// uniform = true: raymarching_iterator of the single-kernel marcher (:269-297): same traversal (dda3, dda.h:140-288), every
+// cell divided into equal steps (sample_size_scaler :262-267), base step scaled by step_scale.
 template <typename B>
-static void march_exec(const Frame& fr, DDAIter& it, V3 org, V3 dir, float tMin, float tMax, const B& body) {
+static void march_exec(const Frame& fr, DDAIter& it, V3 org, V3 dir, float tMin, float tMax, const B& body, bool uniform = false, float step_scale = 1.f) {
   V3 m_org = org * fr.mc_spacing_rcp, m_dir = dir * fr.mc_spacing_rcp;
   (void)m_org;
   auto lambda = [&](const int* cell, float t0, float t1) {
     const uint32_t idx = cell[0] + cell[1] * (uint32_t)fr.mc_dims[0] + cell[2] * (uint32_t)fr.mc_dims[0] * (uint32_t)fr.mc_dims[1];
     float r = fr.mc_max_opacity[idx];
     if (fabsf(r) <= std::numeric_limits<float>::epsilon()) return true;
-    const float ss = adaptive_sampling_rate(fr.step, r);
+    float ss = adaptive_sampling_rate(uniform ? step_scale * fr.step : fr.step, r);
+    if (uniform) { const int32_t N = (int32_t)((t1 - t0) / ss + 1); ss = (t1 - t0) / (float)N; }
     float tx = t0, ty = fminf(t1, t0 + ss);
     while (ty > tx) {
       it.next_cell_begin = ty - tMin;
@@ -1045,11 +1048,97 @@ static void render_wavefront(const int* cfg, float pls, const uint16_t* params_f
   if (stats) { stats[0] = n_hit; stats[1] = n_dec; stats[2] = n_comp; stats[3] = n_rounds; }
 }
 
+// The single-kernel marcher: raymarching_kernel (:489-530) -> raymarching_traceray (:400-487) on a resident volume
+// (sampleVolume / sampleGradient raytracing.h:105-127), with raymarching_transmittance (:365-398) for the single shade.
+// Jitter: get_floats() is taken to draw two floats per call -- camera ray = float #1, shadow ray = float #3.
+static void render_single_kernel(const float* fparams, const int* iparams, const float* mc_max_opacity, const float* colors, const float* alphas,
+                                 const float* volume, const int* dims, int jitter_mode, const Shading& sh,
+                                 float* accum, float* frame, uint64_t* stats) {
+  Frame fr = frame_from(fparams, iparams, mc_max_opacity, colors, alphas);
+  const size_t npix = (size_t)fr.width * fr.height;
+  auto sample_volume = [&](V3 p) -> float {
+    float q[3]; const float c[3] = {p.x, p.y, p.z};
+    for (int d = 0; d < 3; ++d) { float rd = 1.f / (float)dims[d]; q[d] = fmaf(c[d], (1.f - rd), 0.5f * rd); }
+    return tex3d_linear(volume, dims, q[0], q[1], q[2], fr.tex_round);
+  };
+  uint64_t n_hit = 0, n_samples = 0;
+#pragma omp parallel for schedule(dynamic, 64) reduction(+ : n_hit, n_samples)
+  for (long long i = 0; i < (long long)npix; ++i) {
+    V3 org, dir; compute_ray(fr, (uint32_t)i, org, dir);
+    float tmin = 0.f, tmax = FLOAT_LARGE;
+    float color[3] = {0, 0, 0}, alpha = 0.f;
+    if (intersect_box(tmin, tmax, org, dir, fr.bbox_lo, fr.bbox_hi)) {
+      ++n_hit;
+      float jitter = 0.5f, j_shadow = 0.5f;
+      if (jitter_mode == 0) { LcgTea16 rng((uint32_t)fr.frame_index, (uint32_t)i); jitter = rng.next(); rng.next(); j_shadow = rng.next(); }
+      V3 hi_org = v3(0, 0, 0); float hi_col[3] = {0, 0, 0}, hi_alpha = 0.f;
+      DDAIter it; it.init(org * fr.mc_spacing_rcp, dir * fr.mc_spacing_rcp, tmin, tmax, fr.mc_dims);
+      march_exec(fr, it, org, dir, tmin, tmax, [&](float tx, float ty) {
+        const V3 p = madd(fmaf(jitter, ty, (1 - jitter) * tx), dir, org);
+        const float value = sample_volume(p);
+        float rgb[3], a;
+        classify(fr, value, ty - tx, rgb, a);
+        ++n_samples;
+        if (sh.mode == 1) {
+          float st[3] = {sh.grad_step.x, sh.grad_step.y, sh.grad_step.z};
+          const float eps = std::numeric_limits<float>::epsilon();
+          if (p.x + st[0] > 1.f - eps) st[0] = -st[0];
+          if (p.y + st[1] > 1.f - eps) st[1] = -st[1];
+          if (p.z + st[2] > 1.f - eps) st[2] = -st[2];
+          const V3 g = v3((sample_volume(v3(p.x + st[0], p.y, p.z)) - value) / st[0], (sample_volume(v3(p.x, p.y + st[1], p.z)) - value) / st[1],
+                          (sample_volume(v3(p.x, p.y, p.z + st[2])) - value) / st[2]);
+          n_samples += 3;
+          shade_gradient(fr, sh, dir, g, rgb);
+        } else if (sh.mode == 2) {
+          const float contrib = (1.f - alpha) * a;
+          if (hi_alpha < contrib) { hi_org = p; hi_col[0] = rgb[0]; hi_col[1] = rgb[1]; hi_col[2] = rgb[2]; hi_alpha = contrib; }
+        }
+        const float tr = 1.f - alpha;
+        for (int c = 0; c < 3; ++c) color[c] = fmaf(tr * rgb[c], a, color[c]);
+        alpha = fmaf(tr, a, alpha);
+        return alpha < NEARLY_ONE;
+      }, true);
+      if (sh.mode == 2 && hi_alpha > 0.f) {
+        const V3 ldir = xfm_vec(fr.wto_l, normalize(sh.light_dir));
+        float t0 = 0.f, t1 = FLOAT_LARGE, sa = 0.f;
+        if (intersect_box(t0, t1, hi_org, ldir, fr.bbox_lo, fr.bbox_hi)) {
+          DDAIter its; its.init(hi_org * fr.mc_spacing_rcp, ldir * fr.mc_spacing_rcp, t0, t1, fr.mc_dims);
+          march_exec(fr, its, hi_org, ldir, t0, t1, [&](float tx, float ty) {
+            const V3 p = madd(fmaf(j_shadow, ty, (1 - j_shadow) * tx), ldir, hi_org);
+            float rgb[3], a;
+            classify(fr, sample_volume(p), ty - tx, rgb, a);
+            ++n_samples;
+            sa = fmaf(1.f - sa, a, sa);
+            return sa < NEARLY_ONE;
+          }, true, kShadowSamplingScale);
+        }
+        const float tr = 1.f - sa;
+        for (int c = 0; c < 3; ++c) color[c] = lerp1(kShadingScale, color[c], (hi_col[c] * alpha) * tr);
+      }
+    }
+    for (int c = 0; c < 4; ++c) {                               // writePixelColor raytracing.h:196-207
+      const float x = c < 3 ? color[c] : alpha;
+      const float v = fr.frame_index == 1 ? x : accum[4 * (size_t)i + c] + x;
+      accum[4 * (size_t)i + c] = v;
+      frame[4 * (size_t)i + c] = v / (float)fr.frame_index;
+    }
+  }
+  if (stats) { stats[0] = n_hit; stats[1] = n_samples; stats[2] = n_samples; stats[3] = 1; }
+}
+
+ORC_API void orc_render_single_kernel(const float* fparams, const int* iparams, const float* mc_max_opacity, const float* colors, const float* alphas,
+                                      const float* volume, const int* dims, int jitter_mode, float* accum, float* frame, uint64_t* stats);
+
 static Shading shading_from(const float* p, const int* ip) {
   Shading sh;
   sh.mode = ip[10];
   sh.light_dir = v3(p[38], p[39], p[40]); sh.otw_diag = v3(p[41], p[42], p[43]); sh.grad_step = v3(p[44], p[45], p[46]);
   return sh;
+}
+
+ORC_API void orc_render_single_kernel(const float* fparams, const int* iparams, const float* mc_max_opacity, const float* colors, const float* alphas,
+                                      const float* volume, const int* dims, int jitter_mode, float* accum, float* frame, uint64_t* stats) {
+  render_single_kernel(fparams, iparams, mc_max_opacity, colors, alphas, volume, dims, jitter_mode, shading_from(fparams, iparams), accum, frame, stats);
 }
 
 ORC_API void orc_render(const int* cfg, float pls, const uint16_t* params_f16, int acc_mode,

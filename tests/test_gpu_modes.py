@@ -59,22 +59,49 @@ def test_groundtruth_renderer_matches_oracle_and_mode4_marches_the_decoded_volum
     colors = np.concatenate([rgb, np.ones((rgb.shape[0], 1), np.float32)], 1)
     w, h = 72, 56
     fr = O.Frame(DIMS, w, h, *syn.default_camera(DIMS, 2))
-    # ground-truth renderer (SimpleVolume): same wavefront, trilinear volume lookup
-    got_gt, st = _frame(vol, mode=4, gt_source=True)
+    # ground-truth renderer (SimpleVolume), sample-streaming mode: same wavefront, trilinear volume lookup
+    got_gt, st = _frame(vol, mode=5, gt_source=True)
     want_gt, _, ost = O.render(m, p16, fr, mo, colors, alpha, volume=gt)
     assert want_gt[..., 3].max() > 0.3 and st["rays_hit"] == ost["rays_hit"]
     assert syn.psnr(got_gt, want_gt) >= 50.0 and np.abs(got_gt - want_gt).max() <= 4.0 / 255.0
+    # ... and in mode 4 the single-kernel marcher (equal steps per macrocell)
+    got_gt4, st4 = _frame(vol, mode=4, gt_source=True)
+    want_gt4, _, ost4 = O.render_single_kernel(fr, mo, colors, alpha, gt)
+    assert st4["rays_hit"] == ost4["rays_hit"] and abs(st4["samples_decoded"] - ost4["samples_decoded"]) <= 0.002 * ost4["samples_decoded"]
+    assert syn.psnr(got_gt4, want_gt4) >= 50.0 and np.abs(got_gt4 - want_gt4).max() <= 4.0 / 255.0
+    assert syn.psnr(got_gt4, got_gt) >= 35.0                             # two samplings of the same integral
     # mode 4 before any decode: a zero volume renders nothing the transfer function maps to alpha > 0
     empty, _ = _frame(vol, mode=4)
     assert not empty[..., 3].any()
     for _ in range(vol.num_blobs()):
         vol.decode_progressive()
     got4, _ = _frame(vol, mode=4)
-    want4, _, _ = O.render(m, p16, fr, mo, colors, alpha, volume=vol.get_decoded())
+    want4, _, _ = O.render_single_kernel(fr, mo, colors, alpha, vol.get_decoded())
     assert syn.psnr(got4, want4) >= 50.0 and np.abs(got4 - want4).max() <= 4.0 / 255.0
     # and it approximates the per-sample decode of mode 5 (trilinear reconstruction of the decoded voxels)
     got5, _ = _frame(vol, mode=5)
     assert syn.psnr(got4, got5) >= 30.0
+
+
+@pytest.mark.parametrize("mode,shade", [(7, 1), (10, 2), (9, 1), (12, 2)])
+def test_shaded_single_kernel_modes_match_the_oracle(mode, shade):
+    """Decoding modes 7 / 10 march the decoded network, in-shader modes 9 / 12 on a SimpleVolume march the ground truth:
+    both run raymarching_traceray (method_raymarching.cu:400-487) with the boundary-aware gradient and the inline shadow ray."""
+    vol, gt, rgb, alpha = _trained_volume(150)
+    _, _, mo = vol.get_macrocell()
+    colors = np.concatenate([rgb, np.ones((rgb.shape[0], 1), np.float32)], 1)
+    gt_source = mode in (9, 12)
+    if not gt_source:
+        for _ in range(vol.num_blobs()):
+            vol.decode_progressive()
+    src = gt if gt_source else vol.get_decoded()
+    for view in (3, 12):
+        fr = O.Frame(DIMS, 72, 56, *syn.default_camera(DIMS, view), shade_mode=shade)
+        got, st = _frame(vol, mode=mode, gt_source=gt_source, view=view)
+        want, _, ost = O.render_single_kernel(fr, mo, colors, alpha, src)
+        assert want[..., 3].max() > 0.3 and st["rays_hit"] == ost["rays_hit"]
+        assert abs(st["samples_decoded"] - ost["samples_decoded"]) <= 0.002 * ost["samples_decoded"]
+        assert syn.psnr(got, want) >= 50.0 and np.abs(got - want).max() <= 4.0 / 255.0
 
 
 def test_neural_frame_psnr_within_a_tenth_of_a_db_of_the_reference_arithmetic():
@@ -89,7 +116,7 @@ def test_neural_frame_psnr_within_a_tenth_of_a_db_of_the_reference_arithmetic():
     deltas = []
     for view in (1, 6, 11):
         fr = O.Frame(DIMS, 72, 56, *syn.default_camera(DIMS, view))
-        ours_n, _ = _frame(vol, 5, view=view); ours_gt, _ = _frame(vol, 4, gt_source=True, view=view)
+        ours_n, _ = _frame(vol, 5, view=view); ours_gt, _ = _frame(vol, 5, gt_source=True, view=view)
         ref_n, _, _ = O.render(m, p16, fr, mo, colors, alpha, acc_mode=1)     # acc_mode 1: fp16-accumulating MLP as the reference
         ref_gt, _, _ = O.render(m, p16, fr, mo, colors, alpha, volume=gt)
         a, b = syn.psnr(ours_n, ours_gt), syn.psnr(ref_n, ref_gt)

@@ -296,6 +296,42 @@ def test_shaded_marcher_closed_forms():
     assert float(np.dot(fr3.light_dir, fr3.f[3:6])) <= 0
 
 
+def test_single_kernel_marcher_closed_forms():
+    """raymarching_traceray (method_raymarching.cu:400-487): equal steps per macrocell (sample_size_scaler) integrate the
+    same opacity as the streaming marcher; constant volumes shade to 5 % under gradient shading; the single shade is bounded."""
+    dims = (32, 32, 32)
+    n = 16
+    rgb = np.tile(np.array([[1.0, 0.5, 0.25]], np.float32), (n, 1))
+    alpha = np.full(n, 0.02, np.float32)
+    colors = np.concatenate([rgb, np.ones((n, 1), np.float32)], 1)
+    cam = (np.array([0, 0, -100], np.float32), np.zeros(3, np.float32), np.array([0, 1, 0], np.float32))
+    vol = np.full(dims[::-1], 0.5, np.float32)
+    mo = O.macrocell_max_opacity(O.macrocell_update_implicit(vol, dims), alpha)
+    img, _, st = O.render_single_kernel(O.Frame(dims, 33, 33, *cam, fovy=10.0), mo, colors, alpha, vol, jitter_mode=1)
+    want_alpha = 1 - (1 - 0.02) ** 32.0            # opacity correction makes the result independent of the step count
+    assert abs(img[16, 16, 3] - want_alpha) < 2e-3
+    assert np.allclose(img[16, 16, :3], want_alpha * np.array([1.0, 0.5, 0.25]), atol=2e-3)
+    # equal division: a 16-voxel macrocell crossed head-on with max-opacity 0.02 -> adaptive step 1 + 15 * 0.9^2 = 13.15
+    # -> N = int(16 / 13.15 + 1) = 2 steps of 8 per cell (the streaming marcher takes 13.15 + 2.85)
+    assert st["samples_decoded"] // st["rays_hit"] == 4
+    shaded, _, st1 = O.render_single_kernel(O.Frame(dims, 33, 33, *cam, fovy=10.0, shade_mode=1), mo, colors, alpha, vol, jitter_mode=1)
+    assert np.array_equal(shaded[..., 3], img[..., 3]) and st1["samples_decoded"] == 4 * st["samples_decoded"]
+    assert np.allclose(shaded[..., :3], 0.05 * img[..., :3], atol=1e-6)
+    vol = syn.make_volume(dims, seed=3)
+    rgb2, alpha2 = syn.make_tfn(64)
+    colors2 = np.concatenate([rgb2, np.ones((64, 1), np.float32)], 1)
+    mo = O.macrocell_max_opacity(O.macrocell_update_implicit(vol, dims), alpha2)
+    cam2 = syn.default_camera(dims, 3)
+    plain, _, _ = O.render_single_kernel(O.Frame(dims, 40, 40, *cam2), mo, colors2, alpha2, vol)
+    stream, _, _ = O.render(O.ModelCfg(2, 2, 8, 4, 2.0, 1), None, O.Frame(dims, 40, 40, *cam2), mo, colors2, alpha2, volume=vol)
+    assert syn.psnr(plain, stream) > 35.0
+    ssh, _, _ = O.render_single_kernel(O.Frame(dims, 40, 40, *cam2, shade_mode=2), mo, colors2, alpha2, vol)
+    lo = 0.05 * plain[..., :3]
+    assert np.array_equal(ssh[..., 3], plain[..., 3])
+    assert (ssh[..., :3] >= lo - 1e-6).all() and (ssh[..., :3] <= lo + 0.95 * rgb2.max() * plain[..., 3:4] + 1e-6).all()
+    assert (ssh[..., :3] > lo + 1e-4).any()
+
+
 def test_training_reduces_loss_small_model():
     m = O.ModelCfg(4, 2, 10, 4, 2.0, 2)
     dims = (16, 16, 16)
