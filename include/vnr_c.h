@@ -91,6 +91,19 @@ int vnr_volume_set_groundtruth_f32(vnr_volume_t* v, const float* h_volume);
  * in-core (a 1024^3 float volume is 4 GiB of the 180 GB). */
 int vnr_volume_set_groundtruth_file(vnr_volume_t* v, const char* path, int value_type, uint64_t offset, int big_endian,
                                     float vmin, float vmax, float* range_out2);
+/* OutOfCoreSampler (core/samplers/neural_sampler.cpp:1040-1120) with its RandomBuffer (:488-668): the volume stays in the
+ * file; a pool of `num_blocks` random slabs (full x-rows x ceil(32 KiB / row bytes) y-rows x 1 z-slice, + 1 ghost row / slice
+ * per side), kept in HBM in the file's scalar type (little endian), is refreshed by `num_concurrent_blocks` slabs per
+ * training step and sampled on the device: random slab, random voxel, random point in its cell, trilinear interpolation
+ * of the values normalised with [vmin, vmax] BEFORE interpolating.  0 for either count: environment VNR_NUM_CONCURRENT_BLOCKS
+ * (1024) / VNR_NUM_BLOCKS (64 x concurrent), as the reference.  A valid range is required (:1068-1070).  Afterwards
+ * vnr_volume_train / vnr_volume_sample draw from the pool (five uniforms of the sampler's pcg32 stream per sample). */
+int vnr_volume_set_groundtruth_outofcore(vnr_volume_t* v, const char* path, int value_type, uint64_t offset, float vmin, float vmax,
+                                         uint32_t num_concurrent_blocks, uint32_t num_blocks);
+/* pool geometry and, for test restatement, the slab table the next sample call will use (first file voxel and voxel count
+ * per slot; arrays of n_slots entries or NULL); bytes_uploaded counts host->device slab traffic so far */
+int vnr_volume_outofcore_info(vnr_volume_t* v, uint32_t* n_slots, uint32_t* n_refresh, uint64_t* slot_bytes, uint64_t* first_voxel,
+                              uint32_t* length, uint64_t* bytes_uploaded);
 /* same from a device buffer (float[dx*dy*dz], copied): volumes produced / streamed on the GPU */
 int vnr_volume_set_groundtruth_device(vnr_volume_t* v, const float* d_volume);
 /* MacroCell::compute_everything (core/macrocell.cu:221-230): value ranges from ground truth */

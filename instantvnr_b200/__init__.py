@@ -104,6 +104,8 @@ def model_json(n_levels=8, n_features=8, log2_hashmap=19, base_res=16, n_hidden=
 class NeuralVolume:
     """vnrVolume (neural) -- api.h:122-143."""
 
+    uniforms_per_sample = 3          # StaticSampler: x, y, z; the out-of-core sampler draws 5 (+ slab and voxel selectors)
+
     def __init__(self, model_json_text, dims):
         self._h = C.c_void_p()
         _check(lib().vnr_volume_create(model_json_text.encode(), int(dims[0]), int(dims[1]), int(dims[2]), C.byref(self._h)))
@@ -183,6 +185,23 @@ class NeuralVolume:
         _check(lib().vnr_volume_set_groundtruth_file(self._h, str(path).encode(), C.c_int(self.VALUE_TYPES[str(np.dtype(dtype))]), C.c_uint64(offset),
                                                      C.c_int(1 if big_endian else 0), C.c_float(lo), C.c_float(hi), r))
         return float(r[0]), float(r[1])
+
+    def set_groundtruth_outofcore(self, path, dtype, value_range, offset=0, num_concurrent_blocks=0, num_blocks=0):
+        """OutOfCoreSampler: the volume stays in the file; training draws from a pool of random slabs kept in HBM"""
+        _check(lib().vnr_volume_set_groundtruth_outofcore(self._h, str(path).encode(), C.c_int(self.VALUE_TYPES[str(np.dtype(dtype))]), C.c_uint64(offset),
+                                                          C.c_float(value_range[0]), C.c_float(value_range[1]), C.c_uint32(num_concurrent_blocks),
+                                                          C.c_uint32(num_blocks)))
+        self.uniforms_per_sample = 5
+
+    def outofcore_info(self, table=False):
+        ns, nr, sb, up = C.c_uint32(), C.c_uint32(), C.c_uint64(), C.c_uint64()
+        _check(lib().vnr_volume_outofcore_info(self._h, C.byref(ns), C.byref(nr), C.byref(sb), None, None, C.byref(up)))
+        info = {"n_slots": ns.value, "n_refresh": nr.value, "slot_bytes": sb.value, "bytes_uploaded": up.value}
+        if table:
+            first = np.empty(ns.value, dtype=np.uint64); length = np.empty(ns.value, dtype=np.uint32)
+            _check(lib().vnr_volume_outofcore_info(self._h, None, None, None, _ptr(first), _ptr(length), C.byref(up)))
+            info.update(first_voxel=first, length=length, bytes_uploaded=up.value)
+        return info
 
     def set_groundtruth_device(self, d_volume):
         _check(lib().vnr_volume_set_groundtruth_device(self._h, _ptr(d_volume)))

@@ -1,0 +1,269 @@
+// slab_sampler.cu -- the out-of-core training sampler: a pool of random slabs of the volume file resident in HBM,
+// refreshed every step, sampled on the device.
+//
+// Replaces OutOfCoreSampler::sample (core/samplers/neural_sampler.cpp:1065-1120) and its RandomBuffer (:488-668).
+// The reference keeps NUM_BLOCKS (65 536) slabs in HOST memory -- a slab is the full x-row x ceil(32 KiB / row bytes)
+// y-rows x 1 z-slice, plus one ghost row / slice on every side -- replaces NUM_CONCURRENT_BLOCKS (1024) of them per
+// step through libaio, and evaluates every training sample on the CPU with TBB (pick a random slab, a random voxel of
+// it, a random point in that voxel's cell, trilinear interpolation of the values normalised BEFORE interpolating),
+// then uploads 16 B per sample.  Here the pool lives in HBM in the file's own scalar type (the 64 x 1024 default slabs
+// of a 1024^3 float volume are 7.9 GB of the 180 GB); a step uploads the refreshed slabs (pread workers -> pinned
+// double buffer -> two cudaMemcpyAsync) and ONE kernel draws and interpolates the batch where it is consumed.  The
+// per-sample arithmetic (index selection, coordinate, trilinear_vkl :302-329) is restated exactly; the uniforms come
+// from the sampler's pcg32 stream (five per sample) instead of the reference's unseeded std::mt19937.
+#include <atomic>
+#include <cstdlib>
+#include <fcntl.h>
+#include <memory>
+#include <thread>
+#include <unistd.h>
+
+#include "train.h"
+#include "volume.h"
+
+namespace vnr {
+
+enum { SLAB_U8 = 0, SLAB_I8, SLAB_U16, SLAB_I16, SLAB_U32, SLAB_I32, SLAB_F32 = 8, SLAB_F64 = 12 };   // ValueType, core/mathdef.h:51-65
+
+static size_t slab_elem_size(int t) {
+  switch (t) {
+    case SLAB_U8: case SLAB_I8: return 1;
+    case SLAB_U16: case SLAB_I16: return 2;
+    case SLAB_U32: case SLAB_I32: case SLAB_F32: return 4;
+    case SLAB_F64: return 8;
+    default: throw UnsupportedError("unsupported voxel type (scalar uint8/int8/uint16/int16/uint32/int32/float/double only)");
+  }
+}
+
+// RandomBuffer::Block (:497-503), reduced to what the sampling kernel reads
+struct SlabDesc {
+  uint64_t first_voxel;      // flattened file index of the slab's first (non-ghost) voxel
+  uint32_t length;           // voxels in the slab proper
+  int gy0, gz0, gny, gnz;    // ghost-extended bounds: lower y / z and extent in y / z (x is always the full row)
+};
+
+struct SlabSampler {
+  int fd = -1;
+  uint64_t file_offset = 0;
+  int type = SLAB_F32; size_t elem = 4;
+  int dims[3] = {0, 0, 0};
+  float vmin = 0.f, vmax = 1.f;
+  int block_rows = 1;                    // block_dims.y (:541)
+  int nby = 1, nbz = 1;                  // block_index_space (:548-550)
+  size_t slot_bytes = 0;                 // block_size_aligned (:560)
+  uint32_t n_slots = 0, n_refresh = 0;   // NUM_BLOCKS, NUM_CONCURRENT_BLOCKS
+  DevBuf<uint8_t> pool;
+  DevBuf<SlabDesc> table;
+  std::vector<SlabDesc> h_table;
+  uint8_t* h_stage[2] = {nullptr, nullptr};
+  SlabDesc* h_desc[2] = {nullptr, nullptr};
+  cudaEvent_t copied[2] = {nullptr, nullptr};
+  int cur = 0;
+  bool pending = false; uint32_t pending_first = 0;
+  std::vector<std::thread> workers;
+  std::atomic<int> io_error{0};
+  Pcg32 host_rng;                        // slab selection (the reference: std::mt19937, neural_sampler.cu:62-75)
+  uint64_t bytes_uploaded = 0;
+
+  ~SlabSampler() {
+    for (auto& t : workers) if (t.joinable()) t.join();
+    for (int k = 0; k < 2; ++k) { if (h_stage[k]) cudaFreeHost(h_stage[k]); if (h_desc[k]) cudaFreeHost(h_desc[k]); if (copied[k]) cudaEventDestroy(copied[k]); }
+    if (fd >= 0) close(fd);
+  }
+
+  // submit_one_job (:588-646): describe block (by, bz) and read its ghost-extended rows into `dst`
+  SlabDesc describe(int by, int bz) const {
+    const int y0 = by * block_rows, y1 = std::min(y0 + block_rows, dims[1]);
+    const int z0 = bz, z1 = std::min(z0 + 1, dims[2]);
+    SlabDesc d;
+    d.first_voxel = ((uint64_t)z0 * dims[1] + (uint64_t)y0) * dims[0];
+    d.length = (uint32_t)((uint64_t)dims[0] * (y1 - y0) * (z1 - z0));
+    d.gy0 = std::max(y0 - 1, 0); d.gz0 = std::max(z0 - 1, 0);
+    d.gny = std::min(y1 + 1, dims[1]) - d.gy0; d.gnz = std::min(z1 + 1, dims[2]) - d.gz0;
+    return d;
+  }
+  void read_block(const SlabDesc& d, uint8_t* dst) {
+    const size_t slice_bytes = (size_t)dims[0] * d.gny * elem;
+    for (int z = 0; z < d.gnz; ++z) {
+      const uint64_t off = file_offset + (((uint64_t)(d.gz0 + z) * dims[1] + (uint64_t)d.gy0) * dims[0]) * elem;
+      size_t got = 0;
+      while (got < slice_bytes) {
+        const ssize_t r = pread(fd, dst + z * slice_bytes + got, slice_bytes - got, (off_t)(off + got));
+        if (r <= 0) { io_error = 1; return; }
+        got += (size_t)r;
+      }
+    }
+  }
+
+  // submit_all_jobs (:648-656): n_refresh consecutive slots starting at `first` get new random blocks; the reads run on
+  // worker threads into the staging buffer `cur ^ 1` while the GPU works on the current step
+  void submit(int64_t first_or_neg) {
+    const int k = cur ^ 1;
+    VNR_CUDA(cudaEventSynchronize(copied[k]));                 // the staging buffer's previous upload has left the host
+    const uint32_t first = first_or_neg < 0 ? host_rng.next_uint() % n_slots : (uint32_t)first_or_neg;
+    for (uint32_t j = 0; j < n_refresh; ++j) {
+      const uint32_t b = host_rng.next_uint() % (uint32_t)(nby * nbz);      // random_grid_index(block_index_space)
+      h_desc[k][j] = describe((int)(b % (uint32_t)nby), (int)(b / (uint32_t)nby));
+    }
+    const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    const uint32_t nt = std::min<uint32_t>(hw, n_refresh);
+    workers.clear();
+    for (uint32_t t = 0; t < nt; ++t)
+      workers.emplace_back([this, k, t, nt] { for (uint32_t j = t; j < n_refresh; j += nt) read_block(h_desc[k][j], h_stage[k] + (size_t)j * slot_bytes); });
+    pending = true; pending_first = first;
+  }
+
+  // wait_all_jobs (:658-661) + upload: slots first .. first + n_refresh - 1 (mod n_slots) <- staging buffer
+  void wait_and_upload(cudaStream_t s) {
+    if (!pending) return;
+    for (auto& t : workers) if (t.joinable()) t.join();
+    workers.clear();
+    if (io_error) throw InvalidError("reading the volume file failed (shorter than dims * voxel size?)");
+    const int k = cur ^ 1;
+    const uint32_t first = pending_first, n0 = std::min(n_refresh, n_slots - first), n1 = n_refresh - n0;
+    VNR_CUDA(cudaMemcpyAsync(pool.p + (size_t)first * slot_bytes, h_stage[k], (size_t)n0 * slot_bytes, cudaMemcpyHostToDevice, s));
+    VNR_CUDA(cudaMemcpyAsync(table.p + first, h_desc[k], (size_t)n0 * sizeof(SlabDesc), cudaMemcpyHostToDevice, s));
+    if (n1) {
+      VNR_CUDA(cudaMemcpyAsync(pool.p, h_stage[k] + (size_t)n0 * slot_bytes, (size_t)n1 * slot_bytes, cudaMemcpyHostToDevice, s));
+      VNR_CUDA(cudaMemcpyAsync(table.p, h_desc[k] + n0, (size_t)n1 * sizeof(SlabDesc), cudaMemcpyHostToDevice, s));
+    }
+    VNR_CUDA(cudaEventRecord(copied[k], s));
+    for (uint32_t j = 0; j < n_refresh; ++j) h_table[(first + j) % n_slots] = h_desc[k][j];
+    bytes_uploaded += (uint64_t)n_refresh * slot_bytes;
+    pending = false;
+    cur = k;
+  }
+};
+
+template <typename T> __device__ __forceinline__ float slab_load(const uint8_t* __restrict__ p, size_t i) { return (float)reinterpret_cast<const T*>(p)[i]; }
+__device__ __forceinline__ float slab_value(const uint8_t* __restrict__ p, size_t i, int type) {
+  switch (type) {      // read_typed_pointer
+    case SLAB_U8: return slab_load<uint8_t>(p, i);
+    case SLAB_I8: return slab_load<int8_t>(p, i);
+    case SLAB_U16: return slab_load<uint16_t>(p, i);
+    case SLAB_I16: return slab_load<int16_t>(p, i);
+    case SLAB_U32: return slab_load<uint32_t>(p, i);
+    case SLAB_I32: return slab_load<int32_t>(p, i);
+    case SLAB_F64: return slab_load<double>(p, i);
+    default: return slab_load<float>(p, i);
+  }
+}
+
+// One thread per training sample (the body of the tbb::parallel_for, :1087-1113).  Uniforms: stream positions
+// 5 s .. 5 s + 4 of the sampler's pcg32 = cell jitter x, y, z, slab selector, voxel selector.
+__global__ void slab_sample_kernel(uint32_t n, Pcg32 base, const uint8_t* __restrict__ pool, size_t slot_bytes, const SlabDesc* __restrict__ table,
+                                   uint32_t n_slots, int type, int3 dims, float vlo, float vscale,
+                                   float* __restrict__ coords, float* __restrict__ values) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  Pcg32 r = base;
+  r.advance(5ull * s);
+  const float jx = r.next_float(), jy = r.next_float(), jz = r.next_float(), ub = r.next_float(), uv = r.next_float();
+  const uint32_t bidx = min((uint32_t)(ub * (float)n_slots), n_slots - 1u);
+  const SlabDesc d = table[bidx];
+  const uint32_t vidx = min((uint32_t)(uv * (float)d.length), d.length - 1u);
+  // to_grid_index(locate_voxel(bidx, vidx), dims)
+  const uint64_t lin = d.first_voxel + vidx;
+  const uint64_t sy = (uint64_t)dims.x, sz = (uint64_t)dims.x * dims.y;
+  const int vx = (int)(lin % sy), vy = (int)((lin % sz) / sy), vz = (int)(lin / sz);
+  const float px = jx + (float)vx, py = jy + (float)vy, pz = jz + (float)vz;
+  // p * rfdims * (upper - lower) + lower with the training box lower = 0, upper = 1 (network.cu:236-238)
+  coords[3 * (size_t)s] = px * (1.f / (float)dims.x) * 1.f + 0.f;
+  coords[3 * (size_t)s + 1] = py * (1.f / (float)dims.y) * 1.f + 0.f;
+  coords[3 * (size_t)s + 2] = pz * (1.f / (float)dims.z) * 1.f + 0.f;
+  // trilinear_vkl(clamp(p, 0.5, dims - 0.5)) :302-329
+  const float bx = fminf(fmaxf(px, 0.5f), (float)dims.x - 0.5f) - 0.5f;
+  const float by = fminf(fmaxf(py, 0.5f), (float)dims.y - 0.5f) - 0.5f;
+  const float bz = fminf(fmaxf(pz, 0.5f), (float)dims.z - 0.5f) - 0.5f;
+  const float ix = truncf(bx), iy = truncf(by), iz = truncf(bz);           // std::modf: b >= 0 here
+  const float wx = bx - ix, wy = by - iy, wz = bz - iz;
+  const int x0 = min(max((int)ix, 0), dims.x - 1), y0 = min(max((int)iy, 0), dims.y - 1), z0 = min(max((int)iz, 0), dims.z - 1);
+  const int x1 = min(x0 + 1, dims.x - 1), y1 = min(y0 + 1, dims.y - 1), z1 = min(z0 + 1, dims.z - 1);
+  const uint8_t* __restrict__ slab = pool + (size_t)bidx * slot_bytes;
+  auto at = [&](int x, int y, int z) {      // access_voxel :663-673 + normalise before interpolating :1105
+    const size_t i = ((size_t)(z - d.gz0) * d.gny + (size_t)(y - d.gy0)) * dims.x + (size_t)x;
+    const float v = (slab_value(slab, i, type) - vlo) * vscale;
+    return fminf(fmaxf(v, 0.f), 1.f);
+  };
+  const float c000 = at(x0, y0, z0), c001 = at(x1, y0, z0), c010 = at(x0, y1, z0), c011 = at(x1, y1, z0);
+  const float c100 = at(x0, y0, z1), c101 = at(x1, y0, z1), c110 = at(x0, y1, z1), c111 = at(x1, y1, z1);
+  const float ox = 1.f - wx, oy = 1.f - wy, oz = 1.f - wz;
+  values[s] = ox * oy * oz * c000 + wx * oy * oz * c001 + ox * wy * oz * c010 + wx * wy * oz * c011 +
+              ox * oy * wz * c100 + wx * oy * wz * c101 + ox * wy * wz * c110 + wx * wy * wz * c111;
+}
+
+static uint32_t env_u32(const char* name, uint32_t fallback) {
+  if (const char* e = getenv(name)) { const long v = atol(e); if (v > 0) return (uint32_t)v; }
+  return fallback;
+}
+
+void outofcore_release(Volume* v) { delete v->ooc; v->ooc = nullptr; }
+
+// OutOfCoreSampler::OutOfCoreSampler (:1040-1063) + RandomBuffer::RandomBuffer (:526-582)
+void outofcore_open(Volume* v, const char* path, int type, uint64_t offset, float vmin, float vmax, uint32_t n_concurrent, uint32_t n_blocks) {
+  if (!(vmax > vmin)) throw InvalidError("a valid value range must be provided");          // :1068-1070
+  std::unique_ptr<SlabSampler> sp(new SlabSampler);
+  SlabSampler& q = *sp;
+  q.elem = slab_elem_size(type); q.type = type; q.file_offset = offset; q.vmin = vmin; q.vmax = vmax;
+  for (int k = 0; k < 3; ++k) q.dims[k] = v->dims[k];
+  q.fd = open(path, O_RDONLY);
+  if (q.fd < 0) throw InvalidError(std::string("cannot open volume file ") + path);
+  const uint64_t need = offset + (uint64_t)q.dims[0] * q.dims[1] * q.dims[2] * q.elem;
+  if ((uint64_t)lseek(q.fd, 0, SEEK_END) < need) throw InvalidError("volume file is shorter than dims * voxel size");
+  constexpr uint64_t kStream = 32 * 1024, kAlign = 512;                                    // STREAM_SIZE, ALIGNMENT :490-491
+  const uint64_t row_bytes = (uint64_t)q.dims[0] * q.elem;
+  q.block_rows = (int)std::min<uint64_t>((kStream + row_bytes - 1) / row_bytes, (uint64_t)q.dims[1]);
+  q.nby = (q.dims[1] + q.block_rows - 1) / q.block_rows; q.nbz = q.dims[2];
+  const uint64_t gy = std::min(q.block_rows + 2, q.dims[1]), gz = std::min(3, q.dims[2]);
+  q.slot_bytes = (size_t)(((uint64_t)q.dims[0] * gy * gz * q.elem + kAlign - 1) / kAlign * kAlign);
+  q.n_refresh = n_concurrent ? n_concurrent : env_u32("VNR_NUM_CONCURRENT_BLOCKS", 1024);
+  q.n_slots = n_blocks ? n_blocks : env_u32("VNR_NUM_BLOCKS", q.n_refresh * 64);
+  if (q.n_refresh > q.n_slots) throw InvalidError("more concurrent blocks than blocks");
+  if ((uint64_t)q.n_slots * q.slot_bytes > ((uint64_t)96 << 30)) throw InvalidError("slab pool larger than 96 GiB: lower VNR_NUM_BLOCKS");
+  q.pool.alloc((size_t)q.n_slots * q.slot_bytes);
+  q.table.alloc(q.n_slots);
+  q.h_table.resize(q.n_slots);
+  for (int k = 0; k < 2; ++k) {
+    VNR_CUDA(cudaMallocHost((void**)&q.h_stage[k], (size_t)q.n_refresh * q.slot_bytes));
+    VNR_CUDA(cudaMallocHost((void**)&q.h_desc[k], (size_t)q.n_refresh * sizeof(SlabDesc)));
+    VNR_CUDA(cudaEventCreateWithFlags(&q.copied[k], cudaEventDisableTiming));
+  }
+  q.host_rng.seed(1337, 2);
+  // preload every slot (:571-577), n_refresh at a time; the last group wraps around when n_slots % n_refresh != 0
+  for (uint32_t i = 0; i < q.n_slots; i += q.n_refresh) {
+    q.submit((int64_t)i);
+    q.wait_and_upload(v->stream);
+  }
+  VNR_CUDA(cudaStreamSynchronize(v->stream));
+  q.submit(-1);                                                                              // :579
+  outofcore_release(v);
+  v->ooc = sp.release();
+}
+
+// OutOfCoreSampler::sample (:1065-1120)
+void outofcore_sample(Volume* v, float* d_xyz, float* d_target, size_t n, cudaStream_t s) {
+  SlabSampler& q = *v->ooc;
+  q.wait_and_upload(s);                                                                      // randbuf.wait_all_jobs()
+  const int3 dims = make_int3(q.dims[0], q.dims[1], q.dims[2]);
+  slab_sample_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>((uint32_t)n, v->sampler_rng, q.pool.p, q.slot_bytes, q.table.p, q.n_slots, q.type, dims,
+                                                                  q.vmin, 1.f / (q.vmax - q.vmin), d_xyz, d_target);
+  VNR_CUDA(cudaGetLastError());
+  v->sampler_rng.advance(5 * (uint64_t)n);
+  q.submit(-1);                                                                              // randbuf.submit_all_jobs()
+}
+
+void outofcore_info(Volume* v, uint32_t* n_slots, uint32_t* n_refresh, uint64_t* slot_bytes, uint64_t* first_voxel, uint32_t* length, uint64_t* bytes_uploaded) {
+  if (!v->ooc) throw StateError("no out-of-core sampler on this volume");
+  SlabSampler& q = *v->ooc;
+  if (n_slots) *n_slots = q.n_slots;
+  if (n_refresh) *n_refresh = q.n_refresh;
+  if (slot_bytes) *slot_bytes = q.slot_bytes;
+  if (bytes_uploaded) *bytes_uploaded = q.bytes_uploaded;
+  // the table the NEXT sample call will see: the pending refresh is applied here so the caller can restate the batch
+  if (first_voxel || length) {
+    q.wait_and_upload(v->stream);
+    for (uint32_t i = 0; i < q.n_slots; ++i) { if (first_voxel) first_voxel[i] = q.h_table[i].first_voxel; if (length) length[i] = q.h_table[i].length; }
+  }
+}
+
+}  // namespace vnr

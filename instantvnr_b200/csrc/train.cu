@@ -104,6 +104,11 @@ void decode_progressive(Volume* v, cudaStream_t s) {
 
 void sample_batch(Volume* v, float* d_xyz, float* d_target, size_t n, cudaStream_t s) {
   if (!n) return;
+  if (v->ooc) {                                  // out-of-core ground truth: slabs of the file, sampled where they are resident
+    if (!d_target) { v->train_y.ensure(n); d_target = v->train_y.p; }
+    outofcore_sample(v, d_xyz, d_target, n, s);
+    return;
+  }
   if (d_target && !v->have_gt) throw StateError("[error]: missing a reference volume.");       // network.cu:233
   const size_t n_floats = 3 * n, need = (n_floats + 3) / 4;
   const uint32_t n_threads = (uint32_t)(((need + 127) / 128) * 128);
@@ -807,7 +812,7 @@ double volume_psnr(Volume* v, cudaStream_t s) {
 
 // NeuralVolume::Impl::train (network.cu:231-259)
 void train_steps(Volume* v, int steps, size_t batch, bool update_macrocell, cudaStream_t s) {
-  if (!v->have_gt) throw StateError("[error]: missing a reference volume.");
+  if (!v->have_gt && !v->ooc) throw StateError("[error]: missing a reference volume.");
   if (batch == 0) batch = 1 << 16;                                       // network.cu:183
   if (batch % kTile) throw InvalidError("Batch size must be a multiple of 128.");
   v->train_x.ensure(3 * batch); v->train_y.ensure(batch);

@@ -35,6 +35,7 @@ static void require_device() {
 Volume::Volume() { sampler_rng.seed(1337); }
 Volume::~Volume() {
   if (stream) cudaStreamSynchronize(stream);
+  outofcore_release(this);
   for (int r = 0; r < dp_world; ++r) {          // mappings of the peers' buffers (vnr_volume_dp_attach)
     if (r == dp_rank) continue;
     if (dp_params[r]) cudaIpcCloseMemHandle(dp_params[r]);

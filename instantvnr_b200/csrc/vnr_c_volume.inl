@@ -188,6 +188,19 @@ VNR_EXPORT int vnr_volume_set_groundtruth_file(vnr_volume_t* vh, const char* pat
   });
 }
 
+// OutOfCoreSampler (core/samplers/neural_sampler.cpp:1040-1120): training draws from a pool of random slabs of the file
+VNR_EXPORT int vnr_volume_set_groundtruth_outofcore(vnr_volume_t* vh, const char* path, int value_type, uint64_t offset, float vmin, float vmax,
+                                                    uint32_t num_concurrent_blocks, uint32_t num_blocks) {
+  return guard([&] {
+    if (!path) throw InvalidError("null path");
+    outofcore_open(V(vh), path, value_type, offset, vmin, vmax, num_concurrent_blocks, num_blocks);
+  });
+}
+VNR_EXPORT int vnr_volume_outofcore_info(vnr_volume_t* vh, uint32_t* n_slots, uint32_t* n_refresh, uint64_t* slot_bytes, uint64_t* first_voxel,
+                                         uint32_t* length, uint64_t* bytes_uploaded) {
+  return guard([&] { outofcore_info(V(vh), n_slots, n_refresh, slot_bytes, first_voxel, length, bytes_uploaded); });
+}
+
 VNR_EXPORT int vnr_volume_macrocell_from_groundtruth(vnr_volume_t* vh) {
   return guard([&] {
     Volume* v = V(vh);

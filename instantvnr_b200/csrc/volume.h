@@ -22,6 +22,8 @@ struct DevBuf {
   size_t bytes() const { return n * sizeof(T); }
 };
 
+struct SlabSampler;
+
 struct Volume {
   ModelConfig cfg;
   int dims[3] = {0, 0, 0};
@@ -47,6 +49,7 @@ struct Volume {
   bool have_gt = false;
   Pcg32 sampler_rng;               // neural_sampler.cu:36  `static default_rng_t rng{1337}`
   DevBuf<float> train_x, train_y;
+  SlabSampler* ooc = nullptr;      // out-of-core sampler (slab_sampler.cu): training draws from a pool of random file slabs
 
   // progressively decoded volume (network.cu:290-326): what the "decoding" rendering modes march
   DevBuf<float> decoded; int decode_blob = 0;

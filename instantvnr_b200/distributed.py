@@ -24,9 +24,9 @@ def strip_rows(height, rank, world, strip=4):
     return [y for y in range(height) if (y // strip) % world == rank]
 
 
-def sampler_schedule(rank, world, n):
+def sampler_schedule(rank, world, n, uniforms_per_sample=3):
     """(uniforms to skip before, uniforms to skip after) this rank's draw of n samples in one DP step"""
-    return rank * 3 * n, (world - 1 - rank) * 3 * n
+    return rank * uniforms_per_sample * n, (world - 1 - rank) * uniforms_per_sample * n
 
 
 def make_peer_barrier(group=None):
@@ -126,7 +126,7 @@ class DataParallelTrainer:
         return torch.cuda.stream(st) if st is not None else _Null()
 
     def step(self, n_per_rank, fast_mode=True, want_loss=False):
-        before, after = sampler_schedule(self.rank, self.world, n_per_rank)
+        before, after = sampler_schedule(self.rank, self.world, n_per_rank, getattr(getattr(self.b, "vol", None), "uniforms_per_sample", 3))
         with self._stream_ctx():
             self.b.sampler_skip(before)
             xyz, tgt = self.b.sample(n_per_rank)

@@ -199,6 +199,20 @@ def macrocell_max_opacity(mc, alphas, lo=0.0, hi=1.0):
     return out
 
 
+def ooc_sample(state_inc, n, first_voxel, length, block_rows, raw_f32, dims, vmin, vmax):
+    """OutOfCoreSampler::sample restated: returns (coords[n,3], values[n], bound violations); state_inc is advanced by 5 n."""
+    first_voxel = np.ascontiguousarray(first_voxel, dtype=np.uint64)
+    length = np.ascontiguousarray(length, dtype=np.uint32)
+    raw = _f32(raw_f32)
+    d = np.array(dims, dtype=np.int32)
+    coords = np.empty((n, 3), dtype=np.float32)
+    values = np.empty(n, dtype=np.float32)
+    lib().orc_ooc_sample.restype = C.c_uint64
+    bad = lib().orc_ooc_sample(_p(state_inc), C.c_size_t(n), _p(first_voxel), _p(length), C.c_uint32(first_voxel.size), C.c_int(block_rows),
+                               _p(raw), _p(d), C.c_float(vmin), C.c_float(vmax), _p(coords), _p(values))
+    return coords, values, int(bad)
+
+
 class Frame:
     """Per-frame constants (LaunchParams / DeviceVolume subset, instantvnr_types.h:89-149)."""
 

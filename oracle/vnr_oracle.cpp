@@ -780,6 +780,59 @@ ORC_API void orc_macrocell_max_opacity(const float* mc, size_t cells, const floa
   }
 }
 
+// --------------------------- out-of-core sampler ---------------------------
+// OutOfCoreSampler::sample (core/samplers/neural_sampler.cpp:1065-1120), body of the parallel_for: slab `bidx` and voxel
+// `vidx` from two uniforms, a random point in that voxel's cell from three more, trilinear_vkl (:302-329) over values
+// normalised before interpolating.  `raw` is the whole file converted to float as read_typed_pointer does ((float)v); the
+// reference reads the same voxels from the slab's ghost-extended copy -- every access is checked against those bounds
+// (block_rows y-rows x 1 z-slice + 1 ghost on each side, RandomBuffer :536-552,603-606) and violations are returned.
+// Uniforms: the sampler's pcg32 stream, five per sample (jitter x, y, z, slab selector, voxel selector).
+ORC_API uint64_t orc_ooc_sample(uint64_t* state_inc, size_t n, const uint64_t* first_voxel, const uint32_t* length, uint32_t n_slots, int block_rows,
+                                const float* raw, const int* dims, float vmin, float vmax, float* coords, float* values) {
+  Pcg32 base; base.state = state_inc[0]; base.inc = state_inc[1];
+  const float vscale = 1.f / (vmax - vmin);
+  const float rf[3] = {1.f / (float)dims[0], 1.f / (float)dims[1], 1.f / (float)dims[2]};
+  uint64_t violations = 0;
+#pragma omp parallel for schedule(static) reduction(+ : violations)
+  for (long long s = 0; s < (long long)n; ++s) {
+    Pcg32 r = base; r.advance(5ull * (uint64_t)s);
+    const float j[3] = {r.next_float(), r.next_float(), r.next_float()};
+    const float ub = r.next_float(), uv = r.next_float();
+    uint64_t bidx = (uint64_t)(ub * (float)n_slots); if (bidx >= n_slots) bidx = n_slots - 1;
+    uint64_t vidx = (uint64_t)(uv * (float)length[bidx]); if (vidx >= length[bidx]) vidx = length[bidx] - 1;
+    const uint64_t lin = first_voxel[bidx] + vidx;
+    const uint64_t sy = (uint64_t)dims[0], sz = (uint64_t)dims[0] * dims[1];
+    const int vox[3] = {(int)(lin % sy), (int)((lin % sz) / sy), (int)(lin / sz)};
+    // slab bounds with ghosts
+    const int by0 = (int)((first_voxel[bidx] % sz) / sy), bz0 = (int)(first_voxel[bidx] / sz);
+    const int by1 = std::min(by0 + block_rows, dims[1]), bz1 = std::min(bz0 + 1, dims[2]);
+    const int gy0 = std::max(by0 - 1, 0), gy1 = std::min(by1 + 1, dims[1]), gz0 = std::max(bz0 - 1, 0), gz1 = std::min(bz1 + 1, dims[2]);
+    float p[3], b[3], w[3]; int i0[3], i1[3];
+    for (int d = 0; d < 3; ++d) {
+      p[d] = j[d] + (float)vox[d];
+      coords[3 * s + d] = p[d] * rf[d] * 1.f + 0.f;
+      b[d] = clampf(p[d], 0.5f, (float)dims[d] - 0.5f) - 0.5f;
+      float ip; w[d] = std::modf(b[d], &ip);
+      i0[d] = clampi((int)ip, 0, dims[d] - 1); i1[d] = clampi(i0[d] + 1, 0, dims[d] - 1);
+    }
+    auto at = [&](int x, int y, int z) {
+      if (y < gy0 || y >= gy1 || z < gz0 || z >= gz1) ++violations;
+      const float v = (raw[(size_t)x + (size_t)y * sy + (size_t)z * sz] - vmin) * vscale;
+      return clampf(v, 0.f, 1.f);
+    };
+    const float c000 = at(i0[0], i0[1], i0[2]), c001 = at(i1[0], i0[1], i0[2]), c010 = at(i0[0], i1[1], i0[2]), c011 = at(i1[0], i1[1], i0[2]);
+    const float c100 = at(i0[0], i0[1], i1[2]), c101 = at(i1[0], i0[1], i1[2]), c110 = at(i0[0], i1[1], i1[2]), c111 = at(i1[0], i1[1], i1[2]);
+    const float wx = w[0], wy = w[1], wz = w[2];
+    values[s] = (1 - wx) * (1 - wy) * (1 - wz) * c000 + wx * (1 - wy) * (1 - wz) * c001
+              + (1 - wx) * wy * (1 - wz) * c010 + wx * wy * (1 - wz) * c011
+              + (1 - wx) * (1 - wy) * wz * c100 + wx * (1 - wy) * wz * c101
+              + (1 - wx) * wy * wz * c110 + wx * wy * wz * c111;
+  }
+  base.advance(5ull * n);
+  state_inc[0] = base.state; state_inc[1] = base.inc;
+  return violations;
+}
+
 // --------------------------- marcher ---------------------------------------
 // params (float[64]) layout, see oracle/oracle.py FRAME_* indices.
 static Frame frame_from(const float* p, const int* ip, const float* mc_max_opacity, const float* colors, const float* alphas) {

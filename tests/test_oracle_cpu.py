@@ -332,6 +332,45 @@ def test_single_kernel_marcher_closed_forms():
     assert (ssh[..., :3] > lo + 1e-4).any()
 
 
+def test_outofcore_sampler_restatement_against_numpy():
+    """OutOfCoreSampler::sample (neural_sampler.cpp:1065-1120): the drawn point lies in the chosen voxel's cell, the value
+    is trilinear_vkl of the normalised file there, and one ghost row / slice per side covers every voxel it touches."""
+    dims = (20, 11, 7)
+    rng = np.random.default_rng(2)
+    raw = rng.integers(0, 255, dims[0] * dims[1] * dims[2]).astype(np.float32)
+    block_rows = 4
+    nby = -(-dims[1] // block_rows)
+    blocks = [(by, bz) for bz in range(dims[2]) for by in range(nby)]
+    first = np.array([(bz * dims[1] + by * block_rows) * dims[0] for by, bz in blocks], dtype=np.uint64)
+    length = np.array([dims[0] * (min(by * block_rows + block_rows, dims[1]) - by * block_rows) for by, bz in blocks], dtype=np.uint32)
+    r = O.Rng(1337)
+    s0 = r.state.copy()
+    n = 5000
+    xyz, v, bad = O.ooc_sample(r.state, n, first, length, block_rows, raw, dims, 10.0, 200.0)
+    assert bad == 0
+    assert np.array_equal(r.state, O.Rng(1337).state) is False and not np.array_equal(r.state, s0)     # stream advanced (by 5 n)
+    u = O.pcg32_floats(1337, 1, 5 * n).reshape(n, 5)
+    bidx = np.minimum((u[:, 3] * np.float32(len(blocks))).astype(np.int64), len(blocks) - 1)
+    vidx = np.minimum((u[:, 4] * length[bidx].astype(np.float32)).astype(np.int64), length[bidx] - 1)
+    lin = first[bidx].astype(np.int64) + vidx
+    vox = np.stack([lin % dims[0], (lin // dims[0]) % dims[1], lin // (dims[0] * dims[1])], 1)
+    p = u[:, :3] + vox.astype(np.float32)
+    assert np.array_equal(xyz, (p * (np.float32(1) / np.array(dims, np.float32))).astype(np.float32))
+    norm = np.clip((raw - np.float32(10.0)) * (np.float32(1) / np.float32(190.0)), 0, 1).reshape(dims[2], dims[1], dims[0]).astype(np.float64)
+    q = np.clip(p.astype(np.float64), 0.5, np.array(dims) - 0.5) - 0.5
+    i0 = np.floor(q).astype(int); w = q - i0; i1 = np.minimum(i0 + 1, np.array(dims) - 1)
+    want = np.zeros(n)
+    for cx in (0, 1):
+        for cy in (0, 1):
+            for cz in (0, 1):
+                ix = np.where(cx, i1[:, 0], i0[:, 0]); iy = np.where(cy, i1[:, 1], i0[:, 1]); iz = np.where(cz, i1[:, 2], i0[:, 2])
+                want += norm[iz, iy, ix] * np.where(cx, w[:, 0], 1 - w[:, 0]) * np.where(cy, w[:, 1], 1 - w[:, 1]) * np.where(cz, w[:, 2], 1 - w[:, 2])
+    assert np.abs(v - want).max() < 1e-5
+    # a slab without its ghost rows would not do: shrink the declared slab height and the bound check fires
+    _, _, bad2 = O.ooc_sample(O.Rng(1337).state, n, first, length, 1, raw, dims, 10.0, 200.0)
+    assert bad2 > 0
+
+
 def test_training_reduces_loss_small_model():
     m = O.ModelCfg(4, 2, 10, 4, 2.0, 2)
     dims = (16, 16, 16)
