@@ -207,8 +207,18 @@ int vnr_renderer_device_frame(vnr_renderer_t* r, void** d_rgba, void* stream_out
  * [2] samples composited, [3] wavefront rounds */
 int vnr_renderer_stats(vnr_renderer_t* r, uint64_t* stats4);
 
+/* measurement tap: decode entries emitted per wavefront round of the last frame (the reference reads the same counter back
+ * every round, method_raymarching.cu:923-929) */
+int vnr_renderer_round_counts(vnr_renderer_t* r, uint32_t* out, int max_rounds, int* n_rounds);
+
 /* MainRenderer::framebuffer_skip_download (renderer.cpp:132): 0 = keep frames on the device */
 int vnr_renderer_set_download(vnr_renderer_t* r, int on);
+/* Zero-copy download (default on; no reference counterpart -- the reference copies the frame after it is complete,
+ * renderer.cpp:133): while the download is enabled and no frame target is set, finished pixels are stored by the
+ * compositing kernels straight into the pinned host frame vnr_map_frame returns, overlapping PCIe with the rest of
+ * the wavefront; the device frame buffer (vnr_renderer_device_frame) is then NOT updated.  0 = device frame + one
+ * device->host copy after the frame. */
+int vnr_renderer_set_zero_copy(vnr_renderer_t* r, int on);
 /* framebuffer.download_async (framebuffer.h:35) on demand, for callers that disabled the automatic one:
  * enqueues the device->host copy of the current frame; vnr_map_frame then waits for it */
 int vnr_renderer_download(vnr_renderer_t* r);

@@ -400,6 +400,14 @@ class Renderer:
     def set_download(self, on):
         _check(lib().vnr_renderer_set_download(self._h, C.c_int(1 if on else 0)))
 
+    def round_counts(self, max_rounds=64):
+        out = (C.c_uint32 * max_rounds)(); n = C.c_int()
+        _check(lib().vnr_renderer_round_counts(self._h, out, C.c_int(max_rounds), C.byref(n)))
+        return [int(out[k]) for k in range(n.value)]
+
+    def set_zero_copy(self, on):
+        _check(lib().vnr_renderer_set_zero_copy(self._h, C.c_int(1 if on else 0)))
+
     def download(self):
         _check(lib().vnr_renderer_download(self._h))
 

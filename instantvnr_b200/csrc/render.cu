@@ -36,8 +36,11 @@ struct RayBuffers {
   float* ssh_jitter;   // second float of the pixel's generator: the shadow ray's jitter
 };
 
-__device__ __forceinline__ void write_pixel(const FrameParams& fp, float4* __restrict__ accum, float4* __restrict__ frame, uint32_t pixel, float4 c) {
-  // writePixelColor raytracing.h:196-207
+__device__ __forceinline__ void write_pixel(const FrameParams& fp, float4* __restrict__ accum, uint32_t pixel, float4 c) {
+  // writePixelColor raytracing.h:196-207.  fp.frame is this renderer's frame buffer, rank 0's frame buffer over NVLink
+  // (tile-parallel gather) or the caller-visible pinned host frame (zero-copy download: the pixel crosses PCIe the
+  // moment its ray finishes, overlapped with the rest of the wavefront, instead of a 16 B/pixel copy after the frame).
+  float4* __restrict__ frame = fp.frame;
   if (fp.frame_index != 1) {
     const float4 a = accum[pixel];
     c = make_float4(a.x + c.x, a.y + c.y, a.z + c.z, a.w + c.w);
@@ -49,17 +52,17 @@ __device__ __forceinline__ void write_pixel(const FrameParams& fp, float4* __res
 
 // what a finished ray leaves behind (iterative_compose_kernel :813-833)
 template <int SHADE>
-__device__ __forceinline__ void finish_ray(const FrameParams& fp, const RayBuffers& rb, float4* __restrict__ accum, float4* __restrict__ frame,
+__device__ __forceinline__ void finish_ray(const FrameParams& fp, const RayBuffers& rb, float4* __restrict__ accum,
                                            uint32_t i, uint32_t pixel, float4 rgba, float4 hi_org, float4 hi_col) {
   if (SHADE == 2) {                 // camera pass of the single-shade heuristic: park the result for the shadow pass
     rb.ssh_org[i] = hi_org; rb.ssh_col[i] = hi_col; rb.ssh_rgba[i] = rgba;
   } else if (SHADE == 3) {          // shadow pass: blend the single shade in
     const float tr = 1.f - rgba.w;
     const float4 sc = rb.ssh_rgba[i], hc = rb.ssh_col[i];
-    write_pixel(fp, accum, frame, pixel, make_float4(lerp1(VNR_SHADING_SCALE, sc.x, (hc.x * sc.w) * tr), lerp1(VNR_SHADING_SCALE, sc.y, (hc.y * sc.w) * tr),
+    write_pixel(fp, accum, pixel, make_float4(lerp1(VNR_SHADING_SCALE, sc.x, (hc.x * sc.w) * tr), lerp1(VNR_SHADING_SCALE, sc.y, (hc.y * sc.w) * tr),
                                                      lerp1(VNR_SHADING_SCALE, sc.z, (hc.z * sc.w) * tr), sc.w));
   } else {
-    write_pixel(fp, accum, frame, pixel, rgba);
+    write_pixel(fp, accum, pixel, rgba);
   }
 }
 
@@ -83,7 +86,7 @@ template <bool FIRST, int SHADE>
 __global__ void __launch_bounds__(128)
 march_round_kernel(const FrameParams* __restrict__ fpp, RayBuffers rb, float4* __restrict__ samples0, float4* __restrict__ samples1,
                    const float* __restrict__ values, uint32_t* __restrict__ counters, int round_host, const uint32_t* __restrict__ round_dev,
-                   float4* __restrict__ accum, float4* __restrict__ frame) {
+                   float4* __restrict__ accum) {
   constexpr uint32_t EPS = SHADE == 1 ? 4u : 1u;             // decode entries per sample
   const int round = FIRST ? 0 : (round_dev ? (int)(*round_dev) + 1 : round_host);
   if (!FIRST && counters[2 + round - 1] == 0) return;      // nothing was alive in the previous round
@@ -130,8 +133,8 @@ march_round_kernel(const FrameParams* __restrict__ fpp, RayBuffers rb, float4* _
         rb.jitter[i] = jitter;
         hit = true;
       } else {
-        if (SHADE == 3) write_pixel(fp, accum, frame, pixel, rb.ssh_rgba[i]);
-        else finish_ray<SHADE>(fp, rb, accum, frame, i, pixel, rgba, hi_org, hi_col);     // SHADE 2: zeros for the shadow pass (the reference memsets)
+        if (SHADE == 3) write_pixel(fp, accum, pixel, rb.ssh_rgba[i]);
+        else finish_ray<SHADE>(fp, rb, accum, i, pixel, rgba, hi_org, hi_col);     // SHADE 2: zeros for the shadow pass (the reference memsets)
         rb.state[i] = 0;
         active = false;
       }
@@ -169,7 +172,7 @@ march_round_kernel(const FrameParams* __restrict__ fpp, RayBuffers rb, float4* _
       }
       const bool resumable = dda_resumable(dda, m_dir, tmin, tmax, fp.mc_dims);
       if (!(rgba.w < VNR_NEARLY_ONE && resumable)) {
-        finish_ray<SHADE>(fp, rb, accum, frame, i, pixel, rgba, hi_org, hi_col);
+        finish_ray<SHADE>(fp, rb, accum, i, pixel, rgba, hi_org, hi_col);
         rb.state[i] = 0;
         active = false;
       }
@@ -191,7 +194,7 @@ march_round_kernel(const FrameParams* __restrict__ fpp, RayBuffers rb, float4* _
   if (active && k == 0) {
     // no sample left on this ray: the reference would carry it through one more (empty) round and
     // then find it not resumable; finish it now.
-    finish_ray<SHADE>(fp, rb, accum, frame, i, pixel, rgba, hi_org, hi_col);
+    finish_ray<SHADE>(fp, rb, accum, i, pixel, rgba, hi_org, hi_col);
     rb.state[i] = 0;
     active = false;
   }
@@ -231,7 +234,7 @@ march_round_kernel(const FrameParams* __restrict__ fpp, RayBuffers rb, float4* _
 }
 
 // rays still alive after the last enqueued round (cannot happen when the bound holds; counted)
-__global__ void finalize_kernel(const FrameParams* __restrict__ fpp, RayBuffers rb, uint32_t* __restrict__ leftover, float4* __restrict__ accum, float4* __restrict__ frame) {
+__global__ void finalize_kernel(const FrameParams* __restrict__ fpp, RayBuffers rb, uint32_t* __restrict__ leftover, float4* __restrict__ accum) {
   __shared__ FrameParams fp_s;
   stage_frame_params(&fp_s, fpp);
   const FrameParams& fp = fp_s;
@@ -240,9 +243,9 @@ __global__ void finalize_kernel(const FrameParams* __restrict__ fpp, RayBuffers 
   if (rb.state[i] >> 31) {
     const uint32_t pixel = ray_to_pixel(fp, i);
     const float4 rgba = rb.rgba[i];
-    if (fp.shade_mode == 2) finish_ray<2>(fp, rb, accum, frame, i, pixel, rgba, rb.ssh_org[i], rb.ssh_col[i]);
-    else if (fp.shade_mode == 3) finish_ray<3>(fp, rb, accum, frame, i, pixel, rgba, rb.ssh_org[i], rb.ssh_col[i]);
-    else write_pixel(fp, accum, frame, pixel, rgba);
+    if (fp.shade_mode == 2) finish_ray<2>(fp, rb, accum, i, pixel, rgba, rb.ssh_org[i], rb.ssh_col[i]);
+    else if (fp.shade_mode == 3) finish_ray<3>(fp, rb, accum, i, pixel, rgba, rb.ssh_org[i], rb.ssh_col[i]);
+    else write_pixel(fp, accum, pixel, rgba);
     rb.state[i] = 0;
     atomicAdd(leftover, 1u);
   }
@@ -259,7 +262,7 @@ __global__ void finalize_kernel(const FrameParams* __restrict__ fpp, RayBuffers 
 template <int SHADE>
 __global__ void __launch_bounds__(128)
 march_volume_kernel(const FrameParams* __restrict__ fpp, const float* __restrict__ vol, int3 dims, uint32_t* __restrict__ counters,
-                    float4* __restrict__ accum, float4* __restrict__ frame) {
+                    float4* __restrict__ accum) {
   __shared__ FrameParams fp_s;
   stage_frame_params(&fp_s, fpp);
   const FrameParams& fp = fp_s;
@@ -336,7 +339,7 @@ march_volume_kernel(const FrameParams* __restrict__ fpp, const float* __restrict
         rgba.z = lerp1(VNR_SHADING_SCALE, rgba.z, (hi_col.z * rgba.w) * tr);
       }
     }
-    write_pixel(fp, accum, frame, pixel, rgba);
+    write_pixel(fp, accum, pixel, rgba);
   }
   const uint32_t hits = __ballot_sync(0xffffffffu, hit);
 #pragma unroll
@@ -365,6 +368,7 @@ Renderer::Renderer(Volume* v) : vol(v) {
   VNR_CUDA(cudaMallocHost((void**)&h_counters, sizeof(uint32_t) * 2 * (kMaxRounds + 4)));
   memset(h_counters, 0, sizeof(uint32_t) * 2 * (kMaxRounds + 4));
   if (const char* e = getenv("VNR_RM_GRAPH")) use_graph = atoi(e) != 0;    // 0: host-enqueued rounds (profilers do not see graph-body kernels)
+  if (const char* e = getenv("VNR_FRAME_ZEROCOPY")) zero_copy = atoi(e) != 0;
   if (const char* e = getenv("VNR_RM_N_ITERS")) {       // method_raymarching.cu:30-38
     int n = atoi(e);
     if (n >= 1 && n <= 16) n_iters = n;
@@ -471,7 +475,7 @@ void Renderer::destroy_graph() {
   if (capture_stream) { cudaStreamDestroy(capture_stream); capture_stream = nullptr; }
 }
 
-typedef void (*march_kernel_t)(const FrameParams*, RayBuffers, float4*, float4*, const float*, uint32_t*, int, const uint32_t*, float4*, float4*);
+typedef void (*march_kernel_t)(const FrameParams*, RayBuffers, float4*, float4*, const float*, uint32_t*, int, const uint32_t*, float4*);
 static march_kernel_t march_kernel(bool first, int shade) {
   switch (shade) {
     case 1: return first ? march_round_kernel<true, 1> : march_round_kernel<false, 1>;
@@ -490,7 +494,7 @@ void Renderer::ensure_graph(int pass, int shade, const RayBuffers& rb, unsigned 
   key.desc = vol->cfg.desc; key.params = vol->params.p;
   key.ptrs[0] = rb.rgba; key.ptrs[1] = rb.tn_ncb; key.ptrs[2] = rb.cell_base; key.ptrs[3] = rb.state; key.ptrs[4] = rb.jitter;
   key.ptrs[5] = samples[0].p; key.ptrs[6] = samples[1].p; key.ptrs[7] = values.p; key.ptrs[8] = cnt; key.ptrs[9] = accum.p;
-  key.ptrs[10] = frame_out(); key.ptrs[11] = fpd; key.ptrs[12] = rb.ssh_org; key.ptrs[13] = rb.ssh_col; key.ptrs[14] = rb.ssh_rgba; key.ptrs[15] = rb.ssh_jitter;
+  key.ptrs[11] = fpd; key.ptrs[12] = rb.ssh_org; key.ptrs[13] = rb.ssh_col; key.ptrs[14] = rb.ssh_rgba; key.ptrs[15] = rb.ssh_jitter;
   key.grid = grid; key.cap = cap; key.rounds = rounds; key.volume_src = volume_src; key.shade = shade;
   if (loop_exec[pass] && !memcmp(&key, &graph_key[pass], sizeof key)) return;
   VNR_CUDA(cudaStreamSynchronize(stream));
@@ -520,7 +524,7 @@ void Renderer::ensure_graph(int pass, int shade, const RayBuffers& rb, unsigned 
   VNR_CUDA(cudaStreamBeginCaptureToGraph(capture_stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
   cudaError_t e = volume_src ? launch_volume_samples(volume_src, vol->dims, samples[0].p, samples[1].p, values.p, cnt + 2, round_dev, cap, capture_stream)
                              : launch_decode_samples(vol->cfg.desc, vol->params.p, samples[0].p, samples[1].p, values.p, cnt + 2, round_dev, cap, capture_stream);
-  march_kernel(false, shade)<<<grid, 128, 0, capture_stream>>>(fpd, rb, samples[0].p, samples[1].p, values.p, cnt, 0, round_dev, accum.p, frame_out());
+  march_kernel(false, shade)<<<grid, 128, 0, capture_stream>>>(fpd, rb, samples[0].p, samples[1].p, values.p, cnt, 0, round_dev, accum.p);
   advance_round_kernel<<<1, 1, 0, capture_stream>>>(cnt, round_dev, handle, 0, rounds);
   cudaGraph_t captured = nullptr;
   cudaError_t e2 = cudaStreamEndCapture(capture_stream, &captured);
@@ -551,6 +555,10 @@ void Renderer::render() {
   frame_index++;
   reset = false;
   FrameParams fp[2]; fill_frame_params(fp[0]);
+  // zero-copy download: finished pixels are stored straight into the pinned host frame map_frame() will return
+  // (cudaMallocHost memory is device-addressable under UVA); the device frame buffer is then not written
+  const bool zc = zero_copy && download && !frame_target;
+  fp[0].frame = zc ? h_frame[cur] : frame_out();
   fp[0].shade_mode = shade; fp[1] = fp[0]; fp[1].shade_mode = 3;
   const uint32_t n_rays = fp[0].n_rays;
   const int rounds = round_bound();
@@ -585,9 +593,9 @@ void Renderer::render() {
   if (single_kernel && n_rays) {
     const int3 d3 = make_int3(vol->dims[0], vol->dims[1], vol->dims[2]);
     const FrameParams* fpd = reinterpret_cast<const FrameParams*>(fp_dev.p);
-    if (shade == 1) march_volume_kernel<1><<<grid, 128, 0, stream>>>(fpd, volume_src, d3, counters.p, accum.p, frame_out());
-    else if (shade == 2) march_volume_kernel<2><<<grid, 128, 0, stream>>>(fpd, volume_src, d3, counters.p, accum.p, frame_out());
-    else march_volume_kernel<0><<<grid, 128, 0, stream>>>(fpd, volume_src, d3, counters.p, accum.p, frame_out());
+    if (shade == 1) march_volume_kernel<1><<<grid, 128, 0, stream>>>(fpd, volume_src, d3, counters.p, accum.p);
+    else if (shade == 2) march_volume_kernel<2><<<grid, 128, 0, stream>>>(fpd, volume_src, d3, counters.p, accum.p);
+    else march_volume_kernel<0><<<grid, 128, 0, stream>>>(fpd, volume_src, d3, counters.p, accum.p);
     VNR_CUDA(cudaGetLastError());
     launches = 1;
   }
@@ -595,7 +603,7 @@ void Renderer::render() {
     const int sh = pass == 1 ? 3 : shade;
     uint32_t* cnt = counters.p + (size_t)pass * cstride;
     const FrameParams* fpd = reinterpret_cast<const FrameParams*>(fp_dev.p) + pass;
-    march_kernel(true, sh)<<<grid, 128, 0, stream>>>(fpd, rb, samples[0].p, samples[1].p, nullptr, cnt, 0, nullptr, accum.p, frame_out());
+    march_kernel(true, sh)<<<grid, 128, 0, stream>>>(fpd, rb, samples[0].p, samples[1].p, nullptr, cnt, 0, nullptr, accum.p);
     if (graph_loop) {
       // device-driven loop: WHILE (round has samples) { decode; compose + march; advance }
       ensure_graph(pass, sh, rb, grid, cap, rounds, volume_src);
@@ -606,10 +614,10 @@ void Renderer::render() {
         if (volume_src) VNR_CUDA(launch_volume_samples(volume_src, vol->dims, samples[r & 1].p, nullptr, values.p, cnt + 2 + r, nullptr, cap, stream));
         else VNR_CUDA(launch_decode_samples(vol->cfg.desc, vol->params.p, samples[r & 1].p, nullptr, values.p, cnt + 2 + r, nullptr, cap, stream));
         if (profiling) VNR_CUDA(cudaEventRecord(prof_events[prof_used++], stream));
-        march_kernel(false, sh)<<<grid, 128, 0, stream>>>(fpd, rb, samples[0].p, samples[1].p, values.p, cnt, r + 1, nullptr, accum.p, frame_out());
+        march_kernel(false, sh)<<<grid, 128, 0, stream>>>(fpd, rb, samples[0].p, samples[1].p, values.p, cnt, r + 1, nullptr, accum.p);
       }
     }
-    finalize_kernel<<<grid, 128, 0, stream>>>(fpd, rb, cnt + kMaxRounds + 3, accum.p, frame_out());
+    finalize_kernel<<<grid, 128, 0, stream>>>(fpd, rb, cnt + kMaxRounds + 3, accum.p);
     VNR_CUDA(cudaGetLastError());
     if (!graph_loop) launches += 2 + 2 * (uint64_t)rounds;     // graph path: counted from the device counters in stats()
   }
@@ -618,7 +626,10 @@ void Renderer::render() {
   last_passes = single_kernel ? 1 : n_pass;
   // framebuffer.download_async (renderer.cpp:133)
   downloaded = false;
-  if (download) { VNR_CUDA(cudaMemcpyAsync(h_frame[cur], frame.p, frame.bytes(), cudaMemcpyDeviceToHost, stream)); downloaded = true; }
+  if (download) {
+    if (!zc) VNR_CUDA(cudaMemcpyAsync(h_frame[cur], frame.p, frame.bytes(), cudaMemcpyDeviceToHost, stream));
+    downloaded = true;
+  }
   VNR_CUDA(cudaMemcpyAsync(h_counters, counters.p, sizeof(uint32_t) * 2 * cstride, cudaMemcpyDeviceToHost, stream));
   VNR_CUDA(cudaEventRecord(frame_done[cur], stream));
   rendered = true;

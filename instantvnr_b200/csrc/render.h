@@ -46,6 +46,7 @@ struct Renderer {
   uint32_t* h_counters = nullptr;
   bool downloaded = false;
   bool download = true;                 // framebuffer_skip_download (renderer.cpp:132)
+  bool zero_copy = true;                // finished pixels go straight to the pinned host frame (no D2H copy after the frame)
   bool profiling = false;               // CUDA events around every decode launch
   std::vector<cudaEvent_t> prof_events;
   int prof_used = 0;

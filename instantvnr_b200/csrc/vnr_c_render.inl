@@ -65,7 +65,21 @@ VNR_EXPORT int vnr_renderer_device_frame(vnr_renderer_t* r, void** d_rgba, void*
 }
 VNR_EXPORT int vnr_renderer_stats(vnr_renderer_t* r, uint64_t* s4) { return guard([&] { if (!s4) throw InvalidError("null argument"); R(r)->stats(s4); }); }
 
+// decode entries emitted per wavefront round of the last frame (pass 0): out[r], r < max_rounds; *n_rounds = rounds with samples
+VNR_EXPORT int vnr_renderer_round_counts(vnr_renderer_t* r, uint32_t* out, int max_rounds, int* n_rounds) {
+  return guard([&] {
+    Renderer* s = R(r);
+    if (!out || max_rounds < 0) throw InvalidError("null argument");
+    VNR_CUDA(cudaStreamSynchronize(s->stream));
+    int used = 0;
+    for (int k = 0; k < max_rounds; ++k) { out[k] = k < kMaxRounds ? s->h_counters[2 + k] : 0u; if (out[k]) used = k + 1; }
+    if (n_rounds) *n_rounds = used;
+  });
+}
 VNR_EXPORT int vnr_renderer_set_download(vnr_renderer_t* r, int on) { return guard([&] { R(r)->download = on != 0; }); }
+// on (default): with the download enabled, the compositing kernels store finished pixels straight into the pinned host
+// frame vnr_map_frame returns and the device frame buffer is left untouched; off: device frame + D2H copy after the frame
+VNR_EXPORT int vnr_renderer_set_zero_copy(vnr_renderer_t* r, int on) { return guard([&] { R(r)->zero_copy = on != 0; R(r)->reset = true; }); }
 VNR_EXPORT int vnr_renderer_download(vnr_renderer_t* r) { return guard([&] { R(r)->download_now(); }); }
 VNR_EXPORT int vnr_renderer_set_profiling(vnr_renderer_t* r, int on) { return guard([&] { R(r)->profiling = on != 0; }); }
 VNR_EXPORT int vnr_renderer_profile(vnr_renderer_t* r, float* decode_ms, int* decode_launches, uint64_t* kernel_launches) {

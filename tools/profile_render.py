@@ -14,6 +14,7 @@ for v in range(int(os.environ.get("FRAMES", "3"))):
     ren.set_camera(*syn.default_camera(dims, v))
     ren.render()
     ren.map_frame()
+    print("round_counts", v, ren.round_counts(), flush=True)
 print(ren.stats())
 vol.train(int(os.environ.get("EXTRA_TRAIN", "4")), batch=1 << 18, fast_mode=True)
 print(vol.stats())

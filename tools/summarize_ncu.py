@@ -124,7 +124,32 @@ def kernel_report(name, rep, regex):
     print("wrote", name)
 
 
+def decode_traffic():
+    """profiles/decode_traffic.json: DRAM bytes of the first captured decode launch (round 0 of frame 0) next to its sample count
+    (the per-round counters tools/profile_render.py printed in the same run) -- bench.py's roofline.traffic."""
+    import json
+    rep, log = os.path.join(G, f"decode_{tag}.ncu-rep"), os.path.join(G, "prof_decode.log")
+    if not (os.path.exists(rep) and os.path.exists(log)):
+        return
+    m = re.search(r"round_counts 0 \[(\d+)", open(log).read())
+    if not m:
+        return
+    hdr, units, rows = raw(rep)
+    r = rows[0]
+    def val(k):
+        i = hdr.index(k); v = float(r[i].replace(",", "")); u = units[i].lower()
+        return v * {"gbyte": 1e9, "mbyte": 1e6, "kbyte": 1e3, "byte": 1.0}.get(u, 1.0)
+    dur = float(r[hdr.index("gpu__time_duration.sum")].replace(",", "")); du = units[hdr.index("gpu__time_duration.sum")]
+    dur_us = dur * {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(du, 1.0)
+    out = {"kernel": short(r[hdr.index("Kernel Name")]), "samples": int(m.group(1)), "dram_bytes": val("dram__bytes_read.sum") + val("dram__bytes_write.sum"),
+           "dram_bytes_read": val("dram__bytes_read.sum"), "dram_bytes_write": val("dram__bytes_write.sum"), "duration_us": dur_us,
+           "source": f"profiles/decode_{tag}.md (ncu --set full, first decode launch of frame 0 = wavefront round 0)"}
+    json.dump(out, open(os.path.join(P, "decode_traffic.json"), "w"), indent=1)
+    print("wrote decode_traffic.json", out)
+
+
 launches()
+decode_traffic()
 kernel_report("decode", os.path.join(G, f"decode_{tag}.ncu-rep"), "decode_kernel")
 kernel_report("train", os.path.join(G, f"train_{tag}.ncu-rep"), "train_step")
 kernel_report("march", os.path.join(G, f"march_{tag}.ncu-rep"), "march_round")
