@@ -169,6 +169,19 @@ int vnr_volume_last_loss(vnr_volume_t* v, double* loss);
 /* vnrNeuralVolumeGetPSNR (api.h:129; NeuralVolume::Impl::get_psnr core/network.cu:410-472): decode every voxel
  * centre, 10 log10(range^2 / mse) against the ground truth */
 int vnr_volume_psnr(vnr_volume_t* v, double* psnr);
+/* vnrNeuralVolumeGetSSIM (api.h:130; get_mssim core/network.cu:474-549, compute_ssim :70-125): mean structural
+ * similarity of the decoded volume against the ground truth over 7^3 uniform windows (sample covariance, K1 0.01,
+ * K2 0.03, data range 1), averaged over the (dims-6)^3 window origins.  h_map (optional, (dx-6)(dy-6)(dz-6) floats)
+ * receives the per-window values (test tap). */
+int vnr_volume_ssim(vnr_volume_t* v, double* ssim, float* h_map);
+/* vnrNeuralVolumeGetTestingLoss (api.h:131; NeuralVolume::Impl::test core/network.cu:261-288): mean |decode - target|
+ * over one fresh batch of the training sampler (batch 0 = 65536; the draw advances the sampler stream, as the
+ * reference's shared static generator does) */
+int vnr_volume_test_loss(vnr_volume_t* v, int batch, double* loss);
+/* vnrNeuralVolumeDecodeInference / DecodeReference (api.h:139-140; save_inference_volume / save_reference_volume
+ * core/network.cu:327-408): write the decoded volume (which = 0) or the ground truth (which = 1) as dz records of
+ * next_multiple(dx*dy, 256) floats; h_range2 (optional) receives the min / max written */
+int vnr_volume_export(vnr_volume_t* v, const char* path, int which, float* h_range2);
 
 /* vnrNeuralVolumeDecodeProgressive (api.h:137; infer_progressively_decode_volume core/network.cu:290-326): decode the
  * next blob of 16 z-slices of voxel centres into the decoded volume that the "decoding" rendering modes march;
@@ -176,6 +189,31 @@ int vnr_volume_psnr(vnr_volume_t* v, double* psnr);
 int vnr_volume_decode_progressive(vnr_volume_t* v, void* stream);
 int vnr_volume_num_blobs(const vnr_volume_t* v, int* n);
 int vnr_volume_get_decoded(vnr_volume_t* v, float* h_out);
+
+/* ---- scene descriptions ---------------------------------------------------------------- */
+/* The scene JSON the reference's apps pass to vnrCreateSimpleVolume / vnrCreateCamera / vnrCreateTransferFunction
+ * (api.h:104-106,117,155; serializer.cpp:138-477): "version": "VIDI3D" (default; dataSource[] of
+ * REGULAR_GRID_RAW_BINARY files, view.volume.scalarMappingRange[Unnormalized], view.camera) or "DIVA" (volume{dims,
+ * type, range, filename[, bigendian]}).  is_path != 0: `json` names a file (a vnrJson that is_string(), api.cpp:75-80).
+ * Host-only: no CUDA device is needed. */
+typedef struct vnr_scene vnr_scene_t;
+int vnr_scene_create(const char* json, int is_path, vnr_scene_t** out);
+void vnr_scene_release(vnr_scene_t* s);
+/* MultiVolume (core/instantvnr_types.h:40-56): dims, ValueType, number of time steps, unnormalised value range
+ * (has_range = 0: compute it from the data, as an empty range1f makes StaticSampler::load do) */
+int vnr_scene_volume(const vnr_scene_t* s, int* dims3, int* value_type, int* n_timesteps, float* range2, int* has_range);
+/* MultiVolume::File of time step t; the string lives as long as the scene */
+int vnr_scene_timestep(const vnr_scene_t* s, int t, const char** filename, uint64_t* offset, int* big_endian);
+/* create_json_camera_stringify (serializer.cpp:395-407): eye / center shifted by -dims/2 into the centred world box.
+ * VNR_ERR_STATE when the scene has no camera (DIVA scenes: "TODO" in the reference) */
+int vnr_scene_camera(const vnr_scene_t* s, float* from3, float* at3, float* up3, float* fovy);
+/* create_json_tfn_stringify (:371-377): value range of the transfer function (scalarMappingRangeUnnormalized, or
+ * scalarMappingRange x the integer type's maximum); has_range = 0 when neither key exists.  The colour / alpha TABLE of
+ * the reference comes from tfn::loadTransferFunction of the un-vendored OVR tfn module and is not restated: tables are
+ * returned only for the explicit form {"colors": [[r,g,b],..], "alphas": [[pos,alpha],..]}; otherwise n_rgb = n_alpha = 0
+ * and, when the scene carries some other transferFunction object, the call returns VNR_ERR_UNSUPPORTED after filling
+ * the range.  Pointers live as long as the scene. */
+int vnr_scene_tfn(const vnr_scene_t* s, const float** rgb, int* n_rgb, const float** alpha_pairs, int* n_alpha, float* range2, int* has_range);
 
 /* ---- renderer ------------------------------------------------------------------------- */
 

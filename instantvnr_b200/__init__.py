@@ -322,6 +322,26 @@ class NeuralVolume:
         _check(lib().vnr_volume_psnr(self._h, C.byref(v)))
         return v.value
 
+    def ssim(self, return_map=False):
+        """vnrNeuralVolumeGetSSIM; return_map: also the per-window values [(dz-6), (dy-6), (dx-6)]."""
+        v = C.c_double()
+        m = None
+        if return_map:
+            m = np.empty((self.dims[2] - 6, self.dims[1] - 6, self.dims[0] - 6), dtype=np.float32)
+        _check(lib().vnr_volume_ssim(self._h, C.byref(v), _ptr(m) if m is not None else None))
+        return (v.value, m) if return_map else v.value
+
+    def test_loss(self, batch=0):
+        v = C.c_double()
+        _check(lib().vnr_volume_test_loss(self._h, C.c_int(batch), C.byref(v)))
+        return v.value
+
+    def export(self, path, which=0):
+        """vnrNeuralVolumeDecodeInference (which=0) / DecodeReference (which=1); returns (min, max) written."""
+        r = (C.c_float * 2)()
+        _check(lib().vnr_volume_export(self._h, os.fsencode(path), C.c_int(which), r))
+        return float(r[0]), float(r[1])
+
     def stats(self):
         step, loss = C.c_uint64(), C.c_double()
         _check(lib().vnr_volume_stats(self._h, C.byref(step), C.byref(loss)))
@@ -437,6 +457,55 @@ class Renderer:
         s = np.zeros(4, dtype=np.uint64)
         _check(lib().vnr_renderer_stats(self._h, _ptr(s)))
         return {"rays_hit": int(s[0]), "samples_decoded": int(s[1]), "samples_composited": int(s[2]), "rounds": int(s[3])}
+
+
+class Scene:
+    """Scene description (VIDI3D / DIVA JSON) as the reference's apps pass it to vnrCreateSimpleVolume /
+    vnrCreateCamera / vnrCreateTransferFunction (serializer.cpp:138-477).  Host-only."""
+
+    VALUE_TYPE_NAMES = {0: "uint8", 1: "int8", 2: "uint16", 3: "int16", 4: "uint32", 5: "int32", 8: "float32", 12: "float64"}
+
+    def __init__(self, text=None, path=None):
+        self._h = C.c_void_p()
+        arg = os.fsencode(path) if path is not None else text.encode("utf-8")
+        _check(lib().vnr_scene_create(arg, C.c_int(1 if path is not None else 0), C.byref(self._h)))
+        dims, vt, nt, rg, hr = (C.c_int * 3)(), C.c_int(), C.c_int(), (C.c_float * 2)(), C.c_int()
+        _check(lib().vnr_scene_volume(self._h, dims, C.byref(vt), C.byref(nt), rg, C.byref(hr)))
+        self.dims, self.value_type, self.n_timesteps = tuple(dims), vt.value, nt.value
+        self.dtype = self.VALUE_TYPE_NAMES.get(vt.value)
+        self.value_range = (float(rg[0]), float(rg[1])) if hr.value else None
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().vnr_scene_release.restype = None
+            lib().vnr_scene_release(self._h)
+            self._h = None
+
+    def timestep(self, t=0):
+        name, off, big = C.c_char_p(), C.c_uint64(), C.c_int()
+        _check(lib().vnr_scene_timestep(self._h, C.c_int(t), C.byref(name), C.byref(off), C.byref(big)))
+        return os.fsdecode(name.value), off.value, bool(big.value)
+
+    def camera(self):
+        f, a, u, fov = (C.c_float * 3)(), (C.c_float * 3)(), (C.c_float * 3)(), C.c_float()
+        _check(lib().vnr_scene_camera(self._h, f, a, u, C.byref(fov)))
+        return tuple(f), tuple(a), tuple(u), fov.value
+
+    def tfn(self):
+        """(rgb [n,3] or None, alpha pairs [m,2] or None, value range or None); raises VnrError(-3...) when the scene
+        carries a transfer function in the (unrestated) OVR tfn-module format."""
+        rgb, a = C.POINTER(C.c_float)(), C.POINTER(C.c_float)()
+        n, m, rg, hr = C.c_int(), C.c_int(), (C.c_float * 2)(), C.c_int()
+        _check(lib().vnr_scene_tfn(self._h, C.byref(rgb), C.byref(n), C.byref(a), C.byref(m), rg, C.byref(hr)))
+        col = np.ctypeslib.as_array(rgb, (n.value, 3)).copy() if n.value else None
+        alp = np.ctypeslib.as_array(a, (m.value, 2)).copy() if m.value else None
+        return col, alp, ((float(rg[0]), float(rg[1])) if hr.value else None)
+
+    def load_groundtruth(self, volume, t=0):
+        """vnrCreateSimpleVolume(scene, "GPU") + vnrCreateNeuralVolume(config, simple): time step t -> HBM, normalised
+        with the scene's range (or the data's when it has none); returns the unnormalised range used."""
+        name, off, big = self.timestep(t)
+        return volume.set_groundtruth_file(name, self.dtype, offset=off, big_endian=big, value_range=self.value_range)
 
 
 def ipc_export(d_ptr):

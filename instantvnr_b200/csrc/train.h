@@ -22,5 +22,8 @@ void decode_progressive(Volume* v, cudaStream_t s);
 cudaError_t launch_volume_samples(const float* vol, const int* dims3, const float4* samples, const float4* samples_alt, float* out,
                                   const uint32_t* n_dev, const uint32_t* round_dev, size_t n_max, cudaStream_t stream);
 double volume_psnr(Volume* v, cudaStream_t s);
+double volume_ssim(Volume* v, float* h_map, cudaStream_t s);
+double volume_test_loss(Volume* v, size_t batch, cudaStream_t s);
+void volume_export(Volume* v, const char* path, int which, float* range_out, cudaStream_t s);
 void train_steps(Volume* v, int steps, size_t batch, bool update_macrocell, cudaStream_t s);
 }

@@ -9,6 +9,7 @@
 #include "volume.h"
 #include "render.h"
 #include "train.h"
+#include "scene.h"
 
 using namespace vnr;
 
@@ -227,3 +228,56 @@ VNR_EXPORT int vnr_memory_query(size_t* used_by_renderer, size_t* used_by_networ
 
 #include "vnr_c_volume.inl"
 #include "vnr_c_render.inl"
+
+// ---- scene descriptions (scene.cpp; serializer.cpp:138-477).  Host-only: no device is required. ----
+static const Scene* SC(const vnr_scene_t* s) { if (!s) throw InvalidError("null scene handle"); return reinterpret_cast<const Scene*>(s); }
+VNR_EXPORT int vnr_scene_create(const char* json, int is_path, vnr_scene_t** out) {
+  return guard([&] {
+    if (!json || !out) throw InvalidError("null argument");
+    *out = nullptr;
+    Scene* s = new Scene(is_path ? load_scene(json) : parse_scene(json));
+    *out = reinterpret_cast<vnr_scene_t*>(s);
+  });
+}
+VNR_EXPORT void vnr_scene_release(vnr_scene_t* s) { delete reinterpret_cast<Scene*>(s); }
+VNR_EXPORT int vnr_scene_volume(const vnr_scene_t* sh, int* dims3, int* value_type, int* n_timesteps, float* range2, int* has_range) {
+  return guard([&] {
+    const Scene* s = SC(sh);
+    if (dims3) { dims3[0] = s->dims[0]; dims3[1] = s->dims[1]; dims3[2] = s->dims[2]; }
+    if (value_type) *value_type = s->value_type;
+    if (n_timesteps) *n_timesteps = (int)s->files.size();
+    if (range2) { range2[0] = s->range[0]; range2[1] = s->range[1]; }
+    if (has_range) *has_range = s->has_range ? 1 : 0;
+  });
+}
+VNR_EXPORT int vnr_scene_timestep(const vnr_scene_t* sh, int t, const char** filename, uint64_t* offset, int* big_endian) {
+  return guard([&] {
+    const Scene* s = SC(sh);
+    if (t < 0 || t >= (int)s->files.size()) throw InvalidError("time step out of range");
+    if (filename) *filename = s->files[t].filename.c_str();
+    if (offset) *offset = s->files[t].offset;
+    if (big_endian) *big_endian = s->files[t].big_endian ? 1 : 0;
+  });
+}
+VNR_EXPORT int vnr_scene_camera(const vnr_scene_t* sh, float* from3, float* at3, float* up3, float* fovy) {
+  return guard([&] {
+    const Scene* s = SC(sh);
+    if (!s->has_camera) throw StateError("the scene description has no camera");
+    for (int k = 0; k < 3; ++k) { if (from3) from3[k] = s->cam_from[k]; if (at3) at3[k] = s->cam_at[k]; if (up3) up3[k] = s->cam_up[k]; }
+    if (fovy) *fovy = s->fovy;
+  });
+}
+VNR_EXPORT int vnr_scene_tfn(const vnr_scene_t* sh, const float** rgb, int* n_rgb, const float** alpha_pairs, int* n_alpha, float* range2, int* has_range) {
+  return guard([&] {
+    const Scene* s = SC(sh);
+    if (range2) { range2[0] = s->range[0]; range2[1] = s->range[1]; }
+    if (has_range) *has_range = s->has_range ? 1 : 0;
+    if (rgb) *rgb = s->has_tfn ? s->tfn_color.data() : nullptr;
+    if (n_rgb) *n_rgb = s->has_tfn ? (int)(s->tfn_color.size() / 3) : 0;
+    if (alpha_pairs) *alpha_pairs = s->has_tfn ? s->tfn_alpha.data() : nullptr;
+    if (n_alpha) *n_alpha = s->has_tfn ? (int)(s->tfn_alpha.size() / 2) : 0;
+    if (s->tfn_present && !s->has_tfn)
+      throw UnsupportedError("the scene's transferFunction is in the OVR tfn-module format (tfn::loadTransferFunction, not part of the reference "
+                             "tree); set colours / alphas with the setters");
+  });
+}

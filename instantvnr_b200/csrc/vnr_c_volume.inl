@@ -380,6 +380,25 @@ VNR_EXPORT int vnr_volume_macrocell_refresh(vnr_volume_t* vh, void* stream) {
 VNR_EXPORT int vnr_volume_psnr(vnr_volume_t* vh, double* psnr) {
   return guard([&] { Volume* v = V(vh); if (!psnr) throw InvalidError("null argument"); *psnr = volume_psnr(v, v->stream); });
 }
+// vnrNeuralVolumeGetSSIM / GetTestingLoss / DecodeInference / DecodeReference (api.h:130-131,139-140; evaluate.cu)
+VNR_EXPORT int vnr_volume_ssim(vnr_volume_t* vh, double* ssim, float* h_map) {
+  return guard([&] { Volume* v = V(vh); if (!ssim) throw InvalidError("null argument"); *ssim = volume_ssim(v, h_map, v->stream); });
+}
+VNR_EXPORT int vnr_volume_test_loss(vnr_volume_t* vh, int batch, double* loss) {
+  return guard([&] {
+    Volume* v = V(vh);
+    if (!loss) throw InvalidError("null argument");
+    if (batch < 0) throw InvalidError("negative batch size");
+    *loss = volume_test_loss(v, (size_t)batch, v->stream);
+  });
+}
+VNR_EXPORT int vnr_volume_export(vnr_volume_t* vh, const char* path, int which, float* h_range2) {
+  return guard([&] {
+    Volume* v = V(vh);
+    if (which != 0 && which != 1) throw InvalidError("which must be 0 (decoded volume) or 1 (ground truth)");
+    volume_export(v, path, which, h_range2, v->stream);
+  });
+}
 
 // ---- data-parallel optimizer over peer memory (train.cu) ---------------------------------------------
 // handles192: three cudaIpcMemHandle_t (64 bytes each): parameters (fp16), hash-grid gradients (fp16), MLP gradients (fp32)

@@ -41,6 +41,7 @@ def lib():
         _lib.orc_hadd.restype = C.c_uint16
         _lib.orc_hadd_exact.restype = C.c_uint16
         _lib.orc_f16_selftest.restype = C.c_uint64
+        _lib.orc_ssim.restype = C.c_double
     return _lib
 
 
@@ -291,6 +292,16 @@ def classify(frame, colors_rgba, alphas, values, dts):
     out = np.empty((values.size, 4), dtype=np.float32)
     lib().orc_classify(_p(frame.f), _p(frame.i), _p(colors_rgba), _p(alphas), _p(values), _p(dts), C.c_size_t(values.size), _p(out))
     return out
+
+
+def ssim(reference, prediction, return_map=False):
+    """Mean SSIM of two [z][y][x] float volumes (compute_ssim / get_mssim, core/network.cu:70-125,474-549)."""
+    a, b = _f32(reference), _f32(prediction)
+    assert a.shape == b.shape and a.ndim == 3
+    dims = np.array(a.shape[::-1], dtype=np.int32)
+    out = np.empty(tuple(d - 6 for d in a.shape), dtype=np.float32) if return_map else None
+    v = lib().orc_ssim(_p(a), _p(b), _p(dims), _p(out))
+    return (v, out) if return_map else v
 
 
 def lcg_tea16_first(v0, v1):

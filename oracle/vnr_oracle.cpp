@@ -1204,6 +1204,47 @@ ORC_API void orc_render(const int* cfg, float pls, const uint16_t* params_f16, i
 }
 
 // expose pieces for unit tests
+// ---------------------------------------------------------------------------------------
+// volume SSIM (compute_ssim core/network.cu:70-125; get_mssim :474-549): 7^3 uniform window, moments accumulated in
+// kz, ky, kx order in fp32 (nvcc contracts `a += b*c` into one fma: written explicitly here), sample covariance,
+// K1 = 0.01, K2 = 0.03, data range 1; mean over the (dims-6)^3 window origins.  out (optional): per-window values.
+// ---------------------------------------------------------------------------------------
+ORC_API double orc_ssim(const float* fx_, const float* fy_, const int* dims, float* out) {
+  const int W = 7;
+  const int ox = dims[0] - W + 1, oy = dims[1] - W + 1, oz = dims[2] - W + 1;
+  if (ox <= 0 || oy <= 0 || oz <= 0) return -1.0;
+  double total = 0.0;
+#pragma omp parallel for reduction(+ : total) schedule(static)
+  for (int z = 0; z < oz; ++z)
+    for (int y = 0; y < oy; ++y)
+      for (int x = 0; x < ox; ++x) {
+        float ux = 0.f, uy = 0.f, uxx = 0.f, uyy = 0.f, uxy = 0.f;
+        for (int kz = 0; kz < W; ++kz)
+          for (int ky = 0; ky < W; ++ky)
+            for (int kx = 0; kx < W; ++kx) {
+              const size_t g = (size_t)(x + kx) + (size_t)(y + ky) * dims[0] + (size_t)(z + kz) * dims[0] * dims[1];
+              const float fx = fx_[g], fy = fy_[g];
+              ux += fx; uy += fy;
+              uxx = std::fmaf(fx, fx, uxx); uyy = std::fmaf(fy, fy, uyy); uxy = std::fmaf(fx, fy, uxy);
+            }
+        const float w = 1.f / (float)(W * W * W);
+        ux *= w; uy *= w; uxx *= w; uyy *= w; uxy *= w;
+        const float NP = (float)(W * W * W), cov_norm = NP / (NP - 1.f);
+        const float vx = cov_norm * std::fmaf(-ux, ux, uxx);
+        const float vy = cov_norm * std::fmaf(-uy, uy, uyy);
+        const float vxy = cov_norm * std::fmaf(-ux, uy, uxy);
+        const float C1 = (0.01f * 1.f) * (0.01f * 1.f), C2 = (0.03f * 1.f) * (0.03f * 1.f);
+        const float A1 = std::fmaf(2.f * ux, uy, C1);
+        const float A2 = std::fmaf(2.f, vxy, C2);
+        const float B1 = std::fmaf(ux, ux, uy * uy) + C1;
+        const float B2 = vx + vy + C2;
+        const float S = (A1 * A2) / (B1 * B2);
+        if (out) out[(size_t)x + (size_t)y * ox + (size_t)z * ox * oy] = S;
+        total += (double)S;
+      }
+  return total / ((double)ox * oy * oz);
+}
+
 ORC_API float orc_lcg_tea16_first(uint32_t v0, uint32_t v1) { LcgTea16 r(v0, v1); return r.next(); }
 ORC_API void orc_classify(const float* fparams, const int* iparams, const float* colors, const float* alphas, const float* values, const float* dts, size_t n, float* rgba) {
   Frame fr = frame_from(fparams, iparams, nullptr, colors, alphas);

@@ -380,3 +380,24 @@ def test_training_reduces_loss_small_model():
     rng = O.Rng(1337)
     losses = [tr.step(*O.sample_batch(rng, 2048, vol, dims)) for _ in range(30)]
     assert losses[-1] < 0.6 * losses[0]
+
+
+def test_ssim_oracle_against_the_float64_closed_form():
+    """orc_ssim (compute_ssim core/network.cu:70-125) vs the Wang et al. formula with a 7^3 uniform window and sample
+    covariance evaluated in float64 with scipy (what skimage.metrics.structural_similarity computes for win_size=7)."""
+    from scipy.ndimage import uniform_filter
+    rng = np.random.default_rng(0)
+    a = rng.random((20, 18, 16), dtype=np.float32)
+    b = np.clip(a + 0.05 * rng.standard_normal(a.shape).astype(np.float32), 0, 1)
+    v, m = O.ssim(a, b, return_map=True)
+    A, B = a.astype(np.float64), b.astype(np.float64)
+    f = lambda x: uniform_filter(x, 7, mode="constant")[3:-3, 3:-3, 3:-3]
+    ux, uy, uxx, uyy, uxy = f(A), f(B), f(A * A), f(B * B), f(A * B)
+    cn = 343.0 / 342.0
+    vx, vy, vxy = cn * (uxx - ux * ux), cn * (uyy - uy * uy), cn * (uxy - ux * uy)
+    S = ((2 * ux * uy + 1e-4) * (2 * vxy + 9e-4)) / ((ux * ux + uy * uy + 1e-4) * (vx + vy + 9e-4))
+    assert m.shape == S.shape == (14, 12, 10)
+    assert np.abs(m - S).max() < 2e-5 and abs(v - S.mean()) < 1e-6
+    assert abs(O.ssim(a, a) - 1.0) < 1e-6                      # identical volumes
+    assert O.ssim(a, 1.0 - a) < 0.0                            # anti-correlated structure
+    assert O.ssim(np.zeros((7, 7, 7), np.float32), np.zeros((7, 7, 7), np.float32)) == 1.0   # a single window
