@@ -55,6 +55,11 @@ int vnr_volume_model_info(const vnr_volume_t* v, uint64_t* n_params, uint64_t* n
  * (core/networks/tcnn_network.h:207); here the seed is explicit. Resets optimizer state. */
 int vnr_volume_init_params(vnr_volume_t* v, uint32_t seed);
 
+/* vnrNeuralVolumeSetModel (api.h:126; NeuralVolume::set_network_from_json(config) core/network.cu:731-741): replace the
+ * network of an existing volume -- new encoding / MLP / optimizer from `model_json`, parameters initialised from `seed`,
+ * training step back to 0 -- keeping dims, ground truth, sampler stream, macrocells and transfer function.  A config
+ * that does not parse leaves the volume untouched. */
+int vnr_volume_set_model(vnr_volume_t* v, const char* model_json, uint32_t seed);
 /* tcnn Trainer::set_params / serialize: fp16 parameter blob           trainer.h:281-311 */
 int vnr_volume_set_params_f16(vnr_volume_t* v, const uint16_t* h_params, size_t n);
 int vnr_volume_get_params_f16(const vnr_volume_t* v, uint16_t* h_params, size_t n);
@@ -228,6 +233,9 @@ int vnr_renderer_set_mode(vnr_renderer_t* r, int mode);                /* vnrRen
 int vnr_renderer_set_groundtruth_source(vnr_renderer_t* r, int on);
 int vnr_renderer_set_sampling_rate(vnr_renderer_t* r, float rate);     /* :174 */
 int vnr_renderer_set_density_scale(vnr_renderer_t* r, float scale);    /* :175 */
+/* vnrVolumeSetScaling (api.h:147; api.cpp:350-361): per-axis scale of the world box, multiplied onto the default
+ * data transform translate(-dims/2) * scale(dims) */
+int vnr_renderer_set_scaling(vnr_renderer_t* r, const float* scale3);
 int vnr_renderer_reset_accumulation(vnr_renderer_t* r);                /* :176 */
 /* vnrVolumeSetClippingBox (api.h:146, applied by vnrCreateRenderer api.cpp:454): object-space box inside [0,1]^3 */
 int vnr_renderer_set_clipping_box(vnr_renderer_t* r, const float* lower3, const float* upper3);

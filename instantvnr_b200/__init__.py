@@ -110,12 +110,20 @@ class NeuralVolume:
         self._h = C.c_void_p()
         _check(lib().vnr_volume_create(model_json_text.encode(), int(dims[0]), int(dims[1]), int(dims[2]), C.byref(self._h)))
         self.dims = tuple(int(d) for d in dims)
+        self._read_model_info()
+
+    def _read_model_info(self):
         n, nm = C.c_uint64(), C.c_uint64()
         L, F, H = C.c_int(), C.c_int(), C.c_int()
         _check(lib().vnr_volume_model_info(self._h, C.byref(n), C.byref(nm), C.byref(L), C.byref(F), C.byref(H)))
         self.n_params, self.n_mlp_params = n.value, nm.value
         self.n_levels, self.n_features, self.n_hidden = L.value, F.value, H.value
         self.enc_pad = ((self.n_levels * self.n_features + 15) // 16) * 16
+
+    def set_model(self, model_json_text, seed=1337):
+        """vnrNeuralVolumeSetModel (api.h:126): a new network under the same dims / ground truth / sampler / macrocells."""
+        _check(lib().vnr_volume_set_model(self._h, model_json_text.encode(), C.c_uint32(seed)))
+        self._read_model_info()
 
     def close(self):
         if self._h:
@@ -389,6 +397,9 @@ class Renderer:
 
     def set_clipping_box(self, lower, upper):
         _check(lib().vnr_renderer_set_clipping_box(self._h, _ptr(_f32(lower)), _ptr(_f32(upper))))
+
+    def set_scaling(self, scale):
+        _check(lib().vnr_renderer_set_scaling(self._h, _ptr(_f32(scale))))
 
     def reset_accumulation(self):
         _check(lib().vnr_renderer_reset_accumulation(self._h))

@@ -153,6 +153,29 @@ VNR_EXPORT int vnr_volume_init_params(vnr_volume_t* vh, uint32_t seed) {
   });
 }
 
+// vnrNeuralVolumeSetModel (api.h:126; NeuralVolume::set_network_from_json(config) core/network.cu:731-741 ->
+// TcnnNetwork::deserialize_model): a new network, optimizer state and freshly initialised parameters under the same
+// dims, ground truth, sampler stream, macrocells and transfer function.
+VNR_EXPORT int vnr_volume_set_model(vnr_volume_t* vh, const char* model_json, uint32_t seed) {
+  int rc = guard([&] {
+    Volume* v = V(vh);
+    if (!model_json) throw InvalidError("null argument");
+    if (v->dp_world) throw StateError("detach the data-parallel peers before changing the model");
+    ModelConfig cfg = parse_model_config(model_json);       // throws before anything is touched
+    VNR_CUDA(cudaStreamSynchronize(v->stream));
+    VNR_CUDA(cudaDeviceSynchronize());                      // renderers of this volume may still be decoding the old table
+    v->cfg = cfg;
+    v->master.release(); v->m1.release(); v->m2.release(); v->steps.release();
+    v->grid_grads.release(); v->mlp_grads.release(); v->mlp_partial.release();
+    v->have_params = false; v->have_opt = false; v->grads_clean = false; v->grads_pending = false;
+    v->decode_blob = 0;
+    v->params.alloc(cfg.n_params());
+    v->params.zero(v->stream);
+    VNR_CUDA(cudaStreamSynchronize(v->stream));
+  });
+  return rc != VNR_OK ? rc : vnr_volume_init_params(vh, seed);
+}
+
 VNR_EXPORT int vnr_volume_set_params_f16(vnr_volume_t* vh, const uint16_t* h_params, size_t n) {
   return guard([&] {
     Volume* v = V(vh);

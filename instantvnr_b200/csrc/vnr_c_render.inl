@@ -39,6 +39,15 @@ VNR_EXPORT int vnr_renderer_set_clipping_box(vnr_renderer_t* r, const float* low
     s->reset = true;
   });
 }
+// vnrVolumeSetScaling (api.h:147, api.cpp:350-361): data transform = scale(s) * translate(-dims/2) * scale(dims)
+VNR_EXPORT int vnr_renderer_set_scaling(vnr_renderer_t* r, const float* scale3) {
+  return guard([&] {
+    Renderer* s = R(r);
+    if (!scale3) throw InvalidError("null scaling");
+    for (int k = 0; k < 3; ++k) { if (!(scale3[k] > 0.f)) throw InvalidError("scaling must be positive"); s->scale[k] = scale3[k]; }
+    s->reset = true;
+  });
+}
 VNR_EXPORT int vnr_renderer_reset_accumulation(vnr_renderer_t* r) { return guard([&] { R(r)->reset = true; }); }
 VNR_EXPORT int vnr_renderer_set_partition(vnr_renderer_t* r, int rank, int world) {
   return guard([&] {

@@ -1,0 +1,93 @@
+"""The C++ mirror of the reference's api.h (include/vnr_api.hpp) exercised by apps/vnr_api_check.cpp: every api.h function is
+called with the reference's argument meaning.  The host part (scene ingest, camera, transfer function, handle-type errors)
+runs without a GPU; the device part runs the scene -> simple volume -> neural volume -> train -> evaluate -> render flow."""
+import os
+import re
+import subprocess
+
+import pytest
+
+import instantvnr_b200 as vnr
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+APP = os.path.join(ROOT, "apps", "_build", "vnr_api_check")
+REF_API = """vnrRequireDecoding vnrCreateJsonText vnrCreateJsonBinary vnrLoadJsonText vnrLoadJsonBinary vnrSaveJsonText vnrSaveJsonBinary
+vnrCreateCamera vnrCameraSet vnrCameraGetPosition vnrCameraGetFocus vnrCameraGetUpVec vnrCreateSimpleVolume
+vnrSimpleVolumeSetCurrentTimeStep vnrSimpleVolumeGetNumberOfTimeSteps vnrCreateNeuralVolume vnrNeuralVolumeSetModel
+vnrNeuralVolumeSetParams vnrNeuralVolumeGetPSNR vnrNeuralVolumeGetSSIM vnrNeuralVolumeGetTestingLoss vnrNeuralVolumeGetTrainingLoss
+vnrNeuralVolumeGetTrainingStep vnrNeuralVolumeGetNumberOfBlobs vnrNeuralVolumeTrain vnrNeuralVolumeDecodeProgressive
+vnrNeuralVolumeDecodeInference vnrNeuralVolumeDecodeReference vnrNeuralVolumeSerializeParams vnrVolumeSetClippingBox
+vnrVolumeSetScaling vnrVolumeGetValueRange vnrCreateTransferFunction vnrTransferFunctionSetColor vnrTransferFunctionSetAlpha
+vnrTransferFunctionSetValueRange vnrTransferFunctionGetColor vnrTransferFunctionGetAlpha vnrTransferFunctionGetValueRange
+vnrCreateRenderer vnrRendererSetFramebufferSize vnrRendererSetTransferFunction vnrRendererSetCamera vnrRendererSetMode
+vnrRendererSetDenoiser vnrRendererSetVolumeSamplingRate vnrRendererSetVolumeDensityScale vnrRendererResetAccumulation vnrRender
+vnrRendererMapFrame vnrRelease vnrMemoryQuery vnrMemoryQueryPrint vnrFreeTemporaryGPUMemory""".split()   # api.h:62-188, all of it
+
+
+def _build():
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "apps"), "-s"])
+    assert os.path.exists(APP)
+
+
+def _pairs(out):
+    return {k: float(v) for k, v in re.findall(r"^(\w+) ([-+.\deE]+|nan|inf)$", out, flags=re.M)}
+
+
+def test_header_and_app_cover_the_whole_reference_api():
+    hdr = open(os.path.join(ROOT, "include", "vnr_api.hpp")).read()
+    app = open(os.path.join(ROOT, "apps", "vnr_api_check.cpp")).read()
+    assert [f for f in REF_API if not re.search(r"\b%s\s*\(" % f, hdr)] == []
+    assert [f for f in REF_API if not re.search(r"\b%s\s*\(" % f, app)] == []
+
+
+def test_api_host_part(tmp_path):
+    _build()
+    r = subprocess.run([APP, "--host", str(tmp_path)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert _pairs(r.stdout)["host_checks_failed"] == 0
+
+
+def test_api_device_part_fails_loudly_without_a_device(tmp_path):
+    if vnr.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    _build()
+    r = subprocess.run([APP, "--device", str(tmp_path)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 1 and "no CPU fallback" in r.stderr
+
+
+@pytest.mark.gpu
+def test_api_device_part(tmp_path):
+    _build()
+    r = subprocess.run([APP, "--device", str(tmp_path)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    kv = _pairs(r.stdout)
+    assert kv["device_checks_failed"] == 0
+    assert kv["train_step"] == 300 and kv["psnr"] > 25.0 and 0.5 < kv["ssim"] <= 1.0
+    assert kv["reloaded_frame_max_abs"] == 0.0           # params.json round trip reproduces the frame bit for bit
+    assert kv["timestep_frame_max_abs"] > 0.01 and kv["coverage_clipped"] < kv["coverage_simple"]
+    for mode in range(4, 13):
+        assert abs(kv[f"coverage_mode_{mode}"] - kv["coverage_neural"]) < 0.05
+
+
+@pytest.mark.gpu
+def test_set_model_python():
+    import numpy as np
+    from instantvnr_b200 import synthetic as syn
+    dims = (32, 32, 32)
+    vol = vnr.NeuralVolume(vnr.model_json(n_levels=8, n_features=8, log2_hashmap=14, base_res=16, n_hidden=4), dims)
+    vol.set_groundtruth(syn.make_volume(dims, seed=5))
+    vol.init_params(3)
+    vol.train(10, batch=4096)
+    n_old = vol.n_params
+    vol.set_model(vnr.model_json(n_levels=4, n_features=4, log2_hashmap=12, base_res=8, n_hidden=2), seed=9)
+    assert vol.n_params != n_old and (vol.n_levels, vol.n_features, vol.n_hidden) == (4, 4, 2)
+    assert vol.stats()[0] == 0
+    vol.train(20, batch=4096)
+    step, loss = vol.stats()
+    assert step == 20 and 0 < loss < 1
+    xyz = np.random.default_rng(1).random((512, 3), dtype=np.float32)
+    assert np.isfinite(vol.decode_host(xyz)).all()
+    with pytest.raises(vnr.VnrError):                   # a bad config leaves the volume as it was
+        vol.set_model('{"encoding": {"otype": "Frequency"}}')
+    assert (vol.n_levels, vol.n_features, vol.n_hidden) == (4, 4, 2)
+    vol.train(1, batch=4096)
