@@ -64,6 +64,7 @@ def test_api_device_part(tmp_path):
     assert kv["device_checks_failed"] == 0
     assert kv["train_step"] == 300 and kv["psnr"] > 25.0 and 0.5 < kv["ssim"] <= 1.0
     assert kv["reloaded_frame_max_abs"] == 0.0           # params.json round trip reproduces the frame bit for bit
+    assert kv["restored_frame_max_abs"] == 0.0           # ... also into a volume whose model had been replaced
     assert kv["timestep_frame_max_abs"] > 0.01 and kv["coverage_clipped"] < kv["coverage_simple"]
     for mode in range(4, 13):
         assert abs(kv[f"coverage_mode_{mode}"] - kv["coverage_neural"]) < 0.05
