@@ -1203,6 +1203,199 @@ ORC_API void orc_render(const int* cfg, float pls, const uint16_t* params_f16, i
                    jitter_mode, shading_from(fparams, iparams), accum, frame, stats);
 }
 
+// ---------------------------------------------------------------------------------------
+// Path tracer (core/renderer/method_pathtracing.cu, VARYING_MAJORANT = USE_DELTA_TRACKING_ITER = 1): delta tracking with
+// the macrocell max opacity as the local majorant, one directional light sampled through a shadow ray, uniform-sphere
+// phase function with albedo x 0.6, Russian roulette after 4 scatters.  Two restated variants, each as the reference
+// writes it (they differ where the reference's differ):
+//   streaming = 0: path_tracing_kernel / path_tracing_traceray / delta_tracking (:260-296,424-470,478-516) -- the
+//                  single-kernel tracer of the "decoding" / in-shader modes 13 / 15;
+//   streaming = 1: iterative_raygen_kernel / iterative_shade_kernel with iterative_take_sample / iterative_shade
+//                  (:596-747) -- the sample-streaming mode 14.  Each ray is run to completion here (rays are independent;
+//                  the reference re-derives tnear / tfar from the stored origin / direction on every load(), :115-145).
+// RandomTEA (OVR gdt/random/random.h) is NOT in /root/reference: it is taken to be the same TEA-16-seeded LCG as
+// gdt::LCG<16>, get_float() one draw, get_floats() two consecutive draws (x first).  PARITY UNPINNED for the sequence.
+// FMA contraction follows what nvcc -fmad=true makes of the reference expressions (a*b+c -> fma), written explicitly.
+// ---------------------------------------------------------------------------------------
+struct PtLights { float density_scale, ambient; V3 rgb, dir; };
+
+static inline void tfn_raw(const Frame& fr, float s, float rgb[3], float& a) {       // sampleTransferFunction, no opacity correction
+  const float v = (clampf(s, fr.tfn_lo, fr.tfn_hi) - fr.tfn_lo) * fr.tfn_rcp;
+  rgb[0] = rgb[1] = rgb[2] = 0.f; a = 0.f;
+  if (fr.n_color > 0) {
+    int i0, i1; float w; tfn_lookup_coeff(v, fr.n_color, fr.tex_round, i0, i1, w);
+    for (int c = 0; c < 3; ++c) rgb[c] = fmaf(w, fr.colors[4 * i1 + c], (1 - w) * fr.colors[4 * i0 + c]);
+  }
+  if (fr.n_alpha > 0) {
+    int i0, i1; float w; tfn_lookup_coeff(v, fr.n_alpha, fr.tex_round, i0, i1, w);
+    a = fmaf(w, fr.alphas[i1], (1 - w) * fr.alphas[i0]);
+  }
+}
+
+// DeltaTrackingIter::hashit (:545-573)
+static bool dt_hashit(const Frame& fr, const PtLights& P, DDAIter& it, V3 dir, float tnear, float tfar, LcgTea16& rng, float& rayt, float& majorant) {
+  const V3 m_dir = dir * fr.mc_spacing_rcp;
+  bool found = false;
+  float tau = -logf(1.f - rng.next());
+  float t = it.next_cell_begin + tnear;
+  auto lambda = [&](const int* c, float /*t0*/, float t1) {
+    const uint32_t idx = c[0] + c[1] * (uint32_t)fr.mc_dims[0] + c[2] * (uint32_t)fr.mc_dims[0] * (uint32_t)fr.mc_dims[1];
+    majorant = fr.mc_max_opacity[idx] * P.density_scale;
+    if (fabsf(majorant) <= std::numeric_limits<float>::epsilon()) return true;      // next macrocell (t is NOT advanced, as in the reference)
+    tau = fmaf(-(t1 - t), majorant, tau);
+    t = t1;
+    if (tau > 0.f) return true;
+    t = t + tau / majorant;
+    found = true;
+    it.next_cell_begin = t - tnear;
+    rayt = t;
+    return false;
+  };
+  while (it.next(m_dir, tnear, tfar, fr.mc_dims, lambda)) {}
+  return found;
+}
+
+static inline V3 uniform_sample_sphere(float sx, float sy) {                          // raytracing.h:250-269 (radius 1)
+  const float phi = (float)(2 * M_PI * (double)sx);
+  const float cosTheta = 1.f - 2.f * sy;
+  const float sinTheta = 2.f * sqrtf(sy * (1.f - sy));
+  return v3(cosf(phi) * sinTheta, sinf(phi) * sinTheta, cosTheta);
+}
+
+static inline bool russian_roulette(V3& thr, LcgTea16& rng, int scatter_index) {     // :366-376, russian_roulette_length 4
+  if (scatter_index > 4) {
+    const float q = fminf(0.95f, fmaxf(thr.x, fmaxf(thr.y, thr.z)));
+    if (rng.next() > q) return true;
+    thr = v3(thr.x / q, thr.y / q, thr.z / q);
+  }
+  return false;
+}
+
+template <typename S>
+static void pt_pixel(const Frame& fr, const PtLights& P, int streaming, uint32_t pixel, const S& sample, float L_out[3], uint64_t& n_samples, bool& hit_box) {
+  LcgTea16 rng((uint32_t)fr.frame_index, pixel);
+  V3 org, dir; compute_ray(fr, pixel, org, dir);
+  V3 L = v3(0, 0, 0), thr = v3(1, 1, 1);
+  const V3 light_obj = xfm_vec(fr.wto_l, normalize(P.dir));
+  auto add = [](V3& acc, V3 t, V3 c) { acc = v3(fmaf(t.x, c.x, acc.x), fmaf(t.y, c.y, acc.y), fmaf(t.z, c.z, acc.z)); };
+  auto sphere_dir = [&]() { const float sx = rng.next(), sy = rng.next(); return xfm_vec(fr.wto_l, uniform_sample_sphere(sx, sy)); };
+  auto new_iter = [&](DDAIter& it, float tnear, float tfar) { it.init(org * fr.mc_spacing_rcp, dir * fr.mc_spacing_rcp, tnear, tfar, fr.mc_dims); };
+  float tnear = 0.f, tfar = FLOAT_LARGE;
+  bool shadow = false; int scatter = 0;
+  hit_box = false;
+  if (!streaming) {
+    bool first = true;
+    while (intersect_box(tnear, tfar, org, dir, fr.bbox_lo, fr.bbox_hi)) {
+      if (first) { hit_box = true; first = false; }
+      // delta_tracking (:260-296)
+      float t = tnear, majorant = 0.f; float albedo[3] = {0, 0, 0}; bool found = false;
+      DDAIter it; new_iter(it, tnear, tfar);
+      while (dt_hashit(fr, P, it, dir, tnear, tfar, rng, t, majorant)) {
+        const V3 c = madd(t, dir, org);
+        float a; float rgb[3]; tfn_raw(fr, sample(c), rgb, a); ++n_samples;
+        if (rng.next() * majorant < a * P.density_scale) { albedo[0] = rgb[0]; albedo[1] = rgb[1]; albedo[2] = rgb[2]; found = true; break; }
+      }
+      const bool exited = !found;
+      if (shadow) {
+        if (exited) add(L, thr, P.rgb);
+        tnear = 0.f; tfar = FLOAT_LARGE;
+        dir = sphere_dir();
+        shadow = false;
+      } else {
+        if (exited) { if (scatter > 0) add(L, thr, v3(P.ambient, P.ambient, P.ambient)); break; }
+        if (russian_roulette(thr, rng, scatter)) break;
+        ++scatter;
+        org = madd(t, dir, org);
+        thr = thr * v3(albedo[0] * 0.6f, albedo[1] * 0.6f, albedo[2] * 0.6f);
+        tnear = 0.f; tfar = FLOAT_LARGE;
+        dir = light_obj;
+        shadow = true;
+      }
+    }
+  } else {
+    DDAIter it; float majorant = 0.f; V3 coord = v3(0, 0, 0);
+    // iterative_take_sample (:596-633)
+    auto take_sample = [&]() -> bool {
+      float t;
+      if (dt_hashit(fr, P, it, dir, tnear, tfar, rng, t, majorant)) { coord = madd(t, dir, org); return true; }
+      if (scatter > 0) {
+        if (shadow) {
+          add(L, thr, P.rgb);
+          shadow = false;
+          dir = sphere_dir();
+          if (!intersect_box(tnear, tfar, org, dir, fr.bbox_lo, fr.bbox_hi)) return false;     // tnear / tfar carried in, as the reference does
+          new_iter(it, tnear, tfar);
+          if (dt_hashit(fr, P, it, dir, tnear, tfar, rng, t, majorant)) { coord = madd(t, dir, org); return true; }
+        } else add(L, thr, v3(P.ambient, P.ambient, P.ambient));
+      }
+      return false;
+    };
+    // iterative_shade (:635-672)
+    auto shade = [&](float value) -> bool {
+      float a; float rgb[3]; tfn_raw(fr, value, rgb, a);
+      if (rng.next() * majorant >= a * P.density_scale) return true;
+      if (shadow) {
+        shadow = false;
+        dir = sphere_dir();
+      } else {
+        if (russian_roulette(thr, rng, scatter)) return false;
+        ++scatter;
+        org = coord; tnear = 0.f; tfar = FLOAT_LARGE;
+        thr = thr * v3(rgb[0] * 0.6f, rgb[1] * 0.6f, rgb[2] * 0.6f);
+        shadow = true;
+        dir = light_obj;
+      }
+      if (!intersect_box(tnear, tfar, org, dir, fr.bbox_lo, fr.bbox_hi)) return false;
+      new_iter(it, tnear, tfar);
+      return true;
+    };
+    bool alive = false;
+    if (intersect_box(tnear, tfar, org, dir, fr.bbox_lo, fr.bbox_hi)) { hit_box = true; new_iter(it, tnear, tfar); alive = take_sample(); }
+    while (alive) {
+      const float value = sample(coord); ++n_samples;
+      tnear = 0.f; tfar = FLOAT_LARGE;                                                          // load() (:127-130)
+      intersect_box(tnear, tfar, org, dir, fr.bbox_lo, fr.bbox_hi);
+      alive = shade(value) && take_sample();
+    }
+  }
+  L_out[0] = L.x; L_out[1] = L.y; L_out[2] = L.z;
+}
+
+// volume_mode 0: network decode per sample; 1: trilinear lookup in `volume` (ground truth or the decoded volume).
+// lights: {density_scale, light_ambient, light_rgb[3], light_dir[3] (world space, sign-corrected)}.
+// stats: [0] rays that hit the volume box, [1] volume samples taken
+ORC_API void orc_render_pathtracing(const int* cfg, float pls, const uint16_t* params_f16, int acc_mode,
+                                    const float* fparams, const int* iparams, const float* mc_max_opacity, const float* colors, const float* alphas,
+                                    int volume_mode, const float* volume, const int* dims, int streaming, const float* lights,
+                                    float* accum, float* frame, uint64_t* stats) {
+  Frame fr = frame_from(fparams, iparams, mc_max_opacity, colors, alphas);
+  PtLights P; P.density_scale = lights[0]; P.ambient = lights[1]; P.rgb = v3(lights[2], lights[3], lights[4]); P.dir = v3(lights[5], lights[6], lights[7]);
+  Model m; const h16* grid = nullptr; MlpF mf;
+  if (volume_mode == 0) { m = make_model(cfg, pls); grid = params_f16 + m.n_mlp; mf = make_mlpf(m, params_f16); }
+  auto sample = [&](V3 p) -> float {
+    const float c[3] = {p.x, p.y, p.z};
+    if (volume_mode == 0) { h16 enc[128]; encode_one(m, grid, c, enc); return mlp_forward_one(m, mf, enc, acc_mode, nullptr); }
+    float q[3];
+    for (int d = 0; d < 3; ++d) { float rd = 1.f / (float)dims[d]; q[d] = fmaf(c[d], (1.f - rd), 0.5f * rd); }
+    return tex3d_linear(volume, dims, q[0], q[1], q[2], fr.tex_round);
+  };
+  const size_t npix = (size_t)fr.width * fr.height;
+  uint64_t n_hit = 0, n_samples = 0;
+#pragma omp parallel for schedule(dynamic, 64) reduction(+ : n_hit, n_samples)
+  for (long long i = 0; i < (long long)npix; ++i) {
+    float L[3]; uint64_t ns = 0; bool hit = false;
+    pt_pixel(fr, P, streaming, (uint32_t)i, sample, L, ns, hit);
+    n_samples += ns; n_hit += hit ? 1 : 0;
+    const float rgba[4] = {L[0], L[1], L[2], 1.f};                                                // writePixelColor(vec4f(L, 1))
+    for (int c = 0; c < 4; ++c) {
+      const float v = fr.frame_index == 1 ? rgba[c] : accum[4 * (size_t)i + c] + rgba[c];
+      accum[4 * (size_t)i + c] = v;
+      frame[4 * (size_t)i + c] = v / (float)fr.frame_index;
+    }
+  }
+  if (stats) { stats[0] = n_hit; stats[1] = n_samples; }
+}
+
 // expose pieces for unit tests
 // ---------------------------------------------------------------------------------------
 // volume SSIM (compute_ssim core/network.cu:70-125; get_mssim :474-549): 7^3 uniform window, moments accumulated in
