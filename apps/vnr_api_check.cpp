@@ -173,13 +173,22 @@ static void device_part(const std::string& dir) {
   vnrRendererResetAccumulation(rn);
   vnrRender(rn);
   CHECK(max_diff(frame_n, vnrRendererMapFrame(rn)) == 0.0);
-  // every marching mode renders; OptiX / path-tracing modes report unsupported
+  // every marching mode renders
   for (int mode = VNR_RAYMARCHING_NO_SHADING_DECODING; mode <= VNR_RAYMARCHING_SINGLE_SHADE_HEURISTIC_IN_SHADER; ++mode) {
     vnrRendererSetMode(rn, mode);
     vnrRender(rn);
     const double c = mean_alpha(vnrRendererMapFrame(rn), fb.x * fb.y);
     std::cout << "coverage_mode_" << mode << " " << c << std::endl;
     CHECK(std::fabs(c - cover_n) < 0.05);
+  }
+  // path tracing: every pixel is written with alpha 1 (writePixelColor(vec4f(L, 1))), scattered light is positive
+  for (int mode = VNR_PATHTRACING_DECODING; mode <= VNR_PATHTRACING_IN_SHADER; ++mode) {
+    vnrRendererSetMode(rn, mode);
+    vnrRender(rn);
+    const vnr::vec4f* p = vnrRendererMapFrame(rn);
+    double light = 0; for (int i = 0; i < fb.x * fb.y; ++i) light += p[i].x + p[i].y + p[i].z;
+    std::cout << "pathtracing_light_mode_" << mode << " " << light / (fb.x * fb.y) << std::endl;
+    CHECK(mean_alpha(p, fb.x * fb.y) == 1.0 && light > 0);
   }
   vnrRendererSetMode(rn, VNR_OPTIX_NO_SHADING);
   CHECK(throws([&] { vnrRender(rn); }));

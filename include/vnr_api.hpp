@@ -10,7 +10,7 @@
 //     (serializer.cpp:138-477; other OVR readers are not vendored); an in-memory overload takes a normalised
 //     float volume.  A simple volume is carried by a vnr_volume_t with a minimal model, so that its
 //     ground truth, macrocells and transfer function live where the renderer expects them;
-//   * rendering modes 0-3 (OptiX) and 13-15 (path tracing) return "unsupported" from vnrRender.
+//   * rendering modes 0-3 (OptiX) return "unsupported" from vnrRender.
 // apps/vnr_cmd_train.cpp and apps/vnr_cmd_render.cpp are the reference's two headless drivers
 // (apps/batch_trainer.cpp:72-141, apps/batch_renderer.cpp:156-239) written against this header.
 #pragma once

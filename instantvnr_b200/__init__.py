@@ -570,3 +570,12 @@ class PeerBarrier:
 VNR_RAYMARCHING_NO_SHADING_DECODING = 4
 VNR_RAYMARCHING_NO_SHADING_SAMPLE_STREAMING = 5
 VNR_RAYMARCHING_NO_SHADING_IN_SHADER = 6
+VNR_RAYMARCHING_GRADIENT_SHADING_DECODING = 7
+VNR_RAYMARCHING_GRADIENT_SHADING_SAMPLE_STREAMING = 8
+VNR_RAYMARCHING_GRADIENT_SHADING_IN_SHADER = 9
+VNR_RAYMARCHING_SINGLE_SHADE_HEURISTIC_DECODING = 10
+VNR_RAYMARCHING_SINGLE_SHADE_HEURISTIC_SAMPLE_STREAMING = 11
+VNR_RAYMARCHING_SINGLE_SHADE_HEURISTIC_IN_SHADER = 12
+VNR_PATHTRACING_DECODING = 13
+VNR_PATHTRACING_SAMPLE_STREAMING = 14
+VNR_PATHTRACING_IN_SHADER = 15

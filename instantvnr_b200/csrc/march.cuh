@@ -42,6 +42,8 @@ struct FrameParams {
   float light_dir[3];                // world space, sign-corrected against the camera (renderer.cpp:98-101)
   float otw_diag[3];                 // object->world linear part (network.cu:569)
   float grad_step[3];                // object.cpp:305
+  // path tracer (method_pathtracing.cu): majorant scale and lights (instantvnr_types.h:102,146-147)
+  float density_scale, light_ambient, light_rgb[3];
   float4* frame;                     // where finished pixels go: local / peer frame buffer or the mapped pinned host frame
 };
 

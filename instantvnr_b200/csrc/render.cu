@@ -350,6 +350,10 @@ march_volume_kernel(const FrameParams* __restrict__ fpp, const float* __restrict
   }
 }
 
+}  // namespace vnr
+#include "pathtrace.cuh"
+namespace vnr {
+
 // Loop control of the graph-driven wavefront: one thread advances the device round index and tells
 // the WHILE node whether the round that was just emitted holds any sample.
 __global__ void advance_round_kernel(uint32_t* __restrict__ counters, uint32_t* __restrict__ round_dev, cudaGraphConditionalHandle handle, int init, int bound) {
@@ -455,7 +459,10 @@ void Renderer::fill_frame_params(FrameParams& fp) {
     fp.light_dir[k] = light_dir[k];
     fp.otw_diag[k] = d[k];
     fp.grad_step[k] = 1.f / (float)vol->dims[k];                       // object.cpp:305
+    fp.light_rgb[k] = 1.0f;                                            // light_directional_rgb, instantvnr_types.h:147
   }
+  fp.density_scale = density_scale;                                    // object.cpp:356-359
+  fp.light_ambient = 1.5f;                                             // instantvnr_types.h:146
 }
 
 int Renderer::round_bound() const {
@@ -472,6 +479,8 @@ void Renderer::destroy_graph() {
     if (loop_exec[k]) { cudaGraphExecDestroy(loop_exec[k]); loop_exec[k] = nullptr; }
     if (loop_graph[k]) { cudaGraphDestroy(loop_graph[k]); loop_graph[k] = nullptr; }
   }
+  if (pt_exec) { cudaGraphExecDestroy(pt_exec); pt_exec = nullptr; }
+  if (pt_graph) { cudaGraphDestroy(pt_graph); pt_graph = nullptr; }
   if (capture_stream) { cudaStreamDestroy(capture_stream); capture_stream = nullptr; }
 }
 
@@ -533,16 +542,92 @@ void Renderer::ensure_graph(int pass, int shade, const RayBuffers& rb, unsigned 
   graph_key[pass] = key;
 }
 
+// The path-tracing wavefront (do_path_tracing_iterative, method_pathtracing.cu:796-812): raygen, then rounds of
+// [decode the sample queue -> shade + next delta-tracking step + compaction] until no ray is alive.  graph_loop: the
+// rounds are the body of a CUDA-graph WHILE node; otherwise the host reads the live count back every round (the
+// reference's loop; what profilers see).
+void Renderer::render_pathtracing(const float* volume_src, unsigned grid, size_t cap, bool graph_loop) {
+  uint32_t* cnt = counters.p;
+  const FrameParams* fpd = reinterpret_cast<const FrameParams*>(fp_dev.p);
+  PtBuffers pb{pt_org.p, pt_dir.p, pt_rad.p, pt_thr.p, pt_tn.p, pt_cell.p, pt_list[0].p, pt_list[1].p};
+  const unsigned shade_grid = std::min<unsigned>(grid, (unsigned)num_sms() * 16u);
+  auto decode = [&](cudaStream_t s) {
+    return volume_src ? launch_volume_samples(volume_src, vol->dims, samples[0].p, samples[1].p, values.p, cnt + kPtLive, cnt + kPtParity, cap, s)
+                      : launch_decode_samples(vol->cfg.desc, vol->params.p, samples[0].p, samples[1].p, values.p, cnt + kPtLive, cnt + kPtParity, cap, s);
+  };
+  pt_raygen_kernel<<<grid, 128, 0, stream>>>(fpd, pb, samples[0].p, cnt, accum.p);
+  VNR_CUDA(cudaGetLastError());
+  if (graph_loop) {
+    GraphKey key;
+    memset(&key, 0, sizeof key);
+    key.desc = vol->cfg.desc; key.params = vol->params.p;
+    key.ptrs[0] = pb.org; key.ptrs[1] = pb.dir; key.ptrs[2] = pb.radiance; key.ptrs[3] = pb.thr_rng; key.ptrs[4] = pb.tn; key.ptrs[5] = pb.cell;
+    key.ptrs[6] = pb.list0; key.ptrs[7] = pb.list1; key.ptrs[8] = samples[0].p; key.ptrs[9] = samples[1].p; key.ptrs[10] = values.p;
+    key.ptrs[11] = cnt; key.ptrs[12] = accum.p; key.ptrs[13] = fpd;
+    key.grid = shade_grid; key.cap = cap; key.volume_src = volume_src;
+    if (!pt_exec || memcmp(&key, &pt_key, sizeof key)) {
+      VNR_CUDA(cudaStreamSynchronize(stream));
+      if (pt_exec) { cudaGraphExecDestroy(pt_exec); pt_exec = nullptr; }
+      if (pt_graph) { cudaGraphDestroy(pt_graph); pt_graph = nullptr; }
+      VNR_CUDA(cudaGraphCreate(&pt_graph, 0));
+      cudaGraphConditionalHandle handle;
+      VNR_CUDA(cudaGraphConditionalHandleCreate(&handle, pt_graph, 0, 0));
+      cudaGraphNode_t init_node;
+      {
+        int init = 1, use = 1;
+        void* args[] = {&cnt, &handle, &init, &use};
+        cudaKernelNodeParams kp = {};
+        kp.func = (void*)pt_advance_kernel; kp.gridDim = dim3(1); kp.blockDim = dim3(1); kp.kernelParams = args;
+        VNR_CUDA(cudaGraphAddKernelNode(&init_node, pt_graph, nullptr, 0, &kp));
+      }
+      cudaGraphNodeParams wp = {};
+      wp.type = cudaGraphNodeTypeConditional;
+      wp.conditional.handle = handle; wp.conditional.type = cudaGraphCondTypeWhile; wp.conditional.size = 1;
+      cudaGraphNode_t while_node;
+      VNR_CUDA(cudaGraphAddNode(&while_node, pt_graph, &init_node, 1, &wp));
+      cudaGraph_t body = wp.conditional.phGraph_out[0];
+      if (!capture_stream) VNR_CUDA(cudaStreamCreateWithFlags(&capture_stream, cudaStreamNonBlocking));
+      VNR_CUDA(cudaStreamBeginCaptureToGraph(capture_stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
+      cudaError_t e = decode(capture_stream);
+      pt_shade_kernel<<<shade_grid, 128, 0, capture_stream>>>(fpd, pb, samples[0].p, samples[1].p, values.p, cnt, 0, cnt + kPtParity, accum.p);
+      pt_advance_kernel<<<1, 1, 0, capture_stream>>>(cnt, handle, 0, 1);
+      cudaGraph_t captured = nullptr;
+      cudaError_t e2 = cudaStreamEndCapture(capture_stream, &captured);
+      VNR_CUDA(e); VNR_CUDA(e2);
+      VNR_CUDA(cudaGraphInstantiate(&pt_exec, pt_graph, 0));
+      pt_key = key;
+    }
+    VNR_CUDA(cudaGraphLaunch(pt_exec, stream));
+    launches = 0;
+  } else {
+    cudaGraphConditionalHandle none = 0;
+    pt_advance_kernel<<<1, 1, 0, stream>>>(cnt, none, 1, 0);
+    launches = 2;
+    for (uint32_t r = 0;; ++r) {
+      uint32_t live = 0;                                               // iterative_ray_compaction (:789-794)
+      VNR_CUDA(cudaMemcpyAsync(&live, cnt + kPtLive + (r & 1u), sizeof live, cudaMemcpyDeviceToHost, stream));
+      VNR_CUDA(cudaStreamSynchronize(stream));
+      if (!live) break;
+      VNR_CUDA(decode(stream));
+      pt_shade_kernel<<<shade_grid, 128, 0, stream>>>(fpd, pb, samples[0].p, samples[1].p, values.p, cnt, 0, cnt + kPtParity, accum.p);
+      pt_advance_kernel<<<1, 1, 0, stream>>>(cnt, none, 0, 0);
+      VNR_CUDA(cudaGetLastError());
+      launches += 3;
+    }
+  }
+}
+
 // vnrRenderMode -> shading of the marcher (renderer.cpp:152-225): 4-6 none, 7-9 gradient shading, 10-12 single-shade heuristic
 static int shade_of_mode(int mode) { return mode >= 10 ? 2 : (mode >= 7 ? 1 : 0); }
 
 void Renderer::render() {
   if (width <= 0 || height <= 0) return;                               // renderer.cpp:62
-  if (mode < 4 || mode > 12) throw UnsupportedError("rendering mode " + std::to_string(mode) + " is outside this library's path (ray-marching modes 4-12)");
+  if (mode < 4 || mode > 15) throw UnsupportedError("rendering mode " + std::to_string(mode) + " is outside this library's path (OptiX modes 0-3 are not built)");
+  const bool pathtracing = mode >= 13;
   // value source of the wavefront: the network (sample streaming / in-shader modes), the progressively decoded volume
   // (decoding modes 4 / 7 / 10: the reference marches neural.texture(), api.cpp:429-438) or the ground truth (SimpleVolume renderer)
-  const bool decoding = mode == 4 || mode == 7 || mode == 10;
-  const int shade = shade_of_mode(mode);
+  const bool decoding = mode == 4 || mode == 7 || mode == 10 || mode == 13;
+  const int shade = pathtracing ? 0 : shade_of_mode(mode);
   const float* volume_src = nullptr;
   if (gt_source) {
     if (!vol->have_gt) throw StateError("no ground-truth volume set");
@@ -568,11 +653,14 @@ void Renderer::render() {
   VNR_CUDA(cudaStreamWaitEvent(stream, vol_ready, 0));
 
   // decoding modes, and a SimpleVolume in every mode but the sample-streaming ones, run the single-kernel marcher
-  const bool single_kernel = decoding || (gt_source && mode != 5 && mode != 8 && mode != 11);
+  const bool single_kernel = decoding || (gt_source && mode != 5 && mode != 8 && mode != 11 && mode != 14);
   const size_t cap = (size_t)n_rays * n_iters * (shade == 1 ? 4 : 1);
   if (!single_kernel) {
     samples[0].ensure(cap); samples[1].ensure(cap); values.ensure(cap);
-    ray_rgba.ensure(n_rays); ray_tn.ensure(n_rays); ray_cell.ensure(n_rays); ray_state.ensure(n_rays); ray_jitter.ensure(n_rays);
+    if (pathtracing) {
+      pt_org.ensure(n_rays); pt_dir.ensure(n_rays); pt_rad.ensure(n_rays); pt_thr.ensure(n_rays); pt_tn.ensure(n_rays); pt_cell.ensure(n_rays);
+      pt_list[0].ensure(n_rays); pt_list[1].ensure(n_rays);
+    } else { ray_rgba.ensure(n_rays); ray_tn.ensure(n_rays); ray_cell.ensure(n_rays); ray_state.ensure(n_rays); ray_jitter.ensure(n_rays); }
     if (shade == 2) { ssh_org.ensure(n_rays); ssh_col.ensure(n_rays); ssh_rgba.ensure(n_rays); ssh_jitter.ensure(n_rays); }
   }
   const size_t cstride = kMaxRounds + 4;
@@ -593,13 +681,15 @@ void Renderer::render() {
   if (single_kernel && n_rays) {
     const int3 d3 = make_int3(vol->dims[0], vol->dims[1], vol->dims[2]);
     const FrameParams* fpd = reinterpret_cast<const FrameParams*>(fp_dev.p);
-    if (shade == 1) march_volume_kernel<1><<<grid, 128, 0, stream>>>(fpd, volume_src, d3, counters.p, accum.p);
+    if (pathtracing) pt_volume_kernel<<<grid, 128, 0, stream>>>(fpd, volume_src, d3, counters.p, accum.p);
+    else if (shade == 1) march_volume_kernel<1><<<grid, 128, 0, stream>>>(fpd, volume_src, d3, counters.p, accum.p);
     else if (shade == 2) march_volume_kernel<2><<<grid, 128, 0, stream>>>(fpd, volume_src, d3, counters.p, accum.p);
     else march_volume_kernel<0><<<grid, 128, 0, stream>>>(fpd, volume_src, d3, counters.p, accum.p);
     VNR_CUDA(cudaGetLastError());
     launches = 1;
   }
-  for (int pass = 0; pass < n_pass && n_rays && !single_kernel; ++pass) {
+  if (pathtracing && !single_kernel && n_rays) render_pathtracing(volume_src, grid, cap, graph_loop);
+  for (int pass = 0; pass < n_pass && n_rays && !single_kernel && !pathtracing; ++pass) {
     const int sh = pass == 1 ? 3 : shade;
     uint32_t* cnt = counters.p + (size_t)pass * cstride;
     const FrameParams* fpd = reinterpret_cast<const FrameParams*>(fp_dev.p) + pass;
@@ -622,6 +712,7 @@ void Renderer::render() {
     if (!graph_loop) launches += 2 + 2 * (uint64_t)rounds;     // graph path: counted from the device counters in stats()
   }
   last_graph = graph_loop && !single_kernel;
+  last_pt = pathtracing;
   last_rounds = rounds;
   last_passes = single_kernel ? 1 : n_pass;
   // framebuffer.download_async (renderer.cpp:133)
@@ -670,6 +761,12 @@ void Renderer::profile(float* decode_ms, int* decode_launches) {
 void Renderer::stats(uint64_t* s4) {
   VNR_CUDA(cudaStreamSynchronize(stream));
   uint64_t dec = 0, rounds = 0, comp = 0, leftover = 0;
+  if (last_pt) {                       // path tracer: every sample taken is one collision event; rounds counted on the device
+    const bool wavefront = h_counters[kPtRounds] != 0;
+    s4[0] = h_counters[0]; s4[1] = h_counters[1]; s4[2] = h_counters[1]; s4[3] = wavefront ? h_counters[kPtRounds] : 1;
+    if (last_graph) launches = 2 + 3 * (uint64_t)h_counters[kPtRounds];
+    return;
+  }
   for (int pass = 0; pass < last_passes; ++pass) {
     const uint32_t* c = h_counters + (size_t)pass * (kMaxRounds + 4);
     for (int r = 0; r <= last_rounds && r < kMaxRounds; ++r) { dec += c[2 + r]; if (c[2 + r]) ++rounds; }

@@ -42,6 +42,9 @@ struct Renderer {
   DevBuf<int4> ray_cell;
   DevBuf<float> values, ray_jitter, ssh_jitter;
   DevBuf<uint32_t> ray_state, counters;
+  // path tracer (pathtrace.cuh): per-ray state, live-ray lists (ping-pong), its own loop graph
+  DevBuf<float4> pt_org, pt_dir, pt_rad, pt_thr, pt_tn; DevBuf<int4> pt_cell; DevBuf<uint32_t> pt_list[2];
+  cudaGraph_t pt_graph = nullptr; cudaGraphExec_t pt_exec = nullptr; GraphKey pt_key; bool last_pt = false;
   float4* h_frame[2] = {nullptr, nullptr};
   uint32_t* h_counters = nullptr;
   bool downloaded = false;
@@ -69,6 +72,7 @@ struct Renderer {
   void destroy_graph();
   void ensure_graph(int pass, int shade, const RayBuffers& rb, unsigned grid, size_t cap, int rounds, const float* volume_src);
   void render();
+  void render_pathtracing(const float* volume_src, unsigned grid, size_t cap, bool graph_loop);
   void download_now();
   const float* map_frame();
   void stats(uint64_t* s4);

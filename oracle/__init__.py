@@ -278,6 +278,29 @@ def render_single_kernel(frame, mc_max_opacity, colors_rgba, alphas, volume, jit
                                                               "samples_composited": int(stats[2]), "rounds": int(stats[3])}
 
 
+def render_pathtracing(frame, mc_max_opacity, colors_rgba, alphas, volume=None, m=None, params_f16=None, streaming=True, density_scale=1.0,
+                       light_ambient=1.5, light_rgb=(1.0, 1.0, 1.0), acc_mode=0, accum=None):
+    """The path tracer (method_pathtracing.cu): streaming=True -> the sample-streaming state machine (mode 14 / 15 on a network),
+    False -> the single-kernel tracer (mode 13 / 15 on a SimpleVolume).  volume given -> trilinear lookups, else the network."""
+    colors_rgba = _f32(colors_rgba).reshape(-1, 4)
+    alphas = _f32(alphas)
+    frame.set_tfn_sizes(colors_rgba.shape[0], alphas.size)
+    npix = frame.width * frame.height
+    if accum is None:
+        accum = np.zeros((npix, 4), dtype=np.float32)
+    out = np.zeros((npix, 4), dtype=np.float32)
+    stats = np.zeros(2, dtype=np.uint64)
+    mc_max_opacity = _f32(mc_max_opacity)
+    vol = _f32(volume) if volume is not None else None
+    gd = np.array(frame.dims, dtype=np.int32)
+    lights = _f32([density_scale, light_ambient, *light_rgb, *frame.f[38:41]])
+    cfg = m.cfg if m is not None else None
+    lib().orc_render_pathtracing(cfg, C.c_float(m.pls if m is not None else 2.0), _p(params_f16) if params_f16 is not None else None, C.c_int(acc_mode),
+                                 _p(frame.f), _p(frame.i), _p(mc_max_opacity), _p(colors_rgba), _p(alphas), C.c_int(0 if vol is None else 1),
+                                 _p(vol), _p(gd), C.c_int(1 if streaming else 0), _p(lights), _p(accum), _p(out), _p(stats))
+    return out.reshape(frame.height, frame.width, 4), accum, {"rays_hit": int(stats[0]), "samples_decoded": int(stats[1])}
+
+
 def rays(frame):
     out = np.empty((frame.width * frame.height, 8), dtype=np.float32)
     lib().orc_rays(_p(frame.f), _p(frame.i), _p(out))
