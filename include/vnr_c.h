@@ -226,8 +226,11 @@ int vnr_renderer_create(vnr_volume_t* v, vnr_renderer_t** out);        /* vnrCre
 void vnr_renderer_release(vnr_renderer_t* r);
 int vnr_renderer_set_size(vnr_renderer_t* r, int width, int height);   /* SetFramebufferSize :169 */
 int vnr_renderer_set_camera(vnr_renderer_t* r, const float* from, const float* at, const float* up, float fovy); /* :171 */
-int vnr_renderer_set_mode(vnr_renderer_t* r, int mode);                /* vnrRenderMode, api.h:36-60: 4 (march the decoded
-                                                                          volume), 5 / 6 (decode the network per sample) */
+int vnr_renderer_set_mode(vnr_renderer_t* r, int mode);                /* vnrRenderMode, api.h:36-60.  Ray marching: 4 / 7 / 10 march
+                                                                          the progressively decoded volume, 5 / 8 / 11 and 6 / 9 / 12 decode
+                                                                          the network per sample (no / gradient / single-shade shading);
+                                                                          path tracing: 13 decoded volume, 14 / 15 network per collision.
+                                                                          0-3 (OptiX): vnr_render returns VNR_ERR_UNSUPPORTED */
 /* what a SimpleVolume renderer marches (vnrCreateRenderer on a simple volume, api.cpp:441-452): 1 = the ground-truth
  * volume of `v` through the same wavefront (the "GT render" frames are compared against); 0 = per mode */
 int vnr_renderer_set_groundtruth_source(vnr_renderer_t* r, int on);
