@@ -503,6 +503,53 @@ def run_train(args):
         dist.destroy_process_group()
 
 
+def run_interleaved(args):
+    """BASELINE configs[2] as the interactive app runs it (apps/int_dual_volume.cpp:636-671): every iteration is one online
+    training step (2^18 samples, macrocell value ranges updated from the batch, max opacity refreshed) followed by one
+    1024^2 frame of the volume as trained so far, mapped to the host.  value = iterations (= frames = steps) per second."""
+    import torch
+    import instantvnr_b200 as vnr
+    from instantvnr_b200 import synthetic as syn
+    torch.cuda.set_device(0)
+    dims = (args.volume,) * 3
+    W, H = (args.width or args.frame), (args.height or args.frame)
+    vol, gt, (rgb, alpha) = build_scene(vnr, dims, 50, 1 << 16, dict(log2_hashmap=args.log2_hashmap))
+    ren = vnr.Renderer(vol)
+    ren.set_size(W, H)
+    ren.set_mode(vnr.VNR_RAYMARCHING_NO_SHADING_SAMPLE_STREAMING)
+    cams = [syn.default_camera(dims, v, 16) for v in range(16)]
+    n = args.batch
+
+    def iteration(i):
+        vol.train(1, batch=n, fast_mode=False)
+        ren.set_camera(*cams[i % 16])
+        ren.render()
+        return ren.map_frame(copy=False)
+
+    for i in range(max(args.warmup, 3)):
+        iteration(i)
+    torch.cuda.synchronize()
+    clocks = ClockSampler(0); clocks.start()
+    decoded = 0
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        img = iteration(i)
+        decoded += ren.stats()["samples_decoded"]
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    clk = clocks.stop()
+    step_count, mean_loss = vol.stats()
+    emit({"metric": "interleaved_train_render_iterations_per_sec", "value": args.steps / dt, "unit": "iterations/s", "n_gpus": 1, "steps": args.steps,
+          "warmup": max(args.warmup, 3), "ms_per_step": dt * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+          "dtype": "f16", "data": "synthetic",
+          "config": {"workload": f"interleaved: per iteration one training step ({n} samples, fwd + L1 + bwd + Adam + macrocell update) and one {W}x{H} "
+                                 f"mode-5 frame of the synthetic {args.volume}^3 volume, frame mapped to the host (host-timed, every frame synchronised)",
+                     "parallelism": "single GPU"},
+          "train_samples_per_sec": args.steps * n / dt, "render_samples_per_sec": decoded / dt, "training_step": step_count, "mean_loss": mean_loss,
+          "volume_psnr_db": vol.psnr(), "e2e": {"value": args.steps / dt, "unit": "iterations/s", "h2d_bytes_per_step": 480, "d2h_bytes_per_step": W * H * 16},
+          "gpu_launches": None, "clocks": clk})
+
+
 def run_reference_train(args):
     """reference arm of the train workload: the reference's own Trainer::training_step (tiny-cuda-nn built unmodified from
     /root/reference/tcnn, oracle/_ref) on the same GPU, samples drawn by the oracle-checked sampler of our library (the
@@ -622,7 +669,7 @@ def main():
     ap.add_argument("--width", type=int, default=0, help="frame width (default --frame)")
     ap.add_argument("--height", type=int, default=0, help="frame height (default --frame)")
     ap.add_argument("--log2-hashmap", type=int, default=19, help="hash table size per level (config 5: 22)")
-    ap.add_argument("--workload", default="render", choices=["render", "train"],
+    ap.add_argument("--workload", default="render", choices=["render", "train", "interleaved"],
                     help="render = BASELINE configs[1] (the headline; --width 3840 --height 2160 --log2-hashmap 22 = configs[4]); "
                          "train = configs[2]/[3]: data-parallel training steps/s at --batch samples per rank")
     ap.add_argument("--batch", type=int, default=1 << 18, help="train workload: samples per rank per step")
@@ -637,6 +684,9 @@ def main():
         run_reference(args)
     elif args.workload == "train":
         run_train(args)
+    elif args.workload == "interleaved":
+        if int(os.environ.get("RANK", "0")) == 0:
+            run_interleaved(args)
     else:
         run_ours(args)
 
