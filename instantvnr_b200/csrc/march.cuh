@@ -25,6 +25,7 @@ namespace vnr {
 struct FrameParams {
   int width, height, frame_index, n_iters;
   int jitter_mode, tex_round, part_rank, part_world;
+  int tiled, transpose, pad_[2];                // rays are dealt to warps in 8 x 4 pixel tiles (width % 8 == 0, local rows % 4 == 0)
   uint32_t n_rays, strip_rows;       // local rays of this partition; rows per interleaved strip
   float cam_pos[3], cam_dir[3], cam_hor[3], cam_ver[3];
   float wto_l[9], wto_p[3];
@@ -54,12 +55,19 @@ __device__ __forceinline__ F3 madd(float s, F3 a, F3 b) { return f3(__fmaf_rn(s,
 __device__ __forceinline__ float dot3(F3 a, F3 b) { return __fmaf_rn(a.z, b.z, __fmaf_rn(a.y, b.y, a.x * b.x)); }
 __device__ __forceinline__ float clampf(float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
-// local ray index -> pixel index.  Partition: strips of `strip_rows` image rows are dealt
-// round-robin to the ranks; rank r owns strips r, r+world, ...
+// local ray index -> pixel index.  tiled: a warp owns an 8 x 4 pixel tile (its 32 rays stay spatially close all along their
+// way through the volume, so the samples a warp emits share hash-grid cells on the coarse and middle levels); otherwise
+// scanline order.  Partition: strips of `strip_rows` image rows are dealt round-robin to the ranks; rank r owns strips
+// r, r+world, ...
 __device__ __forceinline__ uint32_t ray_to_pixel(const FrameParams& fp, uint32_t i) {
-  if (fp.part_world <= 1) return i;
   const uint32_t w = (uint32_t)fp.width;
-  const uint32_t lrow = i / w, x = i - lrow * w;
+  uint32_t lrow, x;
+  if (fp.tiled) {
+    const uint32_t tiles_x = w >> 3, tile = i >> 5, lane = i & 31u;
+    const uint32_t ty = tile / tiles_x, tx = tile - ty * tiles_x;
+    lrow = ty * 4u + (lane >> 3); x = tx * 8u + (lane & 7u);
+  } else { lrow = i / w; x = i - lrow * w; }
+  if (fp.part_world <= 1) return lrow * w + x;
   const uint32_t strip = lrow / fp.strip_rows, in = lrow - strip * fp.strip_rows;
   const uint32_t y = (strip * (uint32_t)fp.part_world + (uint32_t)fp.part_rank) * fp.strip_rows + in;
   return y * w + x;

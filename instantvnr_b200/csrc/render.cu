@@ -112,8 +112,8 @@ march_round_kernel(const FrameParams* __restrict__ fpp, RayBuffers rb, float4* _
   float4 rgba = make_float4(0, 0, 0, 0);
   float4 hi_org = make_float4(0, 0, 0, 0), hi_col = make_float4(0, 0, 0, 0);
   DDAState dda; dda.tnx = dda.tny = dda.tnz = 0.f; dda.cx = dda.cy = dda.cz = 0; dda.ncb = 0.f;
-  uint32_t n_comp = 0;
-  bool hit = false;
+  uint32_t n_comp = 0, cnt = 0, cbase = 0;
+  bool hit = false, composing = false;
 
   if (active) {
     if (SHADE == 3) { const float4 o = rb.ssh_org[i]; org = f3(o.x, o.y, o.z); hi_org = o; dir = shadow_dir(fp); }
@@ -145,16 +145,34 @@ march_round_kernel(const FrameParams* __restrict__ fpp, RayBuffers rb, float4* _
       const float4 t = rb.tn_ncb[i];
       const int4 c = rb.cell_base[i];
       dda.tnx = t.x; dda.tny = t.y; dda.tnz = t.z; dda.ncb = t.w; dda.cx = c.x; dda.cy = c.y; dda.cz = c.z;
-      // ---- compose the samples of the previous round (iterative_compose_kernel :757-806)
-      const uint32_t cnt = st & 0xFFFFu, base = (uint32_t)c.w;
-      for (uint32_t k = 0; k < cnt; ++k) {
-        const float value = values[base + EPS * k];
-        const float4 smp = prev_samples[base + EPS * k];
+      cnt = st & 0xFFFFu; cbase = (uint32_t)c.w;
+      composing = true;
+    }
+  }
+
+  // ---- compose the samples of the previous round (iterative_compose_kernel :757-806).  Transposed layout: the slots of a
+  // warp are depth-major (the j-th samples of all its rays are adjacent), so the slot of (ray, j) follows from the warp's
+  // sample counts -- the same 32 rays sit in the same lanes in every round.
+  if (!FIRST) {
+    const uint32_t lt = (1u << lane) - 1u;
+    const uint32_t maxcnt = __reduce_max_sync(0xffffffffu, cnt);
+    uint32_t off = 0;
+    bool open = composing;
+    for (uint32_t j = 0; j < maxcnt; ++j) {
+      uint32_t e;
+      if (fp.transpose) {
+        const uint32_t mask = __ballot_sync(0xffffffffu, cnt > j);
+        e = cbase + EPS * (off + (uint32_t)__popc(mask & lt));
+        off += (uint32_t)__popc(mask);
+      } else e = cbase + EPS * j;
+      if (open && cnt > j) {
+        const float value = values[e];
+        const float4 smp = prev_samples[e];
         float r, g, b, a;
         classify(fp, fp.tfn_color, fp.tfn_alpha, value, smp.w, r, g, b, a);
         if (SHADE == 1) {
-          const F3 grad = f3(__fdiv_rn(values[base + 4 * k + 1] - value, fp.grad_step[0]), __fdiv_rn(values[base + 4 * k + 2] - value, fp.grad_step[1]),
-                             __fdiv_rn(values[base + 4 * k + 3] - value, fp.grad_step[2]));
+          const F3 grad = f3(__fdiv_rn(values[e + 1] - value, fp.grad_step[0]), __fdiv_rn(values[e + 2] - value, fp.grad_step[1]),
+                             __fdiv_rn(values[e + 3] - value, fp.grad_step[2]));
           shade_gradient(fp, dir, grad, r, g, b);
         } else if (SHADE == 2) {
           const float contrib = (1.f - rgba.w) * a;
@@ -168,8 +186,10 @@ march_round_kernel(const FrameParams* __restrict__ fpp, RayBuffers rb, float4* _
           rgba.z = __fmaf_rn(tr * b, a, rgba.z);
         }
         ++n_comp;
-        if (!(rgba.w < VNR_NEARLY_ONE)) break;
+        if (!(rgba.w < VNR_NEARLY_ONE)) open = false;
       }
+    }
+    if (composing) {
       const bool resumable = dda_resumable(dda, m_dir, tmin, tmax, fp.mc_dims);
       if (!(rgba.w < VNR_NEARLY_ONE && resumable)) {
         finish_ray<SHADE>(fp, rb, accum, i, pixel, rgba, hi_org, hi_col);
@@ -203,19 +223,34 @@ march_round_kernel(const FrameParams* __restrict__ fpp, RayBuffers rb, float4* _
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (uint32_t)o) incl += t; }
   const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-  uint32_t base = 0;
-  if (lane == 31 && total) base = atomicAdd(&counters[2 + round], EPS * total);
-  base = __shfl_sync(0xffffffffu, base, 31) + EPS * (incl - k);
-  if (active) {
-    for (uint32_t j = 0; j < k; ++j) {
-      const float4 c = local[j];
-      next_samples[base + EPS * j] = c;
-      if (SHADE == 1) {
-        next_samples[base + 4 * j + 1] = make_float4(c.x + fp.grad_step[0], c.y, c.z, 0.f);
-        next_samples[base + 4 * j + 2] = make_float4(c.x, c.y + fp.grad_step[1], c.z, 0.f);
-        next_samples[base + 4 * j + 3] = make_float4(c.x, c.y, c.z + fp.grad_step[2], 0.f);
-      }
+  uint32_t wbase = 0;
+  if (lane == 31 && total) wbase = atomicAdd(&counters[2 + round], EPS * total);
+  wbase = __shfl_sync(0xffffffffu, wbase, 31);
+  auto put = [&](uint32_t e, const float4 c) {
+    next_samples[e] = c;
+    if (SHADE == 1) {
+      next_samples[e + 1] = make_float4(c.x + fp.grad_step[0], c.y, c.z, 0.f);
+      next_samples[e + 2] = make_float4(c.x, c.y + fp.grad_step[1], c.z, 0.f);
+      next_samples[e + 3] = make_float4(c.x, c.y, c.z + fp.grad_step[2], 0.f);
     }
+  };
+  uint32_t base = wbase;
+  if (fp.transpose) {
+    // depth-major within the warp: adjacent decode rows are the same step of neighbouring rays (8 x 4 pixel tile), which
+    // share hash-grid cells on the coarse and middle levels; the warp's stores and next round's loads coalesce
+    const uint32_t lt = (1u << lane) - 1u;
+    uint32_t off = 0;
+    for (uint32_t j = 0; j < 16u; ++j) {
+      const uint32_t mask = __ballot_sync(0xffffffffu, k > j);
+      if (!mask) break;
+      if (k > j) put(wbase + EPS * (off + (uint32_t)__popc(mask & lt)), local[j]);
+      off += (uint32_t)__popc(mask);
+    }
+  } else {
+    base = wbase + EPS * (incl - k);
+    if (active) for (uint32_t j = 0; j < k; ++j) put(base + EPS * j, local[j]);
+  }
+  if (active) {
     rb.rgba[i] = rgba;
     if (SHADE == 2) { rb.ssh_org[i] = hi_org; rb.ssh_col[i] = hi_col; }
     rb.tn_ncb[i] = make_float4(dda.tnx, dda.tny, dda.tnz, dda.ncb);
@@ -373,6 +408,8 @@ Renderer::Renderer(Volume* v) : vol(v) {
   memset(h_counters, 0, sizeof(uint32_t) * 2 * (kMaxRounds + 4));
   if (const char* e = getenv("VNR_RM_GRAPH")) use_graph = atoi(e) != 0;    // 0: host-enqueued rounds (profilers do not see graph-body kernels)
   if (const char* e = getenv("VNR_FRAME_ZEROCOPY")) zero_copy = atoi(e) != 0;
+  if (const char* e = getenv("VNR_RM_TILED")) tiled = atoi(e) != 0;          // 0: scanline ray order (A/B)
+  if (const char* e = getenv("VNR_RM_TRANSPOSE")) transpose = atoi(e) != 0;  // 0: per-ray contiguous sample slots (A/B)
   if (const char* e = getenv("VNR_RM_N_ITERS")) {       // method_raymarching.cu:30-38
     int n = atoi(e);
     if (n >= 1 && n <= 16) n_iters = n;
@@ -424,6 +461,8 @@ void Renderer::fill_frame_params(FrameParams& fp) {
   fp.width = width; fp.height = height; fp.frame_index = frame_index; fp.n_iters = n_iters;
   fp.jitter_mode = jitter_mode; fp.tex_round = 0; fp.part_rank = part_rank; fp.part_world = part_world;
   fp.strip_rows = strip_rows; fp.n_rays = local_rays();
+  fp.transpose = transpose ? 1 : 0;
+  fp.tiled = (tiled && width % 8 == 0 && (fp.n_rays / (uint32_t)width) % 4u == 0) ? 1 : 0;
   // camera basis (renderer.cpp:87-96)
   const float t = 2.f * tanf(fovy * 0.5f * (float)M_PI / 180.f);
   const float aspect = width / float(height);

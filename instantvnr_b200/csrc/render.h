@@ -29,6 +29,8 @@ struct Renderer {
   bool gt_source = false;               // march the ground-truth volume (SimpleVolume renderer)
   int n_iters = 16;                     // N_ITERS (method_raymarching.cu:30-40)
   int jitter_mode = 0;
+  bool tiled = true;                    // warps own 8 x 4 pixel tiles instead of 32-pixel scanline segments
+  bool transpose = true;                // sample slots of a warp are depth-major (all rays' j-th samples adjacent)
   int part_rank = 0, part_world = 1; uint32_t strip_rows = 4;
   float cam_from[3] = {0, 0, -1}, cam_at[3] = {0, 0, 0}, cam_up[3] = {0, 1, 0}, fovy = 60.f;   // instantvnr_types.h:74-83
   float sampling_rate = 1.f, density_scale = 1.f;
