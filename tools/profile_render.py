@@ -10,10 +10,13 @@ dims = (256, 256, 256)
 vol, gt, (rgb, alpha) = bench.build_scene(vnr, dims, int(os.environ.get("TRAIN_STEPS", "200")), 1 << 16)
 ren = vnr.Renderer(vol)
 ren.set_size(1024, 1024)
+if os.environ.get("NO_DOWNLOAD") == "1":      # device-resident frames (what bench.py's `value` times): no PCIe stores in the kernels
+    ren.set_download(False)
 for v in range(int(os.environ.get("FRAMES", "3"))):
     ren.set_camera(*syn.default_camera(dims, v))
     ren.render()
-    ren.map_frame()
+    if os.environ.get("NO_DOWNLOAD") != "1":
+        ren.map_frame()
     print("round_counts", v, ren.round_counts(), flush=True)
 print(ren.stats())
 vol.train(int(os.environ.get("EXTRA_TRAIN", "4")), batch=1 << 18, fast_mode=True)
