@@ -598,6 +598,33 @@ def run_reference_train(args):
     emit(base)
 
 
+def reference_round_coords(dims, W, H, view=1, n_views=16, n_iters=16, fovy=60.0):
+    """Coordinates of the first wavefront round as the reference's marcher writes them (renderer.cpp:87-96 camera basis,
+    method_raymarching.cu:658-730): for every camera ray that hits the volume box, `n_iters` unit steps from the entry point,
+    stored step-major over the live rays (coords[numRays * k + ray]).  Pure torch; none of this repo's kernels."""
+    import torch
+    from instantvnr_b200 import synthetic as syn
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    cam_from, cam_at, cam_up = [torch.tensor(v, device=dev, dtype=torch.float32) for v in syn.default_camera(dims, view, n_views)]
+    d = torch.tensor(dims, device=dev, dtype=torch.float32)
+    t = 2.0 * float(np.tan(fovy * 0.5 * np.pi / 180.0)); aspect = W / float(H)
+    fwd = torch.nn.functional.normalize(cam_at - cam_from, dim=0)
+    hor = t * aspect * torch.nn.functional.normalize(torch.linalg.cross(fwd, cam_up), dim=0)
+    ver = torch.linalg.cross(hor, fwd) / aspect
+    ix = (torch.arange(W, device=dev, dtype=torch.float32) + 0.5) / W - 0.5
+    iy = (torch.arange(H, device=dev, dtype=torch.float32) + 0.5) / H - 0.5
+    dirs = torch.nn.functional.normalize(fwd[None, None, :] + ix[None, :, None] * hor[None, None, :] + iy[:, None, None] * ver[None, None, :], dim=-1).reshape(-1, 3)
+    inv = 1.0 / dirs
+    lo = (-d / 2 - cam_from) * inv; hi = (d / 2 - cam_from) * inv
+    t0 = torch.minimum(lo, hi).amax(-1).clamp_min(0.0); t1 = torch.maximum(lo, hi).amin(-1)
+    live = t1 > t0
+    dirs, t0, t1 = dirs[live], t0[live], t1[live]
+    k = torch.arange(n_iters, device=dev, dtype=torch.float32)[:, None]
+    tt = torch.minimum(t0[None, :] + k + 0.5, t1[None, :])                       # [n_iters][live rays]: step-major
+    p = cam_from[None, None, :] + tt[:, :, None] * dirs[None, :, :]
+    return ((p + d / 2) / d).clamp(0.0, 1.0).reshape(-1, 3).contiguous()
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -619,24 +646,42 @@ def run_reference(args):
         ref = tcnn_ref.RefNetwork(vnr.example_model_json(), 1337)
         st = torch.cuda.Stream()
         torch.manual_seed(0)
-        xyz = torch.rand(n, 3, device="cuda"); out = torch.empty(n, device="cuda")
-        with torch.cuda.stream(st):
-            for _ in range(max(3, args.warmup)):
-                ref.inference(xyz, out, n, st.cuda_stream)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(st)
-            for _ in range(args.steps):
-                ref.inference(xyz, out, n, st.cuda_stream)
-            e1.record(st)
-        st.synchronize()
-        ms = e0.elapsed_time(e1)
-        v = n * args.steps / (ms * 1e-3)
-        base.update({"value": v, "ms_per_step": ms / args.steps,
+
+        def time_decode(xyz):
+            cnt = xyz.shape[0]
+            out = torch.empty(cnt, device="cuda")
+            with torch.cuda.stream(st):
+                for _ in range(max(3, args.warmup)):
+                    ref.inference(xyz, out, cnt, st.cuda_stream)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(st)
+                for _ in range(args.steps):
+                    ref.inference(xyz, out, cnt, st.cuda_stream)
+                e1.record(st)
+            st.synchronize()
+            ms_ = e0.elapsed_time(e1)
+            return cnt * args.steps / (ms_ * 1e-3), ms_ / args.steps
+
+        # (a) the decode batch of a wavefront round laid out as the reference's marcher lays it out (iterative_intersect_kernel,
+        # method_raymarching.cu:687-730: coords[numRays * k + ray], k < 16): camera rays of the same orbit, 16 unit steps from the
+        # entry point, live rays only.  Built with torch ops -- neighbouring rows are neighbouring rays at the same step, the
+        # coherence the reference's own decode sees inside a frame.
+        dims = (args.volume,) * 3
+        W, H = (args.width or args.frame), (args.height or args.frame)
+        xyz_frame = reference_round_coords(dims, W, H, view=1)
+        v_frame, ms_frame = time_decode(xyz_frame)
+        # (b) uniform random coordinates (no coherence): the lower bracket
+        n = 1 << 24
+        v_uniform, ms_uniform = time_decode(torch.rand(n, 3, device="cuda"))
+        v, ms_step = (v_frame, ms_frame) if v_frame >= v_uniform else (v_uniform, ms_uniform)
+        base.update({"value": v, "ms_per_step": ms_step,
                      "config": {"workload": "the reference's own decode (tiny-cuda-nn NetworkWithInputEncoding::inference, built unmodified from "
-                                            "/root/reference/tcnn for sm_100) on 2^24-sample batches of uniform coordinates, the kernel sequence mode 5 "
-                                            "issues per wavefront round; the reference's marcher kernels cannot be built offline (OVR framework missing), so "
-                                            "its frame rate is bounded above by this rate / samples per frame"},
-                     "cpu_baseline": {"value": v, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "2^24 uniform samples per step on the same GPU"},
+                                            f"/root/reference/tcnn for sm_100): the first-round batch of a {W}x{H} mode-5 frame of the {args.volume}^3 volume "
+                                            f"in the reference marcher's layout ({xyz_frame.shape[0]} coordinates: 16 per live ray, step-major), the kernel "
+                                            "sequence mode 5 issues per wavefront round.  The reference's marcher kernels cannot be built offline (OVR "
+                                            "framework missing), so its frame rate is bounded above by this rate / samples per frame"},
+                     "decode_samples_per_sec_frame_layout": v_frame, "decode_samples_per_sec_uniform_2p24": v_uniform,
+                     "cpu_baseline": {"value": v, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "the reference's GPU decode on the same B200 (it has no CPU path); frame-layout and uniform batches, the faster one reported"},
                      "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
         emit(base)
         return
