@@ -648,6 +648,10 @@ def run_reference(args):
         torch.manual_seed(0)
 
         def time_decode(xyz):
+            useful = xyz.shape[0]
+            pad = (-useful) % 256                      # NeuralVolume::inference pads the batch to a multiple of 256 (network.cu:1043-1052)
+            if pad:
+                xyz = torch.cat([xyz, xyz[-1:].expand(pad, 3)]).contiguous()
             cnt = xyz.shape[0]
             out = torch.empty(cnt, device="cuda")
             with torch.cuda.stream(st):
@@ -660,7 +664,7 @@ def run_reference(args):
                 e1.record(st)
             st.synchronize()
             ms_ = e0.elapsed_time(e1)
-            return cnt * args.steps / (ms_ * 1e-3), ms_ / args.steps
+            return useful * args.steps / (ms_ * 1e-3), ms_ / args.steps
 
         # (a) the decode batch of a wavefront round laid out as the reference's marcher lays it out (iterative_intersect_kernel,
         # method_raymarching.cu:687-730: coords[numRays * k + ray], k < 16): camera rays of the same orbit, 16 unit steps from the
