@@ -247,6 +247,10 @@ int vnr_renderer_set_clipping_box(vnr_renderer_t* r, const float* lower3, const 
 int vnr_renderer_set_partition(vnr_renderer_t* r, int rank, int world);
 /* jitter source: 0 = gdt::LCG<16>(frame_index, pixel) as the reference, 1 = fixed 0.5 */
 int vnr_renderer_set_jitter_mode(vnr_renderer_t* r, int mode);
+/* no reference counterpart (measurement / test tap): how the wavefront deals rays to warps (1: 8 x 4 pixel tiles, 0: scanline
+ * segments) and lays out the sample slots of a warp (1: depth-major, 0: contiguous per ray).  Defaults 1, 1; frames are
+ * identical under all four combinations. */
+int vnr_renderer_set_layout(vnr_renderer_t* r, int tiled, int transpose);
 int vnr_render(vnr_renderer_t* r);                                     /* vnrRender :177 (async) */
 /* vnrRendererMapFrame :178: syncs, returns host float4[w*h] valid until the second-next map */
 const float* vnr_map_frame(vnr_renderer_t* r);

@@ -398,6 +398,9 @@ class Renderer:
     def set_clipping_box(self, lower, upper):
         _check(lib().vnr_renderer_set_clipping_box(self._h, _ptr(_f32(lower)), _ptr(_f32(upper))))
 
+    def set_layout(self, tiled=True, transpose=True):
+        _check(lib().vnr_renderer_set_layout(self._h, C.c_int(1 if tiled else 0), C.c_int(1 if transpose else 0)))
+
     def set_scaling(self, scale):
         _check(lib().vnr_renderer_set_scaling(self._h, _ptr(_f32(scale))))
 

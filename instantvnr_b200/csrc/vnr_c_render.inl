@@ -58,6 +58,11 @@ VNR_EXPORT int vnr_renderer_set_partition(vnr_renderer_t* r, int rank, int world
 VNR_EXPORT int vnr_renderer_set_jitter_mode(vnr_renderer_t* r, int mode) {
   return guard([&] { if (mode != 0 && mode != 1) throw InvalidError("bad jitter mode"); R(r)->jitter_mode = mode; R(r)->reset = true; });
 }
+// measurement / test tap: ray order (8 x 4 pixel tiles per warp vs scanline) and sample-slot layout (depth-major per warp vs
+// contiguous per ray) of the wavefront.  Frames do not depend on either.
+VNR_EXPORT int vnr_renderer_set_layout(vnr_renderer_t* r, int tiled, int transpose) {
+  return guard([&] { R(r)->tiled = tiled != 0; R(r)->transpose = transpose != 0; R(r)->reset = true; });
+}
 VNR_EXPORT int vnr_render(vnr_renderer_t* r) { return guard([&] { R(r)->render(); }); }
 VNR_EXPORT const float* vnr_map_frame(vnr_renderer_t* r) {
   const float* p = nullptr;
