@@ -30,10 +30,12 @@ __device__ __forceinline__ float sample_volume_linear(const float* __restrict__ 
   return lerp(az, lerp(ay, c00, c10), lerp(ay, c01, c11));
 }
 
-// sampleVolume (raytracing.h:105-110): p * (1 - rdims) + 0.5 * rdims, then tex3D
+// sampleVolume (raytracing.h:105-110): `p = p * (1 - rdims) + 0.5 * rdims; tex3D(p)` -- with Array3DScalar::rdims = 0: the
+// member is default-initialised (core/array.h:43) and nothing in the reference ever assigns it (set_volume, object.cpp:362-383,
+// sets dims / data / type only), so the lookup is the plain normalised-coordinate texture fetch.  Confirmed against the
+// reference's own marcher compiled in place (oracle/ref_marcher).
 __device__ __forceinline__ float sample_volume(const float* __restrict__ vol, int3 dims, float x, float y, float z) {
-  const float rx = 1.f / (float)dims.x, ry = 1.f / (float)dims.y, rz = 1.f / (float)dims.z;
-  return sample_volume_linear(vol, dims, __fmaf_rn(x, 1.f - rx, 0.5f * rx), __fmaf_rn(y, 1.f - ry, 0.5f * ry), __fmaf_rn(z, 1.f - rz, 0.5f * rz));
+  return sample_volume_linear(vol, dims, x, y, z);
 }
 
 }  // namespace vnr

@@ -973,9 +973,9 @@ static void render_wavefront(const int* cfg, float pls, const uint16_t* params_f
       h16 enc[128]; encode_one(m, grid, c, enc);
       return mlp_forward_one(m, mf, enc, acc_mode, nullptr);
     }
-    // sampleVolume: p*(1-rdims)+0.5*rdims then tex3D
+    // sampleVolume (raytracing.h:105-110) with rdims = 0: tex3D at p
     float q[3];
-    for (int d = 0; d < 3; ++d) { float rd = 1.f / (float)gt_dims[d]; q[d] = fmaf(c[d], (1.f - rd), 0.5f * rd); }
+    for (int d = 0; d < 3; ++d) q[d] = c[d];                          // rdims = 0: never assigned in the reference (array.h:43, object.cpp:362-383)
     return tex3d_linear(gt_volume, gt_dims, q[0], q[1], q[2], fr.tex_round);
   };
   // per-pixel outputs of the SINGLE_SHADE_HEURISTIC camera pass (final_highest_*, shading_color, jitter_ssh)
@@ -1111,7 +1111,7 @@ static void render_single_kernel(const float* fparams, const int* iparams, const
   const size_t npix = (size_t)fr.width * fr.height;
   auto sample_volume = [&](V3 p) -> float {
     float q[3]; const float c[3] = {p.x, p.y, p.z};
-    for (int d = 0; d < 3; ++d) { float rd = 1.f / (float)dims[d]; q[d] = fmaf(c[d], (1.f - rd), 0.5f * rd); }
+    for (int d = 0; d < 3; ++d) q[d] = c[d];                          // rdims = 0: never assigned in the reference (array.h:43, object.cpp:362-383)
     return tex3d_linear(volume, dims, q[0], q[1], q[2], fr.tex_round);
   };
   uint64_t n_hit = 0, n_samples = 0;
@@ -1376,7 +1376,7 @@ ORC_API void orc_render_pathtracing(const int* cfg, float pls, const uint16_t* p
     const float c[3] = {p.x, p.y, p.z};
     if (volume_mode == 0) { h16 enc[128]; encode_one(m, grid, c, enc); return mlp_forward_one(m, mf, enc, acc_mode, nullptr); }
     float q[3];
-    for (int d = 0; d < 3; ++d) { float rd = 1.f / (float)dims[d]; q[d] = fmaf(c[d], (1.f - rd), 0.5f * rd); }
+    for (int d = 0; d < 3; ++d) q[d] = c[d];                          // rdims = 0: never assigned in the reference (array.h:43, object.cpp:362-383)
     return tex3d_linear(volume, dims, q[0], q[1], q[2], fr.tex_round);
   };
   const size_t npix = (size_t)fr.width * fr.height;
