@@ -625,6 +625,61 @@ def reference_round_coords(dims, W, H, view=1, n_views=16, n_iters=16, fovy=60.0
     return ((p + d / 2) / d).clamp(0.0, 1.0).reshape(-1, 3).contiguous()
 
 
+def run_reference_frames(args, base):
+    """The reference's OWN frame pipeline on this GPU: its ray marcher (core/renderer/method_raymarching.cu, mode 5: raygen ->
+    [intersect -> NeuralVolume::inference -> compose] with a host sync per round), its macrocells (core/macrocell.cu) and its
+    tiny-cuda-nn decode and training step -- all compiled unmodified from /root/reference (oracle/ref_marcher, oracle/ref_driver;
+    only the un-vendored OVR headers are stood in for).  Same scene as our arm: the synthetic volume, 600 training steps of
+    batch 2^16 (here through the reference's Trainer on torch-drawn samples), the 256-entry transfer function, the 16-view orbit,
+    every frame downloaded to the host (refm_render copies the frame and synchronises, as vnrRender + vnrRendererMapFrame).
+    value = network evaluations per second as the reference issues them (16 slots per live ray and round, padded to 256)."""
+    import torch
+    import instantvnr_b200 as vnr            # model_json / synthetic helpers only: no kernel of this repo runs in this arm
+    from instantvnr_b200 import synthetic as syn
+    from oracle import marcher_ref, tcnn_ref
+    dims = (args.volume,) * 3
+    W, H = (args.width or args.frame), (args.height or args.frame)
+    gt = syn.make_volume(dims, seed=42)
+    net = tcnn_ref.RefNetwork(vnr.model_json(log2_hashmap=args.log2_hashmap), 1337)
+    # training samples: uniform coordinates, trilinear targets of the normalised volume (what StaticSampler's tex3D returns)
+    g = torch.from_numpy(gt).cuda().view(1, 1, dims[2], dims[1], dims[0])
+    nb = 1 << 16
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        for _ in range(args.train_steps):
+            xyz = torch.rand(nb, 3, device="cuda")
+            tgt = torch.nn.functional.grid_sample(g, (xyz * 2 - 1).view(1, 1, 1, nb, 3), mode="bilinear", padding_mode="border", align_corners=False).view(nb).contiguous()
+            loss = net.training_step(xyz, tgt, nb, st.cuda_stream, want_loss=False)
+    st.synchronize()
+    ref = marcher_ref.RefMarcher(dims, gt)
+    rgb, alpha = syn.make_tfn(256)
+    ref.set_transfer_function(rgb, alpha, (0.0, 1.0))
+    ref.set_decoder(marcher_ref.function_address(tcnn_ref.lib(), "ref_inference"), net.h)
+    cams = [syn.default_camera(dims, v, 16) for v in range(16)]
+    for i in range(max(3, args.warmup)):
+        ref.reset_accumulation(); ref.render(5, (W, H), *cams[i % 16], neural=True)
+    torch.cuda.synchronize()
+    coords = 0; calls = 0
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        ref.reset_accumulation()
+        img, rs = ref.render(5, (W, H), *cams[i % 16], neural=True)
+        coords += rs["decode_coords"]; calls += rs["decode_calls"]
+    dt = time.perf_counter() - t0
+    v = coords / dt
+    base.update({"value": v, "ms_per_step": dt * 1e3 / args.steps, "fps": args.steps / dt, "scaling": "strong",
+                 "config": {"workload": f"render: synthetic {args.volume}^3 volume, example-model.json (T=2^{args.log2_hashmap}), {W}x{H} frame, macrocell skipping, "
+                                        "mode 5 (sample streaming), 16-view orbit -- through the reference's own marcher + macrocell + tiny-cuda-nn sources "
+                                        "(compiled unmodified from /root/reference), every frame downloaded",
+                            "weights": f"trained here for {args.train_steps} steps (batch 2^16) by the reference's Trainer::training_step"},
+                 "decode_coords_per_frame": coords / args.steps, "wavefront_rounds_per_frame": calls / args.steps,
+                 "cpu_baseline": {"value": v, "unit": UNIT, "cores": 0, "kind": "reference",
+                                  "sample": f"{args.steps} frames of the same workload on the same B200 (the reference has no CPU path)"},
+                 "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": W * H * 16, "fps": args.steps / dt},
+                 "note": "value counts the reference's network evaluations (16 slots per live ray per round, used or not); compare frames per second for equal work"})
+    emit(base)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -641,6 +696,13 @@ def run_reference(args):
         have_gpu = torch.cuda.is_available() and tcnn_ref.available()
     except Exception:
         have_gpu = False
+    try:
+        from oracle import marcher_ref
+        have_marcher = have_gpu and marcher_ref.available()
+    except Exception:
+        have_marcher = False
+    if have_marcher:
+        return run_reference_frames(args, base)
     if have_gpu:
         import instantvnr_b200 as vnr
         ref = tcnn_ref.RefNetwork(vnr.example_model_json(), 1337)
