@@ -17,8 +17,8 @@
 // The reference re-uses slot indices it is still reading when it compacts (save() into params.*[atomicAdd] while other
 // threads load() the same arrays, :147-170,735-746); results here are those of the race-free reading.
 //
-// RandomTEA (OVR gdt/random/random.h) is not in /root/reference: taken to be the TEA-16-seeded LCG of gdt::LCG<16>,
-// get_float() one draw, get_floats() two consecutive draws -- the same assumption as the marcher's jitter.
+// RandomTEA is gdt::LCG<16> (instantvnr_types.h:155), the TEA-16-seeded LCG of the marcher's jitter; get_float() one draw,
+// get_floats() two consecutive draws.  Checked against the reference's own path tracer compiled in place (oracle/ref_marcher).
 #pragma once
 
 namespace vnr {

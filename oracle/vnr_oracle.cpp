@@ -23,10 +23,12 @@
 //      tools/make_golden_tcnn.py);
 //  (b) pcg32 by its published demo vector, the level tables / hash by the
 //      closed-form constants of the reference;
-//  (c) the marcher (DDA, adaptive step, classification, compositing) has NO
-//      reference output to compare with -- "parity unpinned" for that part: it
-//      is checked only on closed-form scenes (constant volume, empty macrocells,
-//      early termination).
+//  (c) the marcher (DDA, adaptive step, classification, compositing, shaded modes), the path tracer and the macrocells
+//      are pinned by tests/golden/marcher_ref_golden.npz: frames rendered on a B200 by the reference's OWN
+//      core/renderer/method_raymarching.cu, method_pathtracing.cu and core/macrocell.cu, compiled unmodified in place
+//      (oracle/ref_marcher -> oracle/_ref/libvnr_marcher_ref.so, tools/make_golden_marcher.py); the headers of the
+//      un-vendored OVR framework those sources include are stood in for by oracle/ovr_shim (two assumptions stated
+//      there: LCG::get_floats() = two consecutive draws, vec4f::xyz() aliases the components).
 //
 // Third-party arithmetic not vendored in /root/reference and restated from the
 // published algorithm:  gdt::LCG<16> (TEA-initialised LCG, OVR/owl
@@ -1214,7 +1216,8 @@ ORC_API void orc_render(const int* cfg, float pls, const uint16_t* params_f16, i
 //                  (:596-747) -- the sample-streaming mode 14.  Each ray is run to completion here (rays are independent;
 //                  the reference re-derives tnear / tfar from the stored origin / direction on every load(), :115-145).
 // RandomTEA (OVR gdt/random/random.h) is NOT in /root/reference: it is taken to be the same TEA-16-seeded LCG as
-// gdt::LCG<16>, get_float() one draw, get_floats() two consecutive draws (x first).  PARITY UNPINNED for the sequence.
+// gdt::LCG<16> (instantvnr_types.h:155: `using RandomTEA = gdt::LCG<16>`), get_float() one draw, get_floats() two consecutive
+// draws (x first; the one assumption left, shared with oracle/ovr_shim).
 // FMA contraction follows what nvcc -fmad=true makes of the reference expressions (a*b+c -> fma), written explicitly.
 // ---------------------------------------------------------------------------------------
 struct PtLights { float density_scale, ambient; V3 rgb, dir; };
