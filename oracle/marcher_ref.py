@@ -78,6 +78,13 @@ class RefMarcher:
         vr = _f32(value_range)
         _chk(lib().refm_set_macrocell_value_range(self._h, vr.ctypes.data_as(C.c_void_p)))
 
+    def macrocell_reset(self):
+        _chk(lib().refm_macrocell_reset(self._h))
+
+    def macrocell_update_explicit(self, d_xyz_ptr, d_values_ptr, n):
+        """device pointers: n x (x, y, z) coordinates and n values (MacroCell::update_explicit, core/macrocell.cu:42-73)"""
+        _chk(lib().refm_macrocell_update_explicit(self._h, C.c_void_p(d_xyz_ptr), C.c_void_p(d_values_ptr), C.c_size_t(n)))
+
     def get_macrocell(self):
         d = np.zeros(3, dtype=np.int32)
         _chk(lib().refm_get_macrocell(self._h, d.ctypes.data_as(C.c_void_p), None, None))

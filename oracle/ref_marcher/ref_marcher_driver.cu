@@ -113,6 +113,20 @@ int refm_set_macrocell_value_range(void* h, const float* h_value_range) {
   });
 }
 
+// NeuralVolume's online macrocell construction (network.cu:249-257): MacroCell::allocate (zeroed ranges) and, per training
+// batch, MacroCell::update_explicit on the batch's coordinates and target values + update_max_opacity
+int refm_macrocell_reset(void* h) {
+  return guard([&] { Scene* s = (Scene*)h; s->macrocell.allocate(); CUDA_CHECK(cudaDeviceSynchronize()); });
+}
+int refm_macrocell_update_explicit(void* h, const float* d_xyz, const float* d_values, size_t n) {
+  return guard([&] {
+    Scene* s = (Scene*)h;
+    s->macrocell.update_explicit((vec3f*)d_xyz, (float*)d_values, n, s->stream);
+    if (s->have_tfn) s->macrocell.update_max_opacity(s->tfn.tfn, s->stream);
+    CUDA_CHECK(cudaStreamSynchronize(s->stream));
+  });
+}
+
 int refm_get_macrocell(void* h, int* mc_dims3, float* h_value_range, float* h_max_opacity) {
   return guard([&] {
     Scene* s = (Scene*)h;

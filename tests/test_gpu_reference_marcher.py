@@ -125,3 +125,57 @@ def test_path_tracing_matches_the_reference_path_tracer(scene, mode, neural):
     assert np.all(got[..., 3] == 1.0) and np.all(want[..., 3] == 1.0) and want[..., :3].max() > 0.2
     assert (d <= 1e-3).mean() >= 0.98, (d <= 1e-3).mean()
     assert abs(got[..., :3].mean() - want[..., :3].mean()) <= 0.02 * want[..., :3].mean()
+
+
+def test_online_macrocell_update_equals_the_reference():
+    """NeuralVolume's online macrocell construction (network.cu:249-257): MacroCell::update_explicit on training batches,
+    the reference's own kernel (macrocell.cu:42-73) against vnr_volume_macrocell_update, from the zeroed state."""
+    import torch
+    dims = (40, 33, 21)
+    gt = syn.make_volume(dims, seed=3)
+    rgb, alpha = syn.make_tfn(32)
+    vol = vnr.NeuralVolume(vnr.model_json(**CFG), dims)
+    vol.set_groundtruth(gt); vol.init_params(1)
+    vol.set_transfer_function(rgb, alpha)
+    ref = MR.RefMarcher(dims, gt)
+    ref.set_transfer_function(rgb, alpha, (0.0, 1.0))
+    ref.macrocell_reset()
+    g = torch.Generator(device="cuda"); g.manual_seed(5)
+    for n in (4096, 1000, 37):
+        xyz = torch.rand(n, 3, device="cuda", generator=g)
+        xyz[:8] = torch.tensor([[0, 0, 0], [1, 1, 1], [0.999999, 0, 1], [0.5, 0.5, 0.5], [0.4, 1.0, 0.0], [1.0, 0.0, 0.4], [0.0, 0.25, 1.0], [0.75, 0.75, 0.0]], device="cuda")
+        val = torch.rand(n, device="cuda", generator=g)
+        vol.macrocell_update(xyz, val, n)
+        vol.macrocell_refresh()
+        torch.cuda.synchronize()
+        ref.macrocell_update_explicit(xyz.data_ptr(), val.data_ptr(), n)
+        md, vr, mo = vol.get_macrocell()
+        rd, rvr, rmo = ref.get_macrocell()
+        assert tuple(md) == rd
+        assert np.array_equal(np.asarray(vr, np.float32).reshape(-1), rvr.reshape(-1))
+        assert np.array_equal(np.asarray(mo, np.float32).reshape(-1), rmo.reshape(-1))
+
+
+def test_full_size_frame_matches_the_reference_marcher():
+    """BASELINE configs[1] at full size: 256^3 volume, example-model.json, 1024^2 frame, mode 5 -- the reference's marcher (around
+    this library's decode, so that only the marcher differs) against the library's frame; and the sample bookkeeping: the
+    reference pushes 16 slots per live ray and round through the network, we decode what the rays take."""
+    import bench
+    dims = (256, 256, 256)
+    vol, gt, (rgb, alpha) = bench.build_scene(vnr, dims, 300, 1 << 16)
+    ref = MR.RefMarcher(dims, gt)
+    ref.set_transfer_function(rgb, alpha, (0.0, 1.0))
+    ref.set_decoder(MR.function_address(vnr.lib(), "vnr_volume_decode"), vol._h)
+    _, vr, _ = vol.get_macrocell()
+    ref.set_macrocell_value_range(np.asarray(vr, np.float32))
+    ren = vnr.Renderer(vol)
+    ren.set_size(1024, 1024)
+    for view in (1, 7):
+        cam = syn.default_camera(dims, view)
+        ren.set_camera(*cam); ren.reset_accumulation(); ren.render()
+        got, st = ren.map_frame().copy(), ren.stats()
+        ref.reset_accumulation()
+        want, rst = ref.render(5, (1024, 1024), *cam, neural=True)
+        assert want[..., 3].max() > 0.9 and st["rays_hit"] > 500000
+        assert syn.psnr(got, want) >= PSNR_MIN and np.abs(got - want).max() <= MAXABS, (syn.psnr(got, want), np.abs(got - want).max())
+        assert rst["decode_coords"] > 3 * st["samples_decoded"]
