@@ -337,6 +337,33 @@ def run_ours(args):
         ren.set_zero_copy(False)                    # comparison: device frame + one cudaMemcpyAsync after the frame (the reference's order)
         ms_e2e_copy = e2e_pass()
         ren.set_zero_copy(True)
+    # the same end-to-end loop with frames in flight (reported next to, not instead of, the strict figure): frame i+1 and i+2 are
+    # launched on the other renderers before frame i is mapped; every frame is still mapped (synchronised, host-visible) exactly
+    # once, its 16 B/pixel crossing PCIe by DMA while the next frames compute
+    fps_inflight = None; inflight = 0
+    if not tp:
+        extra = vnr.Renderer(vol)
+        extra.set_size(W, H); extra.set_mode(vnr.VNR_RAYMARCHING_NO_SHADING_SAMPLE_STREAMING); extra.set_sampling_rate(1.0)
+        ring = pipe + [extra]
+        for r in ring:
+            r.set_download(True); r.set_zero_copy(False)
+        K = len(ring); inflight = K - 1
+
+        def inflight_pass(n):
+            for i in range(n + K - 1):
+                if i < n:
+                    r = ring[i % K]; r.set_camera(*cams[i % n_views]); r.render()
+                j = i - (K - 1)
+                if j >= 0:
+                    img = ring[j % K].map_frame(copy=False)
+                    checksum = float(img[H // 2, W // 2, 3])
+        inflight_pass(2 * K)
+        torch.cuda.synchronize()
+        tq = time.perf_counter()
+        inflight_pass(args.steps)
+        torch.cuda.synchronize()
+        fps_inflight = args.steps / (time.perf_counter() - tq)
+        ren.set_zero_copy(True)
 
     if rank != 0:
         if world > 1:
@@ -390,7 +417,10 @@ def run_ours(args):
         "train_steps_per_sec_batch_2p18": 1000.0 / train_ms, "train_samples_per_sec": (1 << 18) * 1000.0 / train_ms,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 480, "d2h_bytes_per_step": W * H * 16, "fps": args.steps / (ms_e2e * 1e-3),
                 "frame_path": "tile-parallel gather + download on rank 0" if tp else "zero-copy: compositing kernels store finished pixels into the pinned host frame",
-                "fps_copy_after_frame": (args.steps / (ms_e2e_copy * 1e-3)) if ms_e2e_copy else None},
+                "fps_copy_after_frame": (args.steps / (ms_e2e_copy * 1e-3)) if ms_e2e_copy else None,
+                "fps_with_frames_in_flight": fps_inflight, "frames_in_flight": inflight,
+                "note": "value / fps: strict loop, every frame mapped before the next one is launched.  fps_with_frames_in_flight: the same calls with the next "
+                        "frames already launched on other renderers of the volume when a frame is mapped (every frame mapped once; DMA download overlaps compute)"},
         "gpu_launches": int(launches),
         "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "setup_seconds": round(time.time() - t0, 1),
     }
