@@ -45,6 +45,18 @@ def lib():
     return _lib
 
 
+def use_host_cores(n=None):
+    """give the oracle's OpenMP loops `n` threads (default: the cores this process may run on); launchers like torchrun
+    export OMP_NUM_THREADS=1"""
+    if n is None:
+        try:
+            n = len(os.sched_getaffinity(0))
+        except Exception:
+            n = os.cpu_count() or 1
+    lib().orc_set_num_threads(C.c_int(int(n)))
+    return int(lib().orc_num_threads())
+
+
 def _p(a, t=None):
     if a is None:
         return None

@@ -594,6 +594,15 @@ ORC_API int orc_num_threads() {
 #endif
 }
 
+// launchers such as torchrun export OMP_NUM_THREADS=1: the bench legs that time / use the oracle on the host cores ask for them back
+ORC_API void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 ORC_API void orc_f32_to_f16(const float* in, uint16_t* out, size_t n) { for (size_t i = 0; i < n; ++i) out[i] = f2h(in[i]); }
 ORC_API void orc_f16_to_f32(const uint16_t* in, float* out, size_t n) { for (size_t i = 0; i < n; ++i) out[i] = h2f(in[i]); }
 ORC_API uint16_t orc_hadd(uint16_t a, uint16_t b) { return hadd(a, b); }
