@@ -613,7 +613,7 @@ def run_reference_train(args):
     import torch
     import instantvnr_b200 as vnr
     from oracle import tcnn_ref
-    base = {"metric": "train_steps_per_sec", "unit": "steps/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "higher_is_better": True,
+    base = {"metric": "train_steps_per_sec", "unit": "steps/s", "n_gpus": args.gpus, "gpus_used": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic", "impl": "reference"}
     if not (torch.cuda.is_available() and tcnn_ref.available()):
         base.update({"unavailable": "the reference tcnn build (oracle/_ref) or a GPU is missing; the training step has no CPU implementation in the reference"})
@@ -783,7 +783,7 @@ def run_reference(args):
     import oracle as O
     from oracle import tcnn_ref
     n = 1 << 24
-    base = {"metric": METRIC, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",
+    base = {"metric": METRIC, "unit": UNIT, "n_gpus": args.gpus, "gpus_used": 1, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f16", "data": "synthetic", "impl": "reference"}
     try:
         import torch
