@@ -237,20 +237,27 @@ def run_ours(args):
     # with its own ray buffers, so the latency-bound tail rounds of frame i overlap the head of frame i+1 (measured: 1421 ->
     # 1593 fps with two, tools/exp_frame_overlap.py).  Every frame is still rendered completely; the end-to-end pass below
     # maps every frame and therefore runs one frame at a time.
-    pipe = [ren]
-    if not tp:
-        for _ in range(max(1, args.pipeline) - 1):
-            r2 = vnr.Renderer(vol)
-            r2.set_size(W, H); r2.set_mode(vnr.VNR_RAYMARCHING_NO_SHADING_SAMPLE_STREAMING); r2.set_sampling_rate(1.0); r2.set_download(False)
-            pipe.append(r2)
+    # N > 1: every renderer of the pipeline is a tile-parallel renderer of its own (own strips buffer on rank 0, own peer barrier);
+    # all ranks take the frames in the same turn, so frame i of every rank meets in pair i % P.
+    pipe = [ren]; pipe_tp = [tp]
+    for _ in range(max(1, args.pipeline) - 1):
+        r2 = vnr.Renderer(vol)
+        r2.set_size(W, H); r2.set_mode(vnr.VNR_RAYMARCHING_NO_SHADING_SAMPLE_STREAMING); r2.set_sampling_rate(1.0); r2.set_download(False)
+        pipe.append(r2)
+        if tp:
+            t2 = TileParallelRenderer(r2, mode=args.gather); t2.download = False
+            pipe_tp.append(t2)
+        else:
+            pipe_tp.append(None)
     pipe_streams = [torch.cuda.ExternalStream(r.stream()) for r in pipe]
 
     def pipelined_frame(i):
-        if tp:
-            ren.set_camera(*cams[i % n_views]); tp.render()
+        k = i % len(pipe)
+        pipe[k].set_camera(*cams[i % n_views])
+        if pipe_tp[k]:
+            pipe_tp[k].render()
         else:
-            r = pipe[i % len(pipe)]
-            r.set_camera(*cams[i % n_views]); r.render()
+            pipe[k].render()
 
     for i in range(max(args.warmup, 2 * len(pipe))):
         pipelined_frame(i)
