@@ -240,7 +240,8 @@ def run_ours(args):
     # N > 1: every renderer of the pipeline is a tile-parallel renderer of its own (own strips buffer on rank 0, own peer barrier);
     # all ranks take the frames in the same turn, so frame i of every rank meets in pair i % P.
     pipe = [ren]; pipe_tp = [tp]
-    for _ in range(max(1, args.pipeline) - 1):
+    n_pipe = 1 if (tp and args.gather == "nccl") else max(1, args.pipeline)     # NCCL gathers of two frames must not overlap on one communicator
+    for _ in range(n_pipe - 1):
         r2 = vnr.Renderer(vol)
         r2.set_size(W, H); r2.set_mode(vnr.VNR_RAYMARCHING_NO_SHADING_SAMPLE_STREAMING); r2.set_sampling_rate(1.0); r2.set_download(False)
         pipe.append(r2)
