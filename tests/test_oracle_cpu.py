@@ -401,3 +401,12 @@ def test_ssim_oracle_against_the_float64_closed_form():
     assert abs(O.ssim(a, a) - 1.0) < 1e-6                      # identical volumes
     assert O.ssim(a, 1.0 - a) < 0.0                            # anti-correlated structure
     assert O.ssim(np.zeros((7, 7, 7), np.float32), np.zeros((7, 7, 7), np.float32)) == 1.0   # a single window
+
+
+def test_oracle_takes_the_host_cores_back(monkeypatch):
+    """torchrun exports OMP_NUM_THREADS=1; the bench legs that run the oracle ask for the cores the process may use"""
+    import os
+    n = O.use_host_cores(2)
+    assert n == 2
+    want = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    assert O.use_host_cores() == want
