@@ -167,6 +167,16 @@ class ClockSampler:
                 "source": "nvidia-smi"}
 
 
+def workload_string(args):
+    """config.workload, identical in both arms (the driver compares the strings)"""
+    W, H = (args.width or args.frame), (args.height or args.frame)
+    if args.workload == "train":
+        return (f"train: synthetic {args.volume}^3 volume, example-model.json (8 levels x 8 features, T=2^{args.log2_hashmap}, 64x4 MLP), "
+                f"{args.batch} samples per rank per step, fwd + L1 + bwd + Adam")
+    return (f"render: synthetic {args.volume}^3 volume, example-model.json (8 levels x 8 features, T=2^{args.log2_hashmap}, 64x4 MLP), "
+            f"{W}x{H} frame, macrocell skipping, mode 5 (sample streaming), 16-view orbit")
+
+
 def build_scene(vnr, dims, train_steps, batch, model_kwargs=None):
     from instantvnr_b200 import synthetic as syn
     gt = syn.make_volume(dims, seed=42)
@@ -233,24 +243,22 @@ def run_ours(args):
         tp.download = False
     else:
         ren.set_download(False)
-    # frame pipelining (single GPU): `--pipeline P` renderers of the same volume take the frames in turn, each on its own stream
-    # with its own ray buffers, so the latency-bound tail rounds of frame i overlap the head of frame i+1 (measured: 1421 ->
-    # 1593 fps with two, tools/exp_frame_overlap.py).  Every frame is still rendered completely; the end-to-end pass below
-    # maps every frame and therefore runs one frame at a time.
-    # N > 1: every renderer of the pipeline is a tile-parallel renderer of its own (own strips buffer on rank 0, own peer barrier);
+    # frames in flight: the renderer owns a ring of `--pipeline P` frame slots (own stream, ray / sample buffers and captured
+    # wavefront graph each; vnr_renderer_set_frames_in_flight), so consecutive vnr_render calls overlap on the device: the
+    # latency-bound tail rounds of frame i run under the head of frame i+1.  Every frame is still rendered completely.
+    # N > 1: every pipeline slot is a tile-parallel renderer of its own (own strips buffer on rank 0, own peer barrier);
     # all ranks take the frames in the same turn, so frame i of every rank meets in pair i % P.
     pipe = [ren]; pipe_tp = [tp]
     n_pipe = 1 if (tp and args.gather == "nccl") else max(1, args.pipeline)     # NCCL gathers of two frames must not overlap on one communicator
-    for _ in range(n_pipe - 1):
+    if not tp:
+        ren.set_frames_in_flight(n_pipe)
+    for _ in range(n_pipe - 1 if tp else 0):
         r2 = vnr.Renderer(vol)
         r2.set_size(W, H); r2.set_mode(vnr.VNR_RAYMARCHING_NO_SHADING_SAMPLE_STREAMING); r2.set_sampling_rate(1.0); r2.set_download(False)
         pipe.append(r2)
-        if tp:
-            t2 = TileParallelRenderer(r2, mode=args.gather); t2.download = False
-            pipe_tp.append(t2)
-        else:
-            pipe_tp.append(None)
-    pipe_streams = [torch.cuda.ExternalStream(r.stream()) for r in pipe]
+        t2 = TileParallelRenderer(r2, mode=args.gather); t2.download = False
+        pipe_tp.append(t2)
+    pipe_streams = [torch.cuda.ExternalStream(s_) for r in pipe for s_ in r.streams()]
 
     def pipelined_frame(i):
         k = i % len(pipe)
@@ -260,11 +268,11 @@ def run_ours(args):
         else:
             pipe[k].render()
 
-    for i in range(max(args.warmup, 2 * len(pipe))):
+    for i in range(max(args.warmup, 2 * n_pipe)):
         pipelined_frame(i)
     barrier()
     clocks = ClockSampler(local); clocks.start()
-    ev0 = [torch.cuda.Event(enable_timing=True) for _ in pipe]; ev1 = [torch.cuda.Event(enable_timing=True) for _ in pipe]
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in pipe_streams]; ev1 = [torch.cuda.Event(enable_timing=True) for _ in pipe_streams]
     decoded = 0; composited = 0; launches = 0; rays = 0
     barrier()
     for e, st_ in zip(ev0, pipe_streams):
@@ -322,16 +330,14 @@ def run_ours(args):
             ren.set_camera(*cams[i % n_views]); render_frame(); map_frame()
         barrier()
         t_e2e0 = time.perf_counter()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
         for i in range(args.steps):
             ren.set_camera(*cams[i % n_views])      # host -> device: the frame constants (kernel arguments)
             render_frame()
             img = map_frame()                       # device -> host: W*H float4 in pinned memory + sync (no extra host copy,
             if img is not None:                     # as vnrRendererMapFrame returns a pointer); touch the result
                 checksum = float(img[H // 2, W // 2, 3])
-        e1.record(stream); stream.synchronize(); barrier()
-        ms_ = max(e0.elapsed_time(e1), (time.perf_counter() - t_e2e0) * 1e3)
+        barrier()                                   # every frame was mapped (synchronised): the host clock brackets the device work
+        ms_ = (time.perf_counter() - t_e2e0) * 1e3
         if world > 1:
             t = torch.tensor([ms_], device="cuda", dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms_ = t.item()
         return ms_
@@ -345,33 +351,31 @@ def run_ours(args):
         ren.set_zero_copy(False)                    # comparison: device frame + one cudaMemcpyAsync after the frame (the reference's order)
         ms_e2e_copy = e2e_pass()
         ren.set_zero_copy(True)
-    # the same end-to-end loop with frames in flight (reported next to, not instead of, the strict figure): frame i+1 and i+2 are
-    # launched on the other renderers before frame i is mapped; every frame is still mapped (synchronised, host-visible) exactly
-    # once, its 16 B/pixel crossing PCIe by DMA while the next frames compute
-    fps_inflight = None; inflight = 0
+    # the same end-to-end calls with frames in flight (reported next to, not instead of, the strict figure): with a ring of K frame
+    # slots inside the renderer, frame i+1 .. i+K-1 are already launched when frame i is mapped (vnr_map_frame returns the oldest
+    # unmapped frame); every frame is still mapped (synchronised, host-visible) exactly once
+    fps_inflight = {}; inflight = 0
     if not tp:
-        extra = vnr.Renderer(vol)
-        extra.set_size(W, H); extra.set_mode(vnr.VNR_RAYMARCHING_NO_SHADING_SAMPLE_STREAMING); extra.set_sampling_rate(1.0)
-        ring = pipe + [extra]
-        for r in ring:
-            r.set_download(True); r.set_zero_copy(False)
-        K = len(ring); inflight = K - 1
+        K = 3; inflight = K - 1
+        ren.set_frames_in_flight(K)
 
         def inflight_pass(n):
             for i in range(n + K - 1):
                 if i < n:
-                    r = ring[i % K]; r.set_camera(*cams[i % n_views]); r.render()
-                j = i - (K - 1)
-                if j >= 0:
-                    img = ring[j % K].map_frame(copy=False)
+                    ren.set_camera(*cams[i % n_views]); ren.render()
+                if i >= K - 1:
+                    img = ren.map_frame(copy=False)
                     checksum = float(img[H // 2, W // 2, 3])
-        inflight_pass(2 * K)
-        torch.cuda.synchronize()
-        tq = time.perf_counter()
-        inflight_pass(args.steps)
-        torch.cuda.synchronize()
-        fps_inflight = args.steps / (time.perf_counter() - tq)
+        for zc in (True, False):
+            ren.set_zero_copy(zc)
+            inflight_pass(2 * K)
+            torch.cuda.synchronize()
+            tq = time.perf_counter()
+            inflight_pass(args.steps)
+            torch.cuda.synchronize()
+            fps_inflight["zero_copy" if zc else "dma_copy"] = args.steps / (time.perf_counter() - tq)
         ren.set_zero_copy(True)
+        ren.set_frames_in_flight(n_pipe)
 
     if rank != 0:
         if world > 1:
@@ -379,24 +383,60 @@ def run_ours(args):
         return
 
     peak, peak_kind = measured_peaks()
-    # roofline of the dominant kernel on this rank (decode): event-timed launches of the profiling pass
-    achieved = prof_decoded * BYTES_PER_SAMPLE / (decode_ms * 1e-3) / 1e9 if decode_ms > 0 else 0.0
-    # DRAM bytes of the largest decode launch of a frame from the committed `ncu --set full` capture (per launch), next to the
-    # algorithmic bytes of that same launch
+    # ---- roofline of the dominant kernel on this rank (decode): event-timed launches of the profiling pass.
+    # The kernel is a gather: 64 random 16-byte loads per sample out of the hash table.  Its ceiling is what the memory system
+    # delivers for that access pattern, measured HERE by an independent microbenchmark (csrc/probe.cu: plain ld.global.nc.v4 at
+    # random offsets, full occupancy, nothing of the product's gather code): over a 46.7 MB buffer (the example model's table,
+    # L2-resident) -> l2_gather_gbs, over a 306.8 MB buffer (T = 2^22, larger than L2) -> hbm_gather_gbs.  `peak` is the probe
+    # over a buffer of THIS run's table size; `achieved` counts the algorithmic gather bytes (1024 B per decoded sample).
+    GATHER_BYTES = 1024
+    table_bytes = (vol.n_params - vol.n_mlp_params) * 2
+    probe_ops = (1 << 22) * 64
+    l2_ms, _ = vnr.probe_memory("loads", 2920448 * 16, probe_ops, 3)
+    hbm_ms, _ = vnr.probe_memory("loads", 19173376 * 16, probe_ops, 3)
+    own_ms, _ = vnr.probe_memory("loads", table_bytes, probe_ops, 3)
+    gbs = lambda ms_: probe_ops * 16 / (ms_ * 1e-3) / 1e9
+    gather_peak = gbs(own_ms)
+    bound = "l2_gather" if table_bytes <= 100e6 else "hbm_gather"
+    decode_rate = prof_decoded / (decode_ms * 1e-3) if decode_ms > 0 else 0.0
+    achieved = decode_rate * GATHER_BYTES / 1e9
+    # the same kernel on uniform random coordinates (no coherence between neighbouring rows): apples to apples with the probe
+    nu = 1 << 22
+    xyz_u = torch.rand(nu, 3, device="cuda"); out_u = torch.empty(nu, device="cuda")
+    vst = torch.cuda.ExternalStream(vol.stream())
+    for _ in range(2):
+        vol.decode(xyz_u, out_u, nu)
+    eu0, eu1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    eu0.record(vst)
+    for _ in range(5):
+        vol.decode(xyz_u, out_u, nu)
+    eu1.record(vst); vst.synchronize()
+    uniform_rate = 5 * nu / (eu0.elapsed_time(eu1) * 1e-3)
+    # DRAM bytes of the largest decode launch of a frame from the committed `ncu --set full` capture of THIS configuration (per
+    # launch), next to the algorithmic bytes of that same launch; null when no capture of this configuration is committed
     traffic = None; traffic_detail = None
-    try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "decode_traffic.json")))
-        traffic = tj["dram_bytes"]
-        traffic_detail = {"unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)", "algorithmic_bytes_of_that_launch": tj["samples"] * BYTES_PER_SAMPLE,
-                          "samples_of_that_launch": tj["samples"], "launch_us_under_ncu": tj["duration_us"], "source": tj["source"]}
-    except Exception:
-        pass
-    roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_detail": traffic_detail,
-                "kernel": "decode_kernel<8,4> (fused hash-grid gather + tcgen05 MLP)", "peak_source": peak_kind,
-                "algorithmic_bytes_per_sample": BYTES_PER_SAMPLE, "decode_ms_per_frame": round(decode_ms / prof_steps, 4),
-                "decode_launches_per_frame": decode_launches / prof_steps,
-                "decode_samples_per_sec": prof_decoded / (decode_ms * 1e-3) if decode_ms > 0 else 0.0,
-                "note": "the 46.7 MB table is L2-resident, so the gather is bounded by L2 random-sector bandwidth rather than HBM; frac is quoted against the measured HBM copy peak as the contract asks"}
+    tpath = os.path.join(ROOT, "profiles", f"decode_traffic_t{args.log2_hashmap}_{W}x{H}.json")
+    if world == 1 and os.path.exists(tpath):
+        try:
+            tj = json.load(open(tpath))
+            traffic = tj["dram_bytes"]
+            traffic_detail = {"unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)", "algorithmic_bytes_of_that_launch": tj["samples"] * BYTES_PER_SAMPLE,
+                              "samples_of_that_launch": tj["samples"], "launch_us_under_ncu": tj["duration_us"], "source": tj["source"]}
+        except Exception:
+            pass
+    roofline = {"bound": bound, "achieved": round(achieved, 1), "peak": round(gather_peak, 1), "unit": "GB/s", "frac": round(achieved / gather_peak, 4),
+                "traffic": traffic, "traffic_detail": traffic_detail,
+                "kernel": "decode_kernel<8,4> (fused hash-grid gather + tcgen05 MLP)", "peak_source": "measured in this run: random 16-byte ld.global.nc over a buffer of the table's size (csrc/probe.cu)",
+                "l2_gather_gbs": round(gbs(l2_ms), 1), "hbm_gather_gbs": round(gbs(hbm_ms), 1), "table_bytes": table_bytes,
+                "algorithmic_bytes_per_sample": GATHER_BYTES, "decode_ms_per_frame": round(decode_ms / prof_steps, 4),
+                "decode_launches_per_frame": decode_launches / prof_steps, "decode_samples_per_sec": decode_rate,
+                "decode_uniform_samples_per_sec": uniform_rate, "frac_uniform": round(uniform_rate * GATHER_BYTES / 1e9 / gather_peak, 4),
+                "hbm_copy_peak": peak, "hbm_copy_peak_source": peak_kind,
+                "hbm_copy_frac": round(decode_rate * BYTES_PER_SAMPLE / 1e9 / peak, 4),
+                "note": "frac = in-frame decode rate x 1024 B / the random-gather probe.  Inside a frame neighbouring rows are the same step of neighbouring rays and share "
+                        "hash-grid cells (sectors), which the random probe does not, so frac can exceed frac_uniform (same kernel, uniform random coordinates).  hbm_copy_frac "
+                        "(all 1044 algorithmic B/sample against the HBM copy peak) is kept for comparison with round 1; the table is read from L2, not HBM, when it fits"}
 
     # training throughput of the same volume (steps/s), reported next to the headline
     s_train = torch.cuda.Event(enable_timing=True); e_train = torch.cuda.Event(enable_timing=True)
@@ -414,21 +454,21 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f16", "data": "synthetic",
-        "config": {"workload": f"render: synthetic {args.volume}^3 volume, example-model.json (8 levels x 8 features, T=2^{args.log2_hashmap}, 64x4 MLP), "
-                               f"{W}x{H} frame, macrocell skipping, mode 5 (sample streaming), 16-view orbit",
+        "config": {"workload": workload_string(args),
                    "weights": f"trained here for {train_step_count} steps (batch 2^16), mean L1 loss {train_loss:.4f}",
                    "l2_flush": "inputs larger than L2: per-frame sample/value/ray-state buffers (~500 MB) stream through the 126 MB L2 between frames",
                    "parallelism": f"tile-parallel x{world}" if world > 1 else "single GPU",
-                   "frame_pipelining": f"{len(pipe)} renderer(s) of the volume take the frames in turn for the device-resident `value` (the end-to-end pass maps every frame and runs one at a time)"},
+                   "frames_in_flight": f"{n_pipe} frame slot(s) inside the renderer for the device-resident `value` (vnr_renderer_set_frames_in_flight; the strict end-to-end pass maps every frame before the next is launched)"},
         "fps": args.steps / (ms * 1e-3), "samples_per_frame": decoded / args.steps, "composited_per_frame": composited / args.steps,
         "rays_hit_per_frame": rays / args.steps,
         "train_steps_per_sec_batch_2p18": 1000.0 / train_ms, "train_samples_per_sec": (1 << 18) * 1000.0 / train_ms,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 480, "d2h_bytes_per_step": W * H * 16, "fps": args.steps / (ms_e2e * 1e-3),
                 "frame_path": "tile-parallel gather + download on rank 0" if tp else "zero-copy: compositing kernels store finished pixels into the pinned host frame",
                 "fps_copy_after_frame": (args.steps / (ms_e2e_copy * 1e-3)) if ms_e2e_copy else None,
-                "fps_with_frames_in_flight": fps_inflight, "frames_in_flight": inflight,
-                "note": "value / fps: strict loop, every frame mapped before the next one is launched.  fps_with_frames_in_flight: the same calls with the next "
-                        "frames already launched on other renderers of the volume when a frame is mapped (every frame mapped once; DMA download overlaps compute)"},
+                "fps_with_frames_in_flight": (max(fps_inflight.values()) if fps_inflight else None), "fps_with_frames_in_flight_by_download": fps_inflight,
+                "frames_in_flight": inflight,
+                "note": "value / fps: strict loop, every frame mapped before the next one is launched.  fps_with_frames_in_flight: the same two calls on ONE renderer whose "
+                        "frame ring holds 3 slots (vnr_renderer_set_frames_in_flight): vnr_map_frame returns the oldest unmapped frame while the next two compute"},
         "gpu_launches": int(launches),
         "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "setup_seconds": round(time.time() - t0, 1),
     }
@@ -551,8 +591,8 @@ def run_train(args):
         out = {"metric": "train_steps_per_sec", "value": args.steps / (ms * 1e-3), "unit": "steps/s", "n_gpus": world, "steps": args.steps,
                "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "f16", "data": "synthetic",
-               "config": {"workload": f"train: synthetic {args.volume}^3 volume resident in HBM, example-model.json (T=2^{args.log2_hashmap}), "
-                                      f"{n} samples per rank per step, fwd + L1 + bwd + Adam" + ("" if world == 1 else ", gradient all-reduce (fp16 grid + fp32 MLP) over NCCL + replicated Adam" if dp.mode == "allreduce"
+               "config": {"workload": workload_string(args),
+                          "path": "volume resident in HBM, sampled on the device" + ("" if world == 1 else ", gradient all-reduce (fp16 grid + fp32 MLP) over NCCL + replicated Adam" if dp.mode == "allreduce"
                                                                else ", optimizer fused with its collectives over NVLink peer memory (reduce-scatter + Adam + all-gather in one kernel)"),
                           "global_batch": n * world, "l2_flush": "per-step parameter-state sweep (~0.9 GB) exceeds L2",
                           "parallelism": f"dp{world}"},
@@ -663,8 +703,9 @@ def run_reference_train(args):
     ms_e2e = (time.perf_counter() - t0) * 1e3
     v = args.steps / (ms * 1e-3)
     base.update({"value": v, "ms_per_step": ms / args.steps, "last_loss": loss,
-                 "config": {"workload": f"train: synthetic {args.volume}^3 volume, example-model.json (T=2^{args.log2_hashmap}), {n} samples per step, the reference's "
-                                        "Trainer::training_step (tcnn, CUDA-graph captured fwd+loss+bwd, Adam) on the same B200; batches pre-drawn (sampling not timed)", "global_batch": n, "parallelism": "dp1"},
+                 "config": {"workload": workload_string(args),
+                            "path": "the reference's Trainer::training_step (tcnn, CUDA-graph captured fwd+loss+bwd, Adam) on the same B200; batches pre-drawn (sampling not timed)",
+                            "global_batch": n, "parallelism": "dp1"},
                  "cpu_baseline": {"value": v, "unit": "steps/s", "cores": 0, "kind": "reference", "sample": f"{args.steps} steps of {n} samples on the same GPU"},
                  "e2e": {"value": args.steps / (ms_e2e * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 4}})
     emit(base)
@@ -767,9 +808,8 @@ def run_reference_frames(args, base):
     useful = sum(useful_per_view[i % n_count] for i in range(args.steps))
     v = useful / dt
     base.update({"value": v, "ms_per_step": dt * 1e3 / args.steps, "fps": args.steps / dt, "scaling": "strong",
-                 "config": {"workload": f"render: synthetic {args.volume}^3 volume, example-model.json (T=2^{args.log2_hashmap}), {W}x{H} frame, macrocell skipping, "
-                                        "mode 5 (sample streaming), 16-view orbit -- through the reference's own marcher + macrocell + tiny-cuda-nn sources "
-                                        "(compiled unmodified from /root/reference), every frame downloaded",
+                 "config": {"workload": workload_string(args),
+                            "path": "the reference's own marcher + macrocell + tiny-cuda-nn sources (compiled unmodified from /root/reference), every frame downloaded",
                             "weights": f"trained here for {args.train_steps} steps (batch 2^16) by the reference's Trainer::training_step"},
                  "samples_per_frame": useful / args.steps, "network_evaluations_per_frame": coords / args.steps, "network_evaluations_per_sec": coords / dt,
                  "wavefront_rounds_per_frame": calls / args.steps,

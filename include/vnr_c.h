@@ -84,6 +84,22 @@ int vnr_volume_decode_debug(vnr_volume_t* v, const float* h_xyz, float* h_out, u
  * word per sample; bench.py times it to obtain the gather-rate ceiling of the decode roofline */
 int vnr_volume_gather_probe(vnr_volume_t* v, const float* d_xyz, uint32_t* d_out, size_t n, void* stream);
 
+/* measurement taps (no reference counterpart), independent of the product's gather code: one plain kernel at full
+ * occupancy issuing n_ops random 16-byte operations over a fresh buffer of table_bytes (64 per thread, 8 in flight):
+ * kind 0 = read-only loads (ld.global.nc.v4) -- a 46.7 MB buffer gives the L2 random-gather ceiling of the decode, a
+ * 306.8 MB one the HBM random-gather ceiling (SURVEY 8d `l2_gather_gbs` / `hbm_gather_gbs`); kind 1 = fp16x8 vector
+ * reductions (red.global.add.noftz.v4.f16x2), the ceiling of the hash-grid backward; kind 2 = a streaming copy of the
+ * buffer.  Returns the fastest and the mean of `repeats` CUDA-event-timed launches (after one warm-up). */
+int vnr_probe_memory(int kind, size_t table_bytes, size_t n_ops, int repeats, float* ms_best, float* ms_mean);
+
+/* measurement taps of the fused training kernel (train.cu): variant 1 = current MMA chain, 0 = the round-1 chain
+ * (A/B); flags: 1 = the scatter groups issue no reductions, 2 = the gather groups issue no loads, 4 = the compute
+ * group runs no MMA chain (results are then meaningless: timing only); profile != 0: the next training kernels record
+ * per-CTA role timers, read back with vnr_volume_train_profile (words per CTA returned in *words_per_cta; out may be
+ * NULL to query sizes; layout in train.cu) */
+int vnr_volume_train_debug(vnr_volume_t* v, int variant, uint32_t flags, int profile);
+int vnr_volume_train_profile(vnr_volume_t* v, uint32_t* out, size_t max_words, int* n_ctas, int* words_per_cta);
+
 /* vnrCreateSimpleVolume + StaticSampler ground truth (core/samplers/neural_sampler.cu:86-128):
  * float32 volume of dims dx*dy*dz (x fastest), already normalised to [0,1]. */
 int vnr_volume_set_groundtruth_f32(vnr_volume_t* v, const float* h_volume);
@@ -279,8 +295,17 @@ int vnr_renderer_download(vnr_renderer_t* r);
  * the non-empty decode launches of the last frame, their number, and all kernels launched by it */
 int vnr_renderer_set_profiling(vnr_renderer_t* r, int on);
 int vnr_renderer_profile(vnr_renderer_t* r, float* decode_ms, int* decode_launches, uint64_t* kernel_launches);
-/* the cudaStream_t all work of this renderer is enqueued on */
+/* the cudaStream_t all work of this renderer is enqueued on (several frames in flight: the stream of the most recent frame) */
 int vnr_renderer_stream(vnr_renderer_t* r, void** stream);
+/* Frames in flight (MainRenderer's double-buffered framebuffer, renderer.h:84-94, framebuffer.h:73-77, generalised): the
+ * renderer owns a ring of n (1..8, default 1, env VNR_FRAMES_IN_FLIGHT) frame slots, each with its own stream, ray /
+ * sample / value buffers, accumulation buffer, captured wavefront graph and pinned host frames.  vnr_render enqueues the
+ * frame on the next slot and returns, so consecutive frames overlap on the device; vnr_map_frame returns the OLDEST rendered
+ * frame that has not been mapped (n = 1: the frame just rendered, as the reference).  A frame that accumulates onto the
+ * previous one (frame_index > 1) waits for it on the device.  Rendering into a full ring drops the oldest unmapped frame. */
+int vnr_renderer_set_frames_in_flight(vnr_renderer_t* r, int n);
+/* the slots' streams (to bracket a run of frames with events); n_streams receives the ring depth */
+int vnr_renderer_streams(vnr_renderer_t* r, void** streams, int max_streams, int* n_streams);
 /* samples per ray per wavefront round (N_ITERS, env VNR_RM_N_ITERS; method_raymarching.cu:30-40) */
 int vnr_renderer_set_n_iters(vnr_renderer_t* r, int n);
 

@@ -84,6 +84,14 @@ def device_count():
     return int(lib().vnr_device_count())
 
 
+def probe_memory(kind, table_bytes, n_ops, repeats=5):
+    """Independent memory-system microbenchmark (csrc/probe.cu): kind "loads" / "reds" / "copy" -> (best ms, mean ms)."""
+    k = {"loads": 0, "reds": 1, "copy": 2}[kind]
+    best, mean = C.c_float(), C.c_float()
+    _check(lib().vnr_probe_memory(C.c_int(k), C.c_size_t(int(table_bytes)), C.c_size_t(int(n_ops)), C.c_int(repeats), C.byref(best), C.byref(mean)))
+    return best.value, mean.value
+
+
 def example_model_json():
     with open(EXAMPLE_MODEL) as f:
         return f.read()
@@ -249,6 +257,19 @@ class NeuralVolume:
 
     def optimizer_step(self, stream=None):
         _check(lib().vnr_volume_optimizer_step(self._h, _stream(stream)))
+
+    # -- measurement taps of the fused training kernel (train.cu)
+    def train_debug(self, variant=1, flags=0, profile=False):
+        _check(lib().vnr_volume_train_debug(self._h, C.c_int(variant), C.c_uint32(flags), C.c_int(1 if profile else 0)))
+
+    def train_profile(self):
+        """per-CTA role timers of the last training kernel: uint32 array [n_ctas][words]"""
+        n, w = C.c_int(), C.c_int()
+        _check(lib().vnr_volume_train_profile(self._h, None, C.c_size_t(0), C.byref(n), C.byref(w)))
+        out = np.zeros((max(n.value, 0), w.value), dtype=np.uint32)
+        if out.size:
+            _check(lib().vnr_volume_train_profile(self._h, _ptr(out), C.c_size_t(out.size), None, None))
+        return out
 
     def grad_buffer(self, which):
         """(device pointer, n_elements, is_f32) of the MLP (which=0) or grid (which=1) gradients."""
@@ -453,6 +474,18 @@ class Renderer:
 
     def set_frame_target(self, d_ptr):
         _check(lib().vnr_renderer_set_frame_target(self._h, C.c_void_p(d_ptr) if d_ptr else None))
+
+    def set_frames_in_flight(self, n):
+        """depth of the renderer's frame ring (vnr_renderer_set_frames_in_flight); map_frame then returns the oldest unmapped frame"""
+        _check(lib().vnr_renderer_set_frames_in_flight(self._h, C.c_int(n)))
+
+    def streams(self):
+        """the cudaStream_t of every frame slot"""
+        n = C.c_int()
+        _check(lib().vnr_renderer_streams(self._h, None, C.c_int(0), C.byref(n)))
+        arr = (C.c_void_p * n.value)()
+        _check(lib().vnr_renderer_streams(self._h, arr, C.c_int(n.value), None))
+        return [int(a or 0) for a in arr]
 
     def set_n_iters(self, n):
         _check(lib().vnr_renderer_set_n_iters(self._h, C.c_int(n)))

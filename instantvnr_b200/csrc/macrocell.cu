@@ -106,6 +106,7 @@ void macrocell_update_implicit(Volume* v, cudaStream_t s) {
 }
 
 void macrocell_update_max_opacity(Volume* v, cudaStream_t s) {
+  wait_for_frames(v, s);                 // frames in flight still walk the current max-opacity grid
   if (v->n_alpha <= 0) return;                       // macrocell.cu:245
   const uint32_t n = (uint32_t)v->cells();
   const float rcp = 1.f / (v->tfn_hi - v->tfn_lo);

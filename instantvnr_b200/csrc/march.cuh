@@ -46,6 +46,8 @@ struct FrameParams {
   // path tracer (method_pathtracing.cu): majorant scale and lights (instantvnr_types.h:102,146-147)
   float density_scale, light_ambient, light_rgb[3];
   float4* frame;                     // where finished pixels go: local / peer frame buffer or the mapped pinned host frame
+  const float4* accum_prev;          // accumulation buffer of the previous frame (read when frame_index != 1; frames in flight
+                                     // accumulate into their own slot's buffer)
 };
 
 struct F3 { float x, y, z; };

@@ -1,0 +1,117 @@
+// probe.cu -- memory-system microbenchmarks that give the decode / training rooflines their denominators.
+//
+// Measurement taps only (no reference counterpart, nothing of the product path runs through them).  They are
+// deliberately INDEPENDENT of the product's gather code (LevelGather / scatter_level): plain grid-stride kernels at
+// full occupancy that issue
+//   * random 16-byte read-only loads (ld.global.nc.v4) over a buffer of a given size -- 46.7 MB (the example model's
+//     table, L2-resident on B200) gives `l2_gather_gbs`, 306.8 MB (T = 2^22, larger than the 126 MB L2) gives
+//     `hbm_gather_gbs`;
+//   * random 16-byte fp16 vector reductions (red.global.add.noftz.v4.f16x2), the instruction of the hash-grid
+//     backward (train.cu), which gives the scatter ceiling of the training step.
+// Addresses come from a counter-based integer hash, so consecutive loads of a thread are independent (8 in flight).
+#include <cstdint>
+#include <cstring>
+
+#include "../../include/vnr_c.h"
+#include "vnr_host.h"
+
+namespace vnr {
+
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {          // murmur3 finalizer
+  x ^= x >> 16; x *= 0x85ebca6bu; x ^= x >> 13; x *= 0xc2b2ae35u; x ^= x >> 16;
+  return x;
+}
+
+__device__ __forceinline__ uint4 ldg_nc_v4(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+
+// every thread: `per_thread` loads in batches of 8 independent ones; n_vec = number of 16-byte vectors in the table
+__global__ void __launch_bounds__(256) probe_loads_kernel(const uint4* __restrict__ table, uint32_t n_vec, uint32_t per_thread, uint32_t seed,
+                                                          uint32_t* __restrict__ sink) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t fold = 0;
+  uint32_t c = mix32(t * 0x9e3779b9u + seed);
+  for (uint32_t k = 0; k < per_thread; k += 8) {
+    uint4 v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      c = c * 1664525u + 1013904223u;
+      const uint32_t idx = (uint32_t)(((uint64_t)mix32(c) * n_vec) >> 32);
+      v[i] = ldg_nc_v4(table + idx);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) fold ^= v[i].x ^ v[i].y ^ v[i].z ^ v[i].w;
+  }
+  if (fold == 0x12345678u) sink[t & 1023u] = fold;               // practically never: keeps the loads alive
+}
+
+__global__ void __launch_bounds__(256) probe_reds_kernel(__half* __restrict__ table, uint32_t n_vec, uint32_t per_thread, uint32_t seed) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t c = mix32(t * 0x9e3779b9u + seed);
+  const uint32_t one = 0x04000400u;                               // two small fp16 values (2^-14): sums stay finite
+  for (uint32_t k = 0; k < per_thread; ++k) {
+    c = c * 1664525u + 1013904223u;
+    const uint32_t idx = (uint32_t)(((uint64_t)mix32(c) * n_vec) >> 32);
+    asm volatile("red.global.add.noftz.v4.f16x2 [%0], {%1, %1, %1, %1};" ::"l"(table + (size_t)idx * 8), "r"(one) : "memory");
+  }
+}
+
+// streaming copy (read + write) for reference next to MEASURED_PEAKS.json's figure
+__global__ void __launch_bounds__(256) probe_copy_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, size_t n_vec) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+}  // namespace vnr
+
+using namespace vnr;
+
+#define VNR_EXPORT extern "C" __attribute__((visibility("default")))
+
+// kind 0: random 16-byte loads, 1: random 16-byte fp16x8 reductions, 2: streaming copy of table_bytes (n_ops ignored).
+// Runs `repeats` timed launches after one warm-up and returns the fastest (ms_best) and the mean (ms_mean) launch time.
+VNR_EXPORT int vnr_probe_memory(int kind, size_t table_bytes, size_t n_ops, int repeats, float* ms_best, float* ms_mean) {
+  if (kind < 0 || kind > 2 || table_bytes < 4096 || repeats < 1 || !ms_best) return VNR_ERR_INVALID;
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) { cudaGetLastError(); return VNR_ERR_CUDA; }
+  void* table = nullptr; void* aux = nullptr;
+  cudaStream_t s = nullptr; cudaEvent_t e0 = nullptr, e1 = nullptr;
+  int rc = VNR_OK;
+  auto ok = [&](cudaError_t e) { if (e != cudaSuccess) { cudaGetLastError(); rc = VNR_ERR_CUDA; } return e == cudaSuccess; };
+  const size_t n_vec = table_bytes / 16;
+  do {
+    if (!ok(cudaMalloc(&table, n_vec * 16))) break;
+    if (!ok(cudaMalloc(&aux, kind == 2 ? n_vec * 16 : 4096))) break;
+    if (!ok(cudaMemset(table, 0, n_vec * 16))) break;
+    if (!ok(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking))) break;
+    if (!ok(cudaEventCreate(&e0)) || !ok(cudaEventCreate(&e1))) break;
+    const uint32_t per_thread = 64;                                 // the example model's loads / reductions per sample
+    const size_t threads = (n_ops + per_thread - 1) / per_thread;
+    const unsigned grid = (unsigned)((threads + 255) / 256);
+    float best = 1e30f, sum = 0.f;
+    for (int it = 0; it <= repeats && rc == VNR_OK; ++it) {
+      if (kind == 1 && !ok(cudaMemsetAsync(table, 0, n_vec * 16, s))) break;
+      ok(cudaEventRecord(e0, s));
+      if (kind == 0) probe_loads_kernel<<<grid, 256, 0, s>>>((const uint4*)table, (uint32_t)n_vec, per_thread, 17u + it, (uint32_t*)aux);
+      else if (kind == 1) probe_reds_kernel<<<grid, 256, 0, s>>>((__half*)table, (uint32_t)n_vec, per_thread, 17u + it);
+      else probe_copy_kernel<<<148 * 16, 256, 0, s>>>((const uint4*)table, (uint4*)aux, n_vec);
+      ok(cudaGetLastError());
+      ok(cudaEventRecord(e1, s));
+      if (!ok(cudaEventSynchronize(e1))) break;
+      float ms = 0.f;
+      ok(cudaEventElapsedTime(&ms, e0, e1));
+      if (it == 0) continue;                                        // warm-up (first touch of the table)
+      best = ms < best ? ms : best; sum += ms;
+    }
+    *ms_best = best;
+    if (ms_mean) *ms_mean = sum / (float)repeats;
+  } while (0);
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+  if (s) cudaStreamDestroy(s);
+  if (table) cudaFree(table);
+  if (aux) cudaFree(aux);
+  return rc;
+}

@@ -42,7 +42,7 @@ __device__ __forceinline__ void write_pixel(const FrameParams& fp, float4* __res
   // moment its ray finishes, overlapped with the rest of the wavefront, instead of a 16 B/pixel copy after the frame).
   float4* __restrict__ frame = fp.frame;
   if (fp.frame_index != 1) {
-    const float4 a = accum[pixel];
+    const float4 a = fp.accum_prev[pixel];
     c = make_float4(a.x + c.x, a.y + c.y, a.z + c.z, a.w + c.w);
   }
   accum[pixel] = c;
@@ -401,13 +401,49 @@ __global__ void advance_round_kernel(uint32_t* __restrict__ counters, uint32_t* 
 
 // ---------------------------------------------------------------------------------------
 
-Renderer::Renderer(Volume* v) : vol(v) {
+
+FrameSlot::FrameSlot() {
   VNR_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
   VNR_CUDA(cudaEventCreateWithFlags(&frame_done[0], cudaEventDisableTiming));
   VNR_CUDA(cudaEventCreateWithFlags(&frame_done[1], cudaEventDisableTiming));
   VNR_CUDA(cudaEventCreateWithFlags(&vol_ready, cudaEventDisableTiming));
   VNR_CUDA(cudaMallocHost((void**)&h_counters, sizeof(uint32_t) * 2 * (kMaxRounds + 4)));
   memset(h_counters, 0, sizeof(uint32_t) * 2 * (kMaxRounds + 4));
+}
+
+FrameSlot::~FrameSlot() {
+  if (stream) cudaStreamSynchronize(stream);
+  for (int k = 0; k < 2; ++k) { if (h_frame[k]) cudaFreeHost(h_frame[k]); if (frame_done[k]) cudaEventDestroy(frame_done[k]); }
+  for (cudaEvent_t e : prof_events) cudaEventDestroy(e);
+  destroy_graph();
+  if (vol_ready) cudaEventDestroy(vol_ready);
+  if (h_counters) cudaFreeHost(h_counters);
+  if (stream) cudaStreamDestroy(stream);
+}
+
+void FrameSlot::resize(size_t npix) {
+  VNR_CUDA(cudaStreamSynchronize(stream));
+  accum.alloc(npix); frame.alloc(npix);
+  accum.zero(stream); frame.zero(stream);
+  for (int k = 0; k < 2; ++k) {
+    if (h_frame[k]) { cudaFreeHost(h_frame[k]); h_frame[k] = nullptr; }
+    VNR_CUDA(cudaMallocHost((void**)&h_frame[k], npix * sizeof(float4)));
+  }
+  rendered = false; downloaded = false; mapped = true;
+}
+
+void FrameSlot::destroy_graph() {
+  for (int k = 0; k < 2; ++k) {
+    if (loop_exec[k]) { cudaGraphExecDestroy(loop_exec[k]); loop_exec[k] = nullptr; }
+    if (loop_graph[k]) { cudaGraphDestroy(loop_graph[k]); loop_graph[k] = nullptr; }
+  }
+  if (pt_exec) { cudaGraphExecDestroy(pt_exec); pt_exec = nullptr; }
+  if (pt_graph) { cudaGraphDestroy(pt_graph); pt_graph = nullptr; }
+  if (capture_stream) { cudaStreamDestroy(capture_stream); capture_stream = nullptr; }
+}
+
+Renderer::Renderer(Volume* v) : vol(v) {
+  slots.emplace_back(new FrameSlot());
   if (const char* e = getenv("VNR_RM_GRAPH")) use_graph = atoi(e) != 0;    // 0: host-enqueued rounds (profilers do not see graph-body kernels)
   if (const char* e = getenv("VNR_FRAME_ZEROCOPY")) zero_copy = atoi(e) != 0;
   if (const char* e = getenv("VNR_RM_TILED")) tiled = atoi(e) != 0;          // 0: scanline ray order (A/B)
@@ -416,16 +452,44 @@ Renderer::Renderer(Volume* v) : vol(v) {
     int n = atoi(e);
     if (n >= 1 && n <= 16) n_iters = n;
   }
+  if (const char* e = getenv("VNR_FRAMES_IN_FLIGHT")) { const int n = atoi(e); if (n >= 1 && n <= kMaxFramesInFlight) set_frames_in_flight(n); }
+  vol->renderers.push_back(this);
 }
 
 Renderer::~Renderer() {
-  if (stream) cudaStreamSynchronize(stream);
-  for (int k = 0; k < 2; ++k) { if (h_frame[k]) cudaFreeHost(h_frame[k]); if (frame_done[k]) cudaEventDestroy(frame_done[k]); }
-  for (cudaEvent_t e : prof_events) cudaEventDestroy(e);
-  destroy_graph();
-  if (vol_ready) cudaEventDestroy(vol_ready);
-  if (h_counters) cudaFreeHost(h_counters);
-  if (stream) cudaStreamDestroy(stream);
+  auto& rs = vol->renderers;
+  rs.erase(std::remove(rs.begin(), rs.end(), this), rs.end());
+  slots.clear();
+}
+
+void Renderer::sync_all() { for (auto& s : slots) VNR_CUDA(cudaStreamSynchronize(s->stream)); }
+
+// Depth of the frame ring.  1 (default) is the reference's behaviour: one frame at a time.  n > 1: vnr_render returns after
+// enqueueing the frame on the next slot's stream, so up to n consecutive frames overlap on the device (the latency-bound tail
+// rounds of one frame run under the head of the next); vnr_map_frame returns the oldest frame that has not been mapped yet.
+void Renderer::set_frames_in_flight(int n) {
+  if (n < 1 || n > kMaxFramesInFlight) throw InvalidError("frames in flight must be in [1, " + std::to_string(kMaxFramesInFlight) + "]");
+  sync_all();
+  while ((int)slots.size() > n) slots.pop_back();
+  while ((int)slots.size() < n) {
+    slots.emplace_back(new FrameSlot());
+    if (width > 0) slots.back()->resize((size_t)width * height);
+    slots.back()->frame_target = nullptr;
+  }
+  n_rendered = n_mapped = 0; last_slot = 0;
+  for (auto& s : slots) { s->rendered = false; s->downloaded = false; s->mapped = true; }
+  reset = true;
+}
+
+// volume-side ordering against frames in flight: work that rewrites what a frame reads (parameters, macrocells, transfer
+// function) waits on `s` for the last frame of every slot of every renderer of the volume
+void wait_for_frames(Volume* v, cudaStream_t s) {
+  for (Renderer* r : v->renderers)
+    for (auto& sl : r->slots)
+      if (sl->rendered && !(sl->vol_waited && sl->vol_waited_on == s)) {
+        VNR_CUDA(cudaStreamWaitEvent(s, sl->frame_done[sl->mapped ? sl->cur ^ 1 : sl->cur], 0));
+        sl->vol_waited = true; sl->vol_waited_on = s;
+      }
 }
 
 uint32_t Renderer::local_rays() const {
@@ -437,15 +501,9 @@ uint32_t Renderer::local_rays() const {
 
 void Renderer::resize(int w, int h) {
   if (w <= 0 || h <= 0) throw InvalidError("framebuffer size must be positive");
-  if (stream) VNR_CUDA(cudaStreamSynchronize(stream));
   width = w; height = h;
-  const size_t npix = (size_t)w * h;
-  accum.alloc(npix); frame.alloc(npix);
-  accum.zero(stream); frame.zero(stream);
-  for (int k = 0; k < 2; ++k) {
-    if (h_frame[k]) { cudaFreeHost(h_frame[k]); h_frame[k] = nullptr; }
-    VNR_CUDA(cudaMallocHost((void**)&h_frame[k], npix * sizeof(float4)));
-  }
+  for (auto& s : slots) s->resize((size_t)w * h);
+  n_rendered = n_mapped = 0; last_slot = 0;
   reset = true;
 }
 
@@ -515,16 +573,6 @@ int Renderer::round_bound() const {
   return (int)std::ceil(max_samples / n_iters) + 1;
 }
 
-void Renderer::destroy_graph() {
-  for (int k = 0; k < 2; ++k) {
-    if (loop_exec[k]) { cudaGraphExecDestroy(loop_exec[k]); loop_exec[k] = nullptr; }
-    if (loop_graph[k]) { cudaGraphDestroy(loop_graph[k]); loop_graph[k] = nullptr; }
-  }
-  if (pt_exec) { cudaGraphExecDestroy(pt_exec); pt_exec = nullptr; }
-  if (pt_graph) { cudaGraphDestroy(pt_graph); pt_graph = nullptr; }
-  if (capture_stream) { cudaStreamDestroy(capture_stream); capture_stream = nullptr; }
-}
-
 typedef void (*march_kernel_t)(const FrameParams*, RayBuffers, float4*, float4*, const float*, uint32_t*, int, const uint32_t*, float4*);
 static march_kernel_t march_kernel(bool first, int shade) {
   switch (shade) {
@@ -535,24 +583,24 @@ static march_kernel_t march_kernel(bool first, int shade) {
   }
 }
 
-// (Re)build the loop graph of one pass when anything baked into its kernel nodes changed.
-void Renderer::ensure_graph(int pass, int shade, const RayBuffers& rb, unsigned grid, size_t cap, int rounds, const float* volume_src) {
-  uint32_t* cnt = counters.p + (size_t)pass * (kMaxRounds + 4);
-  const FrameParams* fpd = reinterpret_cast<const FrameParams*>(fp_dev.p) + pass;
+// (Re)build the loop graph of one pass of one slot when anything baked into its kernel nodes changed.
+void Renderer::ensure_graph(FrameSlot& S, int pass, int shade, const RayBuffers& rb, unsigned grid, size_t cap, int rounds, const float* volume_src) {
+  uint32_t* cnt = S.counters.p + (size_t)pass * (kMaxRounds + 4);
+  const FrameParams* fpd = reinterpret_cast<const FrameParams*>(S.fp_dev.p) + pass;
   GraphKey key;
   memset(&key, 0, sizeof key);
   key.desc = vol->cfg.desc; key.params = vol->params.p;
   key.ptrs[0] = rb.rgba; key.ptrs[1] = rb.tn_ncb; key.ptrs[2] = rb.cell_base; key.ptrs[3] = rb.state; key.ptrs[4] = rb.jitter;
-  key.ptrs[5] = samples[0].p; key.ptrs[6] = samples[1].p; key.ptrs[7] = values.p; key.ptrs[8] = cnt; key.ptrs[9] = accum.p;
+  key.ptrs[5] = S.samples[0].p; key.ptrs[6] = S.samples[1].p; key.ptrs[7] = S.values.p; key.ptrs[8] = cnt; key.ptrs[9] = S.accum.p;
   key.ptrs[11] = fpd; key.ptrs[12] = rb.ssh_org; key.ptrs[13] = rb.ssh_col; key.ptrs[14] = rb.ssh_rgba; key.ptrs[15] = rb.ssh_jitter;
   key.grid = grid; key.cap = cap; key.rounds = rounds; key.volume_src = volume_src; key.shade = shade;
-  if (loop_exec[pass] && !memcmp(&key, &graph_key[pass], sizeof key)) return;
-  VNR_CUDA(cudaStreamSynchronize(stream));
-  if (loop_exec[pass]) { cudaGraphExecDestroy(loop_exec[pass]); loop_exec[pass] = nullptr; }
-  if (loop_graph[pass]) { cudaGraphDestroy(loop_graph[pass]); loop_graph[pass] = nullptr; }
-  VNR_CUDA(cudaGraphCreate(&loop_graph[pass], 0));
+  if (S.loop_exec[pass] && !memcmp(&key, &S.graph_key[pass], sizeof key)) return;
+  VNR_CUDA(cudaStreamSynchronize(S.stream));
+  if (S.loop_exec[pass]) { cudaGraphExecDestroy(S.loop_exec[pass]); S.loop_exec[pass] = nullptr; }
+  if (S.loop_graph[pass]) { cudaGraphDestroy(S.loop_graph[pass]); S.loop_graph[pass] = nullptr; }
+  VNR_CUDA(cudaGraphCreate(&S.loop_graph[pass], 0));
   cudaGraphConditionalHandle handle;
-  VNR_CUDA(cudaGraphConditionalHandleCreate(&handle, loop_graph[pass], 0, 0));
+  VNR_CUDA(cudaGraphConditionalHandleCreate(&handle, S.loop_graph[pass], 0, 0));
   uint32_t* round_dev = cnt + kMaxRounds + 2;
   // node 1: initialise the round index and the loop condition from round 0
   cudaGraphNode_t init_node;
@@ -561,101 +609,102 @@ void Renderer::ensure_graph(int pass, int shade, const RayBuffers& rb, unsigned 
     void* args[] = {&c, &round_dev, &handle, &init, &bound};
     cudaKernelNodeParams kp = {};
     kp.func = (void*)advance_round_kernel; kp.gridDim = dim3(1); kp.blockDim = dim3(1); kp.kernelParams = args;
-    VNR_CUDA(cudaGraphAddKernelNode(&init_node, loop_graph[pass], nullptr, 0, &kp));
+    VNR_CUDA(cudaGraphAddKernelNode(&init_node, S.loop_graph[pass], nullptr, 0, &kp));
   }
   // node 2: WHILE
   cudaGraphNodeParams wp = {};
   wp.type = cudaGraphNodeTypeConditional;
   wp.conditional.handle = handle; wp.conditional.type = cudaGraphCondTypeWhile; wp.conditional.size = 1;
   cudaGraphNode_t while_node;
-  VNR_CUDA(cudaGraphAddNode(&while_node, loop_graph[pass], &init_node, 1, &wp));
+  VNR_CUDA(cudaGraphAddNode(&while_node, S.loop_graph[pass], &init_node, 1, &wp));
   cudaGraph_t body = wp.conditional.phGraph_out[0];
-  if (!capture_stream) VNR_CUDA(cudaStreamCreateWithFlags(&capture_stream, cudaStreamNonBlocking));
-  VNR_CUDA(cudaStreamBeginCaptureToGraph(capture_stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
-  cudaError_t e = volume_src ? launch_volume_samples(volume_src, vol->dims, samples[0].p, samples[1].p, values.p, cnt + 2, round_dev, cap, capture_stream)
-                             : launch_decode_samples(vol->cfg.desc, vol->params.p, samples[0].p, samples[1].p, values.p, cnt + 2, round_dev, cap, capture_stream);
+  if (!S.capture_stream) VNR_CUDA(cudaStreamCreateWithFlags(&S.capture_stream, cudaStreamNonBlocking));
+  VNR_CUDA(cudaStreamBeginCaptureToGraph(S.capture_stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
+  cudaError_t e = volume_src ? launch_volume_samples(volume_src, vol->dims, S.samples[0].p, S.samples[1].p, S.values.p, cnt + 2, round_dev, cap, S.capture_stream)
+                             : launch_decode_samples(vol->cfg.desc, vol->params.p, S.samples[0].p, S.samples[1].p, S.values.p, cnt + 2, round_dev, cap, S.capture_stream);
   // (fusing this 1-thread kernel into the compositing kernel -- last CTA to finish sets the condition -- was measured
   // slower: 0.717 vs 0.693 ms/frame at 1024^2; a kernel that calls cudaGraphSetConditional pays for it in every CTA)
-  march_kernel(false, shade)<<<grid, 128, 0, capture_stream>>>(fpd, rb, samples[0].p, samples[1].p, values.p, cnt, 0, round_dev, accum.p);
-  advance_round_kernel<<<1, 1, 0, capture_stream>>>(cnt, round_dev, handle, 0, rounds);
+  march_kernel(false, shade)<<<grid, 128, 0, S.capture_stream>>>(fpd, rb, S.samples[0].p, S.samples[1].p, S.values.p, cnt, 0, round_dev, S.accum.p);
+  advance_round_kernel<<<1, 1, 0, S.capture_stream>>>(cnt, round_dev, handle, 0, rounds);
   cudaGraph_t captured = nullptr;
-  cudaError_t e2 = cudaStreamEndCapture(capture_stream, &captured);
+  cudaError_t e2 = cudaStreamEndCapture(S.capture_stream, &captured);
   VNR_CUDA(e); VNR_CUDA(e2);
-  VNR_CUDA(cudaGraphInstantiate(&loop_exec[pass], loop_graph[pass], 0));
-  graph_key[pass] = key;
+  VNR_CUDA(cudaGraphInstantiate(&S.loop_exec[pass], S.loop_graph[pass], 0));
+  S.graph_key[pass] = key;
 }
 
 // The path-tracing wavefront (do_path_tracing_iterative, method_pathtracing.cu:796-812): raygen, then rounds of
 // [decode the sample queue -> shade + next delta-tracking step + compaction] until no ray is alive.  graph_loop: the
 // rounds are the body of a CUDA-graph WHILE node; otherwise the host reads the live count back every round (the
 // reference's loop; what profilers see).
-void Renderer::render_pathtracing(const float* volume_src, unsigned grid, size_t cap, bool graph_loop) {
-  uint32_t* cnt = counters.p;
-  const FrameParams* fpd = reinterpret_cast<const FrameParams*>(fp_dev.p);
-  PtBuffers pb{pt_org.p, pt_dir.p, pt_rad.p, pt_thr.p, pt_tn.p, pt_cell.p, pt_list[0].p, pt_list[1].p};
+void Renderer::render_pathtracing(FrameSlot& S, const float* volume_src, unsigned grid, size_t cap, bool graph_loop) {
+  cudaStream_t stream = S.stream;
+  uint32_t* cnt = S.counters.p;
+  const FrameParams* fpd = reinterpret_cast<const FrameParams*>(S.fp_dev.p);
+  PtBuffers pb{S.pt_org.p, S.pt_dir.p, S.pt_rad.p, S.pt_thr.p, S.pt_tn.p, S.pt_cell.p, S.pt_list[0].p, S.pt_list[1].p};
   const unsigned shade_grid = std::min<unsigned>(grid, (unsigned)num_sms() * 16u);
   auto decode = [&](cudaStream_t s) {
-    return volume_src ? launch_volume_samples(volume_src, vol->dims, samples[0].p, samples[1].p, values.p, cnt + kPtLive, cnt + kPtParity, cap, s)
-                      : launch_decode_samples(vol->cfg.desc, vol->params.p, samples[0].p, samples[1].p, values.p, cnt + kPtLive, cnt + kPtParity, cap, s);
+    return volume_src ? launch_volume_samples(volume_src, vol->dims, S.samples[0].p, S.samples[1].p, S.values.p, cnt + kPtLive, cnt + kPtParity, cap, s)
+                      : launch_decode_samples(vol->cfg.desc, vol->params.p, S.samples[0].p, S.samples[1].p, S.values.p, cnt + kPtLive, cnt + kPtParity, cap, s);
   };
-  pt_raygen_kernel<<<grid, 128, 0, stream>>>(fpd, pb, samples[0].p, cnt, accum.p);
+  pt_raygen_kernel<<<grid, 128, 0, stream>>>(fpd, pb, S.samples[0].p, cnt, S.accum.p);
   VNR_CUDA(cudaGetLastError());
   if (graph_loop) {
     GraphKey key;
     memset(&key, 0, sizeof key);
     key.desc = vol->cfg.desc; key.params = vol->params.p;
     key.ptrs[0] = pb.org; key.ptrs[1] = pb.dir; key.ptrs[2] = pb.radiance; key.ptrs[3] = pb.thr_rng; key.ptrs[4] = pb.tn; key.ptrs[5] = pb.cell;
-    key.ptrs[6] = pb.list0; key.ptrs[7] = pb.list1; key.ptrs[8] = samples[0].p; key.ptrs[9] = samples[1].p; key.ptrs[10] = values.p;
-    key.ptrs[11] = cnt; key.ptrs[12] = accum.p; key.ptrs[13] = fpd;
+    key.ptrs[6] = pb.list0; key.ptrs[7] = pb.list1; key.ptrs[8] = S.samples[0].p; key.ptrs[9] = S.samples[1].p; key.ptrs[10] = S.values.p;
+    key.ptrs[11] = cnt; key.ptrs[12] = S.accum.p; key.ptrs[13] = fpd;
     key.grid = shade_grid; key.cap = cap; key.volume_src = volume_src;
-    if (!pt_exec || memcmp(&key, &pt_key, sizeof key)) {
+    if (!S.pt_exec || memcmp(&key, &S.pt_key, sizeof key)) {
       VNR_CUDA(cudaStreamSynchronize(stream));
-      if (pt_exec) { cudaGraphExecDestroy(pt_exec); pt_exec = nullptr; }
-      if (pt_graph) { cudaGraphDestroy(pt_graph); pt_graph = nullptr; }
-      VNR_CUDA(cudaGraphCreate(&pt_graph, 0));
+      if (S.pt_exec) { cudaGraphExecDestroy(S.pt_exec); S.pt_exec = nullptr; }
+      if (S.pt_graph) { cudaGraphDestroy(S.pt_graph); S.pt_graph = nullptr; }
+      VNR_CUDA(cudaGraphCreate(&S.pt_graph, 0));
       cudaGraphConditionalHandle handle;
-      VNR_CUDA(cudaGraphConditionalHandleCreate(&handle, pt_graph, 0, 0));
+      VNR_CUDA(cudaGraphConditionalHandleCreate(&handle, S.pt_graph, 0, 0));
       cudaGraphNode_t init_node;
       {
         int init = 1, use = 1;
         void* args[] = {&cnt, &handle, &init, &use};
         cudaKernelNodeParams kp = {};
         kp.func = (void*)pt_advance_kernel; kp.gridDim = dim3(1); kp.blockDim = dim3(1); kp.kernelParams = args;
-        VNR_CUDA(cudaGraphAddKernelNode(&init_node, pt_graph, nullptr, 0, &kp));
+        VNR_CUDA(cudaGraphAddKernelNode(&init_node, S.pt_graph, nullptr, 0, &kp));
       }
       cudaGraphNodeParams wp = {};
       wp.type = cudaGraphNodeTypeConditional;
       wp.conditional.handle = handle; wp.conditional.type = cudaGraphCondTypeWhile; wp.conditional.size = 1;
       cudaGraphNode_t while_node;
-      VNR_CUDA(cudaGraphAddNode(&while_node, pt_graph, &init_node, 1, &wp));
+      VNR_CUDA(cudaGraphAddNode(&while_node, S.pt_graph, &init_node, 1, &wp));
       cudaGraph_t body = wp.conditional.phGraph_out[0];
-      if (!capture_stream) VNR_CUDA(cudaStreamCreateWithFlags(&capture_stream, cudaStreamNonBlocking));
-      VNR_CUDA(cudaStreamBeginCaptureToGraph(capture_stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
-      cudaError_t e = decode(capture_stream);
-      pt_shade_kernel<<<shade_grid, 128, 0, capture_stream>>>(fpd, pb, samples[0].p, samples[1].p, values.p, cnt, 0, cnt + kPtParity, accum.p);
-      pt_advance_kernel<<<1, 1, 0, capture_stream>>>(cnt, handle, 0, 1);
+      if (!S.capture_stream) VNR_CUDA(cudaStreamCreateWithFlags(&S.capture_stream, cudaStreamNonBlocking));
+      VNR_CUDA(cudaStreamBeginCaptureToGraph(S.capture_stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
+      cudaError_t e = decode(S.capture_stream);
+      pt_shade_kernel<<<shade_grid, 128, 0, S.capture_stream>>>(fpd, pb, S.samples[0].p, S.samples[1].p, S.values.p, cnt, 0, cnt + kPtParity, S.accum.p);
+      pt_advance_kernel<<<1, 1, 0, S.capture_stream>>>(cnt, handle, 0, 1);
       cudaGraph_t captured = nullptr;
-      cudaError_t e2 = cudaStreamEndCapture(capture_stream, &captured);
+      cudaError_t e2 = cudaStreamEndCapture(S.capture_stream, &captured);
       VNR_CUDA(e); VNR_CUDA(e2);
-      VNR_CUDA(cudaGraphInstantiate(&pt_exec, pt_graph, 0));
-      pt_key = key;
+      VNR_CUDA(cudaGraphInstantiate(&S.pt_exec, S.pt_graph, 0));
+      S.pt_key = key;
     }
-    VNR_CUDA(cudaGraphLaunch(pt_exec, stream));
-    launches = 0;
+    VNR_CUDA(cudaGraphLaunch(S.pt_exec, stream));
+    S.launches = 0;
   } else {
     cudaGraphConditionalHandle none = 0;
     pt_advance_kernel<<<1, 1, 0, stream>>>(cnt, none, 1, 0);
-    launches = 2;
+    S.launches = 2;
     for (uint32_t r = 0;; ++r) {
       uint32_t live = 0;                                               // iterative_ray_compaction (:789-794)
       VNR_CUDA(cudaMemcpyAsync(&live, cnt + kPtLive + (r & 1u), sizeof live, cudaMemcpyDeviceToHost, stream));
       VNR_CUDA(cudaStreamSynchronize(stream));
       if (!live) break;
       VNR_CUDA(decode(stream));
-      pt_shade_kernel<<<shade_grid, 128, 0, stream>>>(fpd, pb, samples[0].p, samples[1].p, values.p, cnt, 0, cnt + kPtParity, accum.p);
+      pt_shade_kernel<<<shade_grid, 128, 0, stream>>>(fpd, pb, S.samples[0].p, S.samples[1].p, S.values.p, cnt, 0, cnt + kPtParity, S.accum.p);
       pt_advance_kernel<<<1, 1, 0, stream>>>(cnt, none, 0, 0);
       VNR_CUDA(cudaGetLastError());
-      launches += 3;
+      S.launches += 3;
     }
   }
 }
@@ -679,122 +728,140 @@ void Renderer::render() {
     if (!vol->decoded.p) { vol->decoded.alloc((size_t)vol->dims[0] * vol->dims[1] * vol->dims[2]); vol->decoded.zero(vol->stream); vol->decode_blob = 0; }
     volume_src = vol->decoded.p;
   } else if (!vol->have_params) throw StateError("the neural volume has no parameters");
+  // the slot this frame runs in; a frame that was never mapped is overwritten (the stream orders the reuse of the buffers)
+  const int k = (int)(n_rendered % slots.size());
+  FrameSlot& S = slot(k);
+  FrameSlot& P = last();                                               // the previous frame: accumulation source when frame_index > 1
+  cudaStream_t stream = S.stream;
+  if (n_rendered - n_mapped >= slots.size()) n_mapped = n_rendered - slots.size() + 1;      // ring full: the oldest unmapped frame is dropped
   if (reset) frame_index = 0;
   frame_index++;
   reset = false;
   FrameParams fp[2]; fill_frame_params(fp[0]);
   // zero-copy download: finished pixels are stored straight into the pinned host frame map_frame() will return
   // (cudaMallocHost memory is device-addressable under UVA); the device frame buffer is then not written
-  const bool zc = zero_copy && download && !frame_target;
-  fp[0].frame = zc ? h_frame[cur] : frame_out();
+  const bool zc = zero_copy && download && !S.frame_target;
+  fp[0].frame = zc ? S.h_frame[S.cur] : S.frame_out();
+  fp[0].accum_prev = frame_index > 1 ? P.accum.p : nullptr;
   fp[0].shade_mode = shade; fp[1] = fp[0]; fp[1].shade_mode = 3;
   const uint32_t n_rays = fp[0].n_rays;
   const int rounds = round_bound();
   const int n_pass = shade == 2 ? 2 : 1;
   // make the volume's pending work (training, tfn upload) visible to the frame stream
-  VNR_CUDA(cudaEventRecord(vol_ready, vol->stream));
-  VNR_CUDA(cudaStreamWaitEvent(stream, vol_ready, 0));
+  VNR_CUDA(cudaEventRecord(S.vol_ready, vol->stream));
+  VNR_CUDA(cudaStreamWaitEvent(stream, S.vol_ready, 0));
+  // progressive accumulation reads the previous frame's sums: wait for that frame when it ran in another slot
+  if (frame_index > 1 && &P != &S && P.rendered) VNR_CUDA(cudaStreamWaitEvent(stream, P.frame_done[P.mapped ? P.cur ^ 1 : P.cur], 0));
 
   // decoding modes, and a SimpleVolume in every mode but the sample-streaming ones, run the single-kernel marcher
   const bool single_kernel = decoding || (gt_source && mode != 5 && mode != 8 && mode != 11 && mode != 14);
   const size_t cap = (size_t)n_rays * n_iters * (shade == 1 ? 4 : 1);
   if (!single_kernel) {
-    samples[0].ensure(cap); samples[1].ensure(cap); values.ensure(cap);
+    S.samples[0].ensure(cap); S.samples[1].ensure(cap); S.values.ensure(cap);
     if (pathtracing) {
-      pt_org.ensure(n_rays); pt_dir.ensure(n_rays); pt_rad.ensure(n_rays); pt_thr.ensure(n_rays); pt_tn.ensure(n_rays); pt_cell.ensure(n_rays);
-      pt_list[0].ensure(n_rays); pt_list[1].ensure(n_rays);
-    } else { ray_rgba.ensure(n_rays); ray_tn.ensure(n_rays); ray_cell.ensure(n_rays); ray_state.ensure(n_rays); ray_jitter.ensure(n_rays); }
-    if (shade == 2) { ssh_org.ensure(n_rays); ssh_col.ensure(n_rays); ssh_rgba.ensure(n_rays); ssh_jitter.ensure(n_rays); }
+      S.pt_org.ensure(n_rays); S.pt_dir.ensure(n_rays); S.pt_rad.ensure(n_rays); S.pt_thr.ensure(n_rays); S.pt_tn.ensure(n_rays); S.pt_cell.ensure(n_rays);
+      S.pt_list[0].ensure(n_rays); S.pt_list[1].ensure(n_rays);
+    } else { S.ray_rgba.ensure(n_rays); S.ray_tn.ensure(n_rays); S.ray_cell.ensure(n_rays); S.ray_state.ensure(n_rays); S.ray_jitter.ensure(n_rays); }
+    if (shade == 2) { S.ssh_org.ensure(n_rays); S.ssh_col.ensure(n_rays); S.ssh_rgba.ensure(n_rays); S.ssh_jitter.ensure(n_rays); }
   }
   const size_t cstride = kMaxRounds + 4;
-  counters.ensure(2 * cstride);
+  S.counters.ensure(2 * cstride);
   if (rounds + 3 > kMaxRounds) throw UnsupportedError("sampling rate too high for the round bound");
-  VNR_CUDA(cudaMemsetAsync(counters.p, 0, counters.bytes(), stream));
-  RayBuffers rb{ray_rgba.p, ray_tn.p, ray_cell.p, ray_state.p, ray_jitter.p, ssh_org.p, ssh_col.p, ssh_rgba.p, ssh_jitter.p};
+  VNR_CUDA(cudaMemsetAsync(S.counters.p, 0, S.counters.bytes(), stream));
+  RayBuffers rb{S.ray_rgba.p, S.ray_tn.p, S.ray_cell.p, S.ray_state.p, S.ray_jitter.p, S.ssh_org.p, S.ssh_col.p, S.ssh_rgba.p, S.ssh_jitter.p};
   const unsigned grid = (n_rays + 127) / 128;
-  launches = 0;
-  prof_used = 0;
+  S.launches = 0;
+  S.prof_used = 0;
   if (profiling) {
-    while ((int)prof_events.size() < 2 * rounds * n_pass) { cudaEvent_t e; VNR_CUDA(cudaEventCreate(&e)); prof_events.push_back(e); }
+    while ((int)S.prof_events.size() < 2 * rounds * n_pass) { cudaEvent_t e; VNR_CUDA(cudaEventCreate(&e)); S.prof_events.push_back(e); }
   }
-  fp_dev.ensure(2 * sizeof(FrameParams));
+  S.fp_dev.ensure(2 * sizeof(FrameParams));
   // a few hundred bytes from pageable memory: staged by the driver at call time, ordered on the stream
-  VNR_CUDA(cudaMemcpyAsync(fp_dev.p, fp, sizeof fp, cudaMemcpyHostToDevice, stream));
+  VNR_CUDA(cudaMemcpyAsync(S.fp_dev.p, fp, sizeof fp, cudaMemcpyHostToDevice, stream));
   const bool graph_loop = use_graph && !profiling;
   if (single_kernel && n_rays) {
     const int3 d3 = make_int3(vol->dims[0], vol->dims[1], vol->dims[2]);
-    const FrameParams* fpd = reinterpret_cast<const FrameParams*>(fp_dev.p);
-    if (pathtracing) pt_volume_kernel<<<grid, 128, 0, stream>>>(fpd, volume_src, d3, counters.p, accum.p);
-    else if (shade == 1) march_volume_kernel<1><<<grid, 128, 0, stream>>>(fpd, volume_src, d3, counters.p, accum.p);
-    else if (shade == 2) march_volume_kernel<2><<<grid, 128, 0, stream>>>(fpd, volume_src, d3, counters.p, accum.p);
-    else march_volume_kernel<0><<<grid, 128, 0, stream>>>(fpd, volume_src, d3, counters.p, accum.p);
+    const FrameParams* fpd = reinterpret_cast<const FrameParams*>(S.fp_dev.p);
+    if (pathtracing) pt_volume_kernel<<<grid, 128, 0, stream>>>(fpd, volume_src, d3, S.counters.p, S.accum.p);
+    else if (shade == 1) march_volume_kernel<1><<<grid, 128, 0, stream>>>(fpd, volume_src, d3, S.counters.p, S.accum.p);
+    else if (shade == 2) march_volume_kernel<2><<<grid, 128, 0, stream>>>(fpd, volume_src, d3, S.counters.p, S.accum.p);
+    else march_volume_kernel<0><<<grid, 128, 0, stream>>>(fpd, volume_src, d3, S.counters.p, S.accum.p);
     VNR_CUDA(cudaGetLastError());
-    launches = 1;
+    S.launches = 1;
   }
-  if (pathtracing && !single_kernel && n_rays) render_pathtracing(volume_src, grid, cap, graph_loop);
+  if (pathtracing && !single_kernel && n_rays) render_pathtracing(S, volume_src, grid, cap, graph_loop);
   for (int pass = 0; pass < n_pass && n_rays && !single_kernel && !pathtracing; ++pass) {
     const int sh = pass == 1 ? 3 : shade;
-    uint32_t* cnt = counters.p + (size_t)pass * cstride;
-    const FrameParams* fpd = reinterpret_cast<const FrameParams*>(fp_dev.p) + pass;
-    march_kernel(true, sh)<<<grid, 128, 0, stream>>>(fpd, rb, samples[0].p, samples[1].p, nullptr, cnt, 0, nullptr, accum.p);
+    uint32_t* cnt = S.counters.p + (size_t)pass * cstride;
+    const FrameParams* fpd = reinterpret_cast<const FrameParams*>(S.fp_dev.p) + pass;
+    march_kernel(true, sh)<<<grid, 128, 0, stream>>>(fpd, rb, S.samples[0].p, S.samples[1].p, nullptr, cnt, 0, nullptr, S.accum.p);
     if (graph_loop) {
       // device-driven loop: WHILE (round has samples) { decode; compose + march; advance }
-      ensure_graph(pass, sh, rb, grid, cap, rounds, volume_src);
-      VNR_CUDA(cudaGraphLaunch(loop_exec[pass], stream));
+      ensure_graph(S, pass, sh, rb, grid, cap, rounds, volume_src);
+      VNR_CUDA(cudaGraphLaunch(S.loop_exec[pass], stream));
     } else {
       for (int r = 0; r < rounds; ++r) {
-        if (profiling) VNR_CUDA(cudaEventRecord(prof_events[prof_used++], stream));
-        if (volume_src) VNR_CUDA(launch_volume_samples(volume_src, vol->dims, samples[r & 1].p, nullptr, values.p, cnt + 2 + r, nullptr, cap, stream));
-        else VNR_CUDA(launch_decode_samples(vol->cfg.desc, vol->params.p, samples[r & 1].p, nullptr, values.p, cnt + 2 + r, nullptr, cap, stream));
-        if (profiling) VNR_CUDA(cudaEventRecord(prof_events[prof_used++], stream));
-        march_kernel(false, sh)<<<grid, 128, 0, stream>>>(fpd, rb, samples[0].p, samples[1].p, values.p, cnt, r + 1, nullptr, accum.p);
+        if (profiling) VNR_CUDA(cudaEventRecord(S.prof_events[S.prof_used++], stream));
+        if (volume_src) VNR_CUDA(launch_volume_samples(volume_src, vol->dims, S.samples[r & 1].p, nullptr, S.values.p, cnt + 2 + r, nullptr, cap, stream));
+        else VNR_CUDA(launch_decode_samples(vol->cfg.desc, vol->params.p, S.samples[r & 1].p, nullptr, S.values.p, cnt + 2 + r, nullptr, cap, stream));
+        if (profiling) VNR_CUDA(cudaEventRecord(S.prof_events[S.prof_used++], stream));
+        march_kernel(false, sh)<<<grid, 128, 0, stream>>>(fpd, rb, S.samples[0].p, S.samples[1].p, S.values.p, cnt, r + 1, nullptr, S.accum.p);
       }
     }
-    finalize_kernel<<<grid, 128, 0, stream>>>(fpd, rb, cnt + kMaxRounds + 3, accum.p, cnt, graph_loop ? cnt + kMaxRounds + 2 : nullptr);
+    finalize_kernel<<<grid, 128, 0, stream>>>(fpd, rb, cnt + kMaxRounds + 3, S.accum.p, cnt, graph_loop ? cnt + kMaxRounds + 2 : nullptr);
     VNR_CUDA(cudaGetLastError());
-    if (!graph_loop) launches += 2 + 2 * (uint64_t)rounds;     // graph path: counted from the device counters in stats()
+    if (!graph_loop) S.launches += 2 + 2 * (uint64_t)rounds;     // graph path: counted from the device counters in stats()
   }
-  last_graph = graph_loop && !single_kernel;
-  last_pt = pathtracing;
-  last_rounds = rounds;
-  last_passes = single_kernel ? 1 : n_pass;
+  S.last_graph = graph_loop && !single_kernel;
+  S.last_pt = pathtracing;
+  S.last_rounds = rounds;
+  S.last_passes = single_kernel ? 1 : n_pass;
   // framebuffer.download_async (renderer.cpp:133)
-  downloaded = false;
+  S.downloaded = false;
   if (download) {
-    if (!zc) VNR_CUDA(cudaMemcpyAsync(h_frame[cur], frame.p, frame.bytes(), cudaMemcpyDeviceToHost, stream));
-    downloaded = true;
+    if (!zc) VNR_CUDA(cudaMemcpyAsync(S.h_frame[S.cur], S.frame.p, S.frame.bytes(), cudaMemcpyDeviceToHost, stream));
+    S.downloaded = true;
   }
-  VNR_CUDA(cudaMemcpyAsync(h_counters, counters.p, sizeof(uint32_t) * 2 * cstride, cudaMemcpyDeviceToHost, stream));
-  VNR_CUDA(cudaEventRecord(frame_done[cur], stream));
-  rendered = true;
+  VNR_CUDA(cudaMemcpyAsync(S.h_counters, S.counters.p, sizeof(uint32_t) * 2 * cstride, cudaMemcpyDeviceToHost, stream));
+  VNR_CUDA(cudaEventRecord(S.frame_done[S.cur], stream));
+  S.rendered = true; S.mapped = false; S.frame_index = frame_index; S.vol_waited = false;
+  last_slot = k;
+  ++n_rendered;
 }
 
 // explicit framebuffer.download_async for callers that disabled the automatic one (multi-GPU rank 0
-// downloads after the peers' pixels have arrived)
+// downloads after the peers' pixels have arrived): the most recent frame
 void Renderer::download_now() {
-  if (!rendered) throw StateError("vnr_renderer_download called before vnr_render");
-  VNR_CUDA(cudaMemcpyAsync(h_frame[cur], frame.p, frame.bytes(), cudaMemcpyDeviceToHost, stream));
-  VNR_CUDA(cudaEventRecord(frame_done[cur], stream));
-  downloaded = true;
+  FrameSlot& S = last();
+  if (!S.rendered) throw StateError("vnr_renderer_download called before vnr_render");
+  VNR_CUDA(cudaMemcpyAsync(S.h_frame[S.cur], S.frame.p, S.frame.bytes(), cudaMemcpyDeviceToHost, S.stream));
+  VNR_CUDA(cudaEventRecord(S.frame_done[S.cur], S.stream));
+  S.downloaded = true; S.vol_waited = false;
 }
 
+// vnrRendererMapFrame (renderer.h:84-94): the oldest rendered frame that has not been mapped yet; with one slot that is
+// the frame of the last vnr_render.  The pointer stays valid until the second-next map of the same slot.
 const float* Renderer::map_frame() {
-  if (!rendered) throw StateError("vnr_map_frame called before vnr_render");
-  if (!downloaded) throw StateError("frame download is disabled on this renderer");
-  VNR_CUDA(cudaEventSynchronize(frame_done[cur]));                     // renderer.h:84-94
-  const float* p = reinterpret_cast<const float*>(h_frame[cur]);
-  cur ^= 1;                                                             // double-buffer swap
+  if (n_rendered == n_mapped) throw StateError(n_rendered ? "vnr_map_frame: every rendered frame has already been mapped" : "vnr_map_frame called before vnr_render");
+  FrameSlot& S = slot((int)(n_mapped % slots.size()));
+  if (!S.downloaded) throw StateError("frame download is disabled on this renderer");
+  VNR_CUDA(cudaEventSynchronize(S.frame_done[S.cur]));
+  const float* p = reinterpret_cast<const float*>(S.h_frame[S.cur]);
+  S.cur ^= 1;                                                           // double-buffer swap
+  S.mapped = true;
+  ++n_mapped;
   return p;
 }
 
 void Renderer::profile(float* decode_ms, int* decode_launches) {
-  VNR_CUDA(cudaStreamSynchronize(stream));
+  FrameSlot& S = last();
+  VNR_CUDA(cudaStreamSynchronize(S.stream));
   float total = 0.f; int n = 0;
-  for (int k = 0; k + 1 < prof_used; k += 2) {
-    const int pass = (k / 2) / last_rounds, r = (k / 2) % last_rounds;
-    if (h_counters[(size_t)pass * (kMaxRounds + 4) + 2 + r] == 0) continue;           // empty round: the kernel exits immediately
+  for (int k = 0; k + 1 < S.prof_used; k += 2) {
+    const int pass = (k / 2) / S.last_rounds, r = (k / 2) % S.last_rounds;
+    if (S.h_counters[(size_t)pass * (kMaxRounds + 4) + 2 + r] == 0) continue;           // empty round: the kernel exits immediately
     float ms = 0.f;
-    VNR_CUDA(cudaEventElapsedTime(&ms, prof_events[k], prof_events[k + 1]));
+    VNR_CUDA(cudaEventElapsedTime(&ms, S.prof_events[k], S.prof_events[k + 1]));
     total += ms; ++n;
   }
   if (decode_ms) *decode_ms = total;
@@ -802,21 +869,23 @@ void Renderer::profile(float* decode_ms, int* decode_launches) {
 }
 
 void Renderer::stats(uint64_t* s4) {
-  VNR_CUDA(cudaStreamSynchronize(stream));
+  FrameSlot& S = last();
+  VNR_CUDA(cudaStreamSynchronize(S.stream));
+  const uint32_t* h_counters = S.h_counters;
   uint64_t dec = 0, rounds = 0, comp = 0, leftover = 0;
-  if (last_pt) {                       // path tracer: every sample taken is one collision event; rounds counted on the device
+  if (S.last_pt) {                       // path tracer: every sample taken is one collision event; rounds counted on the device
     const bool wavefront = h_counters[kPtRounds] != 0;
     s4[0] = h_counters[0]; s4[1] = h_counters[1]; s4[2] = h_counters[1]; s4[3] = wavefront ? h_counters[kPtRounds] : 1;
-    if (last_graph) launches = 2 + 3 * (uint64_t)h_counters[kPtRounds];
+    if (S.last_graph) S.launches = 2 + 3 * (uint64_t)h_counters[kPtRounds];
     return;
   }
-  for (int pass = 0; pass < last_passes; ++pass) {
+  for (int pass = 0; pass < S.last_passes; ++pass) {
     const uint32_t* c = h_counters + (size_t)pass * (kMaxRounds + 4);
-    for (int r = 0; r <= last_rounds && r < kMaxRounds; ++r) { dec += c[2 + r]; if (c[2 + r]) ++rounds; }
+    for (int r = 0; r <= S.last_rounds && r < kMaxRounds; ++r) { dec += c[2 + r]; if (c[2 + r]) ++rounds; }
     comp += c[1]; leftover += c[kMaxRounds + 3];
   }
   // graph path: first round + loop init + 3 kernels per non-empty round + finalize, per pass
-  if (last_graph) launches = 3 * (uint64_t)last_passes + 3 * rounds;
+  if (S.last_graph) S.launches = 3 * (uint64_t)S.last_passes + 3 * rounds;
   s4[0] = h_counters[0]; s4[1] = dec; s4[2] = comp; s4[3] = rounds;
   if (leftover) throw StateError("round bound exceeded: " + std::to_string(leftover) + " rays were cut short");
 }

@@ -158,10 +158,20 @@ void sample_at(Volume* v, const float* d_xyz, float* d_out, size_t n, int hw_tex
 //   warps 16-23 two scatter groups (128 threads each): dL/d(encoding) of the PREVIOUS tiles from a ring of
 //               gradient tiles to the hash table (16-byte vector fp16 reductions)
 // so the gather, the MMA chain and the scatter of three different tiles overlap.
+//
+// The MMA chain of one tile (VAR 1) is 2*NH + 1 dependent round trips  MMA -> mbarrier -> tcgen05.ld -> epilogue ->
+// bar.sync -> next MMA:  NH hidden layers, the output layer + loss, and NH data-gradient steps.  What is NOT on that
+// chain: the data gradient through the 1-row output matrix is a rank-1 product and is formed by the loss epilogue
+// itself (d_NH = relu'(X_NH) * (g w_out), bit-identical to the tensor-core result: one exact fp16 x fp16 product
+// rounded once); the weight-gradient MMAs (8 K-steps of 16 samples per matrix) are issued AFTER the data-gradient
+// MMAs of the same step and signal a second mbarrier, which the epilogue only waits for right before it overwrites
+// X_m with d_m in place -- they run on the tensor pipe while the epilogue threads read TMEM and convert.
+// VAR 0 is the round-1 chain (2*NH + 2 round trips, weight gradients first); kept selectable for A/B runs.
 constexpr int kComputeThreads = 256;
 constexpr int kGatherGroupsT = 2, kScatterGroupsT = 2;
 constexpr int kTrainThreads = kComputeThreads + 128 * (kGatherGroupsT + kScatterGroupsT);
-constexpr int kX0Stages = 3, kDxStages = 2;
+constexpr int kMaxX0Stages = 3, kDxStages = 2;
+constexpr int kProfWords = 16;
 
 __device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
@@ -173,6 +183,13 @@ __device__ __forceinline__ void red_add_f16x4(__half* addr, uint2 v) {
 }
 __device__ __forceinline__ void red_add_f16x2(__half* addr, uint32_t v) {
   asm volatile("red.global.add.noftz.f16x2 [%0], %1;" ::"l"(addr), "r"(v) : "memory");
+}
+
+// measurement tap (flags & 8): a packed fp16 pair with subnormal components flushed to (signed) zero
+__device__ __forceinline__ uint32_t ftz_h2(uint32_t v) {
+  if ((v & 0x7C00u) == 0u) v &= 0xFFFF8000u;
+  if ((v & 0x7C000000u) == 0u) v &= 0x8000FFFFu;
+  return v;
 }
 
 // (half)((float)grad * weight) for a packed pair  (grid.h:331)
@@ -213,30 +230,41 @@ struct TrainArgs {
   float* mlp_partial;          // fp32 [gridDim.x][n_mlp], loss-scaled
   double* loss_accum;          // [0] running sum over steps, [1] this step
   float loss_scale;
+  uint32_t x0_stages;          // depth of the X_0 ring (3; 2 when the shared-memory budget asks for it)
+  uint32_t flags;              // measurement taps: 1 = scatter groups issue no reductions, 2 = gather groups issue no loads,
+                               // 4 = compute group runs no MMA chain (hand-over only), 8 = activation gradients below the fp16
+                               // normal range are flushed to zero (emulates an fp16-accumulating backward that loses subnormals),
+                               // 16 = forward epilogues skip the async-proxy fence (timing only; results undefined)
+  uint32_t* prof;              // measurement tap: kProfWords role timers per CTA (clock cycles), or nullptr
 };
 
-template <int F>
+// shared-memory tiles of the training CTA, in order: X_0 ring | X_1..X_NH | dy | d_NH (VAR 1) | dX_0 ring | weights
+__host__ __device__ inline uint32_t train_tiles(int n_hidden, int x0_stages, int var) { return (uint32_t)(x0_stages + n_hidden + 1 + (var ? 1 : 0) + kDxStages); }
+
+template <int F, int VAR>
 __global__ void __launch_bounds__(kTrainThreads, 1)
 train_step_kernel(const DecoderDesc d, const TrainArgs a) {
   using namespace tc05;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int NH = d.n_hidden;
-  uint8_t* x0_ring = smem;                                              // kX0Stages tiles: X_0 of the tiles in flight
-  uint8_t* xs = x0_ring + (size_t)kX0Stages * MlpSmem::kATile;          // X_1 .. X_NH of the tile being computed
-  uint8_t* dy = xs + (size_t)NH * MlpSmem::kATile;                      // dL/dy tile (column 0 = gradient)
-  uint8_t* dx_ring = dy + MlpSmem::kATile;                              // kDxStages tiles: dL/dX_0 (fp16) waiting for the scatter
+  const uint32_t XS = a.x0_stages;
+  uint8_t* x0_ring = smem;                                              // XS tiles: X_0 of the tiles in flight
+  uint8_t* xs = x0_ring + (size_t)XS * MlpSmem::kATile;                 // X_1 .. X_NH of the tile being computed
+  uint8_t* dy = xs + (size_t)NH * MlpSmem::kATile;                      // dL/dy tile (column 0 = gradient, the rest stays zero)
+  uint8_t* dN = dy + MlpSmem::kATile;                                   // VAR 1: d_NH, the gradient entering the last hidden layer
+  uint8_t* dx_ring = dy + (size_t)(VAR ? 2 : 1) * MlpSmem::kATile;      // kDxStages tiles: dL/dX_0 (fp16) waiting for the scatter
   uint8_t* ws = dx_ring + (size_t)kDxStages * MlpSmem::kATile;          // weight tiles
-  __shared__ uint64_t mbar;
-  __shared__ uint64_t x0_full[kX0Stages], x0_empty[kX0Stages], dx_full[kDxStages], dx_empty[kDxStages];
+  __shared__ uint64_t mbar, mbar_w;                                     // data path MMAs / weight-gradient MMAs (VAR 1)
+  __shared__ uint64_t x0_full[kMaxX0Stages], x0_empty[kMaxX0Stages], dx_full[kDxStages], dx_empty[kDxStages];
   __shared__ uint32_t tmem_slot;
   __shared__ double loss_part[kComputeThreads / 32];
 
   const int tid = threadIdx.x;
   const uint32_t tmem_cols = (64u * (uint32_t)(NH + 2)) <= 256u ? 256u : 512u;
   if (tid == 0) {
-    mbar_init(&mbar, 1);
-    for (int s = 0; s < kX0Stages; ++s) { mbar_init(&x0_full[s], 128); mbar_init(&x0_empty[s], 1); }
+    mbar_init(&mbar, 1); mbar_init(&mbar_w, 1);
+    for (int s = 0; s < kMaxX0Stages; ++s) { mbar_init(&x0_full[s], 128); mbar_init(&x0_empty[s], 1); }
     for (int s = 0; s < kDxStages; ++s) { mbar_init(&dx_full[s], kComputeThreads); mbar_init(&dx_empty[s], 128); }
     fence_mbar_init();
   }
@@ -250,40 +278,53 @@ train_step_kernel(const DecoderDesc d, const TrainArgs a) {
   const uint32_t tmem_base = tmem_slot;
   const uint32_t n_tiles = a.n / kTile;
   const uint32_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;   // tile j = blockIdx.x + j * gridDim.x
+  uint32_t* prof = a.prof ? a.prof + (size_t)blockIdx.x * kProfWords : nullptr;
 
   if (tid >= kComputeThreads + 128 * kGatherGroupsT) {
     // ---------------- scatter groups: dL/dX_0 rows -> hash-table gradient reductions ----------------
     const uint32_t sg = (uint32_t)(tid - kComputeThreads - 128 * kGatherGroupsT) >> 7, row = (uint32_t)tid & 127u;
     __half* __restrict__ ggrid = a.grid_grads;
+    uint32_t t_wait = 0, t_work = 0;
     for (uint32_t j = sg; j < my_tiles; j += kScatterGroupsT) {
       const uint32_t stage = j % kDxStages, use = j / kDxStages;
       const uint32_t s = (blockIdx.x + j * gridDim.x) * kTile + row;
       const float x = __ldg(a.coords + 3 * (size_t)s), y = __ldg(a.coords + 3 * (size_t)s + 1), z = __ldg(a.coords + 3 * (size_t)s + 2);
+      const uint32_t c0 = prof ? (uint32_t)clock() : 0u;
       mbar_wait(&dx_full[stage], use & 1u);
+      const uint32_t c1 = prof ? (uint32_t)clock() : 0u;
       const uint8_t* rowp = dx_ring + (size_t)stage * MlpSmem::kATile + row * 128u;
       const uint32_t sw = row & 7u;
-      for (int l = 0; l < d.n_levels; ++l) {
-        const uint8_t* src = rowp + feat_offset<F>((uint32_t)l, sw);
-        if constexpr (F == 8) { const uint4 g = *reinterpret_cast<const uint4*>(src); const uint32_t gg[4] = {g.x, g.y, g.z, g.w}; scatter_level<8>(d.lv[l], ggrid, x, y, z, gg); }
-        else if constexpr (F == 4) { const uint2 g = *reinterpret_cast<const uint2*>(src); const uint32_t gg[2] = {g.x, g.y}; scatter_level<4>(d.lv[l], ggrid, x, y, z, gg); }
-        else if constexpr (F == 2) { const uint32_t gg[1] = {*reinterpret_cast<const uint32_t*>(src)}; scatter_level<2>(d.lv[l], ggrid, x, y, z, gg); }
-        else { const uint32_t gg[1] = {(uint32_t)*reinterpret_cast<const unsigned short*>(src)}; scatter_level<1>(d.lv[l], ggrid, x, y, z, gg); }
+      if (!(a.flags & 1u)) {
+        for (int l = 0; l < d.n_levels; ++l) {
+          const uint8_t* src = rowp + feat_offset<F>((uint32_t)l, sw);
+          if constexpr (F == 8) { const uint4 g = *reinterpret_cast<const uint4*>(src); const uint32_t gg[4] = {g.x, g.y, g.z, g.w}; scatter_level<8>(d.lv[l], ggrid, x, y, z, gg); }
+          else if constexpr (F == 4) { const uint2 g = *reinterpret_cast<const uint2*>(src); const uint32_t gg[2] = {g.x, g.y}; scatter_level<4>(d.lv[l], ggrid, x, y, z, gg); }
+          else if constexpr (F == 2) { const uint32_t gg[1] = {*reinterpret_cast<const uint32_t*>(src)}; scatter_level<2>(d.lv[l], ggrid, x, y, z, gg); }
+          else { const uint32_t gg[1] = {(uint32_t)*reinterpret_cast<const unsigned short*>(src)}; scatter_level<1>(d.lv[l], ggrid, x, y, z, gg); }
+        }
       }
       mbar_arrive(&dx_empty[stage]);
+      if (prof) { t_wait += c1 - c0; t_work += (uint32_t)clock() - c1; }
     }
+    if (prof && row == 0 && sg == 0) { prof[8] = t_wait; prof[9] = t_work; }
   } else if (tid >= kComputeThreads) {
     // ---------------- gather groups: hash-grid features -> X_0 ring ----------------
     const uint32_t gg = (uint32_t)(tid - kComputeThreads) >> 7, row = (uint32_t)tid & 127u;
     const __half* __restrict__ grid = a.params + d.n_mlp;
+    uint32_t t_wait = 0, t_work = 0;
     for (uint32_t j = gg; j < my_tiles; j += kGatherGroupsT) {
-      const uint32_t stage = j % kX0Stages, use = j / kX0Stages;
+      const uint32_t stage = j % XS, use = j / XS;
       const uint32_t s = (blockIdx.x + j * gridDim.x) * kTile + row;
       const float x = __ldg(a.coords + 3 * (size_t)s), y = __ldg(a.coords + 3 * (size_t)s + 1), z = __ldg(a.coords + 3 * (size_t)s + 2);
+      const uint32_t c0 = prof ? (uint32_t)clock() : 0u;
       if (use > 0) mbar_wait(&x0_empty[stage], (use - 1u) & 1u);
-      encode_row<F, false>(x0_ring + (size_t)stage * MlpSmem::kATile, d, grid, x, y, z, row);
+      const uint32_t c1 = prof ? (uint32_t)clock() : 0u;
+      if (!(a.flags & 2u)) encode_row<F, false>(x0_ring + (size_t)stage * MlpSmem::kATile, d, grid, x, y, z, row);
       fence_async_smem();
       mbar_arrive(&x0_full[stage]);
+      if (prof) { t_wait += c1 - c0; t_work += (uint32_t)clock() - c1; }
     }
+    if (prof && row == 0 && gg == 0) { prof[6] = t_wait; prof[7] = t_work; }
   } else {
     // ---------------- compute group ----------------
     const uint32_t row = (uint32_t)tid & 127u;
@@ -291,25 +332,44 @@ train_step_kernel(const DecoderDesc d, const TrainArgs a) {
     const uint32_t warp = (uint32_t)tid >> 5;
     const uint32_t t_row = tmem_base + (((warp & 3u) * 32u) << 16);      // my TMEM lane quarter
     const uint32_t col0 = hlf * 32u;
-    uint32_t phase = 0;
+    uint32_t phase = 0, phase_w = 0;
     double loss_local = 0.0;
+    uint32_t t_x0 = 0, t_mma = 0, t_dx = 0, t_bar = 0, t_w = 0, t_ld = 0, t_st = 0, t_fe = 0;
+    const uint32_t t_begin = prof ? (uint32_t)clock() : 0u;
+    // timed waits (tap): the timers are only meaningful in thread 0, which also issues the MMAs
+    auto wait_t = [&](uint64_t* b, uint32_t parity, uint32_t& acc) {
+      if (prof) { const uint32_t c = (uint32_t)clock(); mbar_wait(b, parity); acc += (uint32_t)clock() - c; }
+      else mbar_wait(b, parity);
+    };
+    auto bar_t = [&]() {
+      if (prof) { const uint32_t c = (uint32_t)clock(); bar_compute(); t_bar += (uint32_t)clock() - c; }
+      else bar_compute();
+    };
 
     constexpr uint32_t idesc_fwd = make_idesc_f16(kTile, kWidth, 0, 0);       // A K-major, B K-major
     constexpr uint32_t idesc_out = make_idesc_f16(kTile, kOutPad, 0, 0);
     constexpr uint32_t idesc_dgrad = make_idesc_f16(kTile, kWidth, 0, 1);     // A K-major, B MN-major (W read transposed)
     constexpr uint32_t idesc_wgrad = make_idesc_f16(64, kWidth, 1, 1);        // both MN-major: D[out][in] += d^T X
 
-    const uint32_t x0_addr = smem_u32(x0_ring), xs_addr = smem_u32(xs), dy_addr = smem_u32(dy), ws_addr = smem_u32(ws);
+    const uint32_t x0_addr = smem_u32(x0_ring), xs_addr = smem_u32(xs), dy_addr = smem_u32(dy), dN_addr = smem_u32(dN), ws_addr = smem_u32(ws);
     auto w_addr = [&](int m) { return ws_addr + (uint32_t)m * MlpSmem::kWHidden; };   // m == NH: output matrix
     auto acc_col = [&](int m) { return tmem_base + 64u * (uint32_t)(m + 1); };
 
     for (uint32_t j = 0; j < my_tiles; ++j) {
       const uint32_t s = (blockIdx.x + j * gridDim.x) * kTile + row;
-      const uint32_t xstage = j % kX0Stages;
+      const uint32_t xstage = j % XS;
       const uint32_t x0a = x0_addr + xstage * MlpSmem::kATile;
       auto x_addr = [&](int l) { return l == 0 ? x0a : xs_addr + (uint32_t)(l - 1) * MlpSmem::kATile; };
       auto x_ptr = [&](int l) { return l == 0 ? x0_ring + (size_t)xstage * MlpSmem::kATile : xs + (size_t)(l - 1) * MlpSmem::kATile; };
-      mbar_wait(&x0_full[xstage], (j / kX0Stages) & 1u);
+      wait_t(&x0_full[xstage], (j / XS) & 1u, t_x0);
+      const uint32_t dstage = j % kDxStages, duse = j / kDxStages;
+      if (a.flags & 4u) {                                         // tap: hand the tiles over without computing
+        bar_compute();                                            // every thread has seen this phase of x0_full before the stage is released
+        if (tid == 0) mbar_arrive(&x0_empty[xstage]);
+        if (duse > 0) wait_t(&dx_empty[dstage], (duse - 1u) & 1u, t_dx);
+        mbar_arrive(&dx_full[dstage]);
+        continue;
+      }
 
       // ---- forward: X_{l+1} = relu(X_l W_l^T)
       for (int l = 0; l < NH; ++l) {
@@ -320,11 +380,13 @@ train_step_kernel(const DecoderDesc d, const TrainArgs a) {
           for (int k = 0; k < ksteps; ++k) mma_f16_ss(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc_fwd, k > 0);
           mma_commit(&mbar);
         }
-        mbar_wait(&mbar, phase); phase ^= 1u;
+        wait_t(&mbar, phase, t_mma); phase ^= 1u;
         fence_after_sync();
+        const uint32_t c_ld = prof ? (uint32_t)clock() : 0u;
         uint32_t r[32];
         tmem_ld32(t_row + col0, r);
         tmem_ld_wait();
+        const uint32_t c_st = prof ? (uint32_t)clock() : 0u;
         uint8_t* dst = x_ptr(l + 1);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -332,9 +394,11 @@ train_step_kernel(const DecoderDesc d, const TrainArgs a) {
                                      relu_pack(r[8 * c + 4], r[8 * c + 5]), relu_pack(r[8 * c + 6], r[8 * c + 7]));
           *reinterpret_cast<uint4*>(dst + sw128_off(row, hlf * 4u + (uint32_t)c)) = v;
         }
+        const uint32_t c_fe = prof ? (uint32_t)clock() : 0u;
         fence_before_sync();
-        fence_async_smem();
-        bar_compute();
+        if (!(a.flags & 16u)) fence_async_smem();
+        if (prof) { const uint32_t c_end = (uint32_t)clock(); t_ld += c_st - c_ld; t_st += c_fe - c_st; t_fe += c_end - c_fe; }
+        bar_t();
       }
       // ---- output layer + L1 loss (l1.h:40-76): prediction is fp16; gradient = 128 * sign / N in fp16
       if (tid == 0) {
@@ -344,93 +408,192 @@ train_step_kernel(const DecoderDesc d, const TrainArgs a) {
         for (int k = 0; k < 4; ++k) mma_f16_ss(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc_out, k > 0);
         mma_commit(&mbar);
       }
-      mbar_wait(&mbar, phase); phase ^= 1u;
+      wait_t(&mbar, phase, t_mma); phase ^= 1u;
       fence_after_sync();
-      if (hlf == 0) {
-        const uint32_t raw = tmem_ld1(t_row);
-        tmem_ld_wait();
-        const float pred = __half2float(__float2half_rn(__uint_as_float(raw)));
-        const float diff = pred - a.targets[s];
-        loss_local += (double)__fdiv_rn(fabsf(diff), (float)a.n_global);
-        const __half g = __float2half_rn(__fdiv_rn(a.loss_scale * copysignf(1.0f, diff), (float)a.n_global));
-        *reinterpret_cast<__half*>(dy + row * 128u + ((row & 7u) << 4)) = g;          // column 0 of the swizzled row
-      }
-      fence_before_sync();
-      fence_async_smem();
-      bar_compute();
 
-      // ---- backward through the output matrix and the hidden matrices NH-1 .. 1
-      for (int m = NH; m >= 1; --m) {
-        // input of matrix m is X_m; its output gradient lives in `dy` (m == NH) or X_{m+1} (in place)
-        const uint32_t dsrc = m == NH ? dy_addr : x_addr(m + 1);
-        if (tid == 0) {
-          fence_after_sync();
-          const uint64_t dmn = make_desc_sw128(dsrc), xmn = make_desc_sw128(x_addr(m)), wmn = make_desc_sw128(w_addr(m));
-          // weight gradient: acc_m[out][in] += sum_s d[s][out] * X_m[s][in]   (K = 128 samples, 8 steps of 16 rows)
-#pragma unroll
-          for (int k = 0; k < 8; ++k) mma_f16_ss(acc_col(m), dmn + (uint64_t)(128 * k), xmn + (uint64_t)(128 * k), idesc_wgrad, (j > 0 || k > 0));
-          // data gradient: D[s][in] = sum_out d[s][out] * W_m[out][in]
-          const int ksteps = m == NH ? 1 : 4;
-          for (int k = 0; k < ksteps; ++k) mma_f16_ss(tmem_base, dmn + (uint64_t)(2 * k), wmn + (uint64_t)(128 * k), idesc_dgrad, k > 0);
-          mma_commit(&mbar);
-        }
-        mbar_wait(&mbar, phase); phase ^= 1u;
-        fence_after_sync();
-        uint32_t r[32];
-        tmem_ld32(t_row + col0, r);
-        tmem_ld_wait();
-        uint8_t* xm = x_ptr(m);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint4* p = reinterpret_cast<uint4*>(xm + sw128_off(row, hlf * 4u + (uint32_t)c));
-          const uint4 fwd = *p;                                   // forward activations (post-ReLU) of these 8 columns
-          const uint32_t fw[4] = {fwd.x, fwd.y, fwd.z, fwd.w};
-          uint32_t o[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            __half2 g = __floats2half2_rn(__uint_as_float(r[8 * c + 2 * q]), __uint_as_float(r[8 * c + 2 * q + 1]));
-            const __half2 mask = __hgt2(u32_as_h2(fw[q]), __float2half2_rn(0.f));       // 1.0 where forward > 0
-            g = __hmul2(g, mask);
-            o[q] = h2_as_u32(g);
-          }
-          *p = make_uint4(o[0], o[1], o[2], o[3]);                // X_m := d_m (in place)
+      if constexpr (VAR == 0) {
+        if (hlf == 0) {
+          const uint32_t raw = tmem_ld1(t_row);
+          tmem_ld_wait();
+          const float pred = __half2float(__float2half_rn(__uint_as_float(raw)));
+          const float diff = pred - a.targets[s];
+          loss_local += (double)__fdiv_rn(fabsf(diff), (float)a.n_global);
+          const __half g = __float2half_rn(__fdiv_rn(a.loss_scale * copysignf(1.0f, diff), (float)a.n_global));
+          *reinterpret_cast<__half*>(dy + row * 128u + ((row & 7u) << 4)) = g;          // column 0 of the swizzled row
         }
         fence_before_sync();
         fence_async_smem();
-        bar_compute();
-      }
-      // ---- input matrix: weight gradient, and dL/d(encoding) handed to the scatter groups
-      if (tid == 0) {
+        bar_t();
+
+        // ---- backward through the output matrix and the hidden matrices NH-1 .. 1
+        for (int m = NH; m >= 1; --m) {
+          // input of matrix m is X_m; its output gradient lives in `dy` (m == NH) or X_{m+1} (in place)
+          const uint32_t dsrc = m == NH ? dy_addr : x_addr(m + 1);
+          if (tid == 0) {
+            fence_after_sync();
+            const uint64_t dmn = make_desc_sw128(dsrc), xmn = make_desc_sw128(x_addr(m)), wmn = make_desc_sw128(w_addr(m));
+            // weight gradient: acc_m[out][in] += sum_s d[s][out] * X_m[s][in]   (K = 128 samples, 8 steps of 16 rows)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) mma_f16_ss(acc_col(m), dmn + (uint64_t)(128 * k), xmn + (uint64_t)(128 * k), idesc_wgrad, (j > 0 || k > 0));
+            // data gradient: D[s][in] = sum_out d[s][out] * W_m[out][in]
+            const int ksteps = m == NH ? 1 : 4;
+            for (int k = 0; k < ksteps; ++k) mma_f16_ss(tmem_base, dmn + (uint64_t)(2 * k), wmn + (uint64_t)(128 * k), idesc_dgrad, k > 0);
+            mma_commit(&mbar);
+          }
+          wait_t(&mbar, phase, t_mma); phase ^= 1u;
+          fence_after_sync();
+          uint32_t r[32];
+          tmem_ld32(t_row + col0, r);
+          tmem_ld_wait();
+          uint8_t* xm = x_ptr(m);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint4* p = reinterpret_cast<uint4*>(xm + sw128_off(row, hlf * 4u + (uint32_t)c));
+            const uint4 fwd = *p;                                   // forward activations (post-ReLU) of these 8 columns
+            const uint32_t fw[4] = {fwd.x, fwd.y, fwd.z, fwd.w};
+            uint32_t o[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              __half2 g = __floats2half2_rn(__uint_as_float(r[8 * c + 2 * q]), __uint_as_float(r[8 * c + 2 * q + 1]));
+              const __half2 mask = __hgt2(u32_as_h2(fw[q]), __float2half2_rn(0.f));       // 1.0 where forward > 0
+              g = __hmul2(g, mask);
+              o[q] = h2_as_u32(g);
+            }
+            *p = make_uint4(o[0], o[1], o[2], o[3]);                // X_m := d_m (in place)
+          }
+          fence_before_sync();
+          fence_async_smem();
+          bar_t();
+        }
+        // ---- input matrix: weight gradient, and dL/d(encoding) handed to the scatter groups
+        if (tid == 0) {
+          fence_after_sync();
+          const uint64_t dmn = make_desc_sw128(x_addr(1)), xmn = make_desc_sw128(x_addr(0)), wmn = make_desc_sw128(w_addr(0));
+#pragma unroll
+          for (int k = 0; k < 8; ++k) mma_f16_ss(acc_col(0), dmn + (uint64_t)(128 * k), xmn + (uint64_t)(128 * k), idesc_wgrad, (j > 0 || k > 0));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) mma_f16_ss(tmem_base, dmn + (uint64_t)(2 * k), wmn + (uint64_t)(128 * k), idesc_dgrad, k > 0);
+          mma_commit(&mbar);
+        }
+        wait_t(&mbar, phase, t_mma); phase ^= 1u;
         fence_after_sync();
-        const uint64_t dmn = make_desc_sw128(x_addr(1)), xmn = make_desc_sw128(x_addr(0)), wmn = make_desc_sw128(w_addr(0));
+        if (tid == 0) mbar_arrive(&x0_empty[xstage]);               // every MMA that reads X_0 has completed
+      } else {
+        // ---- VAR 1.  Loss epilogue: both column halves of a row read the prediction (same TMEM lane), form g and the
+        // masked rank-1 data gradient d_NH[s][c] = relu'(X_NH[s][c]) * half(g_s * w_out[c]) for their 32 columns.
+        {
+          const uint32_t raw = tmem_ld1(t_row);
+          tmem_ld_wait();
+          const float pred = __half2float(__float2half_rn(__uint_as_float(raw)));
+          const float diff = pred - a.targets[s];
+          const __half g = __float2half_rn(__fdiv_rn(a.loss_scale * copysignf(1.0f, diff), (float)a.n_global));
+          if (hlf == 0) {
+            loss_local += (double)__fdiv_rn(fabsf(diff), (float)a.n_global);
+            *reinterpret_cast<__half*>(dy + row * 128u + ((row & 7u) << 4)) = g;        // column 0 of the swizzled row (wgrad operand)
+          }
+          const __half2 g2 = __half2half2(g);
+          const uint8_t* wout = ws + (size_t)NH * MlpSmem::kWHidden;                   // row 0 of the output matrix: chunks in place (row & 7 == 0)
+          const uint8_t* xn = x_ptr(NH);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) mma_f16_ss(acc_col(0), dmn + (uint64_t)(128 * k), xmn + (uint64_t)(128 * k), idesc_wgrad, (j > 0 || k > 0));
+          for (int c = 0; c < 4; ++c) {
+            const uint32_t chunk = hlf * 4u + (uint32_t)c;
+            const uint4 w4 = *reinterpret_cast<const uint4*>(wout + chunk * 16u);
+            const uint4 f4 = *reinterpret_cast<const uint4*>(xn + sw128_off(row, chunk));
+            const uint32_t wv[4] = {w4.x, w4.y, w4.z, w4.w}, fw[4] = {f4.x, f4.y, f4.z, f4.w};
+            uint32_t o[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) mma_f16_ss(tmem_base, dmn + (uint64_t)(2 * k), wmn + (uint64_t)(128 * k), idesc_dgrad, k > 0);
-        mma_commit(&mbar);
+            for (int q = 0; q < 4; ++q) {
+              const __half2 mask = __hgt2(u32_as_h2(fw[q]), __float2half2_rn(0.f));
+              o[q] = h2_as_u32(__hmul2(__hmul2(g2, u32_as_h2(wv[q])), mask));
+              if (a.flags & 8u) o[q] = ftz_h2(o[q]);
+            }
+            *reinterpret_cast<uint4*>(dN + sw128_off(row, chunk)) = make_uint4(o[0], o[1], o[2], o[3]);
+          }
+        }
+        fence_before_sync();
+        fence_async_smem();
+        bar_t();
+        // ---- backward: step m forms d_m = relu'(X_m) * (d_{m+1} W_m) (m >= 1) or dL/dX_0 (m == 0); d_{m+1} lives in
+        // dN (m + 1 == NH) or in place of X_{m+1}
+        for (int m = NH - 1; m >= 0; --m) {
+          if (tid == 0) {
+            fence_after_sync();
+            const uint32_t dsrc = (m + 1 == NH) ? dN_addr : x_addr(m + 1);
+            const uint64_t dmn = make_desc_sw128(dsrc), xmn = make_desc_sw128(x_addr(m)), wmn = make_desc_sw128(w_addr(m));
+            // data gradient first: it alone is on the dependent chain
+#pragma unroll
+            for (int k = 0; k < 4; ++k) mma_f16_ss(tmem_base, dmn + (uint64_t)(2 * k), wmn + (uint64_t)(128 * k), idesc_dgrad, k > 0);
+            mma_commit(&mbar);
+            if (m + 1 == NH) {      // output matrix: acc_NH[0][in] += sum_s g_s X_NH[s][in]  (rows 1.. of dy are zero)
+              const uint64_t gmn = make_desc_sw128(dy_addr), xn = make_desc_sw128(x_addr(NH));
+#pragma unroll
+              for (int k = 0; k < 8; ++k) mma_f16_ss(acc_col(NH), gmn + (uint64_t)(128 * k), xn + (uint64_t)(128 * k), idesc_wgrad, (j > 0 || k > 0));
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) mma_f16_ss(acc_col(m), dmn + (uint64_t)(128 * k), xmn + (uint64_t)(128 * k), idesc_wgrad, (j > 0 || k > 0));
+            mma_commit(&mbar_w);
+          }
+          wait_t(&mbar, phase, t_mma); phase ^= 1u;
+          fence_after_sync();
+          if (m == 0) break;
+          uint32_t r[32];
+          tmem_ld32(t_row + col0, r);
+          tmem_ld_wait();
+          uint8_t* xm = x_ptr(m);
+          uint4 out4[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint4 fwd = *reinterpret_cast<const uint4*>(xm + sw128_off(row, hlf * 4u + (uint32_t)c));
+            const uint32_t fw[4] = {fwd.x, fwd.y, fwd.z, fwd.w};
+            uint32_t o[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              __half2 g = __floats2half2_rn(__uint_as_float(r[8 * c + 2 * q]), __uint_as_float(r[8 * c + 2 * q + 1]));
+              const __half2 mask = __hgt2(u32_as_h2(fw[q]), __float2half2_rn(0.f));       // 1.0 where forward > 0
+              o[q] = h2_as_u32(__hmul2(g, mask));
+              if (a.flags & 8u) o[q] = ftz_h2(o[q]);
+            }
+            out4[c] = make_uint4(o[0], o[1], o[2], o[3]);
+          }
+          // the weight-gradient MMAs of this step still read X_m: wait for them, then X_m := d_m (in place)
+          wait_t(&mbar_w, phase_w, t_w); phase_w ^= 1u;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(xm + sw128_off(row, hlf * 4u + (uint32_t)c)) = out4[c];
+          fence_before_sync();
+          fence_async_smem();
+          bar_t();
+        }
       }
-      mbar_wait(&mbar, phase); phase ^= 1u;
-      fence_after_sync();
-      if (tid == 0) mbar_arrive(&x0_empty[xstage]);               // every MMA that reads X_0 has completed
+      // ---- dL/d(encoding): TMEM -> fp16 -> the scatter groups' ring
       {
-        const uint32_t dstage = j % kDxStages, duse = j / kDxStages;
-        if (duse > 0) mbar_wait(&dx_empty[dstage], (duse - 1u) & 1u);
+        if (duse > 0) wait_t(&dx_empty[dstage], (duse - 1u) & 1u, t_dx);
         uint32_t r[32];
         tmem_ld32(t_row + col0, r);
         tmem_ld_wait();
         uint8_t* dst = dx_ring + (size_t)dstage * MlpSmem::kATile;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          const uint4 v = make_uint4(h2_as_u32(__floats2half2_rn(__uint_as_float(r[8 * c + 0]), __uint_as_float(r[8 * c + 1]))),
-                                     h2_as_u32(__floats2half2_rn(__uint_as_float(r[8 * c + 2]), __uint_as_float(r[8 * c + 3]))),
-                                     h2_as_u32(__floats2half2_rn(__uint_as_float(r[8 * c + 4]), __uint_as_float(r[8 * c + 5]))),
-                                     h2_as_u32(__floats2half2_rn(__uint_as_float(r[8 * c + 6]), __uint_as_float(r[8 * c + 7]))));
+          uint4 v = make_uint4(h2_as_u32(__floats2half2_rn(__uint_as_float(r[8 * c + 0]), __uint_as_float(r[8 * c + 1]))),
+                               h2_as_u32(__floats2half2_rn(__uint_as_float(r[8 * c + 2]), __uint_as_float(r[8 * c + 3]))),
+                               h2_as_u32(__floats2half2_rn(__uint_as_float(r[8 * c + 4]), __uint_as_float(r[8 * c + 5]))),
+                               h2_as_u32(__floats2half2_rn(__uint_as_float(r[8 * c + 6]), __uint_as_float(r[8 * c + 7]))));
+          if (a.flags & 8u) v = make_uint4(ftz_h2(v.x), ftz_h2(v.y), ftz_h2(v.z), ftz_h2(v.w));
           *reinterpret_cast<uint4*>(dst + sw128_off(row, hlf * 4u + (uint32_t)c)) = v;
         }
         mbar_arrive(&dx_full[dstage]);                             // release: the scatter group acquires through the mbarrier
       }
+      if constexpr (VAR == 1) {
+        // the input matrix' weight-gradient MMAs read X_0 and d_1: once they are done the X_0 stage can be refilled and the
+        // next tile's epilogues may overwrite X_1..X_NH
+        wait_t(&mbar_w, phase_w, t_w); phase_w ^= 1u;
+        if (tid == 0) mbar_arrive(&x0_empty[xstage]);
+      }
       fence_before_sync();
-      bar_compute();                                               // TMEM column 0..63 is rewritten by the next tile's first MMA
+      bar_t();                                                     // TMEM column 0..63 is rewritten by the next tile's first MMA
+    }
+    if (prof && tid == 0) {
+      prof[0] = (uint32_t)clock() - t_begin; prof[1] = t_x0; prof[2] = t_mma; prof[3] = t_dx; prof[4] = t_bar; prof[5] = t_w;
+      prof[10] = my_tiles; prof[11] = t_ld; prof[12] = t_st; prof[13] = t_fe;
     }
 
     // ---- write this CTA's weight-gradient accumulators (TMEM, fp32) to its slice of mlp_partial.
@@ -447,7 +610,7 @@ train_step_kernel(const DecoderDesc d, const TrainArgs a) {
         tmem_ld32(acc_col(m) + ((q * 32u) << 16) + col0, r);
         tmem_ld_wait();
         const int o = (int)(q * 16u + lane);
-        if (lane < 16 && o < rows && my_tiles > 0) {
+        if (lane < 16 && o < rows && my_tiles > 0 && !(a.flags & 4u)) {
 #pragma unroll
           for (int k = 0; k < 32; ++k) {
             const int col = (int)col0 + k;
@@ -565,15 +728,30 @@ __global__ void __launch_bounds__(256) adam_grid_kernel(AdamArgs a, uint32_t n_m
 // host
 // ------------------------------------------------------------------------------------------
 
-template <int F>
-static void launch_train_t(Volume* v, const TrainArgs& a, uint32_t grid, cudaStream_t s) {
+// X_0 ring depth that fits the shared-memory budget (227 KB per CTA): 3 stages when they fit, else 2
+static int train_x0_stages(int n_hidden, int var) {
+  for (int xs = kMaxX0Stages; xs >= 2; --xs)
+    if (1024 + (size_t)train_tiles(n_hidden, xs, var) * MlpSmem::kATile + MlpSmem::weights_bytes(n_hidden) + 512 <= 227 * 1024) return xs;
+  return 0;
+}
+
+template <int F, int VAR>
+static void launch_train_v(Volume* v, TrainArgs& a, uint32_t grid, cudaStream_t s) {
   const DecoderDesc& d = v->cfg.desc;
-  const size_t smem = 1024 + (size_t)(kX0Stages + d.n_hidden + 1 + kDxStages) * MlpSmem::kATile + MlpSmem::weights_bytes(d.n_hidden);
+  const int xs = train_x0_stages(d.n_hidden, VAR);
+  if (!xs) throw UnsupportedError("n_hidden_layers too large for the fused training kernel");
+  a.x0_stages = (uint32_t)xs;
+  const size_t smem = 1024 + (size_t)train_tiles(d.n_hidden, xs, VAR) * MlpSmem::kATile + MlpSmem::weights_bytes(d.n_hidden);
   static size_t configured = 0;
-  if (smem > 226 * 1024) throw UnsupportedError("n_hidden_layers too large for the fused training kernel");
-  if (configured < smem) { VNR_CUDA(cudaFuncSetAttribute(train_step_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = smem; }
-  train_step_kernel<F><<<grid, kTrainThreads, smem, s>>>(d, a);
+  if (configured < smem) { VNR_CUDA(cudaFuncSetAttribute(train_step_kernel<F, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = smem; }
+  train_step_kernel<F, VAR><<<grid, kTrainThreads, smem, s>>>(d, a);
   VNR_CUDA(cudaGetLastError());
+}
+
+template <int F>
+static void launch_train_t(Volume* v, TrainArgs& a, uint32_t grid, cudaStream_t s) {
+  if (v->train_variant == 0) launch_train_v<F, 0>(v, a, grid, s);
+  else launch_train_v<F, 1>(v, a, grid, s);
 }
 
 uint32_t train_grid(const Volume* v, size_t n) { return (uint32_t)std::min<size_t>(n / kTile, (size_t)num_sms()); }
@@ -581,13 +759,17 @@ uint32_t train_grid(const Volume* v, size_t n) { return (uint32_t)std::min<size_
 void train_ensure_buffers(Volume* v) {
   const DecoderDesc& d = v->cfg.desc;
   if (!v->have_params) throw StateError("the neural volume has no parameters (call vnr_volume_init_params or load params)");
-  if (d.n_hidden + 2 > 8 || 1024 + (size_t)(kX0Stages + d.n_hidden + 1 + kDxStages) * MlpSmem::kATile + MlpSmem::weights_bytes(d.n_hidden) > 226 * 1024)
+  if (d.n_hidden + 2 > 8 || !train_x0_stages(d.n_hidden, v->train_variant ? 1 : 0))
     throw UnsupportedError("training supports n_hidden_layers <= 5 (shared-memory budget of the fused kernel)");
   v->grid_grads.ensure(d.n_grid);
   if (!v->grads_clean) { v->grid_grads.zero(v->stream); VNR_CUDA(cudaStreamSynchronize(v->stream)); v->grads_clean = true; }
   v->mlp_partial.ensure((size_t)num_sms() * d.n_mlp);
   v->mlp_grads.ensure(d.n_mlp);
+  if (v->train_prof_on) v->train_prof.ensure((size_t)num_sms() * kProfWords);
 }
+
+// measurement tap: role timers of the last training kernel, kProfWords words per CTA
+int train_profile_words() { return kProfWords; }
 
 // forward + loss + backward: leaves grid gradients (fp16) in grid_grads and the reduced MLP gradients
 // (fp32) in mlp_grads; n_global is the global batch size the loss is normalised by.
@@ -598,7 +780,9 @@ void train_grads(Volume* v, const float* d_xyz, const float* d_target, size_t n,
   TrainArgs a;
   a.params = v->params.p; a.coords = d_xyz; a.targets = d_target; a.n = (uint32_t)n; a.n_global = (uint32_t)n_global;
   a.grid_grads = v->grid_grads.p; a.mlp_partial = v->mlp_partial.p; a.loss_accum = v->loss_accum.p; a.loss_scale = 128.f;
+  a.x0_stages = kMaxX0Stages; a.flags = v->train_flags; a.prof = v->train_prof_on ? v->train_prof.p : nullptr;
   const uint32_t grid = train_grid(v, n);
+  if (a.prof) VNR_CUDA(cudaMemsetAsync(a.prof, 0, v->train_prof.bytes(), s));
   VNR_CUDA(cudaMemsetAsync(v->loss_accum.p + 1, 0, sizeof(double), s));
   switch (d.n_feat) {
     case 8: launch_train_t<8>(v, a, grid, s); break;
@@ -627,6 +811,9 @@ static AdamArgs begin_optimizer_step(Volume* v, cudaStream_t s) {
   a.lr = o.lr * v->lr_factor; a.beta1 = o.beta1; a.beta2 = o.beta2; a.eps = o.eps; a.l2_reg = o.l2_reg; a.loss_scale = 128.f;
   a.master = v->master.p; a.params = v->params.p; a.m1 = v->m1.p; a.m2 = v->m2.p; a.steps = v->steps.p;
   ++v->opt_step;
+  if (v->bias_beta1 != o.beta1 || v->bias_beta2 != o.beta2) {      // a new optimizer config (vnrNeuralVolumeSetModel): the table is stale
+    v->bias_filled = 0; v->bias_beta1 = o.beta1; v->bias_beta2 = o.beta2;
+  }
   if (v->opt_step + 1 > v->bias_filled) {
     if (v->opt_step + 1 > v->bias_tab.n) {
       VNR_CUDA(cudaStreamSynchronize(s));
@@ -643,6 +830,7 @@ static AdamArgs begin_optimizer_step(Volume* v, cudaStream_t s) {
 
 void optimizer_step(Volume* v, cudaStream_t s) {
   const DecoderDesc& d = v->cfg.desc;
+  wait_for_frames(v, s);                 // frames in flight still decode the current parameters
   const AdamArgs a = begin_optimizer_step(v, s);
   adam_mlp_from_grads_kernel<<<(d.n_mlp + 255) / 256, 256, 0, s>>>(a, d.n_mlp, v->mlp_grads.p);
   const size_t vecs = ((size_t)d.n_grid + 3) / 4;
@@ -725,6 +913,7 @@ __global__ void adam_mlp_dp_kernel(AdamArgs a, DpPtrs p, uint32_t n_mlp) {
 void dp_optimizer_step(Volume* v, cudaStream_t s) {
   if (v->dp_world < 1) throw StateError("data-parallel peers are not attached (vnr_volume_dp_attach)");
   const DecoderDesc& d = v->cfg.desc;
+  wait_for_frames(v, s);
   const AdamArgs a = begin_optimizer_step(v, s);
   DpPtrs p;
   p.rank = v->dp_rank; p.world = v->dp_world;

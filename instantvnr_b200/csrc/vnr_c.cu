@@ -146,6 +146,8 @@ VNR_EXPORT int vnr_volume_init_params(vnr_volume_t* vh, uint32_t seed) {
     std::vector<__half> h(n);
     for (size_t i = 0; i < n; ++i) h[i] = __float2half_rn(p[i]);
     v->master.alloc(n);
+    wait_for_frames(v, v->stream);
+    VNR_CUDA(cudaStreamSynchronize(v->stream));            // in-flight training kernels still write params / master, frames read params
     VNR_CUDA(cudaMemcpy(v->master.p, p.data(), n * sizeof(float), cudaMemcpyHostToDevice));
     VNR_CUDA(cudaMemcpy(v->params.p, h.data(), n * sizeof(__half), cudaMemcpyHostToDevice));
     v->have_params = true;
@@ -183,6 +185,8 @@ VNR_EXPORT int vnr_volume_set_params_f16(vnr_volume_t* vh, const uint16_t* h_par
     if (n != v->cfg.n_params()) throw InvalidError("Can't set params because CPU buffer has the wrong size.");   // trainer.h:283
     std::vector<__half> h(n);
     memcpy(h.data(), h_params, n * 2);
+    wait_for_frames(v, v->stream);
+    VNR_CUDA(cudaStreamSynchronize(v->stream));            // the copies below run on the legacy stream, which does not order against v->stream
     VNR_CUDA(cudaMemcpy(v->params.p, h.data(), n * 2, cudaMemcpyHostToDevice));
     upload_master_from_f16(v, h);            // params_fp[i] = (float)params_inference[i]  trainer.h:289-291
     v->have_params = true;

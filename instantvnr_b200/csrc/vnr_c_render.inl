@@ -73,8 +73,8 @@ VNR_EXPORT int vnr_renderer_device_frame(vnr_renderer_t* r, void** d_rgba, void*
   return guard([&] {
     Renderer* s = R(r);
     if (!d_rgba) throw InvalidError("null argument");
-    *d_rgba = s->frame.p;
-    if (stream_out) *reinterpret_cast<cudaStream_t*>(stream_out) = s->stream;
+    *d_rgba = s->last().frame.p;
+    if (stream_out) *reinterpret_cast<cudaStream_t*>(stream_out) = s->last().stream;
   });
 }
 VNR_EXPORT int vnr_renderer_stats(vnr_renderer_t* r, uint64_t* s4) { return guard([&] { if (!s4) throw InvalidError("null argument"); R(r)->stats(s4); }); }
@@ -84,9 +84,9 @@ VNR_EXPORT int vnr_renderer_round_counts(vnr_renderer_t* r, uint32_t* out, int m
   return guard([&] {
     Renderer* s = R(r);
     if (!out || max_rounds < 0) throw InvalidError("null argument");
-    VNR_CUDA(cudaStreamSynchronize(s->stream));
+    VNR_CUDA(cudaStreamSynchronize(s->last().stream));
     int used = 0;
-    for (int k = 0; k < max_rounds; ++k) { out[k] = k < kMaxRounds ? s->h_counters[2 + k] : 0u; if (out[k]) used = k + 1; }
+    for (int k = 0; k < max_rounds; ++k) { out[k] = k < kMaxRounds ? s->last().h_counters[2 + k] : 0u; if (out[k]) used = k + 1; }
     if (n_rounds) *n_rounds = used;
   });
 }
@@ -97,9 +97,19 @@ VNR_EXPORT int vnr_renderer_set_zero_copy(vnr_renderer_t* r, int on) { return gu
 VNR_EXPORT int vnr_renderer_download(vnr_renderer_t* r) { return guard([&] { R(r)->download_now(); }); }
 VNR_EXPORT int vnr_renderer_set_profiling(vnr_renderer_t* r, int on) { return guard([&] { R(r)->profiling = on != 0; }); }
 VNR_EXPORT int vnr_renderer_profile(vnr_renderer_t* r, float* decode_ms, int* decode_launches, uint64_t* kernel_launches) {
-  return guard([&] { Renderer* s = R(r); s->profile(decode_ms, decode_launches); if (kernel_launches) *kernel_launches = s->launches; });
+  return guard([&] { Renderer* s = R(r); s->profile(decode_ms, decode_launches); if (kernel_launches) *kernel_launches = s->last().launches; });
 }
-VNR_EXPORT int vnr_renderer_stream(vnr_renderer_t* r, void** stream) { return guard([&] { if (!stream) throw InvalidError("null argument"); *stream = (void*)R(r)->stream; }); }
+// the stream of the most recent frame's slot (with one frame in flight: THE stream of the renderer)
+VNR_EXPORT int vnr_renderer_stream(vnr_renderer_t* r, void** stream) { return guard([&] { if (!stream) throw InvalidError("null argument"); *stream = (void*)R(r)->last().stream; }); }
+// frame ring (MainRenderer's double buffer, renderer.h:84-94, generalised): n slots, each with its own stream and buffers
+VNR_EXPORT int vnr_renderer_set_frames_in_flight(vnr_renderer_t* r, int n) { return guard([&] { R(r)->set_frames_in_flight(n); }); }
+VNR_EXPORT int vnr_renderer_streams(vnr_renderer_t* r, void** streams, int max_streams, int* n_streams) {
+  return guard([&] {
+    Renderer* s = R(r);
+    if (n_streams) *n_streams = (int)s->slots.size();
+    for (int k = 0; streams && k < max_streams && k < (int)s->slots.size(); ++k) streams[k] = (void*)s->slot(k).stream;
+  });
+}
 VNR_EXPORT int vnr_renderer_set_n_iters(vnr_renderer_t* r, int n) {
   return guard([&] { if (n < 1 || n > 16) throw InvalidError("n_iters must be in [1,16]"); R(r)->n_iters = n; R(r)->reset = true; });
 }
@@ -114,8 +124,9 @@ VNR_EXPORT int vnr_renderer_set_graph(vnr_renderer_t* r, int on) { return guard(
 VNR_EXPORT int vnr_renderer_set_frame_target(vnr_renderer_t* r, void* d_rgba) {
   return guard([&] {
     Renderer* s = R(r);
-    VNR_CUDA(cudaStreamSynchronize(s->stream));
-    s->frame_target = reinterpret_cast<float4*>(d_rgba);
+    s->sync_all();
+    if (s->slots.size() != 1) throw StateError("vnr_renderer_set_frame_target addresses a renderer with one frame in flight (multi-frame rings: vnr_comm)");
+    s->slot(0).frame_target = reinterpret_cast<float4*>(d_rgba);
     s->reset = true;
   });
 }

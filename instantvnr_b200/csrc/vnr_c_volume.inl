@@ -63,21 +63,29 @@ VNR_EXPORT int vnr_volume_load_params(vnr_volume_t* vh, const void* bson, size_t
       if (get_int(d, "x") != v->dims[0] || get_int(d, "y") != v->dims[1] || get_int(d, "z") != v->dims[2])
         throw InvalidError("mismatch data dimension");                                                   // network.cu:892
     }
+    bool model_reset = false;
     if (root.contains("model")) {
-      // deserialize_model (tcnn_network.h:163-221): the network is rebuilt from the stored config; the optimizer
-      // options are not part of the file and stay as they are.
+      // deserialize_model (tcnn_network.h:163-221) ALWAYS rebuilds loss, optimizer, network and trainer from the stored config:
+      // fresh Adam moments and per-parameter step counters, m_steps = 0, loss accumulators cleared -- also when the
+      // architecture is unchanged.  The optimizer options are not part of the file ("optimizer" absent -> m_optimizer_opts).
       std::string text; mj::dump(root.at("model"), text);
       ModelConfig c = parse_model_config(text);
       const DecoderDesc &a = c.desc, &b = v->cfg.desc;
       const bool same = a.n_levels == b.n_levels && a.n_feat == b.n_feat && a.n_hidden == b.n_hidden && a.n_grid == b.n_grid && a.n_mlp == b.n_mlp &&
                         c.base_res == v->cfg.base_res && c.per_level_scale == v->cfg.per_level_scale;
       if (!same) {
+        if (v->dp_world) throw StateError("detach the data-parallel peers before loading parameters of a different model");
         c.opt = v->cfg.opt;
-        v->cfg = c;
         VNR_CUDA(cudaStreamSynchronize(v->stream));
+        VNR_CUDA(cudaDeviceSynchronize());                  // renderers of this volume may still be decoding the old table
+        v->cfg = c;
         v->params.alloc(c.n_params());
-        v->have_params = false; v->have_opt = false;
+        v->master.release(); v->m1.release(); v->m2.release(); v->steps.release();
+        v->grid_grads.release(); v->mlp_grads.release(); v->mlp_partial.release();
+        v->have_params = false; v->grads_clean = false; v->decode_blob = 0;
       }
+      v->have_opt = false;
+      model_reset = true;
     }
     const mj::Value& P = root.contains("parameters") ? root.at("parameters") : root;                   // old format: params at the root
     if (!P.contains("params_binary") || P.at("params_binary").type != mj::Value::Binary) throw InvalidError("params blob has no params_binary");
@@ -101,10 +109,12 @@ VNR_EXPORT int vnr_volume_load_params(vnr_volume_t* vh, const void* bson, size_t
     }
     std::vector<__half> h(blob.size() / 2);
     memcpy(h.data(), blob.data(), h.size() * 2);
+    wait_for_frames(v, v->stream);
+    VNR_CUDA(cudaStreamSynchronize(v->stream));            // in-flight training kernels still write params / master, frames read params
     VNR_CUDA(cudaMemcpy(v->params.p, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
     upload_master_from_f16(v, h);
     v->have_params = true;
-    if (!v->have_opt) reset_optimizer(v);
+    if (!v->have_opt || model_reset) reset_optimizer(v);
   });
 }
 
@@ -240,6 +250,7 @@ VNR_EXPORT int vnr_volume_set_tfn(vnr_volume_t* vh, const float* rgb, int n_rgb,
     if (!(hi > lo)) throw InvalidError("empty transfer function value range");
     std::vector<float4> c(n_rgb);
     for (int i = 0; i < n_rgb; ++i) c[i] = make_float4(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2], 1.f);   // object.cpp:324-330
+    wait_for_frames(v, v->stream);                       // frames in flight still classify with the current tables
     VNR_CUDA(cudaStreamSynchronize(v->stream));
     v->tfn_color.alloc(n_rgb); v->tfn_alpha.alloc(n_alpha);
     if (n_rgb) VNR_CUDA(cudaMemcpyAsync(v->tfn_color.p, c.data(), n_rgb * sizeof(float4), cudaMemcpyHostToDevice, v->stream));
@@ -464,5 +475,27 @@ VNR_EXPORT int vnr_volume_get_decoded(vnr_volume_t* vh, float* h_out) {
     if (!v->decoded.p) throw StateError("nothing has been decoded yet");
     VNR_CUDA(cudaStreamSynchronize(v->stream));
     VNR_CUDA(cudaMemcpy(h_out, v->decoded.p, v->decoded.bytes(), cudaMemcpyDeviceToHost));
+  });
+}
+
+// ---- measurement taps of the training kernel ------------------------------------------------------
+VNR_EXPORT int vnr_volume_train_debug(vnr_volume_t* vh, int variant, uint32_t flags, int profile) {
+  return guard([&] {
+    Volume* v = V(vh);
+    if (variant != 0 && variant != 1) throw InvalidError("unknown training-kernel variant");
+    VNR_CUDA(cudaStreamSynchronize(v->stream));
+    v->train_variant = variant; v->train_flags = flags; v->train_prof_on = profile != 0;
+  });
+}
+VNR_EXPORT int vnr_volume_train_profile(vnr_volume_t* vh, uint32_t* out, size_t max_words, int* n_ctas, int* words_per_cta) {
+  return guard([&] {
+    Volume* v = V(vh);
+    const int wpc = train_profile_words();
+    if (n_ctas) *n_ctas = (int)(v->train_prof.n / (size_t)wpc);
+    if (words_per_cta) *words_per_cta = wpc;
+    if (!out) return;
+    VNR_CUDA(cudaStreamSynchronize(v->stream));
+    const size_t n = std::min(max_words, v->train_prof.n);
+    if (n) VNR_CUDA(cudaMemcpy(out, v->train_prof.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
   });
 }

@@ -37,7 +37,10 @@ struct Volume {
   DevBuf<float> mlp_partial;       // fp32 [n_cta][n_mlp] per-CTA weight-gradient partials
   bool grads_clean = false, grads_pending = false;
   DevBuf<uint32_t> steps;
-  DevBuf<float> bias_tab; uint32_t bias_filled = 0;   // Adam bias-correction table (train.cu)
+  DevBuf<float> bias_tab; uint32_t bias_filled = 0;   // Adam bias-correction table (train.cu) ...
+  float bias_beta1 = -1.f, bias_beta2 = -1.f;         // ... and the betas it was built with (refilled when the optimizer config changes)
+  // measurement taps of the training kernel (vnr_volume_train_debug): chain variant, role switches, per-CTA role timers
+  int train_variant = 1; uint32_t train_flags = 0; bool train_prof_on = false; DevBuf<uint32_t> train_prof;
   bool have_params = false, have_opt = false;
   uint32_t opt_step = 0; float lr_factor = 1.f;
   uint64_t train_step = 0;
@@ -67,6 +70,9 @@ struct Volume {
   int dp_rank = 0, dp_world = 0;
   void* dp_params[kMaxPeers] = {}; void* dp_grid_grads[kMaxPeers] = {}; void* dp_mlp_grads[kMaxPeers] = {};
 
+  // renderers created on this volume (they register themselves): what mutating entry points order against
+  std::vector<Renderer*> renderers;
+
   std::string blob;                // last serialized params.json
   std::string peek_json;
 
@@ -74,5 +80,10 @@ struct Volume {
   ~Volume();
   size_t cells() const { return (size_t)mc_dims[0] * mc_dims[1] * mc_dims[2]; }
 };
+
+// Ordering of volume-side writes against frames in flight: work enqueued on `s` after this call starts after the last
+// frame of every slot of every renderer of the volume has finished (render.cu).  The frame side already waits for the
+// volume's pending work (vol_ready), so train / render / train sequences are ordered in both directions without a host sync.
+void wait_for_frames(Volume* v, cudaStream_t s);
 
 }  // namespace vnr

@@ -228,3 +228,97 @@ def test_ray_order_and_slot_layout_do_not_change_the_frame(size):
             rows = [y for y in range(size[1]) if (y // 4) % 3 == rank]
             acc[rows] = part[rows]
         assert np.array_equal(acc, ref)
+
+
+def _ring_renderer(dims=(48, 48, 48), size=(80, 64)):
+    cfg = dict(log2_hashmap=14)
+    m, p16, dec, (lo, hi) = _scene(dims, cfg)
+    rgb, alpha = syn.make_tfn(64)
+    tr = (max(lo, 0.0), min(hi, 1.0))
+    vol = vnr.NeuralVolume(vnr.model_json(**cfg), dims)
+    vol.set_params_f16(p16)
+    vol.set_transfer_function(rgb, alpha, tr)
+    vol.set_macrocell(O.macrocell_update_implicit(np.clip(dec, 0, 1), dims))
+    ren = vnr.Renderer(vol)
+    ren.set_size(*size)
+    ren.set_mode(vnr.VNR_RAYMARCHING_NO_SHADING_SAMPLE_STREAMING)
+    return vol, ren
+
+
+def test_frames_in_flight_ring_is_fifo_and_bit_identical():
+    """vnr_renderer_set_frames_in_flight: consecutive vnr_render calls land in consecutive slots (own stream, buffers, graph);
+    vnr_map_frame returns the oldest unmapped frame; every frame equals the one-at-a-time frame bit for bit."""
+    dims = (48, 48, 48)
+    vol, ren = _ring_renderer(dims)
+    cams = [syn.default_camera(dims, v, 7) for v in range(7)]
+    single = []
+    for cam in cams:
+        ren.set_camera(*cam); ren.render(); single.append(ren.map_frame())
+    assert len({f.tobytes() for f in single}) == len(single)
+    for depth in (2, 3):
+        ren.set_frames_in_flight(depth)
+        assert len(ren.streams()) == depth and len(set(ren.streams())) == depth
+        got = []
+        for i, cam in enumerate(cams):               # keep `depth` frames in flight: map frame i - depth + 1 after launching frame i
+            ren.set_camera(*cam); ren.render()
+            if i >= depth - 1:
+                got.append(ren.map_frame())
+        while len(got) < len(cams):
+            got.append(ren.map_frame())
+        for a, b in zip(got, single):
+            assert np.array_equal(a, b)
+        with pytest.raises(vnr.VnrError):            # nothing left to map
+            ren.map_frame()
+    # a full ring drops the oldest frame
+    ren.set_frames_in_flight(2)
+    for cam in cams[:3]:
+        ren.set_camera(*cam); ren.render()
+    assert np.array_equal(ren.map_frame(), single[1]) and np.array_equal(ren.map_frame(), single[2])
+
+
+def test_accumulation_across_frame_slots():
+    """progressive accumulation (frame_index > 1) reads the previous frame's sums from the previous slot"""
+    dims = (48, 48, 48)
+    vol, ren = _ring_renderer(dims)
+    cam = syn.default_camera(dims, 2)
+    ren.set_camera(*cam)
+    want = []
+    for _ in range(4):
+        ren.render(); want.append(ren.map_frame())
+    assert not np.array_equal(want[0], want[3])      # jitter differs per frame index
+    ren.set_frames_in_flight(3)
+    ren.set_camera(*cam)
+    for _ in range(4):
+        ren.render()
+    # the ring holds the last three frames
+    got = [ren.map_frame() for _ in range(3)]
+    for a, b in zip(got, want[1:]):
+        assert np.array_equal(a, b)
+
+
+def test_second_map_without_render_raises():
+    vol, ren = _ring_renderer()
+    ren.set_camera(*syn.default_camera((48, 48, 48), 1))
+    with pytest.raises(vnr.VnrError):
+        ren.map_frame()
+    ren.render(); ren.map_frame()
+    with pytest.raises(vnr.VnrError):
+        ren.map_frame()
+
+
+def test_training_is_ordered_after_frames_in_flight():
+    """vnr_volume_train right after vnr_render (no map in between) must not change the frame: the optimizer waits on the
+    device for the frames that still decode the current parameters"""
+    dims = (48, 48, 48)
+    vol, ren = _ring_renderer(dims, size=(256, 256))
+    vol.set_groundtruth(syn.make_volume(dims, seed=3))
+    cam = syn.default_camera(dims, 1)
+    ren.set_camera(*cam)
+    ren.render(); want = ren.map_frame()
+    p0 = vol.get_params_f16()
+    ren.reset_accumulation()
+    ren.render()
+    vol.train(3, batch=4096, fast_mode=True)         # rewrites the parameters and (fast_mode, online macrocell) the value ranges
+    got = ren.map_frame()
+    assert np.array_equal(got, want)
+    assert not np.array_equal(vol.get_params_f16(), p0)
