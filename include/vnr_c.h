@@ -333,6 +333,42 @@ int vnr_peer_barrier_sync(void* barrier, void* stream);
 int vnr_peer_barrier_check(void* barrier, uint64_t* timed_out_epoch);
 void vnr_peer_barrier_release(void* barrier);
 
+/* ---- communicators: multi-GPU behind the same calls (SURVEY 8b `vnr_comm_init(n_devices)`; no reference counterpart, the
+ * reference runs on one GPU) -------------------------------------------------------------------------------------------
+ * One NVSwitch box, at most 8 GPUs.  Two ways to span them:
+ *   vnr_comm_init(n, comms[n])            one process, n devices: comms[r] belongs to device r.  Create the objects of
+ *                                         rank r with that device current (vnr_comm_set_device(comms[r])); afterwards every
+ *                                         entry point makes the object's device current itself.
+ *   vnr_comm_init_rank(rank, world, name) one process per GPU (torchrun, mpirun): the ranks meet in a POSIX shared-memory
+ *                                         segment called `name` (unique per job, e.g. "vnr-<port>-<launcher pid>"); the device
+ *                                         is the current one.
+ * Attaching is collective (every rank attaches its k-th volume / renderer; in the one-process form the exchange happens when
+ * the last rank attaches):
+ *   vnr_volume_attach_comm    rank 0's parameters, macrocell value ranges and sampler stream are replicated, the optimizer
+ *                             restarts (as a new Trainer), and vnr_volume_train(v, steps, batch, ..) becomes synchronous data
+ *                             parallel: `batch` samples PER RANK per step (rank r takes the r-th of `world` consecutive batches of
+ *                             the one sampler stream), loss normalised by the global batch, then reduce-scatter + Adam +
+ *                             all-gather in one kernel over NVLink peer memory; value ranges are merged at the end of the call.
+ *                             The result equals one process accumulating `world` consecutive batches per optimizer step.
+ *                             vnr_volume_stats / vnr_volume_last_loss report the loss of the global batch.
+ *   vnr_renderer_attach_comm  after vnr_renderer_set_size (+ frames in flight): rank r renders the image strips r, r + world, ..;
+ *                             finished pixels are stored by the compositing kernels into pinned host frames shared by all ranks
+ *                             (each GPU delivers its strips over its own PCIe link) or, with the download disabled, into rank
+ *                             0's device frame over NVLink; vnr_render on every rank, vnr_map_frame on rank 0.  Camera, mode,
+ *                             transfer function, sampling rate are set identically on every rank by the caller.
+ * Ordering between ranks is a stream-ordered peer barrier kernel; nothing goes through the host or a collective library. */
+typedef struct vnr_comm vnr_comm_t;
+int vnr_comm_init(int n_devices, vnr_comm_t** comms_out /* n_devices entries */);
+int vnr_comm_init_rank(int rank, int world, const char* rendezvous_name, vnr_comm_t** out);
+void vnr_comm_release(vnr_comm_t* c);
+int vnr_comm_info(vnr_comm_t* c, int* rank, int* world, int* device);
+int vnr_comm_set_device(vnr_comm_t* c);                 /* cudaSetDevice(the communicator's device) */
+int vnr_comm_barrier(vnr_comm_t* c);                    /* host barrier between the ranks (one process per GPU) */
+int vnr_volume_attach_comm(vnr_volume_t* v, vnr_comm_t* c);
+int vnr_volume_detach_comm(vnr_volume_t* v);
+int vnr_renderer_attach_comm(vnr_renderer_t* r, vnr_comm_t* c);
+int vnr_renderer_detach_comm(vnr_renderer_t* r);
+
 /* vnrMemoryQuery (api.h:186): bytes of device memory held by volumes / renderers */
 int vnr_memory_query(size_t* used_by_renderer, size_t* used_by_network);
 

@@ -109,6 +109,43 @@ def model_json(n_levels=8, n_features=8, log2_hashmap=19, base_res=16, n_hidden=
     return json.dumps(cfg)
 
 
+class Comm:
+    """vnr_comm_t: multi-GPU behind the same calls (include/vnr_c.h).  `Comm.init_rank` = one process per GPU,
+    `Comm.init_local` = one process driving n devices (returns one communicator per rank)."""
+
+    def __init__(self, handle):
+        self._h = handle
+
+    @staticmethod
+    def init_rank(rank, world, name):
+        h = C.c_void_p()
+        _check(lib().vnr_comm_init_rank(C.c_int(rank), C.c_int(world), str(name).encode(), C.byref(h)))
+        return Comm(h)
+
+    @staticmethod
+    def init_local(n_devices):
+        arr = (C.c_void_p * n_devices)()
+        _check(lib().vnr_comm_init(C.c_int(n_devices), arr))
+        return [Comm(C.c_void_p(a)) for a in arr]
+
+    def info(self):
+        r, w, d = C.c_int(), C.c_int(), C.c_int()
+        _check(lib().vnr_comm_info(self._h, C.byref(r), C.byref(w), C.byref(d)))
+        return r.value, w.value, d.value
+
+    def set_device(self):
+        _check(lib().vnr_comm_set_device(self._h))
+
+    def barrier(self):
+        _check(lib().vnr_comm_barrier(self._h))
+
+    def close(self):
+        if self._h:
+            lib().vnr_comm_release.restype = None
+            lib().vnr_comm_release(self._h)
+            self._h = None
+
+
 class NeuralVolume:
     """vnrVolume (neural) -- api.h:122-143."""
 
@@ -257,6 +294,13 @@ class NeuralVolume:
 
     def optimizer_step(self, stream=None):
         _check(lib().vnr_volume_optimizer_step(self._h, _stream(stream)))
+
+    # -- communicator (data-parallel training through train())
+    def attach_comm(self, comm):
+        _check(lib().vnr_volume_attach_comm(self._h, comm._h))
+
+    def detach_comm(self):
+        _check(lib().vnr_volume_detach_comm(self._h))
 
     # -- measurement taps of the fused training kernel (train.cu)
     def train_debug(self, variant=1, flags=0, profile=False):
@@ -474,6 +518,13 @@ class Renderer:
 
     def set_frame_target(self, d_ptr):
         _check(lib().vnr_renderer_set_frame_target(self._h, C.c_void_p(d_ptr) if d_ptr else None))
+
+    def attach_comm(self, comm):
+        """tile-parallel rendering over the communicator: render() on every rank, map_frame() on rank 0"""
+        _check(lib().vnr_renderer_attach_comm(self._h, comm._h))
+
+    def detach_comm(self):
+        _check(lib().vnr_renderer_detach_comm(self._h))
 
     def set_frames_in_flight(self, n):
         """depth of the renderer's frame ring (vnr_renderer_set_frames_in_flight); map_frame then returns the oldest unmapped frame"""

@@ -99,12 +99,14 @@ __device__ __forceinline__ void mlp_forward_x2(uint8_t* const (&a)[2], uint64_t*
                                                const DecoderDesc& d, int tid, int bar_id, float (&out)[2]) {
   using namespace tc05;
   const uint32_t w_addr = smem_u32(w_smem);
+  const uint32_t warp_u = uniform_u32((uint32_t)tid >> 5);        // warp-uniform: warp 0 of the group issues the MMAs
+  tmem_base = uniform_u32(tmem_base);
   const uint32_t lane_base = ((uint32_t)tid >> 5 & 3u) * 32u;    // TMEM lane quarter this warp may touch
   const int nt = a[1] ? 2 : 1;
   uint32_t a_addr[2], t_acc[2], t_row[2];
 #pragma unroll
   for (int q = 0; q < 2; ++q) {
-    a_addr[q] = a[q] ? smem_u32(a[q]) : 0u;
+    a_addr[q] = a[q] ? uniform_u32(smem_u32(a[q])) : 0u;
     t_acc[q] = tmem_base + 64u * (uint32_t)q;
     t_row[q] = t_acc[q] + (lane_base << 16);
   }
@@ -112,7 +114,7 @@ __device__ __forceinline__ void mlp_forward_x2(uint8_t* const (&a)[2], uint64_t*
   for (int q = 0; q < 2; ++q) {
     if (q >= nt) break;
     mbar_wait(full[q], full_parity[q]);
-    if (tid == 0) mlp_issue_layer(a_addr[q], w_addr, t_acc[q], d, 0, &mbar[q]);
+    if (warp_u == 0) { if (elect_one_sync()) mlp_issue_layer(a_addr[q], w_addr, t_acc[q], d, 0, &mbar[q]); __syncwarp(); }
   }
   for (int layer = 0; layer < d.n_hidden; ++layer) {
 #pragma unroll
@@ -125,7 +127,7 @@ __device__ __forceinline__ void mlp_forward_x2(uint8_t* const (&a)[2], uint64_t*
       fence_before_sync();
       fence_async_smem();
       asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-      if (tid == 0) mlp_issue_layer(a_addr[q], w_addr, t_acc[q], d, layer + 1, &mbar[q]);
+      if (warp_u == 0) { if (elect_one_sync()) mlp_issue_layer(a_addr[q], w_addr, t_acc[q], d, layer + 1, &mbar[q]); __syncwarp(); }
     }
   }
 #pragma unroll

@@ -16,6 +16,7 @@
 #include <cstring>
 
 #include "march.cuh"
+#include "comm.h"
 #include "render.h"
 #include "train.h"
 #include "volume_tex.cuh"
@@ -413,7 +414,7 @@ FrameSlot::FrameSlot() {
 
 FrameSlot::~FrameSlot() {
   if (stream) cudaStreamSynchronize(stream);
-  for (int k = 0; k < 2; ++k) { if (h_frame[k]) cudaFreeHost(h_frame[k]); if (frame_done[k]) cudaEventDestroy(frame_done[k]); }
+  for (int k = 0; k < 2; ++k) { if (h_frame[k] && !h_frame_external) cudaFreeHost(h_frame[k]); if (frame_done[k]) cudaEventDestroy(frame_done[k]); }
   for (cudaEvent_t e : prof_events) cudaEventDestroy(e);
   destroy_graph();
   if (vol_ready) cudaEventDestroy(vol_ready);
@@ -426,9 +427,11 @@ void FrameSlot::resize(size_t npix) {
   accum.alloc(npix); frame.alloc(npix);
   accum.zero(stream); frame.zero(stream);
   for (int k = 0; k < 2; ++k) {
-    if (h_frame[k]) { cudaFreeHost(h_frame[k]); h_frame[k] = nullptr; }
+    if (h_frame[k] && !h_frame_external) cudaFreeHost(h_frame[k]);
+    h_frame[k] = nullptr;
     VNR_CUDA(cudaMallocHost((void**)&h_frame[k], npix * sizeof(float4)));
   }
+  h_frame_external = false;
   rendered = false; downloaded = false; mapped = true;
 }
 
@@ -457,6 +460,7 @@ Renderer::Renderer(Volume* v) : vol(v) {
 }
 
 Renderer::~Renderer() {
+  if (rcomm) { try { comm_detach_renderer(this); } catch (...) {} }
   auto& rs = vol->renderers;
   rs.erase(std::remove(rs.begin(), rs.end(), this), rs.end());
   slots.clear();
@@ -469,6 +473,7 @@ void Renderer::sync_all() { for (auto& s : slots) VNR_CUDA(cudaStreamSynchronize
 // rounds of one frame run under the head of the next); vnr_map_frame returns the oldest frame that has not been mapped yet.
 void Renderer::set_frames_in_flight(int n) {
   if (n < 1 || n > kMaxFramesInFlight) throw InvalidError("frames in flight must be in [1, " + std::to_string(kMaxFramesInFlight) + "]");
+  if (rcomm) throw StateError("detach the renderer from its communicator before changing the frames in flight");
   sync_all();
   while ((int)slots.size() > n) slots.pop_back();
   while ((int)slots.size() < n) {
@@ -487,7 +492,7 @@ void wait_for_frames(Volume* v, cudaStream_t s) {
   for (Renderer* r : v->renderers)
     for (auto& sl : r->slots)
       if (sl->rendered && !(sl->vol_waited && sl->vol_waited_on == s)) {
-        VNR_CUDA(cudaStreamWaitEvent(s, sl->frame_done[sl->mapped ? sl->cur ^ 1 : sl->cur], 0));
+        VNR_CUDA(cudaStreamWaitEvent(s, sl->frame_done[sl->map_idx], 0));
         sl->vol_waited = true; sl->vol_waited_on = s;
       }
 }
@@ -501,6 +506,7 @@ uint32_t Renderer::local_rays() const {
 
 void Renderer::resize(int w, int h) {
   if (w <= 0 || h <= 0) throw InvalidError("framebuffer size must be positive");
+  if (rcomm) throw StateError("detach the renderer from its communicator before resizing");
   width = w; height = h;
   for (auto& s : slots) s->resize((size_t)w * h);
   n_rendered = n_mapped = 0; last_slot = 0;
@@ -740,8 +746,15 @@ void Renderer::render() {
   FrameParams fp[2]; fill_frame_params(fp[0]);
   // zero-copy download: finished pixels are stored straight into the pinned host frame map_frame() will return
   // (cudaMallocHost memory is device-addressable under UVA); the device frame buffer is then not written
-  const bool zc = zero_copy && download && !S.frame_target;
-  fp[0].frame = zc ? S.h_frame[S.cur] : S.frame_out();
+  // Communicator-attached (tile-parallel): the pinned host frames of a slot are shared by all ranks, every rank stores the
+  // pixels of its strips there over its own PCIe link and a peer barrier on the slots' streams closes the frame; with the
+  // download disabled the pixels go to rank 0's device frame over NVLink instead.
+  RendererComm* rc = (rcomm && rcomm->resolved && rcomm->comm->world > 1) ? rcomm : nullptr;
+  if (rc && (rc->width != width || rc->height != height || rc->n_slots != (int)slots.size()))
+    throw StateError("frame size / frames in flight changed after vnr_renderer_attach_comm: detach and attach again on every rank");
+  const int hb = S.cur;                                                // host frame this render writes; the next one takes the other
+  const bool zc = zero_copy && download && (rc || !S.frame_target);
+  fp[0].frame = zc ? S.h_frame[hb] : S.frame_out();
   fp[0].accum_prev = frame_index > 1 ? P.accum.p : nullptr;
   fp[0].shade_mode = shade; fp[1] = fp[0]; fp[1].shade_mode = 3;
   const uint32_t n_rays = fp[0].n_rays;
@@ -750,8 +763,11 @@ void Renderer::render() {
   // make the volume's pending work (training, tfn upload) visible to the frame stream
   VNR_CUDA(cudaEventRecord(S.vol_ready, vol->stream));
   VNR_CUDA(cudaStreamWaitEvent(stream, S.vol_ready, 0));
+  // rank 0 copies the gathered device frame to the host after the frame (download without zero-copy): the peers must not
+  // store pixels of this frame into that buffer before the copy of the slot's previous frame has been issued and finished
+  if (rc && download && !zc) peer_barrier_sync(rc->barriers[(size_t)k], stream);
   // progressive accumulation reads the previous frame's sums: wait for that frame when it ran in another slot
-  if (frame_index > 1 && &P != &S && P.rendered) VNR_CUDA(cudaStreamWaitEvent(stream, P.frame_done[P.mapped ? P.cur ^ 1 : P.cur], 0));
+  if (frame_index > 1 && &P != &S && P.rendered) VNR_CUDA(cudaStreamWaitEvent(stream, P.frame_done[P.map_idx], 0));
 
   // decoding modes, and a SimpleVolume in every mode but the sample-streaming ones, run the single-kernel marcher
   const bool single_kernel = decoding || (gt_source && mode != 5 && mode != 8 && mode != 11 && mode != 14);
@@ -817,16 +833,19 @@ void Renderer::render() {
   S.last_rounds = rounds;
   S.last_passes = single_kernel ? 1 : n_pass;
   // framebuffer.download_async (renderer.cpp:133)
+  if (rc) peer_barrier_sync(rc->barriers[(size_t)k], stream);         // every rank's pixels of this frame have landed
   S.downloaded = false;
-  if (download) {
-    if (!zc) VNR_CUDA(cudaMemcpyAsync(S.h_frame[S.cur], S.frame.p, S.frame.bytes(), cudaMemcpyDeviceToHost, stream));
+  if (download && (!rc || rc->comm->rank == 0)) {                      // the frame is mapped on rank 0
+    if (!zc) VNR_CUDA(cudaMemcpyAsync(S.h_frame[hb], S.frame.p, S.frame.bytes(), cudaMemcpyDeviceToHost, stream));
     S.downloaded = true;
   }
   VNR_CUDA(cudaMemcpyAsync(S.h_counters, S.counters.p, sizeof(uint32_t) * 2 * cstride, cudaMemcpyDeviceToHost, stream));
-  VNR_CUDA(cudaEventRecord(S.frame_done[S.cur], stream));
+  VNR_CUDA(cudaEventRecord(S.frame_done[hb], stream));
+  S.map_idx = hb; S.cur = hb ^ 1;                                      // double-buffer swap (renderer.h:93), at render time on every rank
   S.rendered = true; S.mapped = false; S.frame_index = frame_index; S.vol_waited = false;
   last_slot = k;
   ++n_rendered;
+  if (!S.downloaded) n_mapped = n_rendered;          // nothing to map: frames without a download never enter the map queue
 }
 
 // explicit framebuffer.download_async for callers that disabled the automatic one (multi-GPU rank 0
@@ -834,20 +853,22 @@ void Renderer::render() {
 void Renderer::download_now() {
   FrameSlot& S = last();
   if (!S.rendered) throw StateError("vnr_renderer_download called before vnr_render");
-  VNR_CUDA(cudaMemcpyAsync(S.h_frame[S.cur], S.frame.p, S.frame.bytes(), cudaMemcpyDeviceToHost, S.stream));
-  VNR_CUDA(cudaEventRecord(S.frame_done[S.cur], S.stream));
-  S.downloaded = true; S.vol_waited = false;
+  VNR_CUDA(cudaMemcpyAsync(S.h_frame[S.map_idx], S.frame.p, S.frame.bytes(), cudaMemcpyDeviceToHost, S.stream));
+  VNR_CUDA(cudaEventRecord(S.frame_done[S.map_idx], S.stream));
+  if (!S.downloaded) n_mapped = n_rendered - 1;      // the most recent frame becomes mappable
+  S.downloaded = true; S.mapped = false; S.vol_waited = false;
 }
 
 // vnrRendererMapFrame (renderer.h:84-94): the oldest rendered frame that has not been mapped yet; with one slot that is
 // the frame of the last vnr_render.  The pointer stays valid until the second-next map of the same slot.
 const float* Renderer::map_frame() {
-  if (n_rendered == n_mapped) throw StateError(n_rendered ? "vnr_map_frame: every rendered frame has already been mapped" : "vnr_map_frame called before vnr_render");
+  if (n_rendered == n_mapped)
+    throw StateError(!n_rendered ? "vnr_map_frame called before vnr_render"
+                                 : (!last().downloaded ? "frame download is disabled on this renderer" : "vnr_map_frame: every rendered frame has already been mapped"));
   FrameSlot& S = slot((int)(n_mapped % slots.size()));
   if (!S.downloaded) throw StateError("frame download is disabled on this renderer");
-  VNR_CUDA(cudaEventSynchronize(S.frame_done[S.cur]));
-  const float* p = reinterpret_cast<const float*>(S.h_frame[S.cur]);
-  S.cur ^= 1;                                                           // double-buffer swap
+  VNR_CUDA(cudaEventSynchronize(S.frame_done[S.map_idx]));
+  const float* p = reinterpret_cast<const float*>(S.h_frame[S.map_idx]);
   S.mapped = true;
   ++n_mapped;
   return p;

@@ -8,6 +8,7 @@
 namespace vnr {
 
 struct FrameParams;
+struct RendererComm;
 struct RayBuffers;
 constexpr int kMaxRounds = 1024;
 constexpr int kMaxFramesInFlight = 8;
@@ -42,6 +43,8 @@ struct FrameSlot {
   DevBuf<float4> pt_org, pt_dir, pt_rad, pt_thr, pt_tn; DevBuf<int4> pt_cell; DevBuf<uint32_t> pt_list[2];
   cudaGraph_t pt_graph = nullptr; cudaGraphExec_t pt_exec = nullptr; GraphKey pt_key; bool last_pt = false;
   float4* h_frame[2] = {nullptr, nullptr};
+  bool h_frame_external = false;        // the host frames belong to a communicator (shared by all ranks), not to the slot
+  int map_idx = 0;                      // host frame the last render of this slot wrote (`cur` = the one the next render writes)
   uint32_t* h_counters = nullptr;
   std::vector<cudaEvent_t> prof_events;
   int prof_used = 0;
@@ -88,6 +91,7 @@ struct Renderer {
   int last_slot = 0;                    // slot of the most recent vnr_render (stats / profile / device frame refer to it)
   FrameSlot& slot(int k) { return *slots[(size_t)k]; }
   FrameSlot& last() { return *slots[(size_t)last_slot]; }
+  RendererComm* rcomm = nullptr;        // communicator attachment (comm.h): tile-parallel rendering through vnr_render
 
   explicit Renderer(Volume* v);
   ~Renderer();

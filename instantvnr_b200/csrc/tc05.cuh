@@ -33,6 +33,18 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 template <uint32_t N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <uint32_t N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
+// One lane of a fully active warp (warp-uniform code only).  tcgen05.mma / commit take their operands from UNIFORM registers:
+// issued under `threadIdx.x == 0` the compiler cannot prove the descriptors uniform and wraps every MMA in a
+// VOTE / ELECT / R2UR.BROADCAST waterfall loop (~150-190 cycles per instruction, measured); issued by the elected lane of a
+// warp-uniform branch with operands derived from warp-uniform values (uniform_u32) they become plain UTCHMMA.
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+// a value every lane of the warp holds identically, in a form the compiler knows to be warp-uniform
+__device__ __forceinline__ uint32_t uniform_u32(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+
 // ---- proxy / tcgen05 fences -------------------------------------------------
 // generic-proxy smem writes -> visible to the async proxy (tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

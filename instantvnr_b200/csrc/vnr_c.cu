@@ -7,6 +7,7 @@
 #include "../../include/vnr_c.h"
 #include "mini_json.h"
 #include "volume.h"
+#include "comm.h"
 #include "render.h"
 #include "train.h"
 #include "scene.h"
@@ -16,6 +17,8 @@ using namespace vnr;
 #define VNR_EXPORT extern "C" __attribute__((visibility("default")))
 
 static thread_local std::string g_last_error;
+// one process driving several devices (vnr_comm_init(n > 1)): every entry point makes the object's device current
+static bool g_multi_device = false;
 
 template <typename Fn>
 static int guard(Fn&& fn) {
@@ -35,7 +38,9 @@ static void require_device() {
 
 Volume::Volume() { sampler_rng.seed(1337); }
 Volume::~Volume() {
+  if (g_multi_device) cudaSetDevice(device);
   if (stream) cudaStreamSynchronize(stream);
+  if (vcomm) { try { comm_detach_volume(this); } catch (...) {} }
   outofcore_release(this);
   for (int r = 0; r < dp_world; ++r) {          // mappings of the peers' buffers (vnr_volume_dp_attach)
     if (r == dp_rank) continue;
@@ -46,8 +51,18 @@ Volume::~Volume() {
   if (stream) cudaStreamDestroy(stream);
 }
 
-static Volume* V(vnr_volume_t* v) { if (!v) throw InvalidError("null volume handle"); return reinterpret_cast<Volume*>(v); }
-static const Volume* V(const vnr_volume_t* v) { if (!v) throw InvalidError("null volume handle"); return reinterpret_cast<const Volume*>(v); }
+static Volume* V(vnr_volume_t* v) {
+  if (!v) throw InvalidError("null volume handle");
+  Volume* p = reinterpret_cast<Volume*>(v);
+  if (g_multi_device) VNR_CUDA(cudaSetDevice(p->device));
+  return p;
+}
+static const Volume* V(const vnr_volume_t* v) {
+  if (!v) throw InvalidError("null volume handle");
+  const Volume* p = reinterpret_cast<const Volume*>(v);
+  if (g_multi_device) VNR_CUDA(cudaSetDevice(p->device));
+  return p;
+}
 static cudaStream_t S(Volume* v, void* stream) { return stream ? (cudaStream_t)stream : v->stream; }
 
 VNR_EXPORT const char* vnr_last_error(void) { return g_last_error.c_str(); }
@@ -67,6 +82,7 @@ VNR_EXPORT int vnr_volume_create(const char* model_json, int dx, int dy, int dz,
     std::unique_ptr<Volume> v(new Volume());
     v->cfg = cfg;
     v->dims[0] = dx; v->dims[1] = dy; v->dims[2] = dz;
+    VNR_CUDA(cudaGetDevice(&v->device));
     VNR_CUDA(cudaStreamCreateWithFlags(&v->stream, cudaStreamNonBlocking));
     v->params.alloc(cfg.n_params());
     v->params.zero(v->stream);
@@ -98,17 +114,6 @@ static void upload_master_from_f16(Volume* v, const std::vector<__half>& h) {
   for (size_t i = 0; i < h.size(); ++i) f[i] = __half2float(h[i]);
   v->master.alloc(f.size());
   VNR_CUDA(cudaMemcpy(v->master.p, f.data(), f.size() * sizeof(float), cudaMemcpyHostToDevice));
-}
-
-static void reset_optimizer(Volume* v) {
-  const size_t n = v->cfg.n_params();
-  v->m1.alloc(n); v->m2.alloc(n); v->steps.alloc(n);
-  v->m1.zero(v->stream); v->m2.zero(v->stream); v->steps.zero(v->stream);
-  v->grads_clean = false; v->grads_pending = false;
-  v->opt_step = 0; v->lr_factor = 1.f; v->train_step = 0; v->loss_count = 0;
-  v->loss_accum.zero(v->stream);
-  VNR_CUDA(cudaStreamSynchronize(v->stream));
-  v->have_opt = true;
 }
 
 VNR_EXPORT int vnr_volume_init_params(vnr_volume_t* vh, uint32_t seed) {
@@ -151,7 +156,7 @@ VNR_EXPORT int vnr_volume_init_params(vnr_volume_t* vh, uint32_t seed) {
     VNR_CUDA(cudaMemcpy(v->master.p, p.data(), n * sizeof(float), cudaMemcpyHostToDevice));
     VNR_CUDA(cudaMemcpy(v->params.p, h.data(), n * sizeof(__half), cudaMemcpyHostToDevice));
     v->have_params = true;
-    reset_optimizer(v);
+    reset_optimizer_state(v);
   });
 }
 
@@ -190,7 +195,7 @@ VNR_EXPORT int vnr_volume_set_params_f16(vnr_volume_t* vh, const uint16_t* h_par
     VNR_CUDA(cudaMemcpy(v->params.p, h.data(), n * 2, cudaMemcpyHostToDevice));
     upload_master_from_f16(v, h);            // params_fp[i] = (float)params_inference[i]  trainer.h:289-291
     v->have_params = true;
-    if (!v->have_opt) reset_optimizer(v);
+    if (!v->have_opt) reset_optimizer_state(v);
   });
 }
 

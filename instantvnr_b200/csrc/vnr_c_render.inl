@@ -1,5 +1,10 @@
 // vnr_c_render.inl -- renderer entry points (MainRenderer / api.cpp:419-525)
-static Renderer* R(vnr_renderer_t* r) { if (!r) throw InvalidError("null renderer handle"); return reinterpret_cast<Renderer*>(r); }
+static Renderer* R(vnr_renderer_t* r) {
+  if (!r) throw InvalidError("null renderer handle");
+  Renderer* s = reinterpret_cast<Renderer*>(r);
+  if (g_multi_device) VNR_CUDA(cudaSetDevice(s->vol->device));
+  return s;
+}
 
 VNR_EXPORT int vnr_renderer_create(vnr_volume_t* vh, vnr_renderer_t** out) {
   return guard([&] {
@@ -146,48 +151,17 @@ VNR_EXPORT int vnr_ipc_open(const void* handle64, void** d_ptr) {
 }
 VNR_EXPORT int vnr_ipc_close(void* d_ptr) { return guard([&] { if (d_ptr) VNR_CUDA(cudaIpcCloseMemHandle(d_ptr)); }); }
 
-// ---- cross-rank barrier over peer memory (no reference counterpart) --------------------------------
+// ---- cross-rank barrier over peer memory (no reference counterpart; comm.cu) ---------------------------
 // A stream-ordered barrier between the ranks of one NVSwitch box without a collective library call: every rank
 // owns a small flag array mapped by all peers; `sync` launches ONE kernel of `world` threads on the caller's
 // stream: thread t publishes this rank's epoch into peer t's array (system-scope release) and waits until peer
 // t's epoch has arrived in the local array (acquire).  ~5 us instead of ~25 us for a 4-byte NCCL all-reduce.
 // A peer that never arrives trips a 5 s timeout (error flag, no hang).
-struct PeerBarrier {
-  int rank = 0, world = 1;
-  unsigned long long epoch = 0;
-  unsigned long long* local = nullptr;               // [kMaxPeers + 1]: slot r = rank r's last epoch; slot kMaxPeers = timeout flag
-  unsigned long long* peer[kMaxPeers] = {};
-  ~PeerBarrier() {
-    for (int r = 0; r < world; ++r) if (r != rank && peer[r]) cudaIpcCloseMemHandle(peer[r]);
-    if (local) cudaFree(local);
-  }
-};
-
-struct PeerBarrierArgs { unsigned long long* peer[kMaxPeers]; };
-
-__global__ void peer_barrier_kernel(PeerBarrierArgs a, unsigned long long* local, int rank, unsigned long long epoch) {
-  const int t = threadIdx.x;
-  __threadfence_system();                            // everything this stream did before is visible to the peers
-  if (t != rank) {
-    *reinterpret_cast<volatile unsigned long long*>(a.peer[t] + rank) = epoch;
-    unsigned long long t0 = 0;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    while (*reinterpret_cast<volatile unsigned long long*>(local + t) < epoch) {
-      unsigned long long now;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-      if (now - t0 > 5000000000ull) { *reinterpret_cast<volatile unsigned long long*>(local + kMaxPeers) = epoch; break; }
-    }
-  }
-  __threadfence_system();                            // what the peers published before their flag is visible after this kernel
-}
-
 VNR_EXPORT int vnr_peer_barrier_create(void** out, void* handle64) {
   return guard([&] {
     if (!out || !handle64) throw InvalidError("null argument");
     require_device();
-    std::unique_ptr<PeerBarrier> b(new PeerBarrier());
-    VNR_CUDA(cudaMalloc((void**)&b->local, sizeof(unsigned long long) * (kMaxPeers + 1)));
-    VNR_CUDA(cudaMemset(b->local, 0, sizeof(unsigned long long) * (kMaxPeers + 1)));
+    std::unique_ptr<PeerBarrier> b(peer_barrier_create());
     VNR_CUDA(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(handle64), b->local));
     *out = b.release();
   });
@@ -197,35 +171,51 @@ VNR_EXPORT int vnr_peer_barrier_attach(void* bh, int rank, int world, const void
   return guard([&] {
     PeerBarrier* b = reinterpret_cast<PeerBarrier*>(bh);
     if (!b) throw InvalidError("null barrier");
-    if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world || (world > 1 && !all_handles)) throw InvalidError("bad barrier rank / world");
-    b->rank = rank; b->world = world;
-    for (int r = 0; r < world; ++r) {
-      if (r == rank) { b->peer[r] = b->local; continue; }
-      cudaIpcMemHandle_t h; memcpy(&h, reinterpret_cast<const char*>(all_handles) + (size_t)r * 64, 64);
-      VNR_CUDA(cudaIpcOpenMemHandle((void**)&b->peer[r], h, cudaIpcMemLazyEnablePeerAccess));
-    }
+    peer_barrier_attach_ipc(b, rank, world, all_handles);
   });
 }
 VNR_EXPORT int vnr_peer_barrier_sync(void* bh, void* stream) {
   return guard([&] {
     PeerBarrier* b = reinterpret_cast<PeerBarrier*>(bh);
     if (!b) throw InvalidError("null barrier");
-    if (b->world <= 1) return;
-    PeerBarrierArgs a;
-    for (int r = 0; r < kMaxPeers; ++r) a.peer[r] = b->peer[r];
-    ++b->epoch;
-    peer_barrier_kernel<<<1, b->world, 0, (cudaStream_t)stream>>>(a, b->local, b->rank, b->epoch);
-    VNR_CUDA(cudaGetLastError());
+    peer_barrier_sync(b, (cudaStream_t)stream);
   });
 }
-// number of barrier calls that timed out so far (0 = healthy); synchronises the device
+// epoch of the last barrier call that timed out (0 = healthy); synchronises the device
 VNR_EXPORT int vnr_peer_barrier_check(void* bh, uint64_t* timed_out_epoch) {
   return guard([&] {
     PeerBarrier* b = reinterpret_cast<PeerBarrier*>(bh);
     if (!b || !timed_out_epoch) throw InvalidError("null argument");
-    unsigned long long v = 0;
-    VNR_CUDA(cudaMemcpy(&v, b->local + kMaxPeers, sizeof v, cudaMemcpyDeviceToHost));
-    *timed_out_epoch = v;
+    *timed_out_epoch = peer_barrier_timed_out(b);
   });
 }
 VNR_EXPORT void vnr_peer_barrier_release(void* bh) { delete reinterpret_cast<PeerBarrier*>(bh); }
+
+// ---- communicators (comm.cu): multi-GPU behind the same calls -------------------------------------------------
+static Comm* CM(vnr_comm_t* c) { if (!c) throw InvalidError("null communicator"); return reinterpret_cast<Comm*>(c); }
+VNR_EXPORT int vnr_comm_init(int n_devices, vnr_comm_t** comms_out) {
+  return guard([&] {
+    if (!comms_out) throw InvalidError("null argument");
+    require_device();
+    std::vector<Comm*> cs = comm_create_local(n_devices);
+    for (size_t k = 0; k < cs.size(); ++k) comms_out[k] = reinterpret_cast<vnr_comm_t*>(cs[k]);
+    if (n_devices > 1) g_multi_device = true;
+  });
+}
+VNR_EXPORT int vnr_comm_init_rank(int rank, int world, const char* rendezvous_name, vnr_comm_t** out) {
+  return guard([&] {
+    if (!out) throw InvalidError("null argument");
+    require_device();
+    *out = reinterpret_cast<vnr_comm_t*>(comm_create_rank(rank, world, rendezvous_name));
+  });
+}
+VNR_EXPORT void vnr_comm_release(vnr_comm_t* c) { delete reinterpret_cast<Comm*>(c); }
+VNR_EXPORT int vnr_comm_info(vnr_comm_t* c, int* rank, int* world, int* device) {
+  return guard([&] { Comm* m = CM(c); if (rank) *rank = m->rank; if (world) *world = m->world; if (device) *device = m->device; });
+}
+VNR_EXPORT int vnr_comm_set_device(vnr_comm_t* c) { return guard([&] { VNR_CUDA(cudaSetDevice(CM(c)->device)); }); }
+VNR_EXPORT int vnr_comm_barrier(vnr_comm_t* c) { return guard([&] { CM(c)->host_barrier(); }); }
+VNR_EXPORT int vnr_volume_attach_comm(vnr_volume_t* vh, vnr_comm_t* c) { return guard([&] { comm_attach_volume(V(vh), CM(c)); }); }
+VNR_EXPORT int vnr_volume_detach_comm(vnr_volume_t* vh) { return guard([&] { comm_detach_volume(V(vh)); }); }
+VNR_EXPORT int vnr_renderer_attach_comm(vnr_renderer_t* r, vnr_comm_t* c) { return guard([&] { comm_attach_renderer(R(r), CM(c)); }); }
+VNR_EXPORT int vnr_renderer_detach_comm(vnr_renderer_t* r) { return guard([&] { comm_detach_renderer(R(r)); }); }

@@ -114,7 +114,7 @@ VNR_EXPORT int vnr_volume_load_params(vnr_volume_t* vh, const void* bson, size_t
     VNR_CUDA(cudaMemcpy(v->params.p, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
     upload_master_from_f16(v, h);
     v->have_params = true;
-    if (!v->have_opt || model_reset) reset_optimizer(v);
+    if (!v->have_opt || model_reset) reset_optimizer_state(v);
   });
 }
 
@@ -271,7 +271,8 @@ VNR_EXPORT int vnr_volume_train(vnr_volume_t* vh, int steps, int batch, int fast
     if (steps < 0 || batch < 0) throw InvalidError("negative steps / batch");
     cudaStream_t s = S(v, stream);
     const bool update_mc = !(fast_mode && v->mc_external);
-    train_steps(v, steps, (size_t)batch, update_mc, s);
+    if (v->vcomm && v->vcomm->comm->world > 1) comm_train_steps(v, steps, (size_t)batch, update_mc, s);     // data parallel over the communicator
+    else train_steps(v, steps, (size_t)batch, update_mc, s);
     if (!fast_mode) macrocell_update_max_opacity(v, s);
   });
 }
@@ -347,6 +348,7 @@ VNR_EXPORT int vnr_volume_stats(vnr_volume_t* vh, uint64_t* step, double* loss) 
     double acc[2] = {0, 0};
     VNR_CUDA(cudaStreamSynchronize(v->stream));
     VNR_CUDA(cudaMemcpy(acc, v->loss_accum.p, sizeof acc, cudaMemcpyDeviceToHost));
+    if (v->vcomm && v->vcomm->resolved && v->vcomm->comm->world > 1) acc[0] = comm_global_loss(v, 0);     // the loss of the global batch: sum over ranks
     if (step) *step = v->train_step;
     if (loss) *loss = v->loss_count ? acc[0] / (double)v->loss_count : 0.0;
   });
@@ -358,6 +360,7 @@ VNR_EXPORT int vnr_volume_last_loss(vnr_volume_t* vh, double* loss) {
     double acc[2] = {0, 0};
     VNR_CUDA(cudaStreamSynchronize(v->stream));
     VNR_CUDA(cudaMemcpy(acc, v->loss_accum.p, sizeof acc, cudaMemcpyDeviceToHost));
+    if (v->vcomm && v->vcomm->resolved && v->vcomm->comm->world > 1) acc[1] = comm_global_loss(v, 1);
     if (loss) *loss = acc[1];
   });
 }

@@ -23,10 +23,12 @@ struct DevBuf {
 };
 
 struct SlabSampler;
+struct VolumeComm;
 
 struct Volume {
   ModelConfig cfg;
   int dims[3] = {0, 0, 0};
+  int device = 0;                  // the CUDA device the volume lives on (current device at creation)
   cudaStream_t stream = nullptr;
 
   // parameters: fp16 working copy (MLP matrices, then grid), fp32 master, gradients, Adam state
@@ -69,6 +71,9 @@ struct Volume {
   // data-parallel peers (train.cu dp_optimizer_step): every rank's parameter / gradient buffers, own ones included
   int dp_rank = 0, dp_world = 0;
   void* dp_params[kMaxPeers] = {}; void* dp_grid_grads[kMaxPeers] = {}; void* dp_mlp_grads[kMaxPeers] = {};
+
+  // communicator attachment (comm.h): data-parallel training through vnr_volume_train
+  VolumeComm* vcomm = nullptr;
 
   // renderers created on this volume (they register themselves): what mutating entry points order against
   std::vector<Renderer*> renderers;

@@ -1,0 +1,185 @@
+"""Multi-GPU behind the C ABI (vnr_comm_*; include/vnr_c.h, csrc/comm.cu): tile-parallel rendering and data-parallel training
+driven from C++.  One process drives the ranks (vnr_comm_init); when the box has fewer GPUs than ranks they share a device
+(VNR_COMM_SHARE_DEVICES=1), which runs the same control and data path: peer pointers, barrier kernels, the fused
+reduce-scatter + Adam + all-gather kernel, pixels stored into the shared host frame / rank 0's device frame."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+os.environ.setdefault("VNR_COMM_SHARE_DEVICES", "1")
+
+import instantvnr_b200 as vnr                     # noqa: E402
+import oracle as O                                # noqa: E402
+from instantvnr_b200 import synthetic as syn      # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+CFG = dict(n_levels=8, n_features=8, log2_hashmap=14, base_res=16, n_hidden=4)
+DIMS = (48, 48, 48)
+
+
+def _scene_params():
+    m = O.ModelCfg(CFG["n_levels"], CFG["n_features"], CFG["log2_hashmap"], CFG["base_res"], 2.0, CFG["n_hidden"])
+    p32, _ = O.init_params(m, 7)
+    p32 = p32.copy(); p32[m.n_mlp:] *= 3000.0
+    p16 = O.f32_to_f16(p32)
+    zz, yy, xx = np.meshgrid(*[(np.arange(d, dtype=np.float32) + 0.5) / d for d in DIMS[::-1]], indexing="ij")
+    dec = O.decode(m, p16, np.stack([xx.ravel(), yy.ravel(), zz.ravel()], 1))
+    tr = (max(float(dec.min()), 0.0), min(float(dec.max()), 1.0))
+    mc = O.macrocell_update_implicit(np.clip(dec, 0, 1), DIMS)
+    return p16, tr, mc
+
+
+@pytest.mark.parametrize("world,frames_in_flight,download", [(2, 1, True), (3, 2, True), (2, 2, False)])
+def test_tile_parallel_frame_equals_single_gpu_frame(world, frames_in_flight, download):
+    p16, tr, mc = _scene_params()
+    rgb, alpha = syn.make_tfn(64)
+    size = (96, 72)
+    cams = [syn.default_camera(DIMS, v, 5) for v in range(5)]
+
+    def make_volume(with_params):
+        vol = vnr.NeuralVolume(vnr.model_json(**CFG), DIMS)
+        if with_params:
+            vol.set_params_f16(p16); vol.set_macrocell(mc)
+        vol.set_transfer_function(rgb, alpha, tr)
+        return vol
+
+    def make_renderer(vol):
+        ren = vnr.Renderer(vol)
+        ren.set_size(*size); ren.set_mode(vnr.VNR_RAYMARCHING_NO_SHADING_SAMPLE_STREAMING)
+        return ren
+
+    # single-GPU frames
+    v0 = make_volume(True); r0 = make_renderer(v0)
+    want = []
+    for cam in cams:
+        r0.set_camera(*cam); r0.render(); want.append(r0.map_frame())
+    # the same through a communicator: only rank 0 holds the parameters before the attach
+    comms = vnr.Comm.init_local(world)
+    vols, rens = [], []
+    for r, c in enumerate(comms):
+        c.set_device()
+        vols.append(make_volume(r == 0))
+    for v, c in zip(vols, comms):
+        v.attach_comm(c)
+    for v in vols[1:]:
+        assert np.array_equal(v.get_params_f16(), p16)              # replicated from rank 0
+    for v, c in zip(vols, comms):
+        ren = make_renderer(v)
+        ren.set_frames_in_flight(frames_in_flight)
+        if not download:
+            ren.set_download(False)
+        ren.attach_comm(c)
+        rens.append(ren)
+    if download:
+        got = []
+        for i, cam in enumerate(cams):
+            for ren in rens:
+                ren.set_camera(*cam); ren.render()
+            if i >= frames_in_flight - 1:
+                got.append(rens[0].map_frame())
+        while len(got) < len(cams):
+            got.append(rens[0].map_frame())
+        for a, b in zip(got, want):
+            assert np.array_equal(a, b)
+        with pytest.raises(vnr.VnrError):
+            rens[1].map_frame()                                     # frames are gathered on rank 0
+    else:
+        for cam, w in zip(cams, want):
+            for ren in rens:
+                ren.set_camera(*cam); ren.render()
+            torch.cuda.synchronize()
+            from instantvnr_b200.distributed import _wrap_device
+            frame = _wrap_device(rens[0].device_frame(), size[0] * size[1] * 4, torch.float32).cpu().numpy().reshape(size[1], size[0], 4)
+            assert np.array_equal(frame, w)
+    for ren in rens:
+        ren.detach_comm()
+    for v in vols:
+        v.detach_comm()
+    # after the detach every renderer renders whole frames again
+    rens[1].set_download(True)
+    rens[1].set_camera(*cams[0]); rens[1].render()
+    assert np.array_equal(rens[1].map_frame(), want[0])
+    for c in comms:
+        c.close()
+
+
+def test_data_parallel_training_equals_accumulated_batches():
+    """vnr_volume_train on a communicator == one process accumulating `world` consecutive batches per optimizer step"""
+    world, n, steps = 2, 2048, 4
+    gt = syn.make_volume(DIMS, seed=3)
+
+    def make_volume(init):
+        vol = vnr.NeuralVolume(vnr.model_json(**CFG), DIMS)
+        vol.set_groundtruth(gt)
+        if init:
+            vol.init_params(11)
+        return vol
+
+    # single process: `world` consecutive sampler batches accumulate into one gradient, loss normalised by the global batch
+    ref = make_volume(True)
+    xyz = torch.empty(n, 3, device="cuda"); tgt = torch.empty(n, device="cuda")
+    ref_losses = []
+    for _ in range(steps):
+        loss = 0.0
+        for _ in range(world):
+            ref.sample(xyz, tgt, n)
+            ref.train_grads(xyz, tgt, n, n * world)
+            loss += ref.last_loss()
+        ref.optimizer_step()
+        ref_losses.append(loss)
+    p_ref = ref.get_params_f16().view(np.float16).astype(np.float32)
+
+    comms = vnr.Comm.init_local(world)
+    vols = []
+    for r, c in enumerate(comms):
+        c.set_device()
+        vols.append(make_volume(r == 0))
+    for v, c in zip(vols, comms):
+        v.attach_comm(c)
+    dp_losses = []
+    for _ in range(steps):
+        for v in vols:
+            v.train(1, batch=n, fast_mode=False)
+        dp_losses.append(vols[0].last_loss())
+        assert abs(vols[1].last_loss() - dp_losses[-1]) < 1e-12      # the global loss, on every rank
+    ps = [v.get_params_f16() for v in vols]
+    assert np.array_equal(ps[0], ps[1])                             # replicas bit-identical
+    mcs = [v.get_macrocell()[1] for v in vols]
+    assert np.array_equal(mcs[0], mcs[1])                           # merged value ranges
+    step, mean_loss = vols[0].stats()
+    assert step == steps
+    print("loss accumulated", np.round(ref_losses, 6), "data parallel", np.round(dp_losses, 6))
+    # same batches, same arithmetic up to the order of the fp16 reductions
+    assert np.allclose(dp_losses, ref_losses, rtol=2e-3)
+    assert abs(mean_loss - np.mean(dp_losses)) <= 1e-9
+    p_dp = ps[0].view(np.float16).astype(np.float32)
+    moved = p_dp != p_ref
+    print("parameters that differ from the accumulated run:", moved.mean())
+    assert moved.mean() < 0.02
+    # the value ranges of the data-parallel run cover what either rank saw: equal to the single-process ranges
+    ref.train(0, batch=n, fast_mode=False)
+    for v in vols:
+        v.detach_comm()
+    for c in comms:
+        c.close()
+
+
+def test_single_rank_communicator_is_transparent():
+    p16, tr, mc = _scene_params()
+    rgb, alpha = syn.make_tfn(64)
+    vol = vnr.NeuralVolume(vnr.model_json(**CFG), DIMS)
+    vol.set_params_f16(p16); vol.set_macrocell(mc); vol.set_transfer_function(rgb, alpha, tr)
+    ren = vnr.Renderer(vol)
+    ren.set_size(64, 64); ren.set_camera(*syn.default_camera(DIMS, 1))
+    ren.render(); want = ren.map_frame()
+    c = vnr.Comm.init_rank(0, 1, "unused")
+    assert c.info()[:2] == (0, 1)
+    vol.attach_comm(c); ren.attach_comm(c)
+    ren.reset_accumulation(); ren.render()
+    assert np.array_equal(ren.map_frame(), want)
+    with pytest.raises(vnr.VnrError):
+        ren.set_size(32, 32)                                        # geometry is fixed while attached
+    ren.detach_comm(); vol.detach_comm(); c.close()

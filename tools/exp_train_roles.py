@@ -84,7 +84,7 @@ def time_steps(reps=50):
 NAMES = ["total", "wait_x0_full", "wait_mma", "wait_dx_empty", "bar", "wait_wgrad", "g_wait_empty", "g_work", "s_wait_full", "s_work", "tiles",
          "fwd_ldtm", "fwd_cvt_sts", "fwd_fence"]
 for variant in (1,):
-    for flags in (0, 3, 16, 19):
+    for flags in (0, 32, 3, 35):
         vol.train_debug(variant, flags, False)
         us = time_kernel()
         out[f"kernel_us_v{variant}_f{flags}"] = us
@@ -100,11 +100,14 @@ for variant in (1,):
     out[f"roles_v{variant}"] = rec
     tot = rec["total"]
     log(f"variant {variant} role timers (cycles, mean over CTAs):", {k: (round(v), round(v / tot, 3)) for k, v in rec.items()})
+    log("trace of CTA 0, tile 5 (cycles since tile start; all roles on):", [int(x) for x in prof[0, 16:52]])
     vol.train_debug(variant, 3, True)          # the chain alone (no gather loads, no reductions)
     vol.train_grads(xyz, tgt, n, n)
-    prof = vol.train_profile().astype(np.float64).mean(0)
+    prof2 = vol.train_profile().astype(np.float64)
+    prof = prof2.mean(0)
     vol.optimizer_step()
     log(f"variant {variant} chain alone:", {k: round(float(prof[i])) for i, k in enumerate(NAMES)})
+    log("trace of CTA 0, tile 5 (chain alone):", [int(x) for x in prof2[0, 16:52]])
     vol.init_params(1337)
     vol.train_debug(variant, 0, False)
     us = time_steps()
