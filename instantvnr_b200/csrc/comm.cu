@@ -32,7 +32,7 @@ namespace vnr {
 // ------------------------------------------------------------------------------------------------------------------
 struct PeerBarrierArgs { unsigned long long* peer[kMaxPeers]; };
 
-__global__ void peer_barrier_kernel(PeerBarrierArgs a, unsigned long long* local, int rank, unsigned long long epoch) {
+__global__ void peer_barrier_kernel(PeerBarrierArgs a, unsigned long long* local, unsigned long long* h_flag, int rank, unsigned long long epoch) {
   const int t = threadIdx.x;
   __threadfence_system();                            // everything this stream did before is visible to the peers
   if (t != rank) {
@@ -42,7 +42,11 @@ __global__ void peer_barrier_kernel(PeerBarrierArgs a, unsigned long long* local
     while (*reinterpret_cast<volatile unsigned long long*>(local + t) < epoch) {
       unsigned long long now;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-      if (now - t0 > 5000000000ull) { *reinterpret_cast<volatile unsigned long long*>(local + kMaxPeers) = epoch; break; }
+      if (now - t0 > 5000000000ull) {              // a peer never arrived: flag it (device word + pinned host word the host checks) and go on
+        *reinterpret_cast<volatile unsigned long long*>(local + kMaxPeers) = epoch;
+        *reinterpret_cast<volatile unsigned long long*>(h_flag) = epoch;
+        break;
+      }
     }
   }
   __threadfence_system();                            // what the peers published before their flag is visible after this kernel
@@ -51,12 +55,15 @@ __global__ void peer_barrier_kernel(PeerBarrierArgs a, unsigned long long* local
 PeerBarrier::~PeerBarrier() {
   if (ipc) for (int r = 0; r < world; ++r) if (r != rank && peer[r]) cudaIpcCloseMemHandle(peer[r]);
   if (local) cudaFree(local);
+  if (h_flag) cudaFreeHost(h_flag);
 }
 
 PeerBarrier* peer_barrier_create() {
   std::unique_ptr<PeerBarrier> b(new PeerBarrier());
   VNR_CUDA(cudaMalloc((void**)&b->local, sizeof(unsigned long long) * (kMaxPeers + 1)));
   VNR_CUDA(cudaMemset(b->local, 0, sizeof(unsigned long long) * (kMaxPeers + 1)));
+  VNR_CUDA(cudaMallocHost((void**)&b->h_flag, sizeof(unsigned long long)));
+  *b->h_flag = 0;
   return b.release();
 }
 
@@ -81,14 +88,19 @@ void peer_barrier_sync(PeerBarrier* b, cudaStream_t s) {
   PeerBarrierArgs a;
   for (int r = 0; r < kMaxPeers; ++r) a.peer[r] = b->peer[r];
   ++b->epoch;
-  peer_barrier_kernel<<<1, b->world, 0, s>>>(a, b->local, b->rank, b->epoch);
+  peer_barrier_kernel<<<1, b->world, 0, s>>>(a, b->local, b->h_flag, b->rank, b->epoch);
   VNR_CUDA(cudaGetLastError());
 }
 
-unsigned long long peer_barrier_timed_out(PeerBarrier* b) {
-  unsigned long long v = 0;
-  VNR_CUDA(cudaMemcpy(&v, b->local + kMaxPeers, sizeof v, cudaMemcpyDeviceToHost));
-  return v;
+// epoch of the last barrier that gave up waiting (0 = healthy).  Reads the pinned host word: valid for every barrier kernel
+// that has completed, so callers check after a synchronisation they do anyway (mapping a frame, reading the loss).
+unsigned long long peer_barrier_timed_out(PeerBarrier* b) { return *reinterpret_cast<volatile unsigned long long*>(b->h_flag); }
+
+void peer_barrier_require_healthy(PeerBarrier* b, const char* what) {
+  if (!b || b->world <= 1) return;
+  const unsigned long long e = peer_barrier_timed_out(b);
+  if (e) throw StateError(std::string(what) + ": a rank did not reach the peer barrier within 5 s (barrier call " + std::to_string(e) +
+                          "); its contribution is missing -- the result is not valid");
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -315,6 +327,7 @@ static void wire_volume(Volume* v, const VolumeExport* all, bool ipc) {
   } else peer_barrier_attach_ptrs(vc->barrier, R, W, flags);
   vc->mc_merged.alloc(v->mc_range.n);
   vc->resolved = true;
+  outofcore_set_rank(v, R);                          // out-of-core ground truth: every rank keeps its own random slabs
 }
 
 void comm_attach_volume(Volume* v, Comm* c) {
@@ -415,6 +428,7 @@ void comm_train_steps(Volume* v, int steps, size_t batch, bool update_macrocell,
 double comm_global_loss(Volume* v, int which) {
   VolumeComm* vc = v->vcomm;
   VNR_CUDA(cudaStreamSynchronize(v->stream));
+  peer_barrier_require_healthy(vc->barrier, "data-parallel training");
   double total = 0;
   for (int r = 0; r < vc->comm->world; ++r) {
     double x = 0;

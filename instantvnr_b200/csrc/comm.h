@@ -30,6 +30,7 @@ struct PeerBarrier {
   unsigned long long epoch = 0;
   unsigned long long* local = nullptr;               // [kMaxPeers + 1]: slot r = rank r's last epoch; slot kMaxPeers = timeout flag
   unsigned long long* peer[kMaxPeers] = {};
+  unsigned long long* h_flag = nullptr;              // pinned host word: epoch of the last barrier that timed out (0 = healthy)
   ~PeerBarrier();
 };
 PeerBarrier* peer_barrier_create();
@@ -37,6 +38,7 @@ void peer_barrier_attach_ipc(PeerBarrier* b, int rank, int world, const void* al
 void peer_barrier_attach_ptrs(PeerBarrier* b, int rank, int world, unsigned long long* const* flags);
 void peer_barrier_sync(PeerBarrier* b, cudaStream_t s);
 unsigned long long peer_barrier_timed_out(PeerBarrier* b);
+void peer_barrier_require_healthy(PeerBarrier* b, const char* what);   // throws StateError after a timed-out barrier
 
 struct CommBoard;      // shared-memory rendezvous board (one process per GPU)
 struct CommLocal;      // in-process registry (one process, n devices)

@@ -868,6 +868,7 @@ const float* Renderer::map_frame() {
   FrameSlot& S = slot((int)(n_mapped % slots.size()));
   if (!S.downloaded) throw StateError("frame download is disabled on this renderer");
   VNR_CUDA(cudaEventSynchronize(S.frame_done[S.map_idx]));
+  if (rcomm && rcomm->resolved) peer_barrier_require_healthy(rcomm->barriers[(size_t)(n_mapped % slots.size())], "tile-parallel frame");
   const float* p = reinterpret_cast<const float*>(S.h_frame[S.map_idx]);
   S.mapped = true;
   ++n_mapped;

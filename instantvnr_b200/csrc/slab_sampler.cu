@@ -63,12 +63,32 @@ struct SlabSampler {
   std::vector<std::thread> workers;
   std::atomic<int> io_error{0};
   Pcg32 host_rng;                        // slab selection (the reference: std::mt19937, neural_sampler.cu:62-75)
+  int rank = 0;                          // data-parallel rank: selects the pcg32 stream of host_rng
   uint64_t bytes_uploaded = 0;
 
   ~SlabSampler() {
     for (auto& t : workers) if (t.joinable()) t.join();
     for (int k = 0; k < 2; ++k) { if (h_stage[k]) cudaFreeHost(h_stage[k]); if (h_desc[k]) cudaFreeHost(h_desc[k]); if (copied[k]) cudaEventDestroy(copied[k]); }
     if (fd >= 0) close(fd);
+  }
+
+  // finish (and drop) a refresh that is still being read
+  void drain() {
+    for (auto& t : workers) if (t.joinable()) t.join();
+    workers.clear();
+    pending = false;
+  }
+
+  // preload every slot (:571-577), n_refresh at a time (the last group wraps around when n_slots % n_refresh != 0), and
+  // start the first refresh (:579)
+  void preload(cudaStream_t s) {
+    host_rng.seed(1337, 2 + (uint64_t)rank);
+    for (uint32_t i = 0; i < n_slots; i += n_refresh) {
+      submit((int64_t)i);
+      wait_and_upload(s);
+    }
+    VNR_CUDA(cudaStreamSynchronize(s));
+    submit(-1);
   }
 
   // submit_one_job (:588-646): describe block (by, bz) and read its ghost-extended rows into `dst`
@@ -228,16 +248,25 @@ void outofcore_open(Volume* v, const char* path, int type, uint64_t offset, floa
     VNR_CUDA(cudaMallocHost((void**)&q.h_desc[k], (size_t)q.n_refresh * sizeof(SlabDesc)));
     VNR_CUDA(cudaEventCreateWithFlags(&q.copied[k], cudaEventDisableTiming));
   }
-  q.host_rng.seed(1337, 2);
-  // preload every slot (:571-577), n_refresh at a time; the last group wraps around when n_slots % n_refresh != 0
-  for (uint32_t i = 0; i < q.n_slots; i += q.n_refresh) {
-    q.submit((int64_t)i);
-    q.wait_and_upload(v->stream);
-  }
-  VNR_CUDA(cudaStreamSynchronize(v->stream));
-  q.submit(-1);                                                                              // :579
+  // a rank of a data-parallel group selects its slabs from its own pcg32 stream (see outofcore_set_rank)
+  q.rank = v->dp_world > 0 ? v->dp_rank : 0;
+  q.preload(v->stream);
   outofcore_release(v);
   v->ooc = sp.release();
+}
+
+// Data-parallel training (BASELINE configs[3]): every rank keeps its OWN pool of random slabs and refreshes it from its own
+// selection stream, so `world` ranks together cover `world` times as many distinct slabs per step -- the ranks' pools must
+// not be copies of each other.  The reference has one process and an unseeded std::mt19937 (neural_sampler.cu:62-75); here
+// rank r draws its slab choices from pcg32 stream 2 + r of seed 1337.  Called when a volume that already has an out-of-core
+// sampler joins a group (vnr_volume_attach_comm / vnr_volume_dp_attach); a changed rank re-draws and re-reads the pool.
+void outofcore_set_rank(Volume* v, int rank) {
+  if (!v->ooc || v->ooc->rank == rank) return;
+  SlabSampler& q = *v->ooc;
+  VNR_CUDA(cudaStreamSynchronize(v->stream));
+  q.drain();
+  q.rank = rank;
+  q.preload(v->stream);
 }
 
 // OutOfCoreSampler::sample (:1065-1120)

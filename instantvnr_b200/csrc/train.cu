@@ -812,6 +812,10 @@ void reset_optimizer_state(Volume* v) {
   v->opt_step = 0; v->lr_factor = 1.f; v->train_step = 0; v->loss_count = 0;
   v->loss_accum.zero(v->stream);
   VNR_CUDA(cudaStreamSynchronize(v->stream));
+  for (float* p : v->bias_retired) cudaFree(p);
+  v->bias_retired.clear();
+  v->bias_tab.ensure(1 << 16);                       // the bias-correction table exists before the first step (no allocation inside a step)
+  v->bias_filled = 0;
   v->have_opt = true;
 }
 
@@ -877,7 +881,10 @@ static AdamArgs begin_optimizer_step(Volume* v, cudaStream_t s) {
   }
   if (v->opt_step + 1 > v->bias_filled) {
     if (v->opt_step + 1 > v->bias_tab.n) {
-      VNR_CUDA(cudaStreamSynchronize(s));
+      // Grow WITHOUT a stream synchronisation or a cudaFree: in a data-parallel group driven by one host thread the stream holds a
+      // peer barrier that waits for ranks whose work is not enqueued yet.  Kernels in flight keep reading the old table, which is
+      // parked until the optimizer is reset or the volume released.
+      if (v->bias_tab.p) { v->bias_retired.push_back(v->bias_tab.p); v->bias_tab.p = nullptr; v->bias_tab.n = 0; }
       v->bias_tab.alloc(std::max<size_t>(1 << 16, 2 * (size_t)(v->opt_step + 1)));
       v->bias_filled = 0;
     }

@@ -17,6 +17,7 @@ void dp_finish_step(Volume* v, cudaStream_t s);
 void load_groundtruth_file(Volume* v, const char* path, int type, uint64_t offset, bool big_endian, float vmin, float vmax, float* range_out);
 void outofcore_open(Volume* v, const char* path, int type, uint64_t offset, float vmin, float vmax, uint32_t n_concurrent, uint32_t n_blocks);
 void outofcore_release(Volume* v);
+void outofcore_set_rank(Volume* v, int rank);   // data-parallel rank r selects (and re-reads) its own random slabs
 void outofcore_sample(Volume* v, float* d_xyz, float* d_target, size_t n, cudaStream_t s);
 void outofcore_info(Volume* v, uint32_t* n_slots, uint32_t* n_refresh, uint64_t* slot_bytes, uint64_t* first_voxel, uint32_t* length, uint64_t* bytes_uploaded);
 constexpr int kSlicesPerBlob = 16;

@@ -42,6 +42,7 @@ Volume::~Volume() {
   if (stream) cudaStreamSynchronize(stream);
   if (vcomm) { try { comm_detach_volume(this); } catch (...) {} }
   outofcore_release(this);
+  for (float* p : bias_retired) cudaFree(p);
   for (int r = 0; r < dp_world; ++r) {          // mappings of the peers' buffers (vnr_volume_dp_attach)
     if (r == dp_rank) continue;
     if (dp_params[r]) cudaIpcCloseMemHandle(dp_params[r]);

@@ -186,6 +186,7 @@ VNR_EXPORT int vnr_peer_barrier_check(void* bh, uint64_t* timed_out_epoch) {
   return guard([&] {
     PeerBarrier* b = reinterpret_cast<PeerBarrier*>(bh);
     if (!b || !timed_out_epoch) throw InvalidError("null argument");
+    VNR_CUDA(cudaDeviceSynchronize());
     *timed_out_epoch = peer_barrier_timed_out(b);
   });
 }

@@ -455,6 +455,7 @@ VNR_EXPORT int vnr_volume_dp_attach(vnr_volume_t* vh, int rank, int world, const
       VNR_CUDA(cudaIpcOpenMemHandle(&v->dp_grid_grads[r], h[1], cudaIpcMemLazyEnablePeerAccess));
       VNR_CUDA(cudaIpcOpenMemHandle(&v->dp_mlp_grads[r], h[2], cudaIpcMemLazyEnablePeerAccess));
     }
+    outofcore_set_rank(v, rank);                       // every rank refreshes its own random slabs
   });
 }
 VNR_EXPORT int vnr_volume_dp_detach(vnr_volume_t* vh) { return guard([&] { Volume* v = V(vh); VNR_CUDA(cudaStreamSynchronize(v->stream)); dp_detach_impl(v); }); }

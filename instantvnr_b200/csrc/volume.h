@@ -40,6 +40,7 @@ struct Volume {
   bool grads_clean = false, grads_pending = false;
   DevBuf<uint32_t> steps;
   DevBuf<float> bias_tab; uint32_t bias_filled = 0;   // Adam bias-correction table (train.cu) ...
+  std::vector<float*> bias_retired;                   // outgrown tables still referenced by kernels in flight
   float bias_beta1 = -1.f, bias_beta2 = -1.f;         // ... and the betas it was built with (refilled when the optimizer config changes)
   // measurement taps of the training kernel (vnr_volume_train_debug): chain variant, role switches, per-CTA role timers
   int train_variant = 1; uint32_t train_flags = 0; bool train_prof_on = false; DevBuf<uint32_t> train_prof;

@@ -148,6 +148,9 @@ class DataParallelTrainer:
                     dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=self.group)
                     mc[:, 0] = lo; mc[:, 1] = hi
             if want_loss:
+                bar = getattr(self.b, "barrier", None)
+                if bar is not None and bar.timed_out():       # synchronises: a rank that never arrived leaves incomplete gradients behind
+                    raise RuntimeError("data-parallel step: a rank did not reach the peer barrier within 5 s; the parameters are not valid")
                 loss = torch.tensor([self.b.local_loss()], dtype=torch.float64)
                 if self.world > 1:
                     dev = bufs[0].device
@@ -244,7 +247,12 @@ class TileParallelRenderer:
             self.ren.download()
 
     def map_frame(self, copy=True):
-        return self.ren.map_frame(copy) if self.rank == 0 else None
+        if self.rank != 0:
+            return None
+        img = self.ren.map_frame(copy)                         # synchronises the frame
+        if self.barrier is not None and self.barrier.timed_out():
+            raise RuntimeError("tile-parallel frame: a rank did not reach the peer barrier within 5 s; the frame is incomplete")
+        return img
 
     def close(self):
         import instantvnr_b200 as vnr

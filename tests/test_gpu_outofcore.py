@@ -122,3 +122,71 @@ def test_outofcore_errors(tmp_path):
     assert e.value.code == -1
     with pytest.raises(vnr.VnrError):
         vol.outofcore_info()
+
+
+def test_data_parallel_ranks_keep_their_own_slabs_and_the_step_equals_accumulated_batches(tmp_path):
+    """BASELINE configs[3] in small: out-of-core ground truth + data-parallel training behind vnr_comm.  Every rank refreshes its
+    OWN random slabs (pcg32 stream 2 + rank of the slab selector), draws the r-th of `world` consecutive batches of the one
+    sample stream from them, and the fused reduce-scatter + Adam + all-gather step equals one process accumulating the same
+    batches (restated by the oracle from each rank's slab table) into one optimizer step."""
+    import os
+    os.environ.setdefault("VNR_COMM_SHARE_DEVICES", "1")       # a one-GPU box runs both ranks on the device
+    from instantvnr_b200 import synthetic as syn
+    dims, dtype, world, n, steps = (64, 48, 40), "float32", 2, 2048, 3
+    gt = syn.make_volume(dims, seed=9)
+    raw = (gt * 100.0 - 20.0).astype(np.float32)
+    path = tmp_path / "dp.raw"; raw.tofile(path)
+    lo, hi = -20.0, 80.0
+    row = dims[0] * 4
+    block_rows = min(-(-32768 // row), dims[1])
+
+    def make(init):
+        v = vnr.NeuralVolume(CFG, dims)
+        v.set_groundtruth_outofcore(path, dtype, (lo, hi), num_concurrent_blocks=8, num_blocks=40)
+        if init:
+            v.init_params(21)
+        return v
+
+    solo = make(True)
+    p0 = solo.get_params_f16()
+    comms = vnr.Comm.init_local(world)
+    vols = []
+    for r, c in enumerate(comms):
+        c.set_device()
+        vols.append(make(r == 0))
+    for v, c in zip(vols, comms):
+        v.attach_comm(c)
+    tabs = [v.outofcore_info(table=True) for v in vols]
+    assert np.array_equal(tabs[0]["first_voxel"], solo.outofcore_info(table=True)["first_voxel"])    # rank 0 == a single process
+    assert (tabs[0]["first_voxel"] != tabs[1]["first_voxel"]).mean() > 0.5                            # rank 1 drew its own slabs
+    # the accumulated single-process run on the oracle's restatement of every rank's batch
+    ref = vnr.NeuralVolume(CFG, dims)
+    ref.set_params_f16(p0)
+    rng = O.Rng(1337)
+    f32 = raw.ravel()
+    ref_losses, dp_losses = [], []
+    for step in range(steps):
+        tabs = [v.outofcore_info(table=True) for v in vols]            # the tables this step's batches are drawn from
+        loss = 0.0
+        for r in range(world):
+            xyz, tgt, bad = O.ooc_sample(rng.state, n, tabs[r]["first_voxel"], tabs[r]["length"], block_rows, f32, dims, lo, hi)
+            assert bad == 0
+            ref.train_grads(torch.from_numpy(xyz).cuda(), torch.from_numpy(tgt).cuda(), n, n * world)
+            loss += ref.last_loss()
+        ref.optimizer_step()
+        ref_losses.append(loss)
+        for v in vols:
+            v.train(1, batch=n, fast_mode=True)
+        dp_losses.append(vols[0].last_loss())
+    ps = [v.get_params_f16() for v in vols]
+    assert np.array_equal(ps[0], ps[1])                                # replicas bit-identical
+    assert np.allclose(dp_losses, ref_losses, rtol=2e-3), (dp_losses, ref_losses)
+    a = ps[0].view(np.float16).astype(np.float32); b = ref.get_params_f16().view(np.float16).astype(np.float32)
+    assert (a != b).mean() < 0.02                                      # same batches, same arithmetic up to the fp16 reduction order
+    # the ranks' pools keep diverging: different slots refreshed with different slabs
+    t0, t1 = [v.outofcore_info(table=True)["first_voxel"] for v in vols]
+    assert (t0 != t1).mean() > 0.5
+    for v in vols:
+        v.detach_comm()
+    for c in comms:
+        c.close()
