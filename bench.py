@@ -209,23 +209,55 @@ def run_ours(args):
     t0 = time.time()
     vol, gt, (rgb, alpha) = build_scene(vnr, dims, args.train_steps, 1 << 16, dict(log2_hashmap=args.log2_hashmap))
     train_step_count, train_loss = vol.stats()
-    if world > 1:
-        # replicate rank 0's trained model (the fp16 reductions of training are order-dependent, so independently
-        # trained replicas differ in the last bits) and its learned macrocell value ranges
+    # N > 1: everything multi-GPU goes through the library's communicator (vnr_comm_init_rank; include/vnr_c.h): attaching the
+    # volume replicates rank 0's trained model, macrocell value ranges and sampler stream (independently trained replicas would
+    # differ in the last bits: the fp16 reductions of training are order-dependent) and makes vnr_volume_train data parallel;
+    # attaching the renderer deals the image strips to the ranks -- finished pixels are stored by the compositing kernels into
+    # pinned host frames shared by all ranks (every GPU over its own PCIe link) or, with the download off, into rank 0's device
+    # frame over NVLink; a peer-memory barrier kernel closes the frame.  --gather nccl keeps the round-1 harness (torch.distributed
+    # gather of padded strips) as the comparison.
+    comm = None; tp = None
+    use_comm = world > 1 and args.gather != "nccl"
+    if use_comm:
+        comm = vnr.Comm.init_rank(rank, world, f"vnr-bench-{os.environ.get('MASTER_PORT', '0')}-{os.getppid()}")
+        vol.attach_comm(comm)
+    elif world > 1:
         from instantvnr_b200.distributed import TileParallelRenderer, broadcast_params
         broadcast_params(vol)
         _, vr, _ = vol.get_macrocell()
         t = torch.from_numpy(vr).cuda(); dist.broadcast(t, src=0); vol.set_macrocell(t.cpu().numpy())
-    ren = vnr.Renderer(vol)
-    ren.set_size(W, H)
-    ren.set_mode(vnr.VNR_RAYMARCHING_NO_SHADING_SAMPLE_STREAMING)
-    ren.set_sampling_rate(1.0)
+
+    def make_renderer():
+        r = vnr.Renderer(vol)
+        r.set_size(W, H)
+        r.set_mode(vnr.VNR_RAYMARCHING_NO_SHADING_SAMPLE_STREAMING)
+        r.set_sampling_rate(1.0)
+        return r
+
     n_views = 16
     cams = [syn.default_camera(dims, v, n_views) for v in range(n_views)]
-    stream = torch.cuda.ExternalStream(ren.stream())
-    # N > 1: interleaved pixel strips per rank; finished pixels are stored straight into rank 0's frame buffer over
-    # NVLink by the compositing kernel (peer mapping) and a 4-byte all-reduce closes the frame
-    tp = TileParallelRenderer(ren, mode=args.gather) if world > 1 else None
+    # the frame ring: `--pipeline P` frame slots inside the renderer (own stream, ray / sample buffers and captured wavefront
+    # graph each; vnr_renderer_set_frames_in_flight): consecutive vnr_render calls overlap on the device -- the latency-bound tail
+    # rounds of frame i run under the head of frame i+1.  Every frame is still rendered completely.
+    n_pipe = 1 if (world > 1 and not use_comm) else max(1, args.pipeline)
+    ren = make_renderer()
+    ren.set_frames_in_flight(n_pipe)
+    parity = None
+    if use_comm:
+        # pre-flight parity (the driver's GPU-test box has one GPU): the tile-parallel frame must equal the single-GPU frame bit
+        # for bit -- rank 0 renders the whole frame alone first, then the attached renderers render it together
+        solo = make_renderer(); solo.set_camera(*cams[1]); solo.render(); want = solo.map_frame(); del solo
+        ren.attach_comm(comm)
+        ren.set_camera(*cams[1]); ren.render()
+        ok = bool(np.array_equal(ren.map_frame(), want)) if rank == 0 else True
+        for _ in range(n_pipe - 1):                      # leave every slot of the ring in the same state on every rank
+            ren.render()
+            if rank == 0:
+                ren.map_frame()
+        flag = torch.tensor([1.0 if ok else 0.0], device="cuda"); dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        parity = {"tile_parallel_frame_equals_single_gpu_frame": bool(flag.item() == 1.0)}
+    elif world > 1:
+        tp = TileParallelRenderer(ren, mode="nccl")
 
     def render_frame():
         if tp:
@@ -242,31 +274,12 @@ def run_ours(args):
     if tp:
         tp.download = False
     else:
-        ren.set_download(False)
-    # frames in flight: the renderer owns a ring of `--pipeline P` frame slots (own stream, ray / sample buffers and captured
-    # wavefront graph each; vnr_renderer_set_frames_in_flight), so consecutive vnr_render calls overlap on the device: the
-    # latency-bound tail rounds of frame i run under the head of frame i+1.  Every frame is still rendered completely.
-    # N > 1: every pipeline slot is a tile-parallel renderer of its own (own strips buffer on rank 0, own peer barrier);
-    # all ranks take the frames in the same turn, so frame i of every rank meets in pair i % P.
-    pipe = [ren]; pipe_tp = [tp]
-    n_pipe = 1 if (tp and args.gather == "nccl") else max(1, args.pipeline)     # NCCL gathers of two frames must not overlap on one communicator
-    if not tp:
-        ren.set_frames_in_flight(n_pipe)
-    for _ in range(n_pipe - 1 if tp else 0):
-        r2 = vnr.Renderer(vol)
-        r2.set_size(W, H); r2.set_mode(vnr.VNR_RAYMARCHING_NO_SHADING_SAMPLE_STREAMING); r2.set_sampling_rate(1.0); r2.set_download(False)
-        pipe.append(r2)
-        t2 = TileParallelRenderer(r2, mode=args.gather); t2.download = False
-        pipe_tp.append(t2)
-    pipe_streams = [torch.cuda.ExternalStream(s_) for r in pipe for s_ in r.streams()]
+        ren.set_download(False)            # N > 1: pixels now go to rank 0's device frame over NVLink
+    pipe_streams = [torch.cuda.ExternalStream(s_) for s_ in ren.streams()]
 
     def pipelined_frame(i):
-        k = i % len(pipe)
-        pipe[k].set_camera(*cams[i % n_views])
-        if pipe_tp[k]:
-            pipe_tp[k].render()
-        else:
-            pipe[k].render()
+        ren.set_camera(*cams[i % n_views])
+        render_frame()
 
     for i in range(max(args.warmup, 2 * n_pipe)):
         pipelined_frame(i)
@@ -323,7 +336,9 @@ def run_ours(args):
         ren.set_download(True)
 
     def map_frame():
-        return tp.map_frame(copy=False) if tp else ren.map_frame(copy=False)
+        if tp:
+            return tp.map_frame(copy=False)
+        return ren.map_frame(copy=False) if rank == 0 else None     # tile-parallel frames are mapped on rank 0
 
     def e2e_pass():
         for i in range(3):
@@ -354,28 +369,68 @@ def run_ours(args):
     # the same end-to-end calls with frames in flight (reported next to, not instead of, the strict figure): with a ring of K frame
     # slots inside the renderer, frame i+1 .. i+K-1 are already launched when frame i is mapped (vnr_map_frame returns the oldest
     # unmapped frame); every frame is still mapped (synchronised, host-visible) exactly once
+    def set_ring(k):
+        """frames in flight of the renderer; a communicator-attached renderer is re-attached (collective, every rank)"""
+        if use_comm:
+            ren.detach_comm(); ren.set_frames_in_flight(k); ren.attach_comm(comm)
+        else:
+            ren.set_frames_in_flight(k)
+
     fps_inflight = {}; inflight = 0
     if not tp:
         K = 3; inflight = K - 1
-        ren.set_frames_in_flight(K)
+        set_ring(K)
 
         def inflight_pass(n):
             for i in range(n + K - 1):
                 if i < n:
                     ren.set_camera(*cams[i % n_views]); ren.render()
-                if i >= K - 1:
+                if i >= K - 1 and rank == 0:
                     img = ren.map_frame(copy=False)
                     checksum = float(img[H // 2, W // 2, 3])
         for zc in (True, False):
             ren.set_zero_copy(zc)
             inflight_pass(2 * K)
-            torch.cuda.synchronize()
+            barrier()
             tq = time.perf_counter()
             inflight_pass(args.steps)
-            torch.cuda.synchronize()
-            fps_inflight["zero_copy" if zc else "dma_copy"] = args.steps / (time.perf_counter() - tq)
+            barrier()
+            dt_ = time.perf_counter() - tq
+            if world > 1:
+                t = torch.tensor([dt_], device="cuda", dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); dt_ = t.item()
+            fps_inflight["zero_copy" if zc else "dma_copy"] = args.steps / dt_
         ren.set_zero_copy(True)
-        ren.set_frames_in_flight(n_pipe)
+        set_ring(n_pipe)
+
+    # ---------------- training throughput of the same volume (steps/s), reported next to the headline ----------------
+    # N = 1: vnr_volume_train on the one GPU.  N > 1: the SAME call on every rank of the communicator = synchronous data parallel,
+    # 2^18 samples per rank per step (weak scaling), reduce-scatter + Adam + all-gather fused in one kernel over NVLink peer
+    # memory; device-timed on every rank between barriers, max over ranks.
+    TB = 1 << 18
+    vst = torch.cuda.ExternalStream(vol.stream())
+    dp_ok = None
+    if world == 1 or use_comm:
+        vol.train(5, batch=TB, fast_mode=True)
+        barrier()
+        et0, et1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        et0.record(vst)
+        vol.train(20, batch=TB, fast_mode=True)
+        et1.record(vst)
+        vst.synchronize(); barrier()
+        train_ms = et0.elapsed_time(et1) / 20
+        if world > 1:
+            t = torch.tensor([train_ms], device="cuda", dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); train_ms = t.item()
+            # pre-flight parity of the data-parallel path: replicas bit-identical after the steps above, the same global loss on every rank
+            p16 = torch.from_numpy(vol.get_params_f16().astype(np.int64)).cuda()
+            sig = torch.stack([p16.sum(), (p16 * (torch.arange(p16.numel(), device="cuda") % 8191 + 1)).sum()]).double()
+            lo_, hi_ = sig.clone(), sig.clone()
+            dist.all_reduce(lo_, op=dist.ReduceOp.MIN); dist.all_reduce(hi_, op=dist.ReduceOp.MAX)
+            loss_t = torch.tensor([vol.last_loss()], device="cuda", dtype=torch.float64); l0, l1 = loss_t.clone(), loss_t.clone()
+            dist.all_reduce(l0, op=dist.ReduceOp.MIN); dist.all_reduce(l1, op=dist.ReduceOp.MAX)
+            dp_ok = bool(torch.equal(lo_, hi_)) and bool(l0.item() == l1.item()) and bool(np.isfinite(l0.item()))
+            parity["data_parallel_replicas_bit_identical"] = dp_ok
+    else:
+        train_ms = float("nan")
 
     if rank != 0:
         if world > 1:
@@ -438,15 +493,6 @@ def run_ours(args):
                         "hash-grid cells (sectors), which the random probe does not, so frac can exceed frac_uniform (same kernel, uniform random coordinates).  hbm_copy_frac "
                         "(all 1044 algorithmic B/sample against the HBM copy peak) is kept for comparison with round 1; the table is read from L2, not HBM, when it fits"}
 
-    # training throughput of the same volume (steps/s), reported next to the headline
-    s_train = torch.cuda.Event(enable_timing=True); e_train = torch.cuda.Event(enable_timing=True)
-    vol.train(5, batch=1 << 18, fast_mode=True)
-    torch.cuda.synchronize()
-    tw0 = time.perf_counter()
-    vol.train(20, batch=1 << 18, fast_mode=True)
-    vol.stats()
-    train_ms = (time.perf_counter() - tw0) * 1e3 / 20
-
     # the CPU baseline is measured at N=1 only (under torchrun the host cores are shared by the ranks)
     cpu = cpu_baseline(vol, dims, cams, rgb, alpha, args) if world == 1 else {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "measured at N=1 only"}
 
@@ -461,9 +507,15 @@ def run_ours(args):
                    "frames_in_flight": f"{n_pipe} frame slot(s) inside the renderer for the device-resident `value` (vnr_renderer_set_frames_in_flight; the strict end-to-end pass maps every frame before the next is launched)"},
         "fps": args.steps / (ms * 1e-3), "samples_per_frame": decoded / args.steps, "composited_per_frame": composited / args.steps,
         "rays_hit_per_frame": rays / args.steps,
-        "train_steps_per_sec_batch_2p18": 1000.0 / train_ms, "train_samples_per_sec": (1 << 18) * 1000.0 / train_ms,
+        "train_steps_per_sec_batch_2p18": 1000.0 / train_ms, "train_samples_per_sec": world * (1 << 18) * 1000.0 / train_ms,
+        "dp_steps_per_sec": (1000.0 / train_ms) if world > 1 else None, "dp_global_batch": world * (1 << 18),
+        "dp_mode": ("sharded optimizer over NVLink peer memory (reduce-scatter + Adam + all-gather in one kernel) behind vnr_volume_train on a communicator; "
+                    "2^18 samples per rank per step (weak scaling)") if world > 1 else "single GPU",
+        "parity_checked": (bool(parity) and all(parity.values())) if world > 1 else None, "parity": parity,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 480, "d2h_bytes_per_step": W * H * 16, "fps": args.steps / (ms_e2e * 1e-3),
-                "frame_path": "tile-parallel gather + download on rank 0" if tp else "zero-copy: compositing kernels store finished pixels into the pinned host frame",
+                "frame_path": ("tile-parallel NCCL gather + download on rank 0" if tp else
+                               "tile-parallel: every rank's compositing kernels store its strips into ONE pinned host frame shared by all ranks (each GPU over its own PCIe link); rank 0 maps it"
+                               if use_comm else "zero-copy: compositing kernels store finished pixels into the pinned host frame"),
                 "fps_copy_after_frame": (args.steps / (ms_e2e_copy * 1e-3)) if ms_e2e_copy else None,
                 "fps_with_frames_in_flight": (max(fps_inflight.values()) if fps_inflight else None), "fps_with_frames_in_flight_by_download": fps_inflight,
                 "frames_in_flight": inflight,
@@ -929,7 +981,8 @@ def main():
     ap.add_argument("--dp-mode", default="sharded", choices=["sharded", "allreduce"], help="train workload, N > 1: peer-memory optimizer or NCCL all-reduce")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--pipeline", type=int, default=2, help="render workload, N = 1: renderers that take the frames in turn (device-resident timing)")
-    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"], help="N > 1: how finished pixels reach rank 0")
+    ap.add_argument("--gather", default="comm", choices=["comm", "nccl"],
+                    help="N > 1: comm = the library's communicator (peer stores from the compositing kernels); nccl = torch.distributed gather of padded strips (comparison)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -89,7 +89,9 @@ int vnr_volume_gather_probe(vnr_volume_t* v, const float* d_xyz, uint32_t* d_out
  * kind 0 = read-only loads (ld.global.nc.v4) -- a 46.7 MB buffer gives the L2 random-gather ceiling of the decode, a
  * 306.8 MB one the HBM random-gather ceiling (SURVEY 8d `l2_gather_gbs` / `hbm_gather_gbs`); kind 1 = fp16x8 vector
  * reductions (red.global.add.noftz.v4.f16x2), the ceiling of the hash-grid backward; kind 2 = a streaming copy of the
- * buffer.  Returns the fastest and the mean of `repeats` CUDA-event-timed launches (after one warm-up). */
+ * buffer; kind 3 = random 32-byte loads (one 256-bit load per sector); kinds 4-7 = one float4 frame of table_bytes
+ * (1024 pixels wide) stored into PINNED HOST memory in scanline / 8x4-tile / 32-byte scanline / 16x2-tile order (what
+ * bounds the zero-copy frame download).  Returns the fastest and the mean of `repeats` CUDA-event-timed launches (after one warm-up). */
 int vnr_probe_memory(int kind, size_t table_bytes, size_t n_ops, int repeats, float* ms_best, float* ms_mean);
 
 /* measurement taps of the fused training kernel (train.cu): variant 1 = current MMA chain, 0 = the round-1 chain
@@ -144,7 +146,11 @@ int vnr_volume_train(vnr_volume_t* v, int steps, int batch, int fast_mode, void*
  * d_xyz float[3*n], d_target float[n]; n must be a multiple of 128. */
 int vnr_volume_train_on(vnr_volume_t* v, const float* d_xyz, const float* d_target, size_t n, void* stream);
 /* Data-parallel split of a step: gradients only (fwd+loss+bwd), then the optimizer.  Between
- * the two the caller all-reduces the gradient buffer (vnr_volume_grad_buffer). */
+ * the two the caller all-reduces the gradient buffer (vnr_volume_grad_buffer).  Calls before the next optimizer step
+ * ACCUMULATE (hash-grid and MLP gradients alike): k calls on k batches with n_global = their total size equal one step
+ * on the concatenated batch.
+ * Arithmetic: the MLP weight gradients are accumulated in HALF like the reference's split-K GEMMs (tcnn cutlass_matmul.h:83;
+ * fully_fused_mlp.cu:863-922): one rounding per 16 samples, one K-slice per SM, slices summed in half. */
 int vnr_volume_train_grads(vnr_volume_t* v, const float* d_xyz, const float* d_target, size_t n, size_t n_global, void* stream);
 int vnr_volume_optimizer_step(vnr_volume_t* v, void* stream);
 /* which = 0: MLP weight gradients (fp32, n_mlp elements); which = 1: hash-grid gradients (fp16,
@@ -326,7 +332,9 @@ int vnr_ipc_close(void* d_ptr);
  * `world`-thread kernel publishes this rank's epoch into every peer's flag array and waits for theirs (system-scope
  * release / acquire); replaces a 4-byte NCCL all-reduce (~25 us) at ~5 us.  create: returns the 64-byte IPC handle
  * of the local flags; attach: all ranks' handles rank-major; a peer that never arrives trips a 5 s timeout that
- * vnr_peer_barrier_check reports. */
+ * vnr_peer_barrier_check reports (it reads a pinned host word: call it after a synchronisation that covers the barrier,
+ * e.g. once the frame is mapped or the loss read).  Volumes / renderers attached to a communicator check their own
+ * barriers there and fail with VNR_ERR_STATE (vnr_map_frame, vnr_volume_stats, vnr_volume_last_loss). */
 int vnr_peer_barrier_create(void** barrier, void* handle64);
 int vnr_peer_barrier_attach(void* barrier, int rank, int world, const void* all_handles);
 int vnr_peer_barrier_sync(void* barrier, void* stream);

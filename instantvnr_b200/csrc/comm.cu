@@ -340,6 +340,13 @@ void comm_attach_volume(Volume* v, Comm* c) {
   v->have_params = true;                             // ranks != 0 receive rank 0's parameters below
   if (!v->have_opt) reset_optimizer_state(v);
   train_ensure_buffers(v);
+  {   // every kernel of a data-parallel step is loaded before the first peer barrier exists (see train_preload_kernels)
+    cudaFuncAttributes fa;
+    VNR_CUDA(cudaFuncGetAttributes(&fa, peer_barrier_kernel));
+    VNR_CUDA(cudaFuncGetAttributes(&fa, mc_merge_kernel));
+    VNR_CUDA(cudaFuncGetAttributes(&fa, master_from_params_kernel));
+    train_preload_kernels(v);
+  }
   std::unique_ptr<VolumeComm> vc(new VolumeComm());
   vc->comm = c; vc->id = c->n_volumes++;
   vc->barrier = peer_barrier_create();
@@ -571,7 +578,11 @@ void comm_detach_renderer(Renderer* r) {
     FrameSlot& S = *sp;
     S.frame_target = nullptr;
     if (S.h_frame_external) {
-      for (int h = 0; h < 2; ++h) { S.h_frame[h] = nullptr; VNR_CUDA(cudaMallocHost((void**)&S.h_frame[h], npix * sizeof(float4))); }
+      for (int h = 0; h < 2; ++h) {
+        S.h_frame[h] = nullptr;
+        VNR_CUDA(cudaMallocHost((void**)&S.h_frame[h], npix * sizeof(float4)));
+        memset(S.h_frame[h], 0, npix * sizeof(float4));
+      }
       S.h_frame_external = false;
     }
     S.rendered = false; S.downloaded = false; S.mapped = true;

@@ -178,8 +178,11 @@ template <int F, int STRIDE>
 static cudaError_t launch_decode_t(const DecoderDesc& d, const __half* params, const float* coords, const float* coords_alt, float* out, size_t n,
                                    const uint32_t* n_dev, const uint32_t* round_dev, size_t n_max, __half* enc_out, cudaStream_t stream) {
   const size_t smem = 1024 + (size_t)kStages * MlpSmem::kATile + MlpSmem::weights_bytes(d.n_hidden);
-  static size_t configured = 0;
+  static size_t configured_dev[kMaxDevices] = {};   // function attributes are per device
   if (smem > 226 * 1024) return cudaErrorInvalidValue;
+  int dev = 0;
+  if (cudaError_t e = cudaGetDevice(&dev)) return e;
+  size_t& configured = configured_dev[dev % kMaxDevices];
   if (configured < smem) {
     cudaError_t e = cudaFuncSetAttribute(decode_kernel<F, STRIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

@@ -90,6 +90,12 @@ __global__ void macrocell_max_opacity_kernel(uint32_t n_cells, const float* __re
   out[i] = op;
 }
 
+void macrocell_preload_kernels() {
+  cudaFuncAttributes fa;
+  VNR_CUDA(cudaFuncGetAttributes(&fa, macrocell_explicit_kernel));
+  VNR_CUDA(cudaFuncGetAttributes(&fa, macrocell_max_opacity_kernel));
+}
+
 void macrocell_update_explicit(Volume* v, const float* d_xyz, const float* d_values, size_t n, cudaStream_t s) {
   if (!n) return;
   const int3 dims = make_int3(v->dims[0], v->dims[1], v->dims[2]), md = make_int3(v->mc_dims[0], v->mc_dims[1], v->mc_dims[2]);

@@ -59,6 +59,56 @@ __global__ void __launch_bounds__(256) probe_reds_kernel(__half* __restrict__ ta
   }
 }
 
+// random 32-byte loads (one 256-bit LDG per 32-byte sector): is the L1 bound per REQUEST or per byte?  If this kernel moves as many
+// requests per second as probe_loads_kernel, fetching the two x-neighbours of a cell with one load pays.
+__global__ void __launch_bounds__(256) probe_loads32_kernel(const uint4* __restrict__ table, uint32_t n_vec, uint32_t per_thread, uint32_t seed,
+                                                            uint32_t* __restrict__ sink) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t fold = 0;
+  uint32_t c = mix32(t * 0x9e3779b9u + seed);
+  const uint32_t n_pair = n_vec / 2;
+  for (uint32_t k = 0; k < per_thread; k += 4) {
+    uint32_t v[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      c = c * 1664525u + 1013904223u;
+      const uint32_t idx = (uint32_t)(((uint64_t)mix32(c) * n_pair) >> 32);
+      asm volatile("ld.global.nc.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                   : "=r"(v[i][0]), "=r"(v[i][1]), "=r"(v[i][2]), "=r"(v[i][3]), "=r"(v[i][4]), "=r"(v[i][5]), "=r"(v[i][6]), "=r"(v[i][7])
+                   : "l"(table + 2 * (size_t)idx));
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int q = 0; q < 8; ++q) fold ^= v[i][q];
+  }
+  if (fold == 0x12345678u) sink[t & 1023u] = fold;
+}
+
+// stores of finished pixels into PINNED HOST memory (the zero-copy frame download): float4 per thread over a `width`-pixel-wide
+// image.  pattern 0: scanline (a warp writes 512 contiguous bytes), 1: 8 x 4 pixel tiles per warp (four 128-byte runs, the
+// marcher's ray order), 2: scanline with one 32-byte store per thread (two pixels), 3: tiles of 16 x 2 pixels (two 256-byte runs)
+__global__ void __launch_bounds__(128) probe_host_store_kernel(float4* __restrict__ dst, uint32_t width, uint32_t height, int pattern) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t npix = width * height;
+  const float4 v = make_float4((float)t, 1.f, 2.f, 3.f);
+  if (pattern == 2) {
+    if (2 * t + 1 >= npix) return;
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %1, %2, %3, %4};" ::"l"(dst + 2 * (size_t)t), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+    return;
+  }
+  if (t >= npix) return;
+  uint32_t pix = t;
+  if (pattern == 1 || pattern == 3) {
+    const uint32_t tw = pattern == 1 ? 8u : 16u, th = 32u / tw;
+    const uint32_t warp = t >> 5, lane = t & 31u, tiles_x = width / tw;
+    const uint32_t x = (warp % tiles_x) * tw + lane % tw, y = (warp / tiles_x) * th + lane / tw;
+    if (y >= height) return;
+    pix = y * width + x;
+  }
+  dst[pix] = v;
+}
+
 // streaming copy (read + write) for reference next to MEASURED_PEAKS.json's figure
 __global__ void __launch_bounds__(256) probe_copy_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, size_t n_vec) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
@@ -70,10 +120,12 @@ using namespace vnr;
 
 #define VNR_EXPORT extern "C" __attribute__((visibility("default")))
 
-// kind 0: random 16-byte loads, 1: random 16-byte fp16x8 reductions, 2: streaming copy of table_bytes (n_ops ignored).
+// kind 0: random 16-byte loads, 1: random 16-byte fp16x8 reductions, 2: streaming copy of table_bytes (n_ops ignored), 3: random
+// 32-byte loads (n_ops loads of 32 bytes), 4..7: stores of a table_bytes frame (float4 pixels, 1024 wide) into pinned HOST memory in
+// pattern kind - 4 (see probe_host_store_kernel).
 // Runs `repeats` timed launches after one warm-up and returns the fastest (ms_best) and the mean (ms_mean) launch time.
 VNR_EXPORT int vnr_probe_memory(int kind, size_t table_bytes, size_t n_ops, int repeats, float* ms_best, float* ms_mean) {
-  if (kind < 0 || kind > 2 || table_bytes < 4096 || repeats < 1 || !ms_best) return VNR_ERR_INVALID;
+  if (kind < 0 || kind > 7 || table_bytes < 4096 || repeats < 1 || !ms_best) return VNR_ERR_INVALID;
   int n_dev = 0;
   if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) { cudaGetLastError(); return VNR_ERR_CUDA; }
   void* table = nullptr; void* aux = nullptr;
@@ -82,9 +134,12 @@ VNR_EXPORT int vnr_probe_memory(int kind, size_t table_bytes, size_t n_ops, int 
   auto ok = [&](cudaError_t e) { if (e != cudaSuccess) { cudaGetLastError(); rc = VNR_ERR_CUDA; } return e == cudaSuccess; };
   const size_t n_vec = table_bytes / 16;
   do {
-    if (!ok(cudaMalloc(&table, n_vec * 16))) break;
+    const bool host_table = kind >= 4;
+    if (host_table) { if (!ok(cudaMallocHost(&table, n_vec * 16))) break; }
+    else if (!ok(cudaMalloc(&table, n_vec * 16))) break;
     if (!ok(cudaMalloc(&aux, kind == 2 ? n_vec * 16 : 4096))) break;
-    if (!ok(cudaMemset(table, 0, n_vec * 16))) break;
+    if (host_table) memset(table, 0, n_vec * 16);
+    else if (!ok(cudaMemset(table, 0, n_vec * 16))) break;
     if (!ok(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking))) break;
     if (!ok(cudaEventCreate(&e0)) || !ok(cudaEventCreate(&e1))) break;
     const uint32_t per_thread = 64;                                 // the example model's loads / reductions per sample
@@ -96,7 +151,9 @@ VNR_EXPORT int vnr_probe_memory(int kind, size_t table_bytes, size_t n_ops, int 
       ok(cudaEventRecord(e0, s));
       if (kind == 0) probe_loads_kernel<<<grid, 256, 0, s>>>((const uint4*)table, (uint32_t)n_vec, per_thread, 17u + it, (uint32_t*)aux);
       else if (kind == 1) probe_reds_kernel<<<grid, 256, 0, s>>>((__half*)table, (uint32_t)n_vec, per_thread, 17u + it);
-      else probe_copy_kernel<<<148 * 16, 256, 0, s>>>((const uint4*)table, (uint4*)aux, n_vec);
+      else if (kind == 2) probe_copy_kernel<<<148 * 16, 256, 0, s>>>((const uint4*)table, (uint4*)aux, n_vec);
+      else if (kind == 3) probe_loads32_kernel<<<grid, 256, 0, s>>>((const uint4*)table, (uint32_t)n_vec, per_thread, 17u + it, (uint32_t*)aux);
+      else { const uint32_t w = 1024, h = (uint32_t)(n_vec / w); probe_host_store_kernel<<<(w * h + 127) / 128, 128, 0, s>>>((float4*)table, w, h, kind - 4); }
       ok(cudaGetLastError());
       ok(cudaEventRecord(e1, s));
       if (!ok(cudaEventSynchronize(e1))) break;
@@ -111,7 +168,7 @@ VNR_EXPORT int vnr_probe_memory(int kind, size_t table_bytes, size_t n_ops, int 
   if (e0) cudaEventDestroy(e0);
   if (e1) cudaEventDestroy(e1);
   if (s) cudaStreamDestroy(s);
-  if (table) cudaFree(table);
+  if (table) { if (kind >= 4) cudaFreeHost(table); else cudaFree(table); }
   if (aux) cudaFree(aux);
   return rc;
 }

@@ -430,6 +430,7 @@ void FrameSlot::resize(size_t npix) {
     if (h_frame[k] && !h_frame_external) cudaFreeHost(h_frame[k]);
     h_frame[k] = nullptr;
     VNR_CUDA(cudaMallocHost((void**)&h_frame[k], npix * sizeof(float4)));
+    memset(h_frame[k], 0, npix * sizeof(float4));      // pixels outside a renderer's partition are never written: they read as zero
   }
   h_frame_external = false;
   rendered = false; downloaded = false; mapped = true;

@@ -218,6 +218,7 @@ static uint32_t env_u32(const char* name, uint32_t fallback) {
 }
 
 void outofcore_release(Volume* v) { delete v->ooc; v->ooc = nullptr; }
+void outofcore_preload_kernels() { cudaFuncAttributes fa; VNR_CUDA(cudaFuncGetAttributes(&fa, slab_sample_kernel)); }
 
 // OutOfCoreSampler::OutOfCoreSampler (:1040-1063) + RandomBuffer::RandomBuffer (:526-582)
 void outofcore_open(Volume* v, const char* path, int type, uint64_t offset, float vmin, float vmax, uint32_t n_concurrent, uint32_t n_blocks) {

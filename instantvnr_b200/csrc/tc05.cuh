@@ -113,8 +113,9 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
 // Instruction descriptor for kind::f16 (cute::UMMA::InstrDescriptor): fp16 A/B, fp32 D.
 //   [4,6) c_format (1 = F32), [7,10) a_format (0 = F16), [10,13) b_format, [15] a_major,
 //   [16] b_major (0 = K, 1 = MN), [17,23) N >> 3, [24,29) M >> 4.
-__host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t M, uint32_t N, uint32_t a_mn_major, uint32_t b_mn_major) {
-  return (1u << 4) | (a_mn_major << 15) | (b_mn_major << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
+//   d_f32 = 0 selects fp16 accumulators (c_format 0): one half per 32-bit TMEM column, rounded after every K = 16 step.
+__host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t M, uint32_t N, uint32_t a_mn_major, uint32_t b_mn_major, uint32_t d_f32 = 1) {
+  return (d_f32 << 4) | (a_mn_major << 15) | (b_mn_major << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
 // D[tmem] (+)= A[smem] * B[smem];  issued by ONE thread.

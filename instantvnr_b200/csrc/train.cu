@@ -234,7 +234,8 @@ struct TrainArgs {
   uint32_t flags;              // measurement taps: 1 = scatter groups issue no reductions, 2 = gather groups issue no loads,
                                // 4 = compute group runs no MMA chain (hand-over only), 8 = activation gradients below the fp16
                                // normal range are flushed to zero (emulates an fp16-accumulating backward that loses subnormals),
-                               // 16 = forward epilogues skip the async-proxy fence (timing only; results undefined)
+                               // 16 = forward epilogues skip the async-proxy fence (timing only; results undefined),
+                               // 32 = compute group in warps 0-7, 64 = weight gradients accumulated in fp32 instead of half
   uint32_t* prof;              // measurement tap: kProfWords role timers per CTA (clock cycles), or nullptr
 };
 
@@ -356,7 +357,13 @@ train_step_kernel(const DecoderDesc d, const TrainArgs a) {
     constexpr uint32_t idesc_fwd = make_idesc_f16(kTile, kWidth, 0, 0);       // A K-major, B K-major
     constexpr uint32_t idesc_out = make_idesc_f16(kTile, kOutPad, 0, 0);
     constexpr uint32_t idesc_dgrad = make_idesc_f16(kTile, kWidth, 0, 1);     // A K-major, B MN-major (W read transposed)
-    constexpr uint32_t idesc_wgrad = make_idesc_f16(64, kWidth, 1, 1);        // both MN-major: D[out][in] += d^T X
+    // both MN-major: D[out][in] += d^T X, accumulated IN HALF as the reference's weight-gradient GEMMs do (cutlass_matmul.h:83
+    // TypeAccumulator = half for a half-precision network; fully_fused_mlp.cu:863-922 split-K over the batch): one rounding per
+    // K = 16 samples, the CTA's tiles form one K-slice, the slices are summed in half (adam_mlp_kernel).  At 2^18 samples this is
+    // what the reference's parameter updates look like (first-step update directions agree 99.7 % against 77 % with exact sums).
+    // flags & 64: fp32 accumulators (exact sums) instead.
+    const bool wg_half = (a.flags & 64u) == 0u;
+    const uint32_t idesc_wgrad = uniform_u32(make_idesc_f16(64, kWidth, 1, 1, wg_half ? 0u : 1u));
 
     const uint32_t x0_addr = smem_u32(x0_ring), xs_addr = smem_u32(xs), dy_addr = smem_u32(dy), dN_addr = smem_u32(dN), ws_addr = smem_u32(ws);
     auto w_addr = [&](int m) { return ws_addr + (uint32_t)m * MlpSmem::kWHidden; };   // m == NH: output matrix
@@ -662,7 +669,7 @@ train_step_kernel(const DecoderDesc d, const TrainArgs a) {
 #pragma unroll
           for (int k = 0; k < 32; ++k) {
             const int col = (int)col0 + k;
-            if (col < in_w) part[off + (size_t)o * in_w + col] = __uint_as_float(r[k]);
+            if (col < in_w) part[off + (size_t)o * in_w + col] = wg_half ? __half2float(__ushort_as_half((unsigned short)(r[k] & 0xFFFFu))) : __uint_as_float(r[k]);
           }
         }
       }
@@ -718,12 +725,20 @@ __device__ __forceinline__ void adam_update(const AdamArgs& a, size_t i, float g
 }
 
 // MLP weights: reduce the per-CTA partial gradients (deterministic, no atomics), then Adam with L2.
-__global__ void adam_mlp_kernel(AdamArgs a, uint32_t n_mlp, const float* __restrict__ partial, uint32_t n_partial, float* __restrict__ mlp_grads) {
+// accumulate != 0: the reduced gradient is ADDED to mlp_grads (a second batch before the optimizer step, as the hash-grid
+// reductions accumulate by themselves)
+__global__ void adam_mlp_kernel(AdamArgs a, uint32_t n_mlp, const float* __restrict__ partial, uint32_t n_partial, float* __restrict__ mlp_grads, int half_sum,
+                                int accumulate) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_mlp) return;
   float g = 0.f;
-  for (uint32_t c = 0; c < n_partial; ++c) g += partial[(size_t)c * n_mlp + i];
-  if (mlp_grads) mlp_grads[i] = g;
+  if (half_sum) {      // the reference's split-K reduction: partials and running sum in half (cutlass ReduceSplitK with ElementAccumulator = half)
+    __half h = __float2half_rn(0.f);
+    for (uint32_t c = 0; c < n_partial; ++c) h = __hadd(h, __float2half_rn(partial[(size_t)c * n_mlp + i]));
+    g = __half2float(h);
+  } else
+    for (uint32_t c = 0; c < n_partial; ++c) g += partial[(size_t)c * n_mlp + i];
+  if (mlp_grads) { if (accumulate) g = mlp_grads[i] + g; mlp_grads[i] = g; }
   if (a.master) adam_update(a, i, __fdiv_rn(g, a.loss_scale), true);
 }
 
@@ -776,6 +791,11 @@ __global__ void __launch_bounds__(256) adam_grid_kernel(AdamArgs a, uint32_t n_m
 // host
 // ------------------------------------------------------------------------------------------
 
+__global__ void loss_fold_kernel(double* acc);
+struct DpPtrs;
+__global__ void adam_grid_sharded_kernel(AdamArgs a, DpPtrs p, uint32_t n_mlp, uint32_t n_grid, uint32_t n_my_vecs);
+__global__ void adam_mlp_dp_kernel(AdamArgs a, DpPtrs p, uint32_t n_mlp);
+
 // X_0 ring depth that fits the shared-memory budget (227 KB per CTA): 3 stages when they fit, else 2
 static int train_x0_stages(int n_hidden, int var) {
   for (int xs = kMaxX0Stages; xs >= 2; --xs)
@@ -790,8 +810,10 @@ static void launch_train_v(Volume* v, TrainArgs& a, uint32_t grid, cudaStream_t 
   if (!xs) throw UnsupportedError("n_hidden_layers too large for the fused training kernel");
   a.x0_stages = (uint32_t)xs;
   const size_t smem = 1024 + (size_t)train_tiles(d.n_hidden, xs, VAR) * MlpSmem::kATile + MlpSmem::weights_bytes(d.n_hidden);
-  static size_t configured = 0;
-  if (configured < smem) { VNR_CUDA(cudaFuncSetAttribute(train_step_kernel<F, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = smem; }
+  static size_t configured[kMaxDevices] = {};      // function attributes are per device
+  int dev = 0; VNR_CUDA(cudaGetDevice(&dev));
+  size_t& conf = configured[dev % kMaxDevices];
+  if (conf < smem) { VNR_CUDA(cudaFuncSetAttribute(train_step_kernel<F, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); conf = smem; }
   train_step_kernel<F, VAR><<<grid, kTrainThreads, smem, s>>>(d, a);
   VNR_CUDA(cudaGetLastError());
 }
@@ -800,6 +822,35 @@ template <int F>
 static void launch_train_t(Volume* v, TrainArgs& a, uint32_t grid, cudaStream_t s) {
   if (v->train_variant == 0) launch_train_v<F, 0>(v, a, grid, s);
   else launch_train_v<F, 1>(v, a, grid, s);
+}
+
+// Load every kernel a training step launches NOW (CUDA loads kernels lazily, at their first launch, and loading synchronises the
+// context): inside a data-parallel step that would happen behind a peer barrier that is still waiting for ranks whose work the same
+// host thread has not enqueued yet (one process driving several ranks) -- the barrier would run into its timeout.
+template <int F>
+static void preload_train_f() {
+  cudaFuncAttributes fa;
+  VNR_CUDA(cudaFuncGetAttributes(&fa, train_step_kernel<F, 0>));
+  VNR_CUDA(cudaFuncGetAttributes(&fa, train_step_kernel<F, 1>));
+}
+void train_preload_kernels(const Volume* v) {
+  cudaFuncAttributes fa;
+  switch (v->cfg.desc.n_feat) { case 8: preload_train_f<8>(); break; case 4: preload_train_f<4>(); break; case 2: preload_train_f<2>(); break; default: preload_train_f<1>(); break; }
+  VNR_CUDA(cudaFuncGetAttributes(&fa, sampler_kernel));
+  VNR_CUDA(cudaFuncGetAttributes(&fa, adam_bias_fill_kernel));
+  VNR_CUDA(cudaFuncGetAttributes(&fa, adam_mlp_kernel));
+  VNR_CUDA(cudaFuncGetAttributes(&fa, adam_mlp_from_grads_kernel));
+  VNR_CUDA(cudaFuncGetAttributes(&fa, adam_grid_kernel));
+  VNR_CUDA(cudaFuncGetAttributes(&fa, adam_grid_sharded_kernel));
+  VNR_CUDA(cudaFuncGetAttributes(&fa, adam_mlp_dp_kernel));
+  VNR_CUDA(cudaFuncGetAttributes(&fa, loss_fold_kernel));
+  macrocell_preload_kernels();
+  outofcore_preload_kernels();
+  // memset / small copies use driver-internal kernels: run one of each so they are resident too
+  DevBuf<uint32_t> scratch; scratch.alloc(64);
+  VNR_CUDA(cudaMemsetAsync(scratch.p, 0, scratch.bytes(), v->stream));
+  VNR_CUDA(cudaMemcpyAsync(scratch.p + 32, scratch.p, 32 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, v->stream));
+  VNR_CUDA(cudaStreamSynchronize(v->stream));
 }
 
 // fresh optimizer: zero Adam moments and per-parameter step counters, training step / loss accumulators back to 0
@@ -856,7 +907,7 @@ void train_grads(Volume* v, const float* d_xyz, const float* d_target, size_t n,
     default: launch_train_t<1>(v, a, grid, s); break;
   }
   AdamArgs none = {};
-  adam_mlp_kernel<<<(d.n_mlp + 255) / 256, 256, 0, s>>>(none, d.n_mlp, v->mlp_partial.p, grid, v->mlp_grads.p);
+  adam_mlp_kernel<<<(d.n_mlp + 255) / 256, 256, 0, s>>>(none, d.n_mlp, v->mlp_partial.p, grid, v->mlp_grads.p, (a.flags & 64u) ? 0 : 1, v->grads_pending ? 1 : 0);
   VNR_CUDA(cudaGetLastError());
   v->grads_pending = true;
 }

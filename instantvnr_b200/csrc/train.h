@@ -9,6 +9,9 @@ void sample_batch(Volume* v, float* d_xyz, float* d_target, size_t n, cudaStream
 void sample_at(Volume* v, const float* d_xyz, float* d_out, size_t n, int hw_texture, cudaStream_t s);
 void train_ensure_buffers(Volume* v);
 void reset_optimizer_state(Volume* v);
+void train_preload_kernels(const Volume* v);     // load every kernel of a training step before the first peer barrier is enqueued
+void macrocell_preload_kernels();
+void outofcore_preload_kernels();
 int train_profile_words();
 void train_grads(Volume* v, const float* d_xyz, const float* d_target, size_t n, size_t n_global, cudaStream_t s);
 void optimizer_step(Volume* v, cudaStream_t s);

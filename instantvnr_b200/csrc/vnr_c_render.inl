@@ -181,12 +181,12 @@ VNR_EXPORT int vnr_peer_barrier_sync(void* bh, void* stream) {
     peer_barrier_sync(b, (cudaStream_t)stream);
   });
 }
-// epoch of the last barrier call that timed out (0 = healthy); synchronises the device
+// epoch of the last barrier call that timed out (0 = healthy).  Reads a pinned host word the barrier kernel writes: it covers
+// every barrier whose kernel has completed, so call it after a synchronisation you do anyway (frame mapped, loss read)
 VNR_EXPORT int vnr_peer_barrier_check(void* bh, uint64_t* timed_out_epoch) {
   return guard([&] {
     PeerBarrier* b = reinterpret_cast<PeerBarrier*>(bh);
     if (!b || !timed_out_epoch) throw InvalidError("null argument");
-    VNR_CUDA(cudaDeviceSynchronize());
     *timed_out_epoch = peer_barrier_timed_out(b);
   });
 }

@@ -444,6 +444,7 @@ VNR_EXPORT int vnr_volume_dp_attach(vnr_volume_t* vh, int rank, int world, const
     if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world) throw InvalidError("bad data-parallel rank / world (at most 8 ranks)");
     if (world > 1 && !all_handles) throw InvalidError("null argument");
     train_ensure_buffers(v);
+    train_preload_kernels(v);
     VNR_CUDA(cudaStreamSynchronize(v->stream));
     dp_detach_impl(v);
     v->dp_rank = rank; v->dp_world = world;

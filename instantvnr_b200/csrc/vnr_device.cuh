@@ -19,6 +19,7 @@ constexpr int kOutPad = 16;       // padded output rows (fully_fused_mlp.cu:677)
 constexpr int kTile = 128;        // samples per tensor-core tile (UMMA M)
 constexpr int kMaxHidden = 8;
 constexpr int kMaxPeers = 8;       // GPUs of one NVSwitch box
+constexpr int kMaxDevices = 16;    // per-device caches of per-function attributes
 
 struct LevelDesc {
   uint32_t offset;      // first entry of the level (in entries)

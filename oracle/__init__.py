@@ -370,6 +370,10 @@ class Trainer:
         return float(lib().orc_train_grads(self.h, _p(coords), _p(targets), C.c_size_t(coords.shape[0]), C.c_size_t(n_global),
                                            C.c_int(acc_mode), C.c_int(grad_mode)))
 
+    def set_wgrad_slices(self, n):
+        """grad_mode 2: number of K-slices of the half-accumulated weight gradients (the product: its CTA count, one per SM)"""
+        lib().orc_train_set_wgrad_slices(self.h, C.c_int(n))
+
     def apply(self, grads):
         """optimizer step (ExponentialDecay + Adam) on externally provided (e.g. all-reduced) gradients"""
         g = _f32(grads)

@@ -1478,6 +1478,7 @@ struct TrainState {
   uint32_t current_step = 0; float lr_factor = 1.f;
   float lr, beta1, beta2, eps, l2_reg, decay_base; uint32_t decay_start, decay_interval, decay_end;
   double last_loss = 0;
+  int wgrad_slices = 148;      // grad_mode 2: K-slices of the half-accumulated weight gradients (the product: one per CTA = per SM)
 };
 
 ORC_API void* orc_train_create(const int* cfg, float pls, const float* params_f32, const float* hyper /*lr,b1,b2,eps,l2,decay_base,decay_start,decay_interval*/) {
@@ -1492,6 +1493,7 @@ ORC_API void* orc_train_create(const int* cfg, float pls, const float* params_f3
   return s;
 }
 ORC_API void orc_train_destroy(void* h) { delete (TrainState*)h; }
+ORC_API void orc_train_set_wgrad_slices(void* h, int n) { if (n > 0) ((TrainState*)h)->wgrad_slices = n; }
 ORC_API void orc_train_get_params(void* h, uint16_t* params_f16, float* master) {
   TrainState* s = (TrainState*)h;
   if (params_f16) std::memcpy(params_f16, s->params.data(), s->params.size() * 2);
@@ -1506,6 +1508,12 @@ ORC_API void orc_train_get_grads(void* h, float* grads) { TrainState* s = (Train
 // NOT re-rounded (deterministic ground truth);  grad_mode 1: additionally round
 // the accumulated weight/grid gradients to fp16 before Adam (reference storage
 // type; the reference's atomic/split-K fp16 summation order is not reproducible).
+// grad_mode 2: the MLP weight gradients are accumulated IN HALF as the reference's split-K GEMMs do
+// (cutlass_matmul.h:83 TypeAccumulator = half; fully_fused_mlp.cu:863-922 fc_multiply_split_k over the batch): the batch
+// is cut into K-slices, a slice's accumulator is a half that takes the (exact) sum of 16 consecutive samples' products
+// per step (one tensor-core instruction, K = 16), and the slices' partial results are summed sequentially in half
+// (cutlass ReduceSplitK).  The reference's slices are runs of 4096 samples; the product's are the tiles of one CTA
+// (tile t of 128 samples belongs to slice t mod G, G = min(n / 128, wgrad_slices)) -- that is what is restated here.
 // do_step 0: compute loss+grads only.
 // n_global: the batch size the loss is normalised by (data-parallel: the sum of all ranks' batches).
 // compute 0: skip forward/backward and apply the optimizer to the gradients already in s->grad
@@ -1536,6 +1544,10 @@ static double train_impl(TrainState* s, const float* coords, const float* target
   std::vector<float> denc((size_t)n * E);       // fp16-rounded dL/d(encoding) per sample
   std::vector<double> loss_terms(n);
   float* ggrid = s->grad.data() + m.n_mlp;
+  // grad_mode 2: per-slice half accumulators (bit patterns), filled by whichever thread owns the slice
+  const size_t n_tiles = (n + 127) / 128;
+  const int G = grad_mode == 2 ? (int)std::min<size_t>(n_tiles, (size_t)s->wgrad_slices) : 0;
+  std::vector<std::vector<h16>> slice_acc(G > 0 ? G : 0);
 #pragma omp parallel
   {
 #ifdef _OPENMP
@@ -1546,8 +1558,7 @@ static double train_impl(TrainState* s, const float* coords, const float* target
     double* mg = mlp_grads[tid].data();
     std::vector<h16> hidden((size_t)NH * W); h16 enc[128]; h16 out16[16];
     std::vector<float> dcur(W), dnext(128);
-#pragma omp for schedule(static)
-    for (long long i = 0; i < (long long)n; ++i) {
+    auto one_sample = [&](long long i) {
       encode_one(m, grid, coords + 3 * i, enc);
       float y = mlp_forward_one(m, mf, enc, acc_mode, hidden.data(), out16);
       // l1.h:40-76
@@ -1586,6 +1597,28 @@ static double train_impl(TrainState* s, const float* coords, const float* target
         for (int k = 0; k < E; ++k) { grow[k] += (double)(d * h2f(enc[k])); dnext[k] += d * h2f(row[k]); }
       }
       for (int k = 0; k < E; ++k) denc[(size_t)i * E + k] = h2f(f2h(dnext[k]));
+    };
+    if (grad_mode != 2) {
+#pragma omp for schedule(static)
+      for (long long i = 0; i < (long long)n; ++i) one_sample(i);
+    } else {
+      // `mg` collects ONE chunk of 16 samples at a time; the slice's half accumulator takes it with one rounding
+      std::vector<double> chunk(m.n_mlp, 0.0);
+      mg = chunk.data();
+#pragma omp for schedule(dynamic, 1)
+      for (int c = 0; c < G; ++c) {
+        std::vector<h16>& acc = slice_acc[c];
+        acc.assign(m.n_mlp, f2h(0.f));
+        for (size_t t = (size_t)c; t < n_tiles; t += (size_t)G) {
+          for (int q = 0; q < 8; ++q) {
+            const long long i0 = (long long)t * 128 + 16 * q, i1 = std::min<long long>(i0 + 16, (long long)n);
+            if (i0 >= i1) break;
+            std::fill(chunk.begin(), chunk.end(), 0.0);
+            for (long long i = i0; i < i1; ++i) one_sample(i);
+            for (size_t k = 0; k < m.n_mlp; ++k) acc[k] = f2h((float)((double)h2f(acc[k]) + chunk[k]));
+          }
+        }
+      }
     }
   }
   for (size_t i = 0; i < n; ++i) loss_sum += loss_terms[i];
@@ -1606,6 +1639,9 @@ static double train_impl(TrainState* s, const float* coords, const float* target
       }
     }
   }
+  if (grad_mode == 2) {
+    for (size_t k = 0; k < m.n_mlp; ++k) { h16 a = f2h(0.f); for (int c = 0; c < G; ++c) a = f2h(h2f(a) + h2f(slice_acc[c][k])); s->grad[k] = h2f(a); }
+  } else
   for (size_t k = 0; k < m.n_mlp; ++k) { double acc = 0; for (int t = 0; t < nthreads; ++t) acc += mlp_grads[t][k]; s->grad[k] = (float)acc; }
   if (grad_mode == 1) for (size_t k = 0; k < m.n_params; ++k) s->grad[k] = h2f(f2h(s->grad[k]));
   s->last_loss = loss_sum;

@@ -81,10 +81,25 @@ def test_gradients_match_oracle(cfg):
     want = tr.grads()
     wm, wg = want[:m.n_mlp], want[m.n_mlp:]
     assert abs(vol.last_loss() - loss) <= 1e-5 * max(1.0, loss)
-    # MLP weight gradients: fp32 tensor-core accumulation vs double accumulation of the same fp16 products
     scale = np.abs(wm).max()
     assert scale > 0
-    assert np.abs(gm - wm).max() <= 2e-3 * scale, (np.abs(gm - wm).max(), scale)
+    # MLP weight gradients, default: accumulated in HALF as the reference's split-K GEMMs do (cutlass_matmul.h:83), one rounding
+    # per 16 samples, the CTA's tiles = one K-slice, slices summed in half -- restated by the oracle (grad_mode 2) and equal to it
+    # up to the tensor core's internal summation order inside one K = 16 step
+    tr.set_wgrad_slices(148)
+    tr.step(c, t, acc_mode=0, grad_mode=2, do_step=False)
+    wh = tr.grads()[:m.n_mlp]
+    assert np.mean(gm == wh) >= 0.75, np.mean(gm == wh)      # measured 0.83 - 0.996
+    assert np.abs(gm - wh).max() <= 2e-3 * scale and np.linalg.norm(gm - wh) <= 5e-4 * np.linalg.norm(wh)
+    assert np.abs(gm - wm).max() <= 5e-3 * scale                      # and within half precision of the exact sums
+    # fp32 accumulators (train flag 64): fp32 tensor-core accumulation vs double accumulation of the same fp16 products
+    vol.optimizer_step(); vol.set_params_f16(p16)                     # consumes the gradients; back to the same blob
+    vol.train_debug(1, 64, False)
+    vol.train_grads(dc, dt, n, n, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    gm32, gg16 = vol.get_grads()
+    gg = O.f16_to_f32(gg16)
+    assert np.abs(gm32 - wm).max() <= 2e-3 * scale, (np.abs(gm32 - wm).max(), scale)
     # padded output rows and padded input columns carry no gradient
     W, E, NH = 64, m.enc_pad, m.n_hidden
     out_off = W * E + (NH - 1) * W * W

@@ -63,8 +63,13 @@ def run(n, steps=8, flags=0, psnr_steps=0):
         print(f"  after {psnr_steps} steps: PSNR ours {vol.psnr():.3f} dB, theirs {_ref_psnr(ref, gt, st):.3f} dB")
 
 
-for n in (1 << 12, 1 << 14, 1 << 16, 1 << 18):
-    run(n)
-run(1 << 18, flags=8)
-run(1 << 16, psnr_steps=300)
-run(1 << 18, flags=8, psnr_steps=300)
+if len(sys.argv) > 1:          # n:flags:psnr_steps ...
+    for spec in sys.argv[1:]:
+        n_, f_, p_ = (int(x) for x in spec.split(":"))
+        run(n_, flags=f_, psnr_steps=p_)
+else:
+    for n in (1 << 12, 1 << 14, 1 << 16, 1 << 18):
+        run(n)
+    run(1 << 18, flags=8)
+    run(1 << 16, psnr_steps=300)
+    run(1 << 18, flags=8, psnr_steps=300)
