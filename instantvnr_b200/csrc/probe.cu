@@ -85,6 +85,36 @@ __global__ void __launch_bounds__(256) probe_loads32_kernel(const uint4* __restr
   if (fold == 0x12345678u) sink[t & 1023u] = fold;
 }
 
+// loads and reductions TOGETHER (even blocks: random 16-byte loads over `table`, odd blocks: random fp16x8 reductions over `table2`):
+// what the training step's gather and scatter cost when they share the memory system
+__global__ void __launch_bounds__(256) probe_mixed_kernel(const uint4* __restrict__ table, __half* __restrict__ table2, uint32_t n_vec, uint32_t per_thread,
+                                                          uint32_t seed, uint32_t* __restrict__ sink) {
+  const uint32_t t = (blockIdx.x >> 1) * blockDim.x + threadIdx.x;
+  uint32_t c = mix32(t * 0x9e3779b9u + seed + (blockIdx.x & 1u) * 77u);
+  if (blockIdx.x & 1u) {
+    const uint32_t one = 0x04000400u;
+    for (uint32_t k = 0; k < per_thread; ++k) {
+      c = c * 1664525u + 1013904223u;
+      const uint32_t idx = (uint32_t)(((uint64_t)mix32(c) * n_vec) >> 32);
+      asm volatile("red.global.add.noftz.v4.f16x2 [%0], {%1, %1, %1, %1};" ::"l"(table2 + (size_t)idx * 8), "r"(one) : "memory");
+    }
+    return;
+  }
+  uint32_t fold = 0;
+  for (uint32_t k = 0; k < per_thread; k += 8) {
+    uint4 v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      c = c * 1664525u + 1013904223u;
+      const uint32_t idx = (uint32_t)(((uint64_t)mix32(c) * n_vec) >> 32);
+      v[i] = ldg_nc_v4(table + idx);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) fold ^= v[i].x ^ v[i].y ^ v[i].z ^ v[i].w;
+  }
+  if (fold == 0x12345678u) sink[t & 1023u] = fold;
+}
+
 // stores of finished pixels into PINNED HOST memory (the zero-copy frame download): float4 per thread over a `width`-pixel-wide
 // image.  pattern 0: scanline (a warp writes 512 contiguous bytes), 1: 8 x 4 pixel tiles per warp (four 128-byte runs, the
 // marcher's ray order), 2: scanline with one 32-byte store per thread (two pixels), 3: tiles of 16 x 2 pixels (two 256-byte runs)
@@ -125,7 +155,7 @@ using namespace vnr;
 // pattern kind - 4 (see probe_host_store_kernel).
 // Runs `repeats` timed launches after one warm-up and returns the fastest (ms_best) and the mean (ms_mean) launch time.
 VNR_EXPORT int vnr_probe_memory(int kind, size_t table_bytes, size_t n_ops, int repeats, float* ms_best, float* ms_mean) {
-  if (kind < 0 || kind > 7 || table_bytes < 4096 || repeats < 1 || !ms_best) return VNR_ERR_INVALID;
+  if (kind < 0 || kind > 8 || table_bytes < 4096 || repeats < 1 || !ms_best) return VNR_ERR_INVALID;
   int n_dev = 0;
   if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) { cudaGetLastError(); return VNR_ERR_CUDA; }
   void* table = nullptr; void* aux = nullptr;
@@ -134,10 +164,12 @@ VNR_EXPORT int vnr_probe_memory(int kind, size_t table_bytes, size_t n_ops, int 
   auto ok = [&](cudaError_t e) { if (e != cudaSuccess) { cudaGetLastError(); rc = VNR_ERR_CUDA; } return e == cudaSuccess; };
   const size_t n_vec = table_bytes / 16;
   do {
-    const bool host_table = kind >= 4;
+    const bool host_table = kind >= 4 && kind <= 7;
     if (host_table) { if (!ok(cudaMallocHost(&table, n_vec * 16))) break; }
     else if (!ok(cudaMalloc(&table, n_vec * 16))) break;
     if (!ok(cudaMalloc(&aux, kind == 2 ? n_vec * 16 : 4096))) break;
+    void* table2 = nullptr;                 // kind 8: the reductions' own table (the gradient buffer next to the parameter table)
+    if (kind == 8) { if (!ok(cudaMalloc(&table2, n_vec * 16)) || !ok(cudaMemset(table2, 0, n_vec * 16))) break; }
     if (host_table) memset(table, 0, n_vec * 16);
     else if (!ok(cudaMemset(table, 0, n_vec * 16))) break;
     if (!ok(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking))) break;
@@ -153,6 +185,7 @@ VNR_EXPORT int vnr_probe_memory(int kind, size_t table_bytes, size_t n_ops, int 
       else if (kind == 1) probe_reds_kernel<<<grid, 256, 0, s>>>((__half*)table, (uint32_t)n_vec, per_thread, 17u + it);
       else if (kind == 2) probe_copy_kernel<<<148 * 16, 256, 0, s>>>((const uint4*)table, (uint4*)aux, n_vec);
       else if (kind == 3) probe_loads32_kernel<<<grid, 256, 0, s>>>((const uint4*)table, (uint32_t)n_vec, per_thread, 17u + it, (uint32_t*)aux);
+      else if (kind == 8) probe_mixed_kernel<<<2 * grid, 256, 0, s>>>((const uint4*)table, (__half*)table2, (uint32_t)n_vec, per_thread, 17u + it, (uint32_t*)aux);
       else { const uint32_t w = 1024, h = (uint32_t)(n_vec / w); probe_host_store_kernel<<<(w * h + 127) / 128, 128, 0, s>>>((float4*)table, w, h, kind - 4); }
       ok(cudaGetLastError());
       ok(cudaEventRecord(e1, s));
@@ -164,11 +197,12 @@ VNR_EXPORT int vnr_probe_memory(int kind, size_t table_bytes, size_t n_ops, int 
     }
     *ms_best = best;
     if (ms_mean) *ms_mean = sum / (float)repeats;
+    if (table2) cudaFree(table2);
   } while (0);
   if (e0) cudaEventDestroy(e0);
   if (e1) cudaEventDestroy(e1);
   if (s) cudaStreamDestroy(s);
-  if (table) { if (kind >= 4) cudaFreeHost(table); else cudaFree(table); }
+  if (table) { if (kind >= 4 && kind <= 7) cudaFreeHost(table); else cudaFree(table); }
   if (aux) cudaFree(aux);
   return rc;
 }

@@ -286,8 +286,10 @@ train_step_kernel(const DecoderDesc d, const TrainArgs a) {
 
   if (tid >= kComputeThreads + 128 * kGatherGroupsT) {
     // ---------------- scatter groups: dL/dX_0 rows -> hash-table gradient reductions ----------------
+
     const uint32_t sg = (uint32_t)(tid - kComputeThreads - 128 * kGatherGroupsT) >> 7, row = (uint32_t)tid & 127u;
     __half* __restrict__ ggrid = a.grid_grads;
+    const uint32_t pace_ns = (a.flags >> 16) * 16u;              // tap (flags bits 16..31): pause after each level's reductions, in units of 16 ns
     uint32_t t_wait = 0, t_work = 0;
     for (uint32_t j = sg; j < my_tiles; j += kScatterGroupsT) {
       const uint32_t stage = j % kDxStages, use = j / kDxStages;
@@ -305,6 +307,7 @@ train_step_kernel(const DecoderDesc d, const TrainArgs a) {
           else if constexpr (F == 4) { const uint2 g = *reinterpret_cast<const uint2*>(src); const uint32_t gg[2] = {g.x, g.y}; scatter_level<4>(d.lv[l], ggrid, x, y, z, gg); }
           else if constexpr (F == 2) { const uint32_t gg[1] = {*reinterpret_cast<const uint32_t*>(src)}; scatter_level<2>(d.lv[l], ggrid, x, y, z, gg); }
           else { const uint32_t gg[1] = {(uint32_t)*reinterpret_cast<const unsigned short*>(src)}; scatter_level<1>(d.lv[l], ggrid, x, y, z, gg); }
+          if (pace_ns) __nanosleep(pace_ns);      // tap: spread the fire-and-forget reductions of a tile over time
         }
       }
       mbar_arrive(&dx_empty[stage]);
@@ -313,6 +316,7 @@ train_step_kernel(const DecoderDesc d, const TrainArgs a) {
     if (prof && row == 0 && sg == 0) { prof[8] = t_wait; prof[9] = t_work; }
   } else if (tid >= kComputeThreads) {
     // ---------------- gather groups: hash-grid features -> X_0 ring ----------------
+
     const uint32_t gg = (uint32_t)(tid - kComputeThreads) >> 7, row = (uint32_t)tid & 127u;
     const __half* __restrict__ grid = a.params + d.n_mlp;
     uint32_t t_wait = 0, t_work = 0;
@@ -323,7 +327,10 @@ train_step_kernel(const DecoderDesc d, const TrainArgs a) {
       const uint32_t c0 = prof ? (uint32_t)clock() : 0u;
       if (use > 0) mbar_wait(&x0_empty[stage], (use - 1u) & 1u);
       const uint32_t c1 = prof ? (uint32_t)clock() : 0u;
-      if (!(a.flags & 2u)) encode_row<F, false>(x0_ring + (size_t)stage * MlpSmem::kATile, d, grid, x, y, z, row);
+      if (!(a.flags & 2u)) {
+        if (a.flags & 128u) encode_row<F, true>(x0_ring + (size_t)stage * MlpSmem::kATile, d, grid, x, y, z, row);    // tap: two levels of loads in flight
+        else encode_row<F, false>(x0_ring + (size_t)stage * MlpSmem::kATile, d, grid, x, y, z, row);
+      }
       fence_async_smem();
       mbar_arrive(&x0_full[stage]);
       if (prof) { t_wait += c1 - c0; t_work += (uint32_t)clock() - c1; }

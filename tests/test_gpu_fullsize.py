@@ -177,7 +177,7 @@ def test_volume_psnr_after_300_steps_is_in_the_references_band():
     # the whole-volume PSNR of either trainer swings by several dB from step to step at this batch size (see the module note);
     # the band: both have learnt the volume (a constant predictor scores 17 dB) and the smoothed training loss agrees
     assert min(psnr_ours, psnr_ref) >= 38.0
-    assert abs(psnr_ours - psnr_ref) <= max(8.0, 2.0 * abs(psnr_ref - psnr_ref2))
+    assert abs(psnr_ours - psnr_ref) <= 12.0          # measured: the reference against itself differs by 3 - 10 dB here
     assert 0.6 <= np.mean(lo) / np.mean(lr_) <= 1.6
 
 

@@ -182,7 +182,9 @@ def test_data_parallel_ranks_keep_their_own_slabs_and_the_step_equals_accumulate
     assert np.array_equal(ps[0], ps[1])                                # replicas bit-identical
     assert np.allclose(dp_losses, ref_losses, rtol=2e-3), (dp_losses, ref_losses)
     a = ps[0].view(np.float16).astype(np.float32); b = ref.get_params_f16().view(np.float16).astype(np.float32)
-    assert (a != b).mean() < 0.02                                      # same batches, same arithmetic up to the fp16 reduction order
+    i0 = p0.view(np.float16).astype(np.float32)
+    # same batches, same arithmetic up to where the fp16 hash-grid sums are rounded (per rank, then fp32, against one fp16 buffer)
+    assert np.linalg.norm(a - b) < 0.1 * np.linalg.norm(b - i0) and np.abs(a - b).max() <= 2 * 5e-3
     # the ranks' pools keep diverging: different slots refreshed with different slabs
     t0, t1 = [v.outofcore_info(table=True)["first_voxel"] for v in vols]
     assert (t0 != t1).mean() > 0.5
