@@ -5,7 +5,10 @@
 // function; paths relative to the reference repo): handles are std::shared_ptr, errors are
 // std::runtime_error (api.cpp:129,138,215), a vnrJson that "is a string" is a FILE NAME
 // (api.cpp:180-185).  Differences, all forced by what is (not) vendored in the reference:
-//   * vnrJson is a small value type (JSON text | file name | BSON blob), not nlohmann::json;
+//   * vnrJson IS nlohmann::json, exactly as in the reference's api.h, whenever <json/json.hpp> is on the include path (the
+//     reference tree vendors it: -I<reference>/tcnn/dependencies; its apps then compile against this header unchanged).
+//     Without it (this repo ships no third-party code) vnrJson is a small value type (JSON text | file name | BSON blob)
+//     with the same is_string() = "this is a file name" convention; define VNR_API_NO_NLOHMANN to force that;
 //   * vnrCreateSimpleVolume(scene, mode) reads VIDI3D / DIVA scene descriptions of raw binary volumes
 //     (serializer.cpp:138-477; other OVR readers are not vendored); an in-memory overload takes a normalised
 //     float volume.  A simple volume is carried by a vnr_volume_t with a minimal model, so that its
@@ -26,6 +29,13 @@
 
 #include "vnr_c.h"
 
+#if !defined(VNR_API_NO_NLOHMANN) && defined(__has_include)
+#if __has_include(<json/json.hpp>)
+#include <json/json.hpp>
+#define VNR_API_HAS_NLOHMANN 1
+#endif
+#endif
+
 namespace vnr {
 struct vec2i { int x, y; vec2i(int x_ = 0, int y_ = 0) : x(x_), y(y_) {} };
 struct vec3i { int x, y, z; vec3i(int x_ = 0, int y_ = 0, int z_ = 0) : x(x_), y(y_), z(z_) {} };
@@ -42,6 +52,9 @@ struct Json {
   static Json text(const std::string& t) { Json j; j.kind = Text; j.data = t; return j; }
   static Json filename(const std::string& f) { Json j; j.kind = FileName; j.data = f; return j; }
   static Json binary(const std::string& b) { Json j; j.kind = Binary; j.data = b; return j; }
+  // a string converts to "file name", as a std::string converts to a nlohmann::json string in the reference's apps
+  Json(const std::string& f) : kind(FileName), data(f) {}
+  Json(const char* f) : kind(FileName), data(f) {}
   bool is_string() const { return kind == FileName; }
 };
 
@@ -52,6 +65,52 @@ inline std::string read_file(const std::string& name, bool binary) {
   return ss.str();
 }
 inline void check(int rc) { if (rc != VNR_OK) throw std::runtime_error(vnr_last_error()); }
+
+// ---- the two JSON back ends behind one set of accessors -------------------------------------------
+#ifdef VNR_API_HAS_NLOHMANN
+using json = nlohmann::json;                          // api.h:21
+typedef nlohmann::json ApiJson;
+namespace jx {
+inline ApiJson from_text(const std::string& t) { return nlohmann::json::parse(t, nullptr, true, true); }            // api.cpp:20 (comments allowed)
+inline ApiJson from_bson(const std::string& b) { return nlohmann::json::from_bson(b.begin(), b.end()); }             // api.cpp:30
+// a JSON description (model config, scene): a string is a file name (api.cpp:180-185), anything else is the description itself
+inline std::string text_of(const ApiJson& j, const char* what) {
+  if (j.is_string()) return read_file(j.get<std::string>(), false);
+  if (j.is_binary()) throw std::runtime_error(std::string("expecting ") + what + ", not a params blob");
+  return j.dump();
+}
+inline std::string scene_arg(const ApiJson& j, int& is_path) {
+  if (j.is_string()) { is_path = 1; return j.get<std::string>(); }
+  is_path = 0; return j.dump();
+}
+// serialized parameters: a string is a file name, an object is what json::from_bson produced (api.cpp:246-259)
+inline std::string blob_of(const ApiJson& j) {
+  if (j.is_string()) return read_file(j.get<std::string>(), true);
+  const std::vector<uint8_t> b = nlohmann::json::to_bson(j);
+  return std::string(b.begin(), b.end());
+}
+inline std::string pretty(const ApiJson& j) { return j.dump(4); }                                                    // api.cpp:37 std::setw(4)
+}  // namespace jx
+#else
+typedef Json ApiJson;
+namespace jx {
+inline ApiJson from_text(const std::string& t) { return Json::text(t); }
+inline ApiJson from_bson(const std::string& b) { return Json::binary(b); }
+inline std::string text_of(const ApiJson& j, const char* what) {
+  if (j.kind == Json::Binary) throw std::runtime_error(std::string("expecting ") + what + ", not a params blob");
+  return j.is_string() ? read_file(j.data, false) : j.data;
+}
+inline std::string scene_arg(const ApiJson& j, int& is_path) {
+  if (j.kind == Json::Binary) throw std::runtime_error("expecting a scene description, not a params blob");
+  is_path = j.is_string() ? 1 : 0; return j.data;
+}
+inline std::string blob_of(const ApiJson& j) { return j.is_string() ? read_file(j.data, true) : j.data; }
+inline std::string pretty(const ApiJson& j) {
+  if (j.kind != Json::Text) throw std::runtime_error("vnrSaveJsonText: not a JSON text value");
+  return j.data;
+}
+}  // namespace jx
+#endif
 
 struct Camera { vec3f from{0, 0, -1}, at{0, 0, 0}, up{0, 1, 0}; float fovy = 60.f; };              // instantvnr_types.h:74-83
 struct TransferFunction { std::vector<vec3f> color; std::vector<vec2f> alpha; range1f range; };     // api_internal.h
@@ -92,7 +151,7 @@ typedef std::shared_ptr<vnr::VolumeContext> vnrVolume;
 typedef std::shared_ptr<vnr::RendererContext> vnrRenderer;
 typedef std::shared_ptr<vnr::TransferFunction> vnrTransferFunction;
 typedef std::shared_ptr<vnr::Camera> vnrCamera;
-typedef vnr::Json vnrJson;
+typedef vnr::ApiJson vnrJson;
 
 enum vnrRenderMode {                                                                                 // api.h:36-60
   VNR_OPTIX_NO_SHADING = 0, VNR_OPTIX_GRADIENT_SHADING, VNR_OPTIX_FULL_SHADOW, VNR_OPTIX_SINGLE_SHADE_HEURISTIC,
@@ -109,20 +168,21 @@ inline bool vnrRequireDecoding(int m) {                                         
 }
 
 // ---- json I/O (api.h:89-95) -----------------------------------------------------------------------
-inline vnrJson vnrCreateJsonText(std::string filename) { return vnrJson::text(vnr::read_file(filename, false)); }
-inline vnrJson vnrCreateJsonBinary(std::string filename) { return vnrJson::binary(vnr::read_file(filename, true)); }
+inline vnrJson vnrCreateJsonText(std::string filename) { return vnr::jx::from_text(vnr::read_file(filename, false)); }
+inline vnrJson vnrCreateJsonBinary(std::string filename) { return vnr::jx::from_bson(vnr::read_file(filename, true)); }
 inline void vnrLoadJsonText(vnrJson& j, std::string filename) { j = vnrCreateJsonText(filename); }
 inline void vnrLoadJsonBinary(vnrJson& j, std::string filename) { j = vnrCreateJsonBinary(filename); }
 inline void vnrSaveJsonText(const vnrJson& j, std::string filename) {
-  if (j.kind != vnrJson::Text) throw std::runtime_error("vnrSaveJsonText: not a JSON text value");
+  const std::string text = vnr::jx::pretty(j);
   std::ofstream f(filename);
   if (!f) throw std::runtime_error("cannot write " + filename);
-  f << j.data;
+  f << text << std::endl;
 }
 inline void vnrSaveJsonBinary(const vnrJson& j, std::string filename) {
+  const std::string blob = vnr::jx::blob_of(j);
   std::ofstream f(filename, std::ios::binary);
   if (!f) throw std::runtime_error("cannot write " + filename);
-  f.write(j.data.data(), (std::streamsize)j.data.size());
+  f.write(blob.data(), (std::streamsize)blob.size());
 }
 
 // ---- camera (api.h:102-110) -----------------------------------------------------------------------
@@ -131,9 +191,10 @@ inline void vnrCameraSet(vnrCamera c, vnr::vec3f from, vnr::vec3f at, vnr::vec3f
 namespace vnr {
 struct SceneHandle {                                  // RAII over vnr_scene_t for the scene overloads
   vnr_scene_t* s = nullptr;
-  explicit SceneHandle(const Json& scene) {
-    if (scene.kind == Json::Binary) throw std::runtime_error("expecting a scene description, not a params blob");
-    check(vnr_scene_create(scene.data.c_str(), scene.is_string() ? 1 : 0, &s));
+  explicit SceneHandle(const ApiJson& scene) {
+    int is_path = 0;
+    const std::string arg = jx::scene_arg(scene, is_path);
+    check(vnr_scene_create(arg.c_str(), is_path, &s));
   }
   ~SceneHandle() { vnr_scene_release(s); }
   vnr_scene_t* release() { vnr_scene_t* r = s; s = nullptr; return r; }
@@ -227,8 +288,7 @@ inline int vnrSimpleVolumeGetNumberOfTimeSteps(vnrVolume v) { return castSimpleV
 
 // vnrCreateNeuralVolume(config, dims)                                               api.cpp:190-204
 inline vnrVolume vnrCreateNeuralVolume(const vnrJson& config, vnr::vec3i dims, uint32_t seed = 0) {
-  if (config.kind == vnrJson::Binary) throw std::runtime_error("expecting a model config, not a params blob");
-  const std::string text = config.is_string() ? vnr::read_file(config.data, false) : config.data;
+  const std::string text = vnr::jx::text_of(config, "a model config");
   auto ret = std::make_shared<vnr::NeuralVolumeContext>();
   ret->dims = dims;
   vnr::check(vnr_volume_create(text.c_str(), dims.x, dims.y, dims.z, &ret->h));
@@ -249,22 +309,21 @@ inline vnrVolume vnrCreateNeuralVolume(const vnrJson& config, vnrVolume groundtr
 }
 // vnrNeuralVolumeSetParams                                                           api.cpp:246-259
 inline void vnrNeuralVolumeSetParams(vnrVolume v, const vnrJson& params) {
-  const std::string blob = params.is_string() ? vnr::read_file(params.data, true) : params.data;
+  const std::string blob = vnr::jx::blob_of(params);
   vnr::check(vnr_volume_load_params(castNeuralVolume(v)->h, blob.data(), blob.size()));
 }
 // vnrCreateNeuralVolume(params)                                                      api.cpp:206-220
 inline vnrVolume vnrCreateNeuralVolume(const vnrJson& params) {
-  const std::string blob = params.is_string() ? vnr::read_file(params.data, true) : params.data;
+  const std::string blob = vnr::jx::blob_of(params);
   int dx, dy, dz; const char* model = nullptr;
   vnr::check(vnr_params_peek(blob.data(), blob.size(), &dx, &dy, &dz, &model));   // throws "expecting a model config with volume dims tag"
-  auto ret = vnrCreateNeuralVolume(vnrJson::text(model), vnr::vec3i(dx, dy, dz), 1);
-  vnrNeuralVolumeSetParams(ret, vnrJson::binary(blob));
+  auto ret = vnrCreateNeuralVolume(vnr::jx::from_text(model), vnr::vec3i(dx, dy, dz), 1);
+  vnr::check(vnr_volume_load_params(castNeuralVolume(ret)->h, blob.data(), blob.size()));
   return ret;
 }
 // vnrNeuralVolumeSetModel                                                            api.cpp:261-270
 inline void vnrNeuralVolumeSetModel(vnrVolume v, const vnrJson& config, uint32_t seed = 0) {
-  if (config.kind == vnrJson::Binary) throw std::runtime_error("expecting a model config, not a params blob");
-  const std::string text = config.is_string() ? vnr::read_file(config.data, false) : config.data;
+  const std::string text = vnr::jx::text_of(config, "a model config");
   vnr::check(vnr_volume_set_model(castNeuralVolume(v)->h, text.c_str(), seed ? seed : (uint32_t)time(nullptr)));
 }
 inline void vnrNeuralVolumeTrain(vnrVolume v, int steps, bool fast_mode) { vnr::check(vnr_volume_train(castNeuralVolume(v)->h, steps, 0, fast_mode, nullptr)); }   // api.cpp:222-226
@@ -280,7 +339,7 @@ inline int vnrNeuralVolumeGetNumberOfBlobs(vnrVolume v) { int n; vnr::check(vnr_
 inline void vnrNeuralVolumeSerializeParams(vnrVolume v, vnrJson& params) {                          // api.cpp:292-298
   const void* p; size_t n;
   vnr::check(vnr_volume_save_params(castNeuralVolume(v)->h, &p, &n));
-  params = vnrJson::binary(std::string((const char*)p, n));
+  params = vnr::jx::from_bson(std::string((const char*)p, n));
 }
 inline void vnrNeuralVolumeSerializeParams(vnrVolume v, std::string filename) { vnrJson j; vnrNeuralVolumeSerializeParams(v, j); vnrSaveJsonBinary(j, filename); }
 // vnrVolumeSetClippingBox (api.cpp:330-348): `lower` / `upper` are in voxel units [0, dims]; they go through the inverse

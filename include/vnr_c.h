@@ -312,7 +312,9 @@ int vnr_renderer_stream(vnr_renderer_t* r, void** stream);
 int vnr_renderer_set_frames_in_flight(vnr_renderer_t* r, int n);
 /* the slots' streams (to bracket a run of frames with events); n_streams receives the ring depth */
 int vnr_renderer_streams(vnr_renderer_t* r, void** streams, int max_streams, int* n_streams);
-/* samples per ray per wavefront round (N_ITERS, env VNR_RM_N_ITERS; method_raymarching.cu:30-40) */
+/* samples per ray per wavefront round (N_ITERS, env VNR_RM_N_ITERS; method_raymarching.cu:30-40): 1..32, default 16 as the
+ * reference.  Frames do not depend on it (a ray's samples are the same, only the round that decodes them changes); unshaded
+ * marching (modes 4-6) honours values above 16 -- fewer, fuller rounds -- the shaded passes cap it at 16. */
 int vnr_renderer_set_n_iters(vnr_renderer_t* r, int n);
 
 /* device-driven wavefront loop (default on): the per-round host round trip of iterative_ray_compaction

@@ -83,7 +83,7 @@ __device__ __forceinline__ void stage_frame_params(FrameParams* dst, const Frame
 // SHADE 0: no shading; 1: gradient shading (every sample is 4 consecutive decode entries: the position and its three
 // forward-difference neighbours, :719-726); 2: single-shade heuristic, camera pass; 3: its shadow pass (rays start at the
 // highest-contribution point of pass 2 and run along the light direction; alpha only).
-template <bool FIRST, int SHADE>
+template <bool FIRST, int SHADE, int MAXI>
 __global__ void __launch_bounds__(128)
 march_round_kernel(const FrameParams* __restrict__ fpp, RayBuffers rb, float4* __restrict__ samples0, float4* __restrict__ samples1,
                    const float* __restrict__ values, uint32_t* __restrict__ counters, int round_host, const uint32_t* __restrict__ round_dev,
@@ -201,7 +201,7 @@ march_round_kernel(const FrameParams* __restrict__ fpp, RayBuffers rb, float4* _
   }
 
   // ---- walk the DDA for the next round: up to n_iters samples (iterative_intersect_kernel :687-730)
-  float4 local[16];
+  float4 local[MAXI];           // MAXI = 16 (the reference's N_ITERS) or 32 (unshaded marching only, vnr_renderer_set_n_iters)
   uint32_t k = 0;
   if (active) {
     const uint32_t n_iters = (uint32_t)fp.n_iters;
@@ -241,7 +241,7 @@ march_round_kernel(const FrameParams* __restrict__ fpp, RayBuffers rb, float4* _
     // share hash-grid cells on the coarse and middle levels; the warp's stores and next round's loads coalesce
     const uint32_t lt = (1u << lane) - 1u;
     uint32_t off = 0;
-    for (uint32_t j = 0; j < 16u; ++j) {
+    for (uint32_t j = 0; j < (uint32_t)MAXI; ++j) {
       const uint32_t mask = __ballot_sync(0xffffffffu, k > j);
       if (!mask) break;
       if (k > j) put(wbase + EPS * (off + (uint32_t)__popc(mask & lt)), local[j]);
@@ -454,7 +454,7 @@ Renderer::Renderer(Volume* v) : vol(v) {
   if (const char* e = getenv("VNR_RM_TRANSPOSE")) transpose = atoi(e) != 0;  // 0: per-ray contiguous sample slots (A/B)
   if (const char* e = getenv("VNR_RM_N_ITERS")) {       // method_raymarching.cu:30-38
     int n = atoi(e);
-    if (n >= 1 && n <= 16) n_iters = n;
+    if (n >= 1 && n <= 32) n_iters = n;
   }
   if (const char* e = getenv("VNR_FRAMES_IN_FLIGHT")) { const int n = atoi(e); if (n >= 1 && n <= kMaxFramesInFlight) set_frames_in_flight(n); }
   vol->renderers.push_back(this);
@@ -571,22 +571,24 @@ void Renderer::fill_frame_params(FrameParams& fp) {
   fp.light_ambient = 1.5f;                                             // instantvnr_types.h:146
 }
 
-int Renderer::round_bound() const {
+int Renderer::round_bound(int iters) const {
   // samples per ray <= world-space diagonal * sampling_rate (one per step) + one clipped sample per
   // macrocell crossed + 2; a live ray consumes n_iters samples per round.
   const double dx = vol->dims[0] * scale[0], dy = vol->dims[1] * scale[1], dz = vol->dims[2] * scale[2];
   const double diag = std::sqrt(dx * dx + dy * dy + dz * dz);
   const double max_samples = std::ceil(diag * sampling_rate) + vol->mc_dims[0] + vol->mc_dims[1] + vol->mc_dims[2] + 2;
-  return (int)std::ceil(max_samples / n_iters) + 1;
+  return (int)std::ceil(max_samples / iters) + 1;
 }
 
 typedef void (*march_kernel_t)(const FrameParams*, RayBuffers, float4*, float4*, const float*, uint32_t*, int, const uint32_t*, float4*);
-static march_kernel_t march_kernel(bool first, int shade) {
+static march_kernel_t march_kernel(bool first, int shade, int n_iters = 16) {
   switch (shade) {
-    case 1: return first ? march_round_kernel<true, 1> : march_round_kernel<false, 1>;
-    case 2: return first ? march_round_kernel<true, 2> : march_round_kernel<false, 2>;
-    case 3: return first ? march_round_kernel<true, 3> : march_round_kernel<false, 3>;
-    default: return first ? march_round_kernel<true, 0> : march_round_kernel<false, 0>;
+    case 1: return first ? march_round_kernel<true, 1, 16> : march_round_kernel<false, 1, 16>;
+    case 2: return first ? march_round_kernel<true, 2, 16> : march_round_kernel<false, 2, 16>;
+    case 3: return first ? march_round_kernel<true, 3, 16> : march_round_kernel<false, 3, 16>;
+    default:
+      if (n_iters > 16) return first ? march_round_kernel<true, 0, 32> : march_round_kernel<false, 0, 32>;
+      return first ? march_round_kernel<true, 0, 16> : march_round_kernel<false, 0, 16>;
   }
 }
 
@@ -600,7 +602,7 @@ void Renderer::ensure_graph(FrameSlot& S, int pass, int shade, const RayBuffers&
   key.ptrs[0] = rb.rgba; key.ptrs[1] = rb.tn_ncb; key.ptrs[2] = rb.cell_base; key.ptrs[3] = rb.state; key.ptrs[4] = rb.jitter;
   key.ptrs[5] = S.samples[0].p; key.ptrs[6] = S.samples[1].p; key.ptrs[7] = S.values.p; key.ptrs[8] = cnt; key.ptrs[9] = S.accum.p;
   key.ptrs[11] = fpd; key.ptrs[12] = rb.ssh_org; key.ptrs[13] = rb.ssh_col; key.ptrs[14] = rb.ssh_rgba; key.ptrs[15] = rb.ssh_jitter;
-  key.grid = grid; key.cap = cap; key.rounds = rounds; key.volume_src = volume_src; key.shade = shade;
+  key.grid = grid; key.cap = cap; key.rounds = rounds; key.volume_src = volume_src; key.shade = shade | ((shade == 0 ? n_iters : 16) << 8);
   if (S.loop_exec[pass] && !memcmp(&key, &S.graph_key[pass], sizeof key)) return;
   VNR_CUDA(cudaStreamSynchronize(S.stream));
   if (S.loop_exec[pass]) { cudaGraphExecDestroy(S.loop_exec[pass]); S.loop_exec[pass] = nullptr; }
@@ -631,7 +633,7 @@ void Renderer::ensure_graph(FrameSlot& S, int pass, int shade, const RayBuffers&
                              : launch_decode_samples(vol->cfg.desc, vol->params.p, S.samples[0].p, S.samples[1].p, S.values.p, cnt + 2, round_dev, cap, S.capture_stream);
   // (fusing this 1-thread kernel into the compositing kernel -- last CTA to finish sets the condition -- was measured
   // slower: 0.717 vs 0.693 ms/frame at 1024^2; a kernel that calls cudaGraphSetConditional pays for it in every CTA)
-  march_kernel(false, shade)<<<grid, 128, 0, S.capture_stream>>>(fpd, rb, S.samples[0].p, S.samples[1].p, S.values.p, cnt, 0, round_dev, S.accum.p);
+  march_kernel(false, shade, shade == 0 ? n_iters : 16)<<<grid, 128, 0, S.capture_stream>>>(fpd, rb, S.samples[0].p, S.samples[1].p, S.values.p, cnt, 0, round_dev, S.accum.p);
   advance_round_kernel<<<1, 1, 0, S.capture_stream>>>(cnt, round_dev, handle, 0, rounds);
   cudaGraph_t captured = nullptr;
   cudaError_t e2 = cudaStreamEndCapture(S.capture_stream, &captured);
@@ -757,9 +759,11 @@ void Renderer::render() {
   const bool zc = zero_copy && download && (rc || !S.frame_target);
   fp[0].frame = zc ? S.h_frame[hb] : S.frame_out();
   fp[0].accum_prev = frame_index > 1 ? P.accum.p : nullptr;
+  const int iters = shade == 0 ? n_iters : std::min(n_iters, 16);      // shaded passes keep the reference's 16 samples per round
+  fp[0].n_iters = iters;
   fp[0].shade_mode = shade; fp[1] = fp[0]; fp[1].shade_mode = 3;
   const uint32_t n_rays = fp[0].n_rays;
-  const int rounds = round_bound();
+  const int rounds = round_bound(iters);
   const int n_pass = shade == 2 ? 2 : 1;
   // make the volume's pending work (training, tfn upload) visible to the frame stream
   VNR_CUDA(cudaEventRecord(S.vol_ready, vol->stream));
@@ -772,7 +776,7 @@ void Renderer::render() {
 
   // decoding modes, and a SimpleVolume in every mode but the sample-streaming ones, run the single-kernel marcher
   const bool single_kernel = decoding || (gt_source && mode != 5 && mode != 8 && mode != 11 && mode != 14);
-  const size_t cap = (size_t)n_rays * n_iters * (shade == 1 ? 4 : 1);
+  const size_t cap = (size_t)n_rays * iters * (shade == 1 ? 4 : 1);
   if (!single_kernel) {
     S.samples[0].ensure(cap); S.samples[1].ensure(cap); S.values.ensure(cap);
     if (pathtracing) {
@@ -811,7 +815,7 @@ void Renderer::render() {
     const int sh = pass == 1 ? 3 : shade;
     uint32_t* cnt = S.counters.p + (size_t)pass * cstride;
     const FrameParams* fpd = reinterpret_cast<const FrameParams*>(S.fp_dev.p) + pass;
-    march_kernel(true, sh)<<<grid, 128, 0, stream>>>(fpd, rb, S.samples[0].p, S.samples[1].p, nullptr, cnt, 0, nullptr, S.accum.p);
+    march_kernel(true, sh, iters)<<<grid, 128, 0, stream>>>(fpd, rb, S.samples[0].p, S.samples[1].p, nullptr, cnt, 0, nullptr, S.accum.p);
     if (graph_loop) {
       // device-driven loop: WHILE (round has samples) { decode; compose + march; advance }
       ensure_graph(S, pass, sh, rb, grid, cap, rounds, volume_src);
@@ -822,7 +826,7 @@ void Renderer::render() {
         if (volume_src) VNR_CUDA(launch_volume_samples(volume_src, vol->dims, S.samples[r & 1].p, nullptr, S.values.p, cnt + 2 + r, nullptr, cap, stream));
         else VNR_CUDA(launch_decode_samples(vol->cfg.desc, vol->params.p, S.samples[r & 1].p, nullptr, S.values.p, cnt + 2 + r, nullptr, cap, stream));
         if (profiling) VNR_CUDA(cudaEventRecord(S.prof_events[S.prof_used++], stream));
-        march_kernel(false, sh)<<<grid, 128, 0, stream>>>(fpd, rb, S.samples[0].p, S.samples[1].p, S.values.p, cnt, r + 1, nullptr, S.accum.p);
+        march_kernel(false, sh, iters)<<<grid, 128, 0, stream>>>(fpd, rb, S.samples[0].p, S.samples[1].p, S.values.p, cnt, r + 1, nullptr, S.accum.p);
       }
     }
     finalize_kernel<<<grid, 128, 0, stream>>>(fpd, rb, cnt + kMaxRounds + 3, S.accum.p, cnt, graph_loop ? cnt + kMaxRounds + 2 : nullptr);

@@ -68,7 +68,7 @@ struct Renderer {
   int width = 0, height = 0;
   int mode = 5;                         // vnrCreateRenderer default (api.cpp:456)
   bool gt_source = false;               // march the ground-truth volume (SimpleVolume renderer)
-  int n_iters = 16;                     // N_ITERS (method_raymarching.cu:30-40)
+  int n_iters = 16;                     // N_ITERS (method_raymarching.cu:30-40); up to 32 for unshaded marching (fewer, fuller rounds)
   int jitter_mode = 0;
   bool tiled = true;                    // warps own 8 x 4 pixel tiles instead of 32-pixel scanline segments
   bool transpose = true;                // sample slots of a warp are depth-major (all rays' j-th samples adjacent)
@@ -99,7 +99,7 @@ struct Renderer {
   uint32_t local_rays() const;
   void resize(int w, int h);
   void fill_frame_params(FrameParams& fp);
-  int round_bound() const;
+  int round_bound(int iters) const;
   void sync_all();
   void ensure_graph(FrameSlot& S, int pass, int shade, const RayBuffers& rb, unsigned grid, size_t cap, int rounds, const float* volume_src);
   void render();

@@ -116,7 +116,7 @@ VNR_EXPORT int vnr_renderer_streams(vnr_renderer_t* r, void** streams, int max_s
   });
 }
 VNR_EXPORT int vnr_renderer_set_n_iters(vnr_renderer_t* r, int n) {
-  return guard([&] { if (n < 1 || n > 16) throw InvalidError("n_iters must be in [1,16]"); R(r)->n_iters = n; R(r)->reset = true; });
+  return guard([&] { if (n < 1 || n > 32) throw InvalidError("n_iters must be in [1,32]"); R(r)->n_iters = n; R(r)->reset = true; });
 }
 
 // device-driven wavefront loop (CUDA graph WHILE node) on/off; off = bounded host-enqueued rounds

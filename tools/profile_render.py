@@ -7,9 +7,10 @@ from instantvnr_b200 import synthetic as syn
 import bench
 
 dims = (256, 256, 256)
-vol, gt, (rgb, alpha) = bench.build_scene(vnr, dims, int(os.environ.get("TRAIN_STEPS", "200")), 1 << 16)
+LOG2 = int(os.environ.get("LOG2_HASHMAP", "19")); W = int(os.environ.get("FRAME_W", "1024")); H = int(os.environ.get("FRAME_H", "1024"))
+vol, gt, (rgb, alpha) = bench.build_scene(vnr, dims, int(os.environ.get("TRAIN_STEPS", "200")), 1 << 16, dict(log2_hashmap=LOG2))
 ren = vnr.Renderer(vol)
-ren.set_size(1024, 1024)
+ren.set_size(W, H)
 if os.environ.get("NO_DOWNLOAD") == "1":      # device-resident frames (what bench.py's `value` times): no PCIe stores in the kernels
     ren.set_download(False)
 for v in range(int(os.environ.get("FRAMES", "3"))):

@@ -124,11 +124,11 @@ def kernel_report(name, rep, regex):
     print("wrote", name)
 
 
-def decode_traffic():
-    """profiles/decode_traffic.json: DRAM bytes of the first captured decode launch (round 0 of frame 0) next to its sample count
+def decode_traffic(rep_name="decode", log_name="prof_decode.log", cfg="t19_1024x1024"):
+    """profiles/decode_traffic_<config>.json: DRAM bytes of the first captured decode launch (round 0 of frame 0) next to its sample count
     (the per-round counters tools/profile_render.py printed in the same run) -- bench.py's roofline.traffic."""
     import json
-    rep, log = os.path.join(G, f"decode_{tag}.ncu-rep"), os.path.join(G, "prof_decode.log")
+    rep, log = os.path.join(G, f"{rep_name}_{tag}.ncu-rep"), os.path.join(G, log_name)
     if not (os.path.exists(rep) and os.path.exists(log)):
         return
     m = re.search(r"round_counts 0 \[(\d+)", open(log).read())
@@ -144,12 +144,19 @@ def decode_traffic():
     out = {"kernel": short(r[hdr.index("Kernel Name")]), "samples": int(m.group(1)), "dram_bytes": val("dram__bytes_read.sum") + val("dram__bytes_write.sum"),
            "dram_bytes_read": val("dram__bytes_read.sum"), "dram_bytes_write": val("dram__bytes_write.sum"), "duration_us": dur_us,
            "source": f"profiles/decode_{tag}.md (ncu --set full, first decode launch of frame 0 = wavefront round 0)"}
-    json.dump(out, open(os.path.join(P, "decode_traffic.json"), "w"), indent=1)
-    print("wrote decode_traffic.json", out)
+    out["config"] = cfg
+    out["source"] = f"gpurun_out/{rep_name}_{tag}.ncu-rep (ncu --set full, first decode launch of frame 0 = wavefront round 0)"
+    for k in ("lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+              "lts__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active"):
+        if k in hdr:
+            out[k] = r[hdr.index(k)]
+    json.dump(out, open(os.path.join(P, f"decode_traffic_{cfg}.json"), "w"), indent=1)
+    print(f"wrote decode_traffic_{cfg}.json", out)
 
 
 launches()
 decode_traffic()
+decode_traffic("decode4k", "prof_decode4k.log", "t22_3840x2160")
 kernel_report("decode", os.path.join(G, f"decode_{tag}.ncu-rep"), "decode_kernel")
 kernel_report("train", os.path.join(G, f"train_{tag}.ncu-rep"), "train_step")
 kernel_report("march", os.path.join(G, f"march_{tag}.ncu-rep"), "march_round")
