@@ -596,35 +596,49 @@ def run_train(args):
     del gt
     torch.cuda.empty_cache()
     vol.init_params(1337)
-    if world > 1:
+    # the public call (vnrNeuralVolumeTrain -> vnr_volume_train) is what is timed.  N > 1, --dp-mode sharded: the same call on every
+    # rank of the library's communicator (synchronous data parallel; reduce-scatter + Adam + all-gather in one kernel over NVLink
+    # peer memory).  --dp-mode allreduce keeps the torch.distributed harness (NCCL all-reduce of the gradient buffers) as comparison.
+    comm = None; dp = None
+    if world > 1 and args.dp_mode == "sharded":
+        comm = vnr.Comm.init_rank(rank, world, f"vnr-bench-train-{os.environ.get('MASTER_PORT', '0')}-{os.getppid()}")
+        vol.attach_comm(comm)
+    elif world > 1:
         broadcast_params(vol)
-    dp = DataParallelTrainer(GpuTrainBackend(vol), mode=args.dp_mode)
-    stream = dp.b.stream
+        dp = DataParallelTrainer(GpuTrainBackend(vol), mode=args.dp_mode)
+    stream = torch.cuda.ExternalStream(vol.stream())
     n = args.batch
+
+    def steps_(k, want_loss=False):
+        if dp is not None:
+            loss = None
+            for _ in range(k):
+                loss = dp.step(n, want_loss=want_loss)
+            return loss
+        vol.train(k, batch=n, fast_mode=True)
+        return vol.last_loss() if want_loss else None
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        dp.step(n)
+    steps_(max(args.warmup, 3))
     barrier()
     clocks = ClockSampler(local); clocks.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record(stream)
-    for _ in range(args.steps):
-        dp.step(n)
+    steps_(args.steps)
     ev1.record(stream)
     clocks.sample_now()                                 # the queue is still draining: a sample under load even for a very short region
     stream.synchronize(); barrier()
     ms = ev0.elapsed_time(ev1)
     clk = clocks.stop()
-    # end to end: the same steps through the public call, with the per-step result (the loss) read back to the host
+    # end to end: one step per call, with the per-step result (the loss) read back to the host before the next call
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        loss = dp.step(n, want_loss=True)
+        loss = steps_(1, want_loss=True)
     stream.synchronize(); barrier()
     ms_e2e = (time.perf_counter() - t0) * 1e3
     t = torch.tensor([ms, ms_e2e], device="cuda", dtype=torch.float64)
@@ -644,7 +658,7 @@ def run_train(args):
                "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "f16", "data": "synthetic",
                "config": {"workload": workload_string(args),
-                          "path": "volume resident in HBM, sampled on the device" + ("" if world == 1 else ", gradient all-reduce (fp16 grid + fp32 MLP) over NCCL + replicated Adam" if dp.mode == "allreduce"
+                          "path": "volume resident in HBM, sampled on the device" + ("" if world == 1 else ", gradient all-reduce (fp16 grid + fp32 MLP) over NCCL + replicated Adam" if dp is not None
                                                                else ", optimizer fused with its collectives over NVLink peer memory (reduce-scatter + Adam + all-gather in one kernel)"),
                           "global_batch": n * world, "l2_flush": "per-step parameter-state sweep (~0.9 GB) exceeds L2",
                           "parallelism": f"dp{world}"},

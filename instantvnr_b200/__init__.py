@@ -86,7 +86,7 @@ def device_count():
 
 def probe_memory(kind, table_bytes, n_ops, repeats=5):
     """Independent memory-system microbenchmark (csrc/probe.cu): kind "loads" / "reds" / "copy" -> (best ms, mean ms)."""
-    k = {"loads": 0, "reds": 1, "copy": 2, "loads32": 3, "host_scanline": 4, "host_tiles8x4": 5, "host_scanline32": 6, "host_tiles16x2": 7, "mixed": 8}[kind]
+    k = {"loads": 0, "reds": 1, "copy": 2, "loads32": 3, "host_scanline": 4, "host_tiles8x4": 5, "host_scanline32": 6, "host_tiles16x2": 7, "mixed": 8}.get(kind, kind)
     best, mean = C.c_float(), C.c_float()
     _check(lib().vnr_probe_memory(C.c_int(k), C.c_size_t(int(table_bytes)), C.c_size_t(int(n_ops)), C.c_int(repeats), C.byref(best), C.byref(mean)))
     return best.value, mean.value

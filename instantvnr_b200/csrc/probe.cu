@@ -85,6 +85,28 @@ __global__ void __launch_bounds__(256) probe_loads32_kernel(const uint4* __restr
   if (fold == 0x12345678u) sink[t & 1023u] = fold;
 }
 
+// the same random loads from ONE resident CTA per SM (grid = number of SMs) whose dynamic shared memory shrinks the L1: how the
+// gather rate of a warp-specialised persistent CTA depends on its thread count and on the L1 left over by its shared memory
+__global__ void probe_loads_cta_kernel(const uint4* __restrict__ table, uint32_t n_vec, uint32_t per_thread, uint32_t seed, uint32_t* __restrict__ sink) {
+  extern __shared__ uint8_t probe_smem[];
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (per_thread == 0xFFFFFFFFu) probe_smem[threadIdx.x] = 1;     // never: keeps the allocation referenced
+  uint32_t fold = 0;
+  uint32_t c = mix32(t * 0x9e3779b9u + seed);
+  for (uint32_t k = 0; k < per_thread; k += 8) {
+    uint4 v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      c = c * 1664525u + 1013904223u;
+      const uint32_t idx = (uint32_t)(((uint64_t)mix32(c) * n_vec) >> 32);
+      v[i] = ldg_nc_v4(table + idx);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) fold ^= v[i].x ^ v[i].y ^ v[i].z ^ v[i].w;
+  }
+  if (fold == 0x12345678u) sink[t & 1023u] = fold;
+}
+
 // loads and reductions TOGETHER (even blocks: random 16-byte loads over `table`, odd blocks: random fp16x8 reductions over `table2`):
 // what the training step's gather and scatter cost when they share the memory system
 __global__ void __launch_bounds__(256) probe_mixed_kernel(const uint4* __restrict__ table, __half* __restrict__ table2, uint32_t n_vec, uint32_t per_thread,
@@ -155,7 +177,7 @@ using namespace vnr;
 // pattern kind - 4 (see probe_host_store_kernel).
 // Runs `repeats` timed launches after one warm-up and returns the fastest (ms_best) and the mean (ms_mean) launch time.
 VNR_EXPORT int vnr_probe_memory(int kind, size_t table_bytes, size_t n_ops, int repeats, float* ms_best, float* ms_mean) {
-  if (kind < 0 || kind > 8 || table_bytes < 4096 || repeats < 1 || !ms_best) return VNR_ERR_INVALID;
+  if (kind < 0 || kind > 400 || table_bytes < 4096 || repeats < 1 || !ms_best) return VNR_ERR_INVALID;
   int n_dev = 0;
   if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) { cudaGetLastError(); return VNR_ERR_CUDA; }
   void* table = nullptr; void* aux = nullptr;
@@ -185,6 +207,17 @@ VNR_EXPORT int vnr_probe_memory(int kind, size_t table_bytes, size_t n_ops, int 
       else if (kind == 1) probe_reds_kernel<<<grid, 256, 0, s>>>((__half*)table, (uint32_t)n_vec, per_thread, 17u + it);
       else if (kind == 2) probe_copy_kernel<<<148 * 16, 256, 0, s>>>((const uint4*)table, (uint4*)aux, n_vec);
       else if (kind == 3) probe_loads32_kernel<<<grid, 256, 0, s>>>((const uint4*)table, (uint32_t)n_vec, per_thread, 17u + it, (uint32_t*)aux);
+      else if (kind >= 9) {
+        // kind 9 + 4 * i + j: threads = 256 << i (i = 0..2), dynamic shared memory = {0, 100, 160, 200} KB [j]; one CTA per SM
+        // kind 100 + kb: 256 threads, kb KB of dynamic shared memory
+        const int i = kind >= 100 ? 0 : (kind - 9) / 4, j = kind >= 100 ? 0 : (kind - 9) % 4;
+        const unsigned threads_cta = 256u << i;
+        const size_t smem = kind >= 100 ? (size_t)(kind - 100) << 10 : (size_t[]){0, 100 << 10, 160 << 10, 200 << 10}[j];
+        if (i > 2 || smem > (227u << 10)) { rc = VNR_ERR_INVALID; break; }
+        ok(cudaFuncSetAttribute(probe_loads_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 << 10));
+        const uint32_t pt = (uint32_t)(n_ops / ((size_t)num_sms() * threads_cta)) & ~7u;
+        probe_loads_cta_kernel<<<num_sms(), threads_cta, smem, s>>>((const uint4*)table, (uint32_t)n_vec, pt, 17u + it, (uint32_t*)aux);
+      }
       else if (kind == 8) probe_mixed_kernel<<<2 * grid, 256, 0, s>>>((const uint4*)table, (__half*)table2, (uint32_t)n_vec, per_thread, 17u + it, (uint32_t*)aux);
       else { const uint32_t w = 1024, h = (uint32_t)(n_vec / w); probe_host_store_kernel<<<(w * h + 127) / 128, 128, 0, s>>>((float4*)table, w, h, kind - 4); }
       ok(cudaGetLastError());

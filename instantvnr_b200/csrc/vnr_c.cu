@@ -49,6 +49,9 @@ Volume::~Volume() {
     if (dp_grid_grads[r]) cudaIpcCloseMemHandle(dp_grid_grads[r]);
     if (dp_mlp_grads[r]) cudaIpcCloseMemHandle(dp_mlp_grads[r]);
   }
+  if (side) cudaStreamDestroy(side);
+  if (ev_fork) cudaEventDestroy(ev_fork);
+  if (ev_join) cudaEventDestroy(ev_join);
   if (stream) cudaStreamDestroy(stream);
 }
 
@@ -81,6 +84,7 @@ VNR_EXPORT int vnr_volume_create(const char* model_json, int dx, int dy, int dz,
     ModelConfig cfg = parse_model_config(model_json);
     require_device();
     std::unique_ptr<Volume> v(new Volume());
+    if (const char* e = getenv("VNR_TRAIN_VARIANT")) { const int t = atoi(e); if (t >= 0 && t <= 2) v->train_variant = t; }   // A/B runs of the training kernel
     v->cfg = cfg;
     v->dims[0] = dx; v->dims[1] = dy; v->dims[2] = dz;
     VNR_CUDA(cudaGetDevice(&v->device));

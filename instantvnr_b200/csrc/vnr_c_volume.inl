@@ -487,7 +487,7 @@ VNR_EXPORT int vnr_volume_get_decoded(vnr_volume_t* vh, float* h_out) {
 VNR_EXPORT int vnr_volume_train_debug(vnr_volume_t* vh, int variant, uint32_t flags, int profile) {
   return guard([&] {
     Volume* v = V(vh);
-    if (variant != 0 && variant != 1) throw InvalidError("unknown training-kernel variant");
+    if (variant < 0 || variant > 2) throw InvalidError("unknown training-kernel variant");
     VNR_CUDA(cudaStreamSynchronize(v->stream));
     v->train_variant = variant; v->train_flags = flags; v->train_prof_on = profile != 0;
   });

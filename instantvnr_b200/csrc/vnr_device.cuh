@@ -120,6 +120,19 @@ __device__ __forceinline__ void corner_weights(float wx, float wy, float wz, flo
   for (int i = 0; i < 8; ++i) w[i] = xy[i & 3] * az[i >> 2];
 }
 
+// Table loads.  LD 0: ld.global.nc (allocates an L1 line per miss); 1: ld.global.nc.L1::no_allocate; 2: ld.global.cg (L2 only).
+// A CTA that takes most of the SM's shared memory leaves a small L1 (228 KB - smem): with LD 0 the lines of the misses in
+// flight are bounded by it.
+template <int LD, typename T> __device__ __forceinline__ T table_load(const T* p) {
+  if constexpr (LD == 0) return __ldg(p);
+  else if constexpr (sizeof(T) == 16) {
+    uint4 v;
+    if constexpr (LD == 1) asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    else asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return *reinterpret_cast<T*>(&v);
+  } else return __ldcg(p);
+}
+
 template <int F> struct FeatVec;
 template <> struct FeatVec<8> { typedef uint4 type; };
 template <> struct FeatVec<4> { typedef uint2 type; };
@@ -129,7 +142,7 @@ template <> struct FeatVec<1> { typedef unsigned short type; };
 // One (sample, level) gather split in two halves so that callers can keep the loads of the next
 // level in flight while the current one is reduced: issue() computes the corner indices and
 // starts the 8 vector loads, finish() does the fp16-accumulated trilinear sum.
-template <int F>
+template <int F, int LD = 0>
 struct LevelGather {
   typedef typename FeatVec<F>::type T;
   T v[8];
@@ -142,7 +155,7 @@ struct LevelGather {
     level_indices(lv, c, idx);
     const T* __restrict__ tab = reinterpret_cast<const T*>(grid) + lv.offset;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = __ldg(tab + idx[i]);
+    for (int i = 0; i < 8; ++i) v[i] = table_load<LD>(tab + idx[i]);
   }
 
   __device__ __forceinline__ T finish() const {
@@ -184,12 +197,12 @@ __device__ __forceinline__ uint32_t feat_offset(uint32_t level, uint32_t row_sw)
 
 // Gather levels [l0, l1) of one sample into its swizzled tile row, software-pipelined: the
 // loads of level l+1 are in flight while level l is reduced.
-template <int F>
+template <int F, int LD = 0>
 __device__ __forceinline__ void encode_levels(uint8_t* rowp, uint32_t row_sw, const DecoderDesc& d, const __half* __restrict__ grid,
                                               float x, float y, float z, int l0, int l1) {
   typedef typename FeatVec<F>::type T;
   if (l0 >= l1) return;
-  LevelGather<F> cur, nxt;
+  LevelGather<F, LD> cur, nxt;
   cur.issue(d.lv[l0], grid, x, y, z);
   for (int l = l0; l < l1; ++l) {
     if (l + 1 < l1) nxt.issue(d.lv[l + 1], grid, x, y, z);
@@ -200,12 +213,12 @@ __device__ __forceinline__ void encode_levels(uint8_t* rowp, uint32_t row_sw, co
 
 // Same without the cross-level software pipeline (one level's 8 loads in flight): fewer live registers, for
 // kernels whose gather threads are capped low and whose gather is not the bound (training).
-template <int F>
+template <int F, int LD = 0>
 __device__ __forceinline__ void encode_levels_lean(uint8_t* rowp, uint32_t row_sw, const DecoderDesc& d, const __half* __restrict__ grid,
                                                    float x, float y, float z, int l0, int l1) {
   typedef typename FeatVec<F>::type T;
   for (int l = l0; l < l1; ++l) {
-    LevelGather<F> g;
+    LevelGather<F, LD> g;
     g.issue(d.lv[l], grid, x, y, z);
     *reinterpret_cast<T*>(rowp + feat_offset<F>((uint32_t)l, row_sw)) = g.finish();
   }
@@ -213,12 +226,12 @@ __device__ __forceinline__ void encode_levels_lean(uint8_t* rowp, uint32_t row_s
 
 // Gather all levels of one sample into row `row` of a 128B-swizzled A tile (128 rows of 64 halves) and zero the
 // padding features up to enc_pad (tcnn pads the encoding to a multiple of 16: grid.h:616-620).
-template <int F, bool PIPELINED = true>
+template <int F, bool PIPELINED = true, int LD = 0>
 __device__ __forceinline__ void encode_row(uint8_t* a_smem, const DecoderDesc& d, const __half* __restrict__ grid, float x, float y, float z, uint32_t row) {
   uint8_t* rowp = a_smem + row * 128u;
   const uint32_t sw = (row & 7u);
-  if constexpr (PIPELINED) encode_levels<F>(rowp, sw, d, grid, x, y, z, 0, d.n_levels);
-  else encode_levels_lean<F>(rowp, sw, d, grid, x, y, z, 0, d.n_levels);
+  if constexpr (PIPELINED) encode_levels<F, LD>(rowp, sw, d, grid, x, y, z, 0, d.n_levels);
+  else encode_levels_lean<F, LD>(rowp, sw, d, grid, x, y, z, 0, d.n_levels);
   for (int k = d.enc_dims; k < d.enc_pad; ++k)
     *reinterpret_cast<__half*>(rowp + ((((uint32_t)k >> 3) ^ sw) << 4) + ((uint32_t)k & 7u) * 2u) = __float2half_rn(0.f);
 }

@@ -43,7 +43,7 @@ struct Volume {
   std::vector<float*> bias_retired;                   // outgrown tables still referenced by kernels in flight
   float bias_beta1 = -1.f, bias_beta2 = -1.f;         // ... and the betas it was built with (refilled when the optimizer config changes)
   // measurement taps of the training kernel (vnr_volume_train_debug): chain variant, role switches, per-CTA role timers
-  int train_variant = 1; uint32_t train_flags = 0; bool train_prof_on = false; DevBuf<uint32_t> train_prof;
+  int train_variant = 2; uint32_t train_flags = 0; bool train_prof_on = false; DevBuf<uint32_t> train_prof;
   bool have_params = false, have_opt = false;
   uint32_t opt_step = 0; float lr_factor = 1.f;
   uint64_t train_step = 0;
@@ -55,6 +55,10 @@ struct Volume {
   bool have_gt = false;
   Pcg32 sampler_rng;               // neural_sampler.cu:36  `static default_rng_t rng{1337}`
   DevBuf<float> train_x, train_y;
+  // second batch buffer + side stream of train_steps: the next batch is drawn, the MLP's optimizer step and the macrocell update
+  // run while the hash-grid optimizer sweep (HBM-bound) occupies the main stream
+  DevBuf<float> train_x2, train_y2;
+  cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   SlabSampler* ooc = nullptr;      // out-of-core sampler (slab_sampler.cu): training draws from a pool of random file slabs
 
   // progressively decoded volume (network.cu:290-326): what the "decoding" rendering modes march

@@ -30,7 +30,7 @@ def time_kernel(reps=20):
 
 
 for name, flags in (("baseline", 0), ("gather only (no chain, no reductions)", 5), ("scatter only (no chain, no loads)", 6), ("gather + scatter, no chain", 4),
-                    ("chain + gather", 1), ("chain + scatter", 2), ("chain only", 3)):
+                    ("chain + gather", 1), ("chain + scatter", 2), ("chain only", 3), ("all, two levels in flight", 128), ("gather only, two levels in flight", 128 | 5)):
     vol.train_debug(1, flags, False)
     print(f"{name:45s} {time_kernel():7.1f} us", flush=True)
 # role timers with the chain off
