@@ -438,12 +438,19 @@ def run_ours(args):
         return
 
     peak, peak_kind = measured_peaks()
-    # ---- roofline of the dominant kernel on this rank (decode): event-timed launches of the profiling pass.
-    # The kernel is a gather: 64 random 16-byte loads per sample out of the hash table.  Its ceiling is what the memory system
-    # delivers for that access pattern, measured HERE by an independent microbenchmark (csrc/probe.cu: plain ld.global.nc.v4 at
-    # random offsets, full occupancy, nothing of the product's gather code): over a 46.7 MB buffer (the example model's table,
-    # L2-resident) -> l2_gather_gbs, over a 306.8 MB buffer (T = 2^22, larger than L2) -> hbm_gather_gbs.  `peak` is the probe
-    # over a buffer of THIS run's table size; `achieved` counts the algorithmic gather bytes (1024 B per decoded sample).
+    # ---- roofline of the dominant kernel on this rank (decode): event-timed launches.
+    # The kernel is a gather: 64 scattered 16-byte loads per sample out of the hash table.  What bounds it is the rate at which an
+    # SM's L1TEX turns scattered requests into L2 sector fetches -- ~1 per cycle per SM (csrc/probe.cu: plain ld.global.nc.v4 at
+    # random offsets, nothing of the product's gather code; it does NOT depend on the thread count, 256 threads per SM reach it,
+    # but it halves when the CTA's shared memory selects certain shared-memory / L1 splits: tools/exp_probe_cta.py, DESIGN 3.1,
+    # which is why the decode ring holds 7 tiles and the training kernel stays under 192 KB).  `peak` is that probe over a buffer
+    # of THIS run's table size (46.7 MB: L2-resident -> bound "l1tex_gather"; T = 2^22: 307 MB > L2 -> "hbm_gather").
+    # `achieved` / `frac` are like for like with the probe: the SAME kernel on uniform random coordinates (launches timed here
+    # with CUDA events), 1024 algorithmic gather bytes per sample; above 1.0 because the two x-neighbours of a cell share a 32-byte
+    # sector half the time (an L1 hit the probe's independent addresses never get).  The launches INSIDE the frames run faster
+    # still (`in_frame`): neighbouring rows are the same step of neighbouring rays, lanes of a warp ask for the same table
+    # entries and those requests collapse before the L1TEX -- their algorithmic bytes overcount what the bound unit sees, so
+    # they are reported next to the roofline, not as its fraction.
     GATHER_BYTES = 1024
     table_bytes = (vol.n_params - vol.n_mlp_params) * 2
     probe_ops = (1 << 22) * 64
@@ -452,7 +459,7 @@ def run_ours(args):
     own_ms, _ = vnr.probe_memory("loads", table_bytes, probe_ops, 3)
     gbs = lambda ms_: probe_ops * 16 / (ms_ * 1e-3) / 1e9
     gather_peak = gbs(own_ms)
-    bound = "l2_gather" if table_bytes <= 100e6 else "hbm_gather"
+    bound = "l1tex_gather" if table_bytes <= 100e6 else "hbm_gather"
     decode_rate = prof_decoded / (decode_ms * 1e-3) if decode_ms > 0 else 0.0
     achieved = decode_rate * GATHER_BYTES / 1e9
     # the same kernel on uniform random coordinates (no coherence between neighbouring rows): apples to apples with the probe
@@ -480,18 +487,23 @@ def run_ours(args):
                               "samples_of_that_launch": tj["samples"], "launch_us_under_ncu": tj["duration_us"], "source": tj["source"]}
         except Exception:
             pass
-    roofline = {"bound": bound, "achieved": round(achieved, 1), "peak": round(gather_peak, 1), "unit": "GB/s", "frac": round(achieved / gather_peak, 4),
+    achieved_u = uniform_rate * GATHER_BYTES / 1e9
+    roofline = {"bound": bound, "achieved": round(achieved_u, 1), "peak": round(gather_peak, 1), "unit": "GB/s", "frac": round(achieved_u / gather_peak, 4),
                 "traffic": traffic, "traffic_detail": traffic_detail,
-                "kernel": "decode_kernel<8,4> (fused hash-grid gather + tcgen05 MLP)", "peak_source": "measured in this run: random 16-byte ld.global.nc over a buffer of the table's size (csrc/probe.cu)",
+                "kernel": "decode_kernel<8,.> (fused hash-grid gather + tcgen05 MLP)",
+                "achieved_source": "decode_kernel on 2^22 uniform random coordinates, 5 launches timed with CUDA events in this run; 1024 algorithmic gather bytes per sample",
+                "peak_source": "measured in this run: random 16-byte ld.global.nc over a buffer of the table's size (csrc/probe.cu)",
                 "l2_gather_gbs": round(gbs(l2_ms), 1), "hbm_gather_gbs": round(gbs(hbm_ms), 1), "table_bytes": table_bytes,
-                "algorithmic_bytes_per_sample": GATHER_BYTES, "decode_ms_per_frame": round(decode_ms / prof_steps, 4),
-                "decode_launches_per_frame": decode_launches / prof_steps, "decode_samples_per_sec": decode_rate,
-                "decode_uniform_samples_per_sec": uniform_rate, "frac_uniform": round(uniform_rate * GATHER_BYTES / 1e9 / gather_peak, 4),
+                "algorithmic_bytes_per_sample": GATHER_BYTES, "decode_uniform_samples_per_sec": uniform_rate,
+                "in_frame": {"decode_samples_per_sec": decode_rate, "gather_gbs": round(achieved, 1), "ratio_to_peak": round(achieved / gather_peak, 4),
+                             "decode_ms_per_frame": round(decode_ms / prof_steps, 4), "decode_launches_per_frame": decode_launches / prof_steps,
+                             "note": "the decode launches of the frames (event-timed, host-enqueued rounds of the profiling pass): coherent coordinates, requests of a warp "
+                                     "collapse before the L1TEX, so the algorithmic bytes exceed what the bound unit serves"},
+                "decode_samples_per_sec": decode_rate, "decode_ms_per_frame": round(decode_ms / prof_steps, 4),
                 "hbm_copy_peak": peak, "hbm_copy_peak_source": peak_kind,
                 "hbm_copy_frac": round(decode_rate * BYTES_PER_SAMPLE / 1e9 / peak, 4),
-                "note": "frac = in-frame decode rate x 1024 B / the random-gather probe.  Inside a frame neighbouring rows are the same step of neighbouring rays and share "
-                        "hash-grid cells (sectors), which the random probe does not, so frac can exceed frac_uniform (same kernel, uniform random coordinates).  hbm_copy_frac "
-                        "(all 1044 algorithmic B/sample against the HBM copy peak) is kept for comparison with round 1; the table is read from L2, not HBM, when it fits"}
+                "note": "hbm_copy_frac (all 1044 algorithmic B/sample of the in-frame launches against the HBM copy peak) is kept for comparison with round 1; the table is "
+                        "read from L2, not HBM, when it fits (traffic = DRAM bytes of one launch from the committed ncu capture of this configuration)"}
 
     # the CPU baseline is measured at N=1 only (under torchrun the host cores are shared by the ranks)
     cpu = cpu_baseline(vol, dims, cams, rgb, alpha, args) if world == 1 else {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "measured at N=1 only"}
@@ -647,6 +659,25 @@ def run_train(args):
     ms, ms_e2e = t[0].item(), t[1].item()
     step_count, mean_loss = vol.stats()
     psnr = vol.psnr() if args.volume <= 512 else None
+    # the fused kernel against ITS bound: the SM's L1TEX request stage serves the gather's scattered loads and the backward's
+    # scattered fp16x8 reductions one after the other, so the floor of the kernel is what an independent probe needs for the
+    # same number of random 16-byte loads plus random 16-byte reductions over tables of the same size (csrc/probe.cu kind
+    # "mixed": n x 64 of each, full occupancy, no MLP, no tiles) -- measured here, next to the kernel on a fixed batch
+    kernel_us = floor_us = None
+    if world == 1 and rank == 0:
+        xyz = torch.empty(n, 3, device="cuda"); tgt = torch.empty(n, device="cuda")
+        vol.sample(xyz, tgt, n); torch.cuda.synchronize()
+        for _ in range(3):
+            vol.train_grads(xyz, tgt, n, n)
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record(stream)
+        for _ in range(20):
+            vol.train_grads(xyz, tgt, n, n)
+        k1.record(stream); stream.synchronize()
+        vol.optimizer_step(); torch.cuda.synchronize()
+        kernel_us = k0.elapsed_time(k1) / 20 * 1e3
+        floor_ms, _ = vnr.probe_memory("mixed", (vol.n_params - vol.n_mlp_params) * 2, n * 64, 5)
+        floor_us = floor_ms * 1e3
     if rank == 0:
         peak, peak_kind = measured_peaks()
         n_grid = vol.n_params - vol.n_mlp_params
@@ -667,7 +698,11 @@ def run_train(args):
                        "note": "samples are drawn on the device from the HBM-resident volume (the reference's StaticSampler does the same); the loss is read back every step"},
                "gpu_launches": args.steps * 9, "clocks": clk,
                "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
-                            "kernel": "whole step (train_step_kernel + adam_grid_kernel)", "peak_source": peak_kind, "algorithmic_bytes_per_step": bytes_step}}
+                            "kernel": "whole step (train_step_kernel + adam_grid_kernel)", "peak_source": peak_kind, "algorithmic_bytes_per_step": bytes_step,
+                            "train_step_kernel": None if kernel_us is None else {
+                                "bound": "l1tex_gather + l1tex_reductions", "kernel_us": round(kernel_us, 1), "floor_us": round(floor_us, 1), "frac": round(floor_us / kernel_us, 4),
+                                "note": "kernel_us: train_grads (fused forward + loss + backward kernel and the reduction of its per-CTA weight-gradient partials) on a fixed batch, "
+                                        "20 calls timed with CUDA events; floor_us: the probe's n x 64 random 16-byte loads + n x 64 random fp16x8 reductions in one launch"}}}
         emit(out)
     if world > 1:
         dist.destroy_process_group()

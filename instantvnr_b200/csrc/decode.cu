@@ -26,15 +26,19 @@ namespace vnr {
 // read from device memory (wavefront rounds are sized on the device, no host sync); with
 // round_dev the round index itself lives on the device (graph-driven wavefront): the count is
 // n_dev[round] and odd rounds read coords_alt (the marcher's ping-pong sample buffers).
+//
+// The ring holds 7 tiles, not 8: the CTA's shared memory (7 x 16 KB + weights) then stays below 160 KB, the largest
+// allocation at which the SM's L1TEX still serves scattered 16-byte loads at its full rate (measured one CTA per SM,
+// tools/exp_probe_cta.py: 0.95 addresses per cycle per SM up to 160 KB, 0.89 for 164..192 KB, 0.47 above) -- and that rate is
+// what bounds this kernel.  Tile j lives in stage j % n_stages (one ring shared by the producer groups, in tile order).
 constexpr int kGatherGroups = 4;                 // producer groups (128 threads each)
-constexpr int kStagesPerGroup = 2;               // A-tile ring depth per producer group
-constexpr int kStages = kGatherGroups * kStagesPerGroup;
+constexpr int kMaxStages = 8;                    // A-tile ring depth (n_stages <= kMaxStages, VNR_DECODE_STAGES)
 constexpr int kDecodeThreads = 128 * (1 + kGatherGroups);
 
 template <int F, int STRIDE>
 __global__ void __launch_bounds__(kDecodeThreads, 1)
 decode_kernel(const DecoderDesc d, const __half* __restrict__ params, const float* __restrict__ coords, const float* __restrict__ coords_alt,
-              float* __restrict__ out, uint32_t n, const uint32_t* __restrict__ n_dev, const uint32_t* __restrict__ round_dev, __half* __restrict__ enc_out) {
+              float* __restrict__ out, uint32_t n, const uint32_t* __restrict__ n_dev, const uint32_t* __restrict__ round_dev, __half* __restrict__ enc_out, uint32_t n_stages) {
   if (n_dev) {
     const uint32_t r = round_dev ? *round_dev : 0u;
     n = n_dev[r];
@@ -45,10 +49,10 @@ decode_kernel(const DecoderDesc d, const __half* __restrict__ params, const floa
   if (blockIdx.x >= n_tiles) return;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* a_ring = smem;                                          // kStages tiles of 16 KB
-  uint8_t* w_smem = smem + (size_t)kStages * MlpSmem::kATile;
+  uint8_t* a_ring = smem;                                          // n_stages tiles of 16 KB
+  uint8_t* w_smem = smem + (size_t)n_stages * MlpSmem::kATile;
   __shared__ uint64_t mbar_mma[2];
-  __shared__ uint64_t mbar_full[kStages], mbar_empty[kStages];
+  __shared__ uint64_t mbar_full[kMaxStages], mbar_empty[kMaxStages];
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x;
@@ -56,7 +60,7 @@ decode_kernel(const DecoderDesc d, const __half* __restrict__ params, const floa
   const int gtid = tid & 127;
   if (tid == 0) {
     tc05::mbar_init(&mbar_mma[0], 1); tc05::mbar_init(&mbar_mma[1], 1);
-    for (int s = 0; s < kStages; ++s) { tc05::mbar_init(&mbar_full[s], 128); tc05::mbar_init(&mbar_empty[s], 1); }
+    for (int s = 0; s < kMaxStages; ++s) { tc05::mbar_init(&mbar_full[s], 128); tc05::mbar_init(&mbar_empty[s], 1); }
     tc05::fence_mbar_init();
   }
   if (tid < 32) tc05::tmem_alloc(&tmem_slot, 128);
@@ -66,8 +70,8 @@ decode_kernel(const DecoderDesc d, const __half* __restrict__ params, const floa
   __syncthreads();
   tc05::fence_after_sync();
   const uint32_t tmem_base = tmem_slot;
-  // tiles of this CTA: blockIdx.x + j * gridDim.x, j = 0 .. my_tiles-1; tile j belongs to producer group j % G,
-  // its `it`-th tile (it = j / G) goes to ring stage g * R + it % R, use number it / R of that stage.
+  // tiles of this CTA: blockIdx.x + j * gridDim.x, j = 0 .. my_tiles-1; tile j belongs to producer group j % G and goes to
+  // ring stage j % n_stages, use number j / n_stages of that stage.
   const uint32_t my_tiles = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
 
   if (group == 0) {
@@ -81,9 +85,9 @@ decode_kernel(const DecoderDesc d, const __half* __restrict__ params, const floa
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
         if (q >= nt) break;
-        const uint32_t jj = j + (uint32_t)q, g = jj % kGatherGroups, it = jj / kGatherGroups;
-        stage[q] = g * kStagesPerGroup + it % kStagesPerGroup;
-        parity[q] = (it / kStagesPerGroup) & 1u;
+        const uint32_t jj = j + (uint32_t)q;
+        stage[q] = jj % n_stages;
+        parity[q] = (jj / n_stages) & 1u;
         a[q] = a_ring + (size_t)stage[q] * MlpSmem::kATile;
         full[q] = &mbar_full[stage[q]];
       }
@@ -102,9 +106,8 @@ decode_kernel(const DecoderDesc d, const __half* __restrict__ params, const floa
     // ---------------- producers: hash-grid gather straight into the swizzled A tiles ----------------
     const uint32_t g = (uint32_t)group - 1u;
     const __half* __restrict__ grid = params + d.n_mlp;
-    uint32_t it = 0;
-    for (uint32_t j = g; j < my_tiles; j += kGatherGroups, ++it) {
-      const uint32_t stage = g * kStagesPerGroup + it % kStagesPerGroup, use = it / kStagesPerGroup;
+    for (uint32_t j = g; j < my_tiles; j += kGatherGroups) {
+      const uint32_t stage = j % n_stages, use = j / n_stages;
       const uint32_t s = (blockIdx.x + j * gridDim.x) * kTile + (uint32_t)gtid;
       const uint32_t sc = s < n ? s : n - 1;
       float x, y, z;
@@ -177,7 +180,15 @@ int num_sms() {
 template <int F, int STRIDE>
 static cudaError_t launch_decode_t(const DecoderDesc& d, const __half* params, const float* coords, const float* coords_alt, float* out, size_t n,
                                    const uint32_t* n_dev, const uint32_t* round_dev, size_t n_max, __half* enc_out, cudaStream_t stream) {
-  const size_t smem = 1024 + (size_t)kStages * MlpSmem::kATile + MlpSmem::weights_bytes(d.n_hidden);
+  // ring depth: the deepest (<= 7) that keeps the allocation at or below 160 KB (see kMaxStages), at least 4; allocations that
+  // would land in the slow band measured at 100..104 KB are padded past it
+  int n_stages = 7;
+  while (n_stages > 4 && 1024 + (size_t)n_stages * MlpSmem::kATile + MlpSmem::weights_bytes(d.n_hidden) > 160 * 1024) --n_stages;
+  static int forced = -1;
+  if (forced < 0) { forced = 0; if (const char* e = getenv("VNR_DECODE_STAGES")) { const int k = atoi(e); if (k >= 4 && k <= kMaxStages) forced = k; } }
+  if (forced) n_stages = forced;
+  size_t smem = 1024 + (size_t)n_stages * MlpSmem::kATile + MlpSmem::weights_bytes(d.n_hidden);
+  if (smem > 96 * 1024 && smem < 116 * 1024) smem = 116 * 1024;
   static size_t configured_dev[kMaxDevices] = {};   // function attributes are per device
   if (smem > 226 * 1024) return cudaErrorInvalidValue;
   int dev = 0;
@@ -191,7 +202,7 @@ static cudaError_t launch_decode_t(const DecoderDesc& d, const __half* params, c
   // persistent: one CTA per SM
   const size_t n_tiles = (n_max + kTile - 1) / kTile;
   const uint32_t grid = (uint32_t)std::min<size_t>(n_tiles, (size_t)num_sms());
-  decode_kernel<F, STRIDE><<<grid, kDecodeThreads, smem, stream>>>(d, params, coords, coords_alt, out, (uint32_t)n, n_dev, round_dev, enc_out);
+  decode_kernel<F, STRIDE><<<grid, kDecodeThreads, smem, stream>>>(d, params, coords, coords_alt, out, (uint32_t)n, n_dev, round_dev, enc_out, (uint32_t)n_stages);
   return cudaGetLastError();
 }
 

@@ -742,6 +742,7 @@ void Renderer::render() {
   FrameSlot& S = slot(k);
   FrameSlot& P = last();                                               // the previous frame: accumulation source when frame_index > 1
   cudaStream_t stream = S.stream;
+  apply_l2_policy(vol, stream);            // no-op unless VNR_L2_PERSIST=1 (train.cu)
   if (n_rendered - n_mapped >= slots.size()) n_mapped = n_rendered - slots.size() + 1;      // ring full: the oldest unmapped frame is dropped
   if (reset) frame_index = 0;
   frame_index++;

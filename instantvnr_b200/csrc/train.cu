@@ -1422,10 +1422,12 @@ double volume_psnr(Volume* v, cudaStream_t s) {
 // L2 residency of the parameter blob: kernels launched on `s` treat accesses to it as persisting (cudaAccessPolicyWindow), so
 // the table the gather reads at random survives the streams that pass through L2 between two uses of it -- the optimizer's
 // 0.8 GB state sweep between two training kernels, the ~0.5 GB of sample / ray buffers of a frame between two decode launches.
-// VNR_L2_PERSIST=0 switches it off (A/B runs).
+// OFF by default (VNR_L2_PERSIST=1 switches it on for A/B runs): measured on the training step it costs far more than it gives
+// (0.41 -> 0.70 ms per step at 2^18: the 79 MB persisting carve-out leaves the gradient reductions and the optimizer's streams
+// 47 MB of L2).
 void apply_l2_policy(const Volume* v, cudaStream_t s) {
   static int mode = -1;
-  if (mode < 0) { const char* e = getenv("VNR_L2_PERSIST"); mode = e ? atoi(e) : 1; }
+  if (mode < 0) { const char* e = getenv("VNR_L2_PERSIST"); mode = e ? atoi(e) : 0; }
   if (!mode || !v->params.p) return;
   static size_t max_persist[kMaxDevices] = {}, max_window[kMaxDevices] = {};
   int dev = 0; VNR_CUDA(cudaGetDevice(&dev));

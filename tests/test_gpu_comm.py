@@ -162,7 +162,12 @@ def test_data_parallel_training_equals_accumulated_batches():
     # a last-bit difference of the fp16 parameter here and there, never a different step
     rel = np.linalg.norm(p_dp - p_ref) / np.linalg.norm(p_ref - p_init)
     print("distance of the data-parallel parameters from the accumulated run, relative to the update:", rel, "| bitwise different:", np.mean(p_dp != p_ref))
-    assert rel < 0.1 and np.abs(p_dp - p_ref).max() <= 2 * 5e-3      # measured 0.01 - 0.05 (a few near-zero gradients change sign)
+    # measured 0.01 - 0.05.  A parameter whose near-zero gradient has the other sign in the two runs moves the other way by up to
+    # lr (1 - beta1) / sqrt(1 - beta2) ~ 3 lr per Adam step, so single parameters may be up to steps x 3 x 5e-3 apart; they are rare
+    # (measured 0.2 % beyond 5e-3, max 0.025 -- the same run repeated differs from itself by 0.05 % / 0.019: the order of the fp16
+    # reductions is not reproducible; tools/exp_dp_vs_accum.py)
+    diff = np.abs(p_dp - p_ref)
+    assert rel < 0.1 and diff.max() <= steps * 3 * 5e-3 and np.mean(diff > 5e-3) < 1e-2
     # the value ranges of the data-parallel run cover what either rank saw: equal to the single-process ranges
     ref.train(0, batch=n, fast_mode=False)
     for v in vols:

@@ -1,4 +1,2 @@
 #!/bin/bash
-mkdir -p gpurun_out
-export VNR_L2_PERSIST=0
-VNR_TRAIN_TIMING=1 timeout 200 python bench.py --workload train --steps 200 --warmup 20 2>&1 >/dev/null | grep "train step"
+for v in 1 2; do echo "== variant $v"; VNR_TRAIN_VARIANT=$v timeout 120 python tools/exp_dp_vs_accum.py 2>&1 | tail -5; done
