@@ -602,10 +602,28 @@ def run_train(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dims = (args.volume,) * 3
-    gt = synth_volume_device(dims)
     vol = vnr.NeuralVolume(vnr.model_json(log2_hashmap=args.log2_hashmap), dims)
-    vol.set_groundtruth_device(gt)
-    del gt
+    ooc_info = None
+    if args.out_of_core:
+        # BASELINE configs[3]: the volume stays in a raw file (uint8, written once per box from the same procedural volume);
+        # every rank keeps its own pool of random slabs of it in HBM, refreshed by num_concurrent_blocks slabs per step through
+        # pinned staging buffers, and samples the pool on the device (OutOfCoreSampler, neural_sampler.cpp:1065-1120)
+        path = os.path.join(os.environ.get("VNR_BENCH_TMP", "/tmp"), f"vnr_bench_volume_{args.volume}_u8.raw")
+        if local == 0 and not (os.path.exists(path) and os.path.getsize(path) == args.volume ** 3):
+            gt = synth_volume_device(dims)
+            with open(path + ".tmp", "wb") as f:
+                for z0 in range(0, dims[2], 64):
+                    f.write((gt[z0:z0 + 64] * 255.0 + 0.5).clamp_(0, 255).to(torch.uint8).cpu().numpy().tobytes())
+            os.replace(path + ".tmp", path)
+            del gt
+        if world > 1:
+            dist.barrier()
+        vol.set_groundtruth_outofcore(path, "uint8", (0.0, 255.0))
+        ooc_info = vol.outofcore_info()
+    else:
+        gt = synth_volume_device(dims)
+        vol.set_groundtruth_device(gt)
+        del gt
     torch.cuda.empty_cache()
     vol.init_params(1337)
     # the public call (vnrNeuralVolumeTrain -> vnr_volume_train) is what is timed.  N > 1, --dp-mode sharded: the same call on every
@@ -658,13 +676,15 @@ def run_train(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = t[0].item(), t[1].item()
     step_count, mean_loss = vol.stats()
-    psnr = vol.psnr() if args.volume <= 512 else None
+    psnr = vol.psnr() if args.volume <= 512 and not args.out_of_core else None
+    if ooc_info is not None:
+        up0 = ooc_info["bytes_uploaded"]; ooc_info = vol.outofcore_info(); ooc_info["bytes_uploaded_per_step"] = (ooc_info["bytes_uploaded"] - up0) / max(1, step_count)
     # the fused kernel against ITS bound: the SM's L1TEX request stage serves the gather's scattered loads and the backward's
     # scattered fp16x8 reductions one after the other, so the floor of the kernel is what an independent probe needs for the
     # same number of random 16-byte loads plus random 16-byte reductions over tables of the same size (csrc/probe.cu kind
     # "mixed": n x 64 of each, full occupancy, no MLP, no tiles) -- measured here, next to the kernel on a fixed batch
     kernel_us = floor_us = None
-    if world == 1 and rank == 0:
+    if world == 1 and rank == 0 and not args.out_of_core:
         xyz = torch.empty(n, 3, device="cuda"); tgt = torch.empty(n, device="cuda")
         vol.sample(xyz, tgt, n); torch.cuda.synchronize()
         for _ in range(3):
@@ -689,10 +709,12 @@ def run_train(args):
                "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "f16", "data": "synthetic",
                "config": {"workload": workload_string(args),
-                          "path": "volume resident in HBM, sampled on the device" + ("" if world == 1 else ", gradient all-reduce (fp16 grid + fp32 MLP) over NCCL + replicated Adam" if dp is not None
+                          "path": ("out-of-core: raw uint8 file on local disk, a per-rank pool of random slabs in HBM refreshed every step, sampled on the device"
+                                   if args.out_of_core else "volume resident in HBM, sampled on the device") + ("" if world == 1 else ", gradient all-reduce (fp16 grid + fp32 MLP) over NCCL + replicated Adam" if dp is not None
                                                                else ", optimizer fused with its collectives over NVLink peer memory (reduce-scatter + Adam + all-gather in one kernel)"),
                           "global_batch": n * world, "l2_flush": "per-step parameter-state sweep (~0.9 GB) exceeds L2",
                           "parallelism": f"dp{world}"},
+               "out_of_core": ooc_info,
                "samples_per_sec": args.steps * n * world / (ms * 1e-3), "mean_loss": mean_loss, "last_loss": loss, "volume_psnr_db": psnr,
                "e2e": {"value": args.steps / (ms_e2e * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8,
                        "note": "samples are drawn on the device from the HBM-resident volume (the reference's StaticSampler does the same); the loss is read back every step"},
@@ -1027,6 +1049,7 @@ def main():
                     help="render = BASELINE configs[1] (the headline; --width 3840 --height 2160 --log2-hashmap 22 = configs[4]); "
                          "train = configs[2]/[3]: data-parallel training steps/s at --batch samples per rank")
     ap.add_argument("--batch", type=int, default=1 << 18, help="train workload: samples per rank per step")
+    ap.add_argument("--out-of-core", action="store_true", help="train workload: the ground truth stays in a raw file, sampled through per-rank slab pools (configs[3])")
     ap.add_argument("--dp-mode", default="sharded", choices=["sharded", "allreduce"], help="train workload, N > 1: peer-memory optimizer or NCCL all-reduce")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--pipeline", type=int, default=2, help="render workload, N = 1: renderers that take the frames in turn (device-resident timing)")

@@ -997,9 +997,11 @@ __device__ __forceinline__ void adam_update(const AdamArgs& a, size_t i, float g
 // MLP weights: reduce the per-CTA partial gradients (deterministic, no atomics), then Adam with L2.
 // accumulate != 0: the reduced gradient is ADDED to mlp_grads (a second batch before the optimizer step, as the hash-grid
 // reductions accumulate by themselves)
+// (loss_acc != nullptr: also folds this step's loss into the running sum, loss_fold_kernel's job)
 __global__ void adam_mlp_kernel(AdamArgs a, uint32_t n_mlp, const float* __restrict__ partial, uint32_t n_partial, float* __restrict__ mlp_grads, int half_sum,
-                                int accumulate) {
+                                int accumulate, double* loss_acc) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0 && loss_acc) loss_acc[0] += loss_acc[1];
   if (i >= n_mlp) return;
   // the sum runs in CTA order (deterministic; in half it is the reference's split-K reduction: partials and running sum in half,
   // cutlass ReduceSplitK with ElementAccumulator = half); the loads of 16 partials are issued together
@@ -1189,7 +1191,9 @@ int train_profile_words() { return kProfWords; }
 
 // forward + loss + backward: leaves grid gradients (fp16) in grid_grads and the reduced MLP gradients
 // (fp32) in mlp_grads; n_global is the global batch size the loss is normalised by.
-void train_grads(Volume* v, const float* d_xyz, const float* d_target, size_t n, size_t n_global, cudaStream_t s) {
+// the fused kernel alone: per-CTA weight-gradient partials stay in mlp_partial (train_steps reduces them on its side stream,
+// fused with the MLP's optimizer step); returns the number of partials
+static uint32_t train_grads_kernel(Volume* v, const float* d_xyz, const float* d_target, size_t n, size_t n_global, cudaStream_t s) {
   if (n == 0 || n % kTile) throw InvalidError("Batch size must be a multiple of 128.");        // fully_fused_mlp.cu:606
   train_ensure_buffers(v);
   const DecoderDesc& d = v->cfg.desc;
@@ -1206,8 +1210,14 @@ void train_grads(Volume* v, const float* d_xyz, const float* d_target, size_t n,
     case 2: launch_train_t<2>(v, a, grid, s); break;
     default: launch_train_t<1>(v, a, grid, s); break;
   }
+  return grid;
+}
+
+void train_grads(Volume* v, const float* d_xyz, const float* d_target, size_t n, size_t n_global, cudaStream_t s) {
+  const uint32_t grid = train_grads_kernel(v, d_xyz, d_target, n, n_global, s);
+  const DecoderDesc& d = v->cfg.desc;
   AdamArgs none = {};
-  adam_mlp_kernel<<<(d.n_mlp + 255) / 256, 256, 0, s>>>(none, d.n_mlp, v->mlp_partial.p, grid, v->mlp_grads.p, (a.flags & 64u) ? 0 : 1, v->grads_pending ? 1 : 0);
+  adam_mlp_kernel<<<(d.n_mlp + 255) / 256, 256, 0, s>>>(none, d.n_mlp, v->mlp_partial.p, grid, v->mlp_grads.p, (v->train_flags & 64u) ? 0 : 1, v->grads_pending ? 1 : 0, nullptr);
   VNR_CUDA(cudaGetLastError());
   v->grads_pending = true;
 }
@@ -1486,13 +1496,17 @@ void train_steps(Volume* v, int steps, size_t batch, bool update_macrocell, cuda
   for (int i = 0; i < steps; ++i) {
     const int b = i & 1;
     if (timing) VNR_CUDA(cudaEventRecord(tev[4 * i], s));
-    train_grads(v, xb[b], yb[b], batch, batch, s);
+    const int accumulate = v->grads_pending ? 1 : 0;          // gradients of an earlier vnr_volume_train_grads call are part of this step
+    const uint32_t n_partial = train_grads_kernel(v, xb[b], yb[b], batch, batch, s);
+    v->grads_pending = true;
     if (timing) VNR_CUDA(cudaEventRecord(tev[4 * i + 1], s));
     wait_for_frames(v, s);                 // frames in flight still decode the current parameters
     const AdamArgs a = begin_optimizer_step(v, s);
     VNR_CUDA(cudaEventRecord(v->ev_fork, s));
     VNR_CUDA(cudaStreamWaitEvent(v->side, v->ev_fork, 0));
-    adam_mlp_from_grads_kernel<<<(d.n_mlp + 255) / 256, 256, 0, v->side>>>(a, d.n_mlp, v->mlp_grads.p, v->loss_accum.p);
+    // reduction of the per-CTA weight-gradient partials + the MLP's Adam step + the loss fold, one kernel
+    adam_mlp_kernel<<<(d.n_mlp + 255) / 256, 256, 0, v->side>>>(a, d.n_mlp, v->mlp_partial.p, n_partial, v->mlp_grads.p, (v->train_flags & 64u) ? 0 : 1, accumulate,
+                                                                v->loss_accum.p);
     if (update_macrocell) macrocell_update_explicit(v, xb[b], yb[b], batch, v->side);
     if (i + 1 < steps) sample_batch(v, xb[b ^ 1], yb[b ^ 1], batch, v->side);
     VNR_CUDA(cudaEventRecord(v->ev_join, v->side));

@@ -2,7 +2,7 @@
 # ncu evidence for profiles/ (round 2): launch list of one profiling pass + full captures of the hot kernels, for the default
 # configuration (T = 2^19, 1024^2) and a decode capture of the 4K / T = 2^22 configuration (its DRAM traffic).
 # Run on the GPU box:  gpurun --timeout 2400 -- bash tools/profile_r02.sh r02a
-TAG=${1:-r02}
+TAG=${1:-r02b}
 mkdir -p gpurun_out
 # VNR_RM_GRAPH=0: ncu does not list kernels that run inside a conditional graph body; the host-enqueued path launches the same kernels
 export TRAIN_STEPS=100 FRAMES=3 EXTRA_TRAIN=4 VNR_RM_GRAPH=0
