@@ -239,7 +239,11 @@ def run_ours(args):
     # the frame ring: `--pipeline P` frame slots inside the renderer (own stream, ray / sample buffers and captured wavefront
     # graph each; vnr_renderer_set_frames_in_flight): consecutive vnr_render calls overlap on the device -- the latency-bound tail
     # rounds of frame i run under the head of frame i+1.  Every frame is still rendered completely.
-    n_pipe = 1 if (world > 1 and not use_comm) else max(1, args.pipeline)
+    # frames in flight: --pipeline, default 2 (the reference's double buffer) on one or two GPUs, 3 / 4 on four / eight: a rank's share
+    # of the frame is a few short wavefront rounds there and one more frame in flight fills their launch gaps (measured on one
+    # GPU rendering 1/8 of the frame: 0.187 / 0.130 / 0.111 / 0.105 ms per frame with 1 / 2 / 3 / 4 in flight; tools/exp_partition_cost.py)
+    pipe_default = 2 if world <= 2 else 3 if world <= 4 else 4
+    n_pipe = 1 if (world > 1 and not use_comm) else max(1, args.pipeline or pipe_default)
     ren = make_renderer()
     ren.set_frames_in_flight(n_pipe)
     parity = None
@@ -1052,7 +1056,7 @@ def main():
     ap.add_argument("--out-of-core", action="store_true", help="train workload: the ground truth stays in a raw file, sampled through per-rank slab pools (configs[3])")
     ap.add_argument("--dp-mode", default="sharded", choices=["sharded", "allreduce"], help="train workload, N > 1: peer-memory optimizer or NCCL all-reduce")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
-    ap.add_argument("--pipeline", type=int, default=2, help="render workload, N = 1: renderers that take the frames in turn (device-resident timing)")
+    ap.add_argument("--pipeline", type=int, default=0, help="render workload, N = 1: renderers that take the frames in turn (device-resident timing)")
     ap.add_argument("--gather", default="comm", choices=["comm", "nccl"],
                     help="N > 1: comm = the library's communicator (peer stores from the compositing kernels); nccl = torch.distributed gather of padded strips (comparison)")
     args = ap.parse_args()

@@ -19,8 +19,13 @@ def fps(ren, cams, steps=256):
 for N in (1, 2, 4, 8):
     ren = vnr.Renderer(vol); ren.set_size(W, H); ren.set_partition(0, N)
     ms = fps(ren, cams)
+    line = f"partition 0/{N}: {ms:.4f} ms/frame (graph loop, one frame at a time)"
+    for depth in (2, 3, 4):
+        ren.set_frames_in_flight(depth)
+        line += f", {fps(ren, cams):.4f} with {depth} in flight"
+    ren.set_frames_in_flight(1)
     ren.set_graph(False); ms_host = fps(ren, cams)
-    print(f"partition 0/{N}: {ms:.4f} ms/frame (graph loop), {ms_host:.4f} ms/frame (host-enqueued rounds)", flush=True)
+    print(line + f", {ms_host:.4f} host-enqueued rounds", flush=True)
 away = [(np.array([0, 0, -600], np.float32), np.array([0, 0, -1200], np.float32), np.array([0, 1, 0], np.float32))]
 ren = vnr.Renderer(vol); ren.set_size(W, H)
 print(f"all rays miss: {fps(ren, away):.4f} ms/frame", flush=True)
