@@ -145,3 +145,28 @@ def test_reference_batch_renderer_call_sequence_runs(tmp_path, variant):
     assert m and float(m.group(1)) > 0
     m = re.search(r"centre pixel alpha: ([\d.eE+-]+)", r.stdout)
     assert m and 0.0 <= float(m.group(1)) <= 1.0
+
+
+@pytest.mark.gpu
+def test_headless_trainer_and_renderer_apps_one_and_two_ranks(tmp_path):
+    """apps/vnr_cmd_train -> params.json -> apps/vnr_cmd_render on one device and, through the communicator behind the C ABI
+    (vnr_comm_init, one process), on two ranks: the tile-parallel frame is the single-GPU frame, byte for byte in the screenshot."""
+    _build()
+    train, render = _built("vnr_cmd_train"), _built("vnr_cmd_render")
+    params = tmp_path / "params.json"
+    r = subprocess.run([train, "--dims", "64", "--max-num-steps", "200", "--out", str(params)], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert r.returncode == 0 and params.exists(), r.stdout + r.stderr
+    shots = []
+    for gpus in (1, 2):
+        out = tmp_path / f"shot{gpus}.ppm"
+        env = dict(os.environ)
+        if vnr.device_count() < gpus:
+            env["VNR_COMM_SHARE_DEVICES"] = "1"          # the ranks share the device: same control and data path
+        r = subprocess.run([render, "--volume", str(params), "--num-frames", "8", "--size", "256", "--out", str(out), "--gpus", str(gpus)],
+                           capture_output=True, text=True, timeout=300, env=env)
+        assert r.returncode == 0, r.stdout + r.stderr
+        m = re.search(r"fps: ([\d.eE+-]+)", r.stdout)
+        assert m and float(m.group(1)) > 0 and f"gpus: {gpus}" in r.stdout
+        shots.append(out.read_bytes())
+    assert len(shots[0]) > 256 * 256 * 3 and shots[0] == shots[1]
+    assert len(set(shots[0][20:])) > 8                    # not a blank image
