@@ -967,6 +967,9 @@ train_step_kernel(const DecoderDesc d, const TrainArgs a) {
 struct AdamArgs {
   float lr, beta1, beta2, eps, l2_reg, loss_scale;
   float* master; __half* params; float* m1; float* m2; uint32_t* steps;
+  // steps16 != nullptr: the per-parameter step counters are 16-bit and saturate at 65535 -- exact whenever beta^65535 vanishes
+  // in fp32 (1 - beta^t == 1 for every t beyond; true for the reference's 0.9 / 0.999), and 4 of the sweep's 38 bytes per parameter less
+  uint16_t* steps16;
   const float* bias;           // bias[t] = sqrt(1 - beta2^t) / (1 - beta1^t), t <= current optimizer step
 };
 
@@ -979,6 +982,16 @@ __global__ void adam_bias_fill_kernel(float* __restrict__ tab, uint32_t lo, uint
   tab[t] = t == 0 ? 0.f : __fdiv_rn(sqrtf(1.f - powf(beta2, (float)t)), 1.f - powf(beta1, (float)t));
 }
 
+__device__ __forceinline__ uint4 load_steps4(const AdamArgs& a, size_t i) {
+  if (a.steps16) { const uint2 p = *reinterpret_cast<const uint2*>(a.steps16 + i); return make_uint4(p.x & 0xFFFFu, p.x >> 16, p.y & 0xFFFFu, p.y >> 16); }
+  return *reinterpret_cast<const uint4*>(a.steps + i);
+}
+__device__ __forceinline__ void store_steps4(const AdamArgs& a, size_t i, uint4 c) {
+  if (a.steps16) *reinterpret_cast<uint2*>(a.steps16 + i) = make_uint2(c.x | (c.y << 16), c.z | (c.w << 16));
+  else *reinterpret_cast<uint4*>(a.steps + i) = c;
+}
+__device__ __forceinline__ uint32_t next_step(const AdamArgs& a, uint32_t c) { return a.steps16 ? min(c + 1u, 65535u) : c + 1u; }
+
 __device__ __forceinline__ void adam_update(const AdamArgs& a, size_t i, float gradient, bool is_matrix) {
   const float weight_fp = a.master[i];
   if (is_matrix) gradient = __fmaf_rn(a.l2_reg, weight_fp, gradient);        // gradient += l2_reg * w  (adam.h:87)
@@ -986,7 +999,9 @@ __device__ __forceinline__ void adam_update(const AdamArgs& a, size_t i, float g
   const float fm = __fmaf_rn(a.beta1, a.m1[i], (1.f - a.beta1) * gradient);
   const float sm = __fmaf_rn(a.beta2, a.m2[i], (1.f - a.beta2) * gradient_sq);
   a.m1[i] = fm; a.m2[i] = sm;
-  const uint32_t cs = ++a.steps[i];
+  uint32_t cs;
+  if (a.steps16) { cs = next_step(a, a.steps16[i]); a.steps16[i] = (uint16_t)cs; }
+  else cs = ++a.steps[i];
   const float lr = a.lr * __ldg(a.bias + cs);
   const float eff = fminf(fmaxf(__fdiv_rn(lr, sqrtf(sm) + a.eps), 0.f), 3.402823466e+38f);
   const float new_weight = __fmaf_rn(-eff, fm, weight_fp);
@@ -1049,7 +1064,7 @@ __global__ void __launch_bounds__(256) adam_grid_kernel(AdamArgs a, uint32_t n_m
   float4 w4 = *reinterpret_cast<const float4*>(a.master + i);
   float4 m4 = *reinterpret_cast<const float4*>(a.m1 + i);
   float4 s4 = *reinterpret_cast<const float4*>(a.m2 + i);
-  uint4 c4 = *reinterpret_cast<const uint4*>(a.steps + i);
+  uint4 c4 = load_steps4(a, i);
   float* w = &w4.x; float* fm = &m4.x; float* sm = &s4.x; uint32_t* cs = &c4.x;
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
@@ -1057,7 +1072,7 @@ __global__ void __launch_bounds__(256) adam_grid_kernel(AdamArgs a, uint32_t n_m
     if (gradient == 0.f) continue;
     fm[q] = __fmaf_rn(a.beta1, fm[q], (1.f - a.beta1) * gradient);
     sm[q] = __fmaf_rn(a.beta2, sm[q], (1.f - a.beta2) * (gradient * gradient));
-    const uint32_t t = ++cs[q];
+    const uint32_t t = cs[q] = next_step(a, cs[q]);
     const float lr = a.lr * __ldg(a.bias + t);
     const float eff = fminf(fmaxf(__fdiv_rn(lr, sqrtf(sm[q]) + a.eps), 0.f), 3.402823466e+38f);
     w[q] = __fmaf_rn(-eff, fm[q], w[q]);
@@ -1065,7 +1080,7 @@ __global__ void __launch_bounds__(256) adam_grid_kernel(AdamArgs a, uint32_t n_m
   *reinterpret_cast<float4*>(a.master + i) = w4;
   *reinterpret_cast<float4*>(a.m1 + i) = m4;
   *reinterpret_cast<float4*>(a.m2 + i) = s4;
-  *reinterpret_cast<uint4*>(a.steps + i) = c4;
+  store_steps4(a, i, c4);
   *reinterpret_cast<uint2*>(a.params + i) = make_uint2(h2_as_u32(__floats2half2_rn(w4.x, w4.y)), h2_as_u32(__floats2half2_rn(w4.z, w4.w)));
 }
 
@@ -1159,7 +1174,9 @@ void train_preload_kernels(const Volume* v) {
 // (what a new tcnn Trainer starts from, tcnn_network.h:196-221)
 void reset_optimizer_state(Volume* v) {
   const size_t n = v->cfg.n_params();
-  v->m1.alloc(n); v->m2.alloc(n); v->steps.alloc(n);
+  // 16-bit saturating step counters when they are exact for this optimizer (see AdamArgs::steps16); VNR_ADAM_STEPS32=1 forces 32 bits
+  v->steps16 = std::pow((double)v->cfg.opt.beta1, 65535.0) < 1e-9 && std::pow((double)v->cfg.opt.beta2, 65535.0) < 1e-9 && !getenv("VNR_ADAM_STEPS32");
+  v->m1.alloc(n); v->m2.alloc(n); v->steps.alloc(v->steps16 ? (n + 1) / 2 : n);
   v->m1.zero(v->stream); v->m2.zero(v->stream); v->steps.zero(v->stream);
   v->grads_clean = false; v->grads_pending = false;
   v->opt_step = 0; v->lr_factor = 1.f; v->train_step = 0; v->loss_count = 0;
@@ -1236,12 +1253,14 @@ static AdamArgs begin_optimizer_step(Volume* v, cudaStream_t s) {
   AdamArgs a;
   a.lr = o.lr * v->lr_factor; a.beta1 = o.beta1; a.beta2 = o.beta2; a.eps = o.eps; a.l2_reg = o.l2_reg; a.loss_scale = 128.f;
   a.master = v->master.p; a.params = v->params.p; a.m1 = v->m1.p; a.m2 = v->m2.p; a.steps = v->steps.p;
+  a.steps16 = v->steps16 ? reinterpret_cast<uint16_t*>(v->steps.p) : nullptr;
   ++v->opt_step;
   if (v->bias_beta1 != o.beta1 || v->bias_beta2 != o.beta2) {      // a new optimizer config (vnrNeuralVolumeSetModel): the table is stale
     v->bias_filled = 0; v->bias_beta1 = o.beta1; v->bias_beta2 = o.beta2;
   }
-  if (v->opt_step + 1 > v->bias_filled) {
-    if (v->opt_step + 1 > v->bias_tab.n) {
+  const uint32_t bias_need = v->steps16 ? std::min<uint32_t>(v->opt_step + 1, 65536u) : v->opt_step + 1;
+  if (bias_need > v->bias_filled) {
+    if (bias_need > v->bias_tab.n) {
       // Grow WITHOUT a stream synchronisation or a cudaFree: in a data-parallel group driven by one host thread the stream holds a
       // peer barrier that waits for ranks whose work is not enqueued yet.  Kernels in flight keep reading the old table, which is
       // parked until the optimizer is reset or the volume released.
@@ -1308,7 +1327,7 @@ __global__ void __launch_bounds__(256) adam_grid_sharded_kernel(AdamArgs a, DpPt
   float4 w4 = *reinterpret_cast<const float4*>(a.master + i);
   float4 m4 = *reinterpret_cast<const float4*>(a.m1 + i);
   float4 s4 = *reinterpret_cast<const float4*>(a.m2 + i);
-  uint4 c4 = *reinterpret_cast<const uint4*>(a.steps + i);
+  uint4 c4 = load_steps4(a, i);
   float* w = &w4.x; float* fm = &m4.x; float* sm = &s4.x; uint32_t* cs = &c4.x;
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
@@ -1316,7 +1335,7 @@ __global__ void __launch_bounds__(256) adam_grid_sharded_kernel(AdamArgs a, DpPt
     if (gradient == 0.f) continue;
     fm[q] = __fmaf_rn(a.beta1, fm[q], (1.f - a.beta1) * gradient);
     sm[q] = __fmaf_rn(a.beta2, sm[q], (1.f - a.beta2) * (gradient * gradient));
-    const uint32_t tt = ++cs[q];
+    const uint32_t tt = cs[q] = next_step(a, cs[q]);
     const float lr = a.lr * __ldg(a.bias + tt);
     const float eff = fminf(fmaxf(__fdiv_rn(lr, sqrtf(sm[q]) + a.eps), 0.f), 3.402823466e+38f);
     w[q] = __fmaf_rn(-eff, fm[q], w[q]);
@@ -1324,7 +1343,7 @@ __global__ void __launch_bounds__(256) adam_grid_sharded_kernel(AdamArgs a, DpPt
   *reinterpret_cast<float4*>(a.master + i) = w4;
   *reinterpret_cast<float4*>(a.m1 + i) = m4;
   *reinterpret_cast<float4*>(a.m2 + i) = s4;
-  *reinterpret_cast<uint4*>(a.steps + i) = c4;
+  store_steps4(a, i, c4);
   const uint2 packed = make_uint2(h2_as_u32(__floats2half2_rn(w4.x, w4.y)), h2_as_u32(__floats2half2_rn(w4.z, w4.w)));
   for (int r = 0; r < p.world; ++r) *reinterpret_cast<uint2*>(p.params[r] + i) = packed;
 }

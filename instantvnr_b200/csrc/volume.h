@@ -38,7 +38,7 @@ struct Volume {
   DevBuf<float> mlp_grads;         // fp32 [n_mlp], loss-scaled, reduced over CTAs
   DevBuf<float> mlp_partial;       // fp32 [n_cta][n_mlp] per-CTA weight-gradient partials
   bool grads_clean = false, grads_pending = false;
-  DevBuf<uint32_t> steps;
+  DevBuf<uint32_t> steps; bool steps16 = false;   // per-parameter Adam step counters: 32-bit, or 16-bit saturating packed two per word (train.cu AdamArgs)
   DevBuf<float> bias_tab; uint32_t bias_filled = 0;   // Adam bias-correction table (train.cu) ...
   std::vector<float*> bias_retired;                   // outgrown tables still referenced by kernels in flight
   float bias_beta1 = -1.f, bias_beta2 = -1.f;         // ... and the betas it was built with (refilled when the optimizer config changes)

@@ -160,6 +160,7 @@ def test_volume_psnr_after_300_steps_is_in_the_references_band():
     st = torch.cuda.Stream()
     xyz = torch.empty(N, 3, device="cuda"); tgt = torch.empty(N, device="cuda")
     lo, lr_ = [], []
+    p_ours, p_ref, p_ref2 = [], [], []
     for i in range(300):
         vol.sample(xyz, tgt, N)                      # fresh batches (a short ring of batches over-fits: the PSNR then measures chaos)
         torch.cuda.synchronize()
@@ -170,14 +171,18 @@ def test_volume_psnr_after_300_steps_is_in_the_references_band():
         st.synchronize()
         if i >= 200:
             lo.append(vol.last_loss()); lr_.append(l)
+        if i >= 250 and i % 10 == 9:                 # the whole-volume PSNR at five checkpoints: its median is what is compared
+            torch.cuda.synchronize()
+            p_ours.append(vol.psnr()); p_ref.append(_ref_psnr(ref, gt, st)); p_ref2.append(_ref_psnr(ref2, gt, st))
     torch.cuda.synchronize()
-    psnr_ours, psnr_ref, psnr_ref2 = vol.psnr(), _ref_psnr(ref, gt, st), _ref_psnr(ref2, gt, st)
-    print(f"volume PSNR after 300 steps of 2^18 fresh samples: ours {psnr_ours:.2f} dB, reference {psnr_ref:.2f} dB, reference again {psnr_ref2:.2f} dB; "
-          f"mean L1 loss of steps 200-300: ours {np.mean(lo):.5f}, reference {np.mean(lr_):.5f}")
-    # the whole-volume PSNR of either trainer swings by several dB from step to step at this batch size (see the module note);
-    # the band: both have learnt the volume (a constant predictor scores 17 dB) and the smoothed training loss agrees
+    psnr_ours, psnr_ref, psnr_ref2 = float(np.median(p_ours)), float(np.median(p_ref)), float(np.median(p_ref2))
+    print(f"volume PSNR over steps 260-300 of 2^18 fresh samples (median of 5): ours {psnr_ours:.2f} dB {np.round(p_ours, 1)}, reference {psnr_ref:.2f} dB "
+          f"{np.round(p_ref, 1)}, reference again {psnr_ref2:.2f} dB; mean L1 loss of steps 200-300: ours {np.mean(lo):.5f}, reference {np.mean(lr_):.5f}")
+    # the whole-volume PSNR of either trainer swings by several dB from step to step at this batch size (see the module note; the
+    # reference against itself differs by 3 - 10 dB at a single step), hence the median over five checkpoints.  The band: both have
+    # learnt the volume (a constant predictor scores 17 dB) and the smoothed training loss agrees
     assert min(psnr_ours, psnr_ref) >= 38.0
-    assert abs(psnr_ours - psnr_ref) <= 12.0          # measured: the reference against itself differs by 3 - 10 dB here
+    assert abs(psnr_ours - psnr_ref) <= 12.0
     assert 0.6 <= np.mean(lo) / np.mean(lr_) <= 1.6
 
 
