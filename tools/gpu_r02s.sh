@@ -1,2 +1,3 @@
 #!/bin/bash
-for i in 1 2 3; do timeout 200 python -m pytest tests/test_gpu_fullsize.py -m gpu -x -q -s -k psnr 2>&1 | grep -i "volume PSNR\|passed\|failed\|assert" | head -5; done
+mkdir -p gpurun_out
+for i in 1 2 3; do timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_loop$i.log 2>&1; echo "run $i rc=$?"; tail -2 gpurun_out/pytest_gpu_loop$i.log; done
