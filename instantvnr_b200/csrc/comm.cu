@@ -511,6 +511,7 @@ static void wire_renderer(Renderer* r, const RendererExport* all, bool ipc) {
       S.h_frame[h] = reinterpret_cast<float4*>(rc->host_base) + ((size_t)k * 2 + (size_t)h) * npix;
     }
     S.h_frame_external = true;
+    S.host_nonzero_valid[0] = S.host_nonzero_valid[1] = false;      // other frames: what they hold is unknown to this slot's masks
     S.rendered = false; S.downloaded = false; S.mapped = true;
   }
   r->part_rank = R; r->part_world = W;
@@ -584,6 +585,7 @@ void comm_detach_renderer(Renderer* r) {
         memset(S.h_frame[h], 0, npix * sizeof(float4));
       }
       S.h_frame_external = false;
+      S.host_nonzero_valid[0] = S.host_nonzero_valid[1] = false;
     }
     S.rendered = false; S.downloaded = false; S.mapped = true;
   }

@@ -46,6 +46,10 @@ struct FrameParams {
   // path tracer (method_pathtracing.cu): majorant scale and lights (instantvnr_types.h:102,146-147)
   float density_scale, light_ambient, light_rgb[3];
   float4* frame;                     // where finished pixels go: local / peer frame buffer or the mapped pinned host frame
+  uint32_t* host_nonzero;            // zero-copy host frame only (else nullptr): one bit per pixel, set while the pixel of THAT host
+                                     // buffer holds a non-zero value.  A pixel that is zero and was zero (background around the
+                                     // volume, frame after frame) is not stored again: stores from the SMs into pinned host memory
+                                     // are the slow part of the download (~20-25 GB/s), a third of a frame's pixels are background
   const float4* accum_prev;          // accumulation buffer of the previous frame (read when frame_index != 1; frames in flight
                                      // accumulate into their own slot's buffer)
 };

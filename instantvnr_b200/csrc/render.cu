@@ -48,6 +48,12 @@ __device__ __forceinline__ void write_pixel(const FrameParams& fp, float4* __res
   }
   accum[pixel] = c;
   const float fi = (float)fp.frame_index;
+  if (fp.host_nonzero) {
+    uint32_t* w = fp.host_nonzero + (pixel >> 5);
+    const uint32_t b = 1u << (pixel & 31u);
+    if (c.x == 0.f && c.y == 0.f && c.z == 0.f && c.w == 0.f) { if (!(atomicAnd(w, ~b) & b)) return; }      // zero over zero: nothing to send
+    else atomicOr(w, b);
+  }
   frame[pixel] = make_float4(__fdiv_rn(c.x, fi), __fdiv_rn(c.y, fi), __fdiv_rn(c.z, fi), __fdiv_rn(c.w, fi));
 }
 
@@ -431,6 +437,7 @@ void FrameSlot::resize(size_t npix) {
     h_frame[k] = nullptr;
     VNR_CUDA(cudaMallocHost((void**)&h_frame[k], npix * sizeof(float4)));
     memset(h_frame[k], 0, npix * sizeof(float4));      // pixels outside a renderer's partition are never written: they read as zero
+    host_nonzero[k].alloc((npix + 31) / 32); host_nonzero[k].zero(stream); host_nonzero_valid[k] = true;     // the host frame is all zero
   }
   h_frame_external = false;
   rendered = false; downloaded = false; mapped = true;
@@ -759,6 +766,15 @@ void Renderer::render() {
   const int hb = S.cur;                                                // host frame this render writes; the next one takes the other
   const bool zc = zero_copy && download && (rc || !S.frame_target);
   fp[0].frame = zc ? S.h_frame[hb] : S.frame_out();
+  // zero pixels that are zero in this host buffer already are not stored again (FrameParams::host_nonzero)
+  static const bool skip_zero = !getenv("VNR_ZC_STORE_ALL");
+  const bool track = zc && skip_zero && S.host_nonzero[hb].p;      // tile-parallel: every rank tracks the pixels of its own strips in the shared frame
+  fp[0].host_nonzero = track ? S.host_nonzero[hb].p : nullptr;
+  if (track && !S.host_nonzero_valid[hb]) {            // the buffer was last written by a copy: every pixel may be non-zero
+    VNR_CUDA(cudaMemsetAsync(S.host_nonzero[hb].p, 0xFF, S.host_nonzero[hb].bytes(), stream));
+    S.host_nonzero_valid[hb] = true;
+  }
+  if (download && !track) S.host_nonzero_valid[hb] = false;             // this frame reaches the host buffer some other way
   fp[0].accum_prev = frame_index > 1 ? P.accum.p : nullptr;
   const int iters = shade == 0 ? n_iters : std::min(n_iters, 16);      // shaded passes keep the reference's 16 samples per round
   fp[0].n_iters = iters;
@@ -860,6 +876,7 @@ void Renderer::download_now() {
   FrameSlot& S = last();
   if (!S.rendered) throw StateError("vnr_renderer_download called before vnr_render");
   VNR_CUDA(cudaMemcpyAsync(S.h_frame[S.map_idx], S.frame.p, S.frame.bytes(), cudaMemcpyDeviceToHost, S.stream));
+  S.host_nonzero_valid[S.map_idx] = false;
   VNR_CUDA(cudaEventRecord(S.frame_done[S.map_idx], S.stream));
   if (!S.downloaded) n_mapped = n_rendered - 1;      // the most recent frame becomes mappable
   S.downloaded = true; S.mapped = false; S.vol_waited = false;

@@ -44,6 +44,7 @@ struct FrameSlot {
   cudaGraph_t pt_graph = nullptr; cudaGraphExec_t pt_exec = nullptr; GraphKey pt_key; bool last_pt = false;
   float4* h_frame[2] = {nullptr, nullptr};
   bool h_frame_external = false;        // the host frames belong to a communicator (shared by all ranks), not to the slot
+  DevBuf<uint32_t> host_nonzero[2]; bool host_nonzero_valid[2] = {false, false};   // FrameParams::host_nonzero of each host frame
   int map_idx = 0;                      // host frame the last render of this slot wrote (`cur` = the one the next render writes)
   uint32_t* h_counters = nullptr;
   std::vector<cudaEvent_t> prof_events;

@@ -322,3 +322,40 @@ def test_training_is_ordered_after_frames_in_flight():
     got = ren.map_frame()
     assert np.array_equal(got, want)
     assert not np.array_equal(vol.get_params_f16(), p0)
+
+
+def test_zero_copy_host_frame_skips_unchanged_zero_pixels_and_stays_exact():
+    """Zero-copy download (the default on one GPU): the compositing kernels store finished pixels straight into the pinned host
+    frame and do not store a zero pixel over a zero pixel again (FrameParams::host_nonzero, march.cuh).  Over a camera path that
+    turns hits into misses and back -- including views that miss the volume altogether -- and with the download mode switched in
+    between, every mapped frame equals the frame of the copy-after-the-frame path bit for bit."""
+    dims = (48, 48, 48)
+    vol, ren = _ring_renderer(dims)
+    away = (np.array([0, 0, -600], np.float32), np.array([0, 0, -1200], np.float32), np.array([0, 1, 0], np.float32))
+    near = syn.default_camera(dims, 3, 9)
+    close = (near[0] * 0.6, near[1], near[2])                    # closer: covers more of the image
+    cams = [syn.default_camera(dims, v, 9) for v in range(9)]
+    path = [cams[0], cams[1], away, cams[2], close, cams[3], away, away, close, cams[4], cams[5], cams[0], cams[8]]
+    ren.set_zero_copy(False)
+    want = []
+    for cam in path:
+        ren.set_camera(*cam); ren.render(); want.append(ren.map_frame())
+    assert not want[2].any() and want[4].any()                   # the path really has empty and covered frames
+    bg = [float((f[..., 3] == 0).mean()) for f in want]
+    assert min(bg) < 0.6 < max(bg)
+    for depth in (1, 2, 3):
+        ren.set_frames_in_flight(depth)
+        ren.set_zero_copy(True)
+        got = []
+        for i, cam in enumerate(path):
+            if i == 7:
+                ren.set_zero_copy(False)                         # one frame arrives by copy: the masks of that host buffer are stale afterwards
+            if i == 8:
+                ren.set_zero_copy(True)
+            ren.set_camera(*cam); ren.render()
+            if i >= depth - 1:
+                got.append(ren.map_frame())
+        while len(got) < len(path):
+            got.append(ren.map_frame())
+        for k, (a, b) in enumerate(zip(got, want)):
+            assert np.array_equal(a, b), (depth, k)

@@ -1,3 +1,2 @@
 #!/bin/bash
-mkdir -p gpurun_out
-for i in 1 2 3; do timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_loop$i.log 2>&1; echo "run $i rc=$?"; tail -2 gpurun_out/pytest_gpu_loop$i.log; done
+timeout 600 python -m pytest tests/test_gpu_render.py tests/test_gpu_comm.py tests/test_gpu_distributed.py tests/test_api_app.py tests/test_gpu_modes.py tests/test_gpu_pathtracing.py -m gpu -x -q 2>&1 | tail -4
