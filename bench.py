@@ -529,6 +529,9 @@ def run_ours(args):
                     "2^18 samples per rank per step (weak scaling)") if world > 1 else "single GPU",
         "parity_checked": (bool(parity) and all(parity.values())) if world > 1 else None, "parity": parity,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 480, "d2h_bytes_per_step": W * H * 16, "fps": args.steps / (ms_e2e * 1e-3),
+                "d2h_note": f"the mapped host frame is {W}x{H} float4 = {W * H * 16} bytes; with the zero-copy download a pixel that is zero and was zero in that host "
+                            f"buffer is not stored again, so about 16 B x {int(rays / max(1, args.steps))} (rays that hit the volume) cross PCIe per frame on this orbit; "
+                            "fps_copy_after_frame moves all of it with one cudaMemcpyAsync",
                 "frame_path": ("tile-parallel NCCL gather + download on rank 0" if tp else
                                "tile-parallel: every rank's compositing kernels store its strips into ONE pinned host frame shared by all ranks (each GPU over its own PCIe link); rank 0 maps it"
                                if use_comm else "zero-copy: compositing kernels store finished pixels into the pinned host frame"),
