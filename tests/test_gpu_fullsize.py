@@ -106,10 +106,12 @@ def test_gradients_of_one_baseline_batch_match_the_oracle():
         assert abs(gg[a:b].sum() - wg[a:b].sum()) <= 1e-2 * np.abs(wg[a:b]).sum()
     # fp32 accumulators (train flag 64): the exact sums
     vol.optimizer_step(); vol.set_params_f16(p16)
-    vol.train_debug(1, 64, False)
+    vol.train_debug(2, 64, False)
     vol.train_grads(xyz, tgt, N, N); torch.cuda.synchronize()
     gm32, _ = vol.get_grads()
-    assert np.abs(gm32 - exact[:m.n_mlp]).max() <= 1e-4 * sc
+    # fp32 tensor-core accumulation of 2^18 terms against double sums: 1e-6 .. 2e-4 of the scale, depending on how much the trained
+    # state makes the terms of the output row cancel (tools/exp_var2_fp32.py); the half-accumulated default is 1e-3 .. 1e-2
+    assert np.abs(gm32 - exact[:m.n_mlp]).max() <= 1e-3 * sc
 
 
 def test_training_steps_match_reference_tcnn_at_baseline_size():

@@ -94,7 +94,7 @@ def test_gradients_match_oracle(cfg):
     assert np.abs(gm - wm).max() <= 5e-3 * scale                      # and within half precision of the exact sums
     # fp32 accumulators (train flag 64): fp32 tensor-core accumulation vs double accumulation of the same fp16 products
     vol.optimizer_step(); vol.set_params_f16(p16)                     # consumes the gradients; back to the same blob
-    vol.train_debug(1, 64, False)
+    vol.train_debug(2, 64, False)
     vol.train_grads(dc, dt, n, n, torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     gm32, gg16 = vol.get_grads()
@@ -216,3 +216,39 @@ def test_first_optimizer_step_matches_the_adam_formula(sharded):
     assert np.array_equal(got[~upd], want[~upd])
     d = np.abs(got.astype(np.int32) - want.astype(np.int32))
     assert d.max() <= 1 and (d != 0).mean() < 2e-3    # fp16 ulp: fused vs double-rounded arithmetic
+
+
+@pytest.mark.parametrize("cfg", [CFGS[1], CFGS[2], CFGS[4], dict(n_levels=8, n_features=8, log2_hashmap=12, base_res=8, n_hidden=5)])
+def test_chain_variants_agree(cfg):
+    """The three MMA-chain variants of the fused training kernel -- 2 (default: activations handed from MMA to MMA through tensor
+    memory by a dedicated issuer warp), 1 and 0 (through shared memory; kept for A/B runs and for n_hidden_layers = 6) -- compute
+    the same loss and, with fp32 weight-gradient accumulators (flag 64: no order-dependent half rounding), the same MLP gradients;
+    the hash-grid gradients agree up to the order of the fp16 reductions."""
+    m = _model(cfg)
+    dims = (16, 16, 16)
+    gt = syn.make_volume(dims, seed=9)
+    p32, _ = O.init_params(m, 5)
+    p32 = p32.copy(); p32[m.n_mlp:] *= 2000.0
+    p16 = O.f32_to_f16(p32)
+    n = 128 * 37
+    res = {}
+    for variant in (2, 1, 0):
+        vol = vnr.NeuralVolume(vnr.model_json(**cfg), dims)
+        vol.set_groundtruth(gt)
+        vol.set_params_f16(p16)
+        xyz = torch.empty(n, 3, device="cuda"); tgt = torch.empty(n, device="cuda")
+        vol.sample(xyz, tgt, n)
+        vol.train_debug(variant, 64, False)
+        vol.train_grads(xyz, tgt, n, n)
+        torch.cuda.synchronize()
+        gm, gg16 = vol.get_grads()
+        res[variant] = (vol.last_loss(), gm.copy(), O.f16_to_f32(gg16))
+    l2, gm2, gg2 = res[2]
+    assert np.isfinite(l2) and l2 > 0 and np.abs(gm2).max() > 0 and np.abs(gg2).max() > 0
+    for variant in (1, 0):
+        l, gm, gg = res[variant]
+        assert abs(l - l2) <= 1e-9 * l2
+        sc = np.abs(gm2).max()
+        assert np.abs(gm - gm2).max() <= 1e-5 * sc, (variant, np.abs(gm - gm2).max(), sc)
+        gs = np.abs(gg2).max()
+        assert np.abs(gg - gg2).max() <= 0.05 * gs and np.abs(gg - gg2).mean() <= 1e-4 * gs
