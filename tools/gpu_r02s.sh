@@ -1,2 +1,2 @@
 #!/bin/bash
-REPS=150 timeout 800 python tools/exp_var2_fp32.py 2>&1 | tail -24
+timeout 300 python -m pytest tests/test_gpu_train.py tests/test_gpu_fullsize.py -m gpu -x -q 2>&1 | tail -5
