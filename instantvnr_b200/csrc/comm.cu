@@ -406,17 +406,44 @@ void comm_train_steps(Volume* v, int steps, size_t batch, bool update_macrocell,
   if (batch % kTile) throw InvalidError("Batch size must be a multiple of 128.");
   v->train_x.ensure(3 * batch); v->train_y.ensure(batch);
   const uint64_t ups = v->ooc ? 5 : 3;                                   // uniforms per sample of the sampler in use
-  for (int i = 0; i < steps; ++i) {
-    // rank r takes the r-th of `world` consecutive batches of the one sampler stream
+  // rank r takes the r-th of `world` consecutive batches of the one sampler stream
+  auto draw = [&](float* x, float* y, cudaStream_t st) {
     v->sampler_rng.advance((uint64_t)R * ups * batch);
-    sample_batch(v, v->train_x.p, v->train_y.p, batch, s);
+    sample_batch(v, x, y, batch, st);
     v->sampler_rng.advance((uint64_t)(W - 1 - R) * ups * batch);
-    train_grads(v, v->train_x.p, v->train_y.p, batch, batch * (size_t)W, s);
-    peer_barrier_sync(vc->barrier, s);                                   // every rank's gradients are complete
-    dp_optimizer_step(v, s);                                             // reduce-scatter + Adam + all-gather over peer memory
-    peer_barrier_sync(vc->barrier, s);                                   // every rank's parameters are complete
-    dp_finish_step(v, s);
-    if (update_macrocell) macrocell_update_explicit(v, v->train_x.p, v->train_y.p, batch, s);
+  };
+  if (v->ooc || getenv("VNR_TRAIN_SERIAL")) {                            // out-of-core batches come through pinned staging buffers in stream order
+    for (int i = 0; i < steps; ++i) {
+      draw(v->train_x.p, v->train_y.p, s);
+      train_grads(v, v->train_x.p, v->train_y.p, batch, batch * (size_t)W, s);
+      peer_barrier_sync(vc->barrier, s);                                 // every rank's gradients are complete
+      dp_optimizer_step(v, s);                                           // reduce-scatter + Adam + all-gather over peer memory
+      peer_barrier_sync(vc->barrier, s);                                 // every rank's parameters are complete
+      dp_finish_step(v, s);
+      if (update_macrocell) macrocell_update_explicit(v, v->train_x.p, v->train_y.p, batch, s);
+    }
+  } else {
+    // as train_steps (train.cu): the macrocell update of this batch and the draw of the NEXT batch run on the volume's
+    // high-priority side stream under the barriers and the optimizer; nothing of it touches peer memory
+    train_side_stream(v);
+    v->train_x2.ensure(3 * batch); v->train_y2.ensure(batch);
+    float* xb[2] = {v->train_x.p, v->train_x2.p};
+    float* yb[2] = {v->train_y.p, v->train_y2.p};
+    draw(xb[0], yb[0], s);
+    for (int i = 0; i < steps; ++i) {
+      const int b = i & 1;
+      train_grads(v, xb[b], yb[b], batch, batch * (size_t)W, s);
+      VNR_CUDA(cudaEventRecord(v->ev_fork, s));
+      VNR_CUDA(cudaStreamWaitEvent(v->side, v->ev_fork, 0));
+      if (update_macrocell) macrocell_update_explicit(v, xb[b], yb[b], batch, v->side);
+      if (i + 1 < steps) draw(xb[b ^ 1], yb[b ^ 1], v->side);
+      VNR_CUDA(cudaEventRecord(v->ev_join, v->side));
+      peer_barrier_sync(vc->barrier, s);                                 // every rank's gradients are complete
+      dp_optimizer_step(v, s);                                           // reduce-scatter + Adam + all-gather over peer memory
+      peer_barrier_sync(vc->barrier, s);                                 // every rank's parameters are complete
+      dp_finish_step(v, s);
+      VNR_CUDA(cudaStreamWaitEvent(s, v->ev_join, 0));
+    }
   }
   if (update_macrocell && steps > 0 && W > 1) {
     McMergeArgs a;

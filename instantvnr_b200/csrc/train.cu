@@ -1477,6 +1477,17 @@ void apply_l2_policy(const Volume* v, cudaStream_t s) {
   VNR_CUDA(cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &attr));
 }
 
+// the volume's side stream and its fork / join events (created on first use)
+void train_side_stream(Volume* v) {
+  if (v->side) return;
+  // highest priority: its small kernels must get SMs WHILE the 22 816-block sweep is being dispatched, not after it
+  int prio_lo = 0, prio_hi = 0;
+  VNR_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  VNR_CUDA(cudaStreamCreateWithPriority(&v->side, cudaStreamNonBlocking, prio_hi));
+  VNR_CUDA(cudaEventCreateWithFlags(&v->ev_fork, cudaEventDisableTiming));
+  VNR_CUDA(cudaEventCreateWithFlags(&v->ev_join, cudaEventDisableTiming));
+}
+
 void train_steps(Volume* v, int steps, size_t batch, bool update_macrocell, cudaStream_t s) {
   if (!v->have_gt && !v->ooc) throw StateError("[error]: missing a reference volume.");
   if (batch == 0) batch = 1 << 16;                                       // network.cu:183
@@ -1495,14 +1506,7 @@ void train_steps(Volume* v, int steps, size_t batch, bool update_macrocell, cuda
   // A step's critical path is the fused kernel and the hash-grid optimizer sweep; everything else -- the MLP's optimizer step,
   // the loss fold, the macrocell update of this batch and the draw of the NEXT batch (the reference draws inside the step,
   // neural_sampler.cu:131-164; the sampler stream is the same, only earlier) -- runs on a side stream under the sweep.
-  if (!v->side) {
-    // highest priority: its small kernels must get SMs WHILE the 22 816-block sweep is being dispatched, not after it
-    int prio_lo = 0, prio_hi = 0;
-    VNR_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-    VNR_CUDA(cudaStreamCreateWithPriority(&v->side, cudaStreamNonBlocking, prio_hi));
-    VNR_CUDA(cudaEventCreateWithFlags(&v->ev_fork, cudaEventDisableTiming));
-    VNR_CUDA(cudaEventCreateWithFlags(&v->ev_join, cudaEventDisableTiming));
-  }
+  train_side_stream(v);
   v->train_x2.ensure(3 * batch); v->train_y2.ensure(batch);
   float* xb[2] = {v->train_x.p, v->train_x2.p};
   float* yb[2] = {v->train_y.p, v->train_y2.p};

@@ -32,5 +32,6 @@ double volume_ssim(Volume* v, float* h_map, cudaStream_t s);
 double volume_test_loss(Volume* v, size_t batch, cudaStream_t s);
 void volume_export(Volume* v, const char* path, int which, float* range_out, cudaStream_t s);
 void apply_l2_policy(const Volume* v, cudaStream_t s);
+void train_side_stream(Volume* v);
 void train_steps(Volume* v, int steps, size_t batch, bool update_macrocell, cudaStream_t s);
 }
