@@ -2,7 +2,8 @@
 
 TEST INFRASTRUCTURE ONLY.  Imported by tests/, __graft_entry__.smoke() and the
 cpu_baseline / --impl reference legs of bench.py; never by instantvnr_b200.
-PARITY UNPINNED: see the header of vnr_oracle.cpp.
+Parity: pinned to the reference's own tiny-cuda-nn and renderer sources, except the out-of-core sampler restatement
+(PARITY UNPINNED for that one function group): see the header of vnr_oracle.cpp.
 """
 import ctypes as C
 import os

@@ -1,6 +1,10 @@
 // ============================================================================
 // vnr_oracle.cpp -- CPU ORACLE for the instantvnr hot path.
-// PARITY: decode + training pinned to the reference's own tiny-cuda-nn build; MARCHER UNPINNED.
+// PARITY: decode + training pinned to the reference's own tiny-cuda-nn build; marcher, path tracer and macrocells pinned to the
+// reference's own renderer sources (both compiled in place, see below).  OUT-OF-CORE SAMPLER (orc_outofcore_*): PARITY UNPINNED --
+// core/samplers/neural_sampler.cpp needs TBB and libaio, neither is in the image, so that restatement is checked only against
+// its own properties (tests/test_gpu_outofcore.py: every value is the trilinear interpolation of the normalised file at its
+// coordinate; slab geometry; pool turnover).
 //
 // THIS FILE IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only tests/, the
 // smoke() check in __graft_entry__.py and bench.py's cpu_baseline / --impl
