@@ -5,11 +5,10 @@
 //   (core/networks/tcnn_impl.cu:438-448) = extract_position + kernel_grid
 //   (tcnn encodings/grid.h:106-286) + kernel_mlp_fused (fully_fused_mlp.cu:495-553)
 //   + trim_and_cast (common_device.h:533-542)
-// with no intermediate round trip through global memory: each CTA (128 threads, one
-// sample row each) gathers the hash-grid features of a 128-sample tile straight into
-// the swizzled shared-memory A operand, runs the MLP chain on tcgen05 tensor cores
-// with TMEM accumulators (mlp_tile.cuh) and writes one float per sample.
-// Persistent grid: tiles are strided over gridDim.x CTAs (a multiple of the SM count).
+// with no intermediate round trip through global memory: one persistent, warp-specialised CTA per SM (640 threads): four
+// producer groups gather the hash-grid features of 128-sample tiles straight into swizzled shared-memory A operands, a
+// consumer group runs the MLP chain of finished tiles on tcgen05 tensor cores with TMEM accumulators (mlp_tile.cuh, two
+// tiles interleaved) and writes one float per sample.  Tiles are strided over the CTAs.
 #include "mlp_tile.cuh"
 #include "vnr_host.h"
 
