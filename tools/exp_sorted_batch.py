@@ -50,14 +50,29 @@ def time_kernel(x, t, reps=20):
     return e0.elapsed_time(e1) / reps * 1e3
 
 
+def per_cta_blocks(order, n_cta=148, tile=128):
+    """re-deal a sorted batch so that the kernel's strided tile assignment (tile j of CTA b = b + j * n_cta) gives every CTA a
+    CONTIGUOUS run of the sorted order (its own region of the volume)"""
+    n_tiles = order.numel() // tile
+    src = order.view(n_tiles, tile)
+    dst = torch.empty_like(src)
+    k = 0
+    for b in range(n_cta):
+        for t in range(b, n_tiles, n_cta):
+            dst[t] = src[k]; k += 1
+    return dst.reshape(-1)
+
+
 orders = {"unsorted": None}
-for res in (16, 32, 64, 128, 256):
+for res in (16, 64, 256):
     orders[f"morton {res}^3"] = morton_order(xyz, res)
-orders["linear 64^3"] = linear_order(xyz, 64)
+    orders[f"morton {res}^3 per-CTA"] = per_cta_blocks(morton_order(xyz, res))
+for res in (16, 64, 256):
+    orders[f"linear {res}^3"] = linear_order(xyz, res)
+    orders[f"linear {res}^3 per-CTA"] = per_cta_blocks(linear_order(xyz, res))
 for flags, what in ((0, "all"), (1, "chain + gather"), (2, "chain + scatter")):
     for name, o in orders.items():
         x = xyz if o is None else xyz[o].contiguous(); t = tgt if o is None else tgt[o].contiguous()
         vol.train_debug(2, flags, False)
-        print(f"{what:16s} {name:14s} {time_kernel(x, t):7.1f} us", flush=True)
-# and the loss / gradient are those of the same set
+        print(f"{what:16s} {name:22s} {time_kernel(x, t):7.1f} us", flush=True)
 vol.train_debug(2, 0, False)
