@@ -447,11 +447,10 @@ def run_ours(args):
     # SM's L1TEX turns scattered requests into L2 sector fetches -- ~1 per cycle per SM (csrc/probe.cu: plain ld.global.nc.v4 at
     # random offsets, nothing of the product's gather code; it does NOT depend on the thread count, 256 threads per SM reach it,
     # but it halves when the CTA's shared memory selects certain shared-memory / L1 splits: tools/exp_probe_cta.py, DESIGN 3.1,
-    # which is why the decode ring holds 7 tiles and the training kernel stays under 192 KB).  `peak` is that probe over a buffer
-    # of THIS run's table size (46.7 MB: L2-resident -> bound "l1tex_gather"; T = 2^22: 307 MB > L2 -> "hbm_gather").
+    # which is why the decode ring holds 7 tiles and the training kernel stays under 192 KB).  l2_gather_gbs is that probe over a
+    # flat 46.7 MB buffer, hbm_gather_gbs the same over 307 MB (every load a DRAM miss).
     # `achieved` / `frac` are like for like with the probe: the SAME kernel on uniform random coordinates (launches timed here
-    # with CUDA events), 1024 algorithmic gather bytes per sample; above 1.0 because the two x-neighbours of a cell share a 32-byte
-    # sector half the time (an L1 hit the probe's independent addresses never get).  The launches INSIDE the frames run faster
+    # with CUDA events), 1024 algorithmic gather bytes per sample.  The launches INSIDE the frames run faster
     # still (`in_frame`): neighbouring rows are the same step of neighbouring rays, lanes of a warp ask for the same table
     # entries and those requests collapse before the L1TEX -- their algorithmic bytes overcount what the bound unit sees, so
     # they are reported next to the roofline, not as its fraction.
@@ -463,7 +462,17 @@ def run_ours(args):
     own_ms, _ = vnr.probe_memory("loads", table_bytes, probe_ops, 3)
     gbs = lambda ms_: probe_ops * 16 / (ms_ * 1e-3) / 1e9
     gather_peak = gbs(own_ms)
-    bound = "l1tex_gather" if table_bytes <= 100e6 else "hbm_gather"
+    # the same loads with the decode's level structure (8 per level, uniformly inside that level's table): coarse levels stay
+    # cache-resident, levels larger than the L2 miss in proportion -- the like-for-like ceiling when the table exceeds the L2
+    lv_entries = vnr.hash_grid_level_entries(log2_hashmap=args.log2_hashmap)
+    lv_ms, _ = vnr.probe_levels(lv_entries, 1 << 22, 3)
+    levels_gbs = (1 << 22) * 64 * 16 / (lv_ms * 1e-3) / 1e9
+    # `peak`: the level-structured probe while the table is L2-resident (like for like with the kernel on uniform coordinates: the
+    # coarse levels hit in L1 in both).  A table beyond the L2 (T = 2^22): the request-rate ceiling of an L2-resident table stays
+    # the upper bound and `frac` says how far DRAM latency on the missing levels keeps the kernel below it; the two DRAM-side probes
+    # (levels_gather_gbs, hbm_gather_gbs) are reported next to it -- the kernel exceeds both, its x-neighbour corners share sectors
+    gather_peak = levels_gbs if table_bytes <= 100e6 else gbs(l2_ms)
+    bound = "l1tex_gather"
     decode_rate = prof_decoded / (decode_ms * 1e-3) if decode_ms > 0 else 0.0
     achieved = decode_rate * GATHER_BYTES / 1e9
     # the same kernel on uniform random coordinates (no coherence between neighbouring rows): apples to apples with the probe
@@ -496,8 +505,11 @@ def run_ours(args):
                 "traffic": traffic, "traffic_detail": traffic_detail,
                 "kernel": "decode_kernel<8,.> (fused hash-grid gather + tcgen05 MLP)",
                 "achieved_source": "decode_kernel on 2^22 uniform random coordinates, 5 launches timed with CUDA events in this run; 1024 algorithmic gather bytes per sample",
-                "peak_source": "measured in this run: random 16-byte ld.global.nc over a buffer of the table's size (csrc/probe.cu)",
-                "l2_gather_gbs": round(gbs(l2_ms), 1), "hbm_gather_gbs": round(gbs(hbm_ms), 1), "table_bytes": table_bytes,
+                "peak_source": ("measured in this run: random 16-byte ld.global.nc, 8 per level inside each level's own table (csrc/probe.cu vnr_probe_levels), full occupancy, "
+                                "nothing of the product's gather code" if table_bytes <= 100e6 else
+                                "measured in this run: random 16-byte ld.global.nc over an L2-resident 46.7 MB buffer (the request-rate ceiling); this run's table exceeds the L2"),
+                "table_exceeds_l2": bool(table_bytes > 100e6),
+                "l2_gather_gbs": round(gbs(l2_ms), 1), "hbm_gather_gbs": round(gbs(hbm_ms), 1), "levels_gather_gbs": round(levels_gbs, 1), "table_bytes": table_bytes,
                 "algorithmic_bytes_per_sample": GATHER_BYTES, "decode_uniform_samples_per_sec": uniform_rate,
                 "in_frame": {"decode_samples_per_sec": decode_rate, "gather_gbs": round(achieved, 1), "ratio_to_peak": round(achieved / gather_peak, 4),
                              "decode_ms_per_frame": round(decode_ms / prof_steps, 4), "decode_launches_per_frame": decode_launches / prof_steps,

@@ -93,6 +93,10 @@ int vnr_volume_gather_probe(vnr_volume_t* v, const float* d_xyz, uint32_t* d_out
  * (1024 pixels wide) stored into PINNED HOST memory in scanline / 8x4-tile / 32-byte scanline / 16x2-tile order (what
  * bounds the zero-copy frame download).  Returns the fastest and the mean of `repeats` CUDA-event-timed launches (after one warm-up). */
 int vnr_probe_memory(int kind, size_t table_bytes, size_t n_ops, int repeats, float* ms_best, float* ms_mean);
+/* the same loads with the level structure of a hash-grid decode on uniform random coordinates: n_samples x 8 random 16-byte
+ * loads per level, level l being level_entries[l] entries of 16 bytes (back to back) -- coarse levels stay cache-resident, levels
+ * larger than the L2 miss in proportion.  The like-for-like gather ceiling for tables that exceed the L2 (no reference counterpart) */
+int vnr_probe_levels(const uint32_t* level_entries, int n_levels, size_t n_samples, int repeats, float* ms_best, float* ms_mean);
 
 /* measurement taps of the fused training kernel (train.cu): variant 1 = current MMA chain, 0 = the round-1 chain
  * (A/B); flags: 1 = the scatter groups issue no reductions, 2 = the gather groups issue no loads, 4 = the compute

@@ -92,6 +92,24 @@ def probe_memory(kind, table_bytes, n_ops, repeats=5):
     return best.value, mean.value
 
 
+def probe_levels(level_entries, n_samples, repeats=5):
+    """csrc/probe.cu: n_samples x 8 random 16-byte loads per level of a table laid out like a hash grid -> (best ms, mean ms)"""
+    le = np.ascontiguousarray(level_entries, dtype=np.uint32)
+    best, mean = C.c_float(), C.c_float()
+    _check(lib().vnr_probe_levels(_ptr(le), C.c_int(le.size), C.c_size_t(int(n_samples)), C.c_int(repeats), C.byref(best), C.byref(mean)))
+    return best.value, mean.value
+
+
+def hash_grid_level_entries(n_levels=8, log2_hashmap=19, base_res=16, per_level_scale=2.0):
+    """entries per level of the hash grid (tcnn encodings/grid.h:591-611: dense while (res)^3 fits, rounded up to 8, capped at T)"""
+    out = []
+    for l in range(n_levels):
+        scale = base_res * per_level_scale ** l - 1.0
+        res = int(np.ceil(scale)) + 1
+        out.append(int(min(-(-res ** 3 // 8) * 8, 1 << log2_hashmap)))
+    return out
+
+
 def example_model_json():
     with open(EXAMPLE_MODEL) as f:
         return f.read()

@@ -107,6 +107,31 @@ __global__ void probe_loads_cta_kernel(const uint4* __restrict__ table, uint32_t
   if (fold == 0x12345678u) sink[t & 1023u] = fold;
 }
 
+// random 16-byte loads with the LEVEL STRUCTURE of a hash-grid decode on uniform random coordinates: every "sample" does 8 loads
+// per level at random entries of THAT level's table (small coarse levels stay L2- and partly L1-resident, levels larger than the
+// L2 miss in proportion), nothing else.  The like-for-like ceiling of the decode's gather for a model whose table exceeds the
+// L2 (T = 2^22), independent of the product's index arithmetic.
+struct ProbeLevels { uint32_t n_levels; uint32_t offset[16]; uint32_t size[16]; };      // in 16-byte entries
+__global__ void __launch_bounds__(256) probe_loads_levels_kernel(const uint4* __restrict__ table, ProbeLevels lv, uint32_t n_samples, uint32_t seed,
+                                                                 uint32_t* __restrict__ sink) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_samples) return;
+  uint32_t fold = 0;
+  uint32_t c = mix32(t * 0x9e3779b9u + seed);
+  for (uint32_t l = 0; l < lv.n_levels; ++l) {
+    uint4 v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      c = c * 1664525u + 1013904223u;
+      const uint32_t idx = lv.offset[l] + (uint32_t)(((uint64_t)mix32(c) * lv.size[l]) >> 32);
+      v[i] = ldg_nc_v4(table + idx);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) fold ^= v[i].x ^ v[i].y ^ v[i].z ^ v[i].w;
+  }
+  if (fold == 0x12345678u) sink[t & 1023u] = fold;
+}
+
 // loads and reductions TOGETHER (even blocks: random 16-byte loads over `table`, odd blocks: random fp16x8 reductions over `table2`):
 // what the training step's gather and scatter cost when they share the memory system
 __global__ void __launch_bounds__(256) probe_mixed_kernel(const uint4* __restrict__ table, __half* __restrict__ table2, uint32_t n_vec, uint32_t per_thread,
@@ -236,6 +261,42 @@ VNR_EXPORT int vnr_probe_memory(int kind, size_t table_bytes, size_t n_ops, int 
   if (e1) cudaEventDestroy(e1);
   if (s) cudaStreamDestroy(s);
   if (table) { if (kind >= 4 && kind <= 7) cudaFreeHost(table); else cudaFree(table); }
+  if (aux) cudaFree(aux);
+  return rc;
+}
+
+// n_samples x (8 random 16-byte loads per level) over a table laid out as the levels of a hash grid (level_entries[l] entries of
+// 16 bytes each, back to back): fastest and mean time of `repeats` launches after one warm-up
+VNR_EXPORT int vnr_probe_levels(const uint32_t* level_entries, int n_levels, size_t n_samples, int repeats, float* ms_best, float* ms_mean) {
+  if (!level_entries || n_levels < 1 || n_levels > 16 || repeats < 1 || !ms_best || n_samples < 1 || n_samples > 0xFFFFFFFFull) return VNR_ERR_INVALID;
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) { cudaGetLastError(); return VNR_ERR_CUDA; }
+  ProbeLevels lv; lv.n_levels = (uint32_t)n_levels;
+  size_t total = 0;
+  for (int l = 0; l < n_levels; ++l) { if (!level_entries[l]) return VNR_ERR_INVALID; lv.offset[l] = (uint32_t)total; lv.size[l] = level_entries[l]; total += level_entries[l]; }
+  void* table = nullptr; void* aux = nullptr; cudaStream_t s = nullptr; cudaEvent_t e0 = nullptr, e1 = nullptr;
+  int rc = VNR_OK;
+  auto ok = [&](cudaError_t e) { if (e != cudaSuccess) { cudaGetLastError(); rc = VNR_ERR_CUDA; } return e == cudaSuccess; };
+  do {
+    if (!ok(cudaMalloc(&table, total * 16)) || !ok(cudaMemset(table, 0, total * 16)) || !ok(cudaMalloc(&aux, 4096))) break;
+    if (!ok(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)) || !ok(cudaEventCreate(&e0)) || !ok(cudaEventCreate(&e1))) break;
+    float best = 1e30f, sum = 0.f;
+    for (int it = 0; it <= repeats && rc == VNR_OK; ++it) {
+      ok(cudaEventRecord(e0, s));
+      probe_loads_levels_kernel<<<(unsigned)((n_samples + 255) / 256), 256, 0, s>>>((const uint4*)table, lv, (uint32_t)n_samples, 23u + it, (uint32_t*)aux);
+      ok(cudaGetLastError());
+      ok(cudaEventRecord(e1, s));
+      if (!ok(cudaEventSynchronize(e1))) break;
+      float ms = 0.f; ok(cudaEventElapsedTime(&ms, e0, e1));
+      if (it == 0) continue;
+      best = ms < best ? ms : best; sum += ms;
+    }
+    *ms_best = best; if (ms_mean) *ms_mean = sum / (float)repeats;
+  } while (0);
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+  if (s) cudaStreamDestroy(s);
+  if (table) cudaFree(table);
   if (aux) cudaFree(aux);
   return rc;
 }
