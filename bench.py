@@ -625,8 +625,9 @@ def run_train(args):
     ooc_info = None
     if args.out_of_core:
         # BASELINE configs[3]: the volume stays in a raw file (uint8, written once per box from the same procedural volume);
-        # every rank keeps its own pool of random slabs of it in HBM, refreshed by num_concurrent_blocks slabs per step through
-        # pinned staging buffers, and samples the pool on the device (OutOfCoreSampler, neural_sampler.cpp:1065-1120)
+        # every rank keeps its own pool of random slabs of it in HBM, refreshed by num_concurrent_blocks slabs per step -- pulled by
+        # the GPU itself out of the page cache (the file mapped and registered; csrc/slab_sampler.cu) -- and samples the pool on
+        # the device (OutOfCoreSampler, neural_sampler.cpp:1065-1120)
         path = os.path.join(os.environ.get("VNR_BENCH_TMP", "/tmp"), f"vnr_bench_volume_{args.volume}_u8.raw")
         if local == 0 and not (os.path.exists(path) and os.path.getsize(path) == args.volume ** 3):
             gt = synth_volume_device(dims)
@@ -728,7 +729,7 @@ def run_train(args):
                "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "f16", "data": "synthetic",
                "config": {"workload": workload_string(args),
-                          "path": ("out-of-core: raw uint8 file on local disk, a per-rank pool of random slabs in HBM refreshed every step, sampled on the device"
+                          "path": ("out-of-core: raw uint8 file on local disk, a per-rank pool of random slabs in HBM, 1024 slabs (107 MB) per rank and step pulled by the GPU out of the page cache over PCIe, sampled on the device"
                                    if args.out_of_core else "volume resident in HBM, sampled on the device") + ("" if world == 1 else ", gradient all-reduce (fp16 grid + fp32 MLP) over NCCL + replicated Adam" if dp is not None
                                                                else ", optimizer fused with its collectives over NVLink peer memory (reduce-scatter + Adam + all-gather in one kernel)"),
                           "global_batch": n * world, "l2_flush": "per-step parameter-state sweep (~0.9 GB) exceeds L2",
