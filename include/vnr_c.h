@@ -124,7 +124,9 @@ int vnr_volume_set_groundtruth_file(vnr_volume_t* v, const char* path, int value
  * training step and sampled on the device: random slab, random voxel, random point in its cell, trilinear interpolation
  * of the values normalised with [vmin, vmax] BEFORE interpolating.  0 for either count: environment VNR_NUM_CONCURRENT_BLOCKS
  * (1024) / VNR_NUM_BLOCKS (64 x concurrent), as the reference.  A valid range is required (:1068-1070).  Afterwards
- * vnr_volume_train / vnr_volume_sample draw from the pool (five uniforms of the sampler's pcg32 stream per sample). */
+ * vnr_volume_train / vnr_volume_sample draw from the pool (five uniforms of the sampler's pcg32 stream per sample).  The file is
+ * mapped and registered with the CUDA driver when that is possible (the refresh is then pulled by the GPU out of the page cache,
+ * no host copy); otherwise host threads read the slabs into pinned staging buffers. */
 int vnr_volume_set_groundtruth_outofcore(vnr_volume_t* v, const char* path, int value_type, uint64_t offset, float vmin, float vmax,
                                          uint32_t num_concurrent_blocks, uint32_t num_blocks);
 /* pool geometry and, for test restatement, the slab table the next sample call will use (first file voxel and voxel count
