@@ -311,7 +311,11 @@ void outofcore_open(Volume* v, const char* path, int type, uint64_t offset, floa
   // pull mode (see the header): map + register the file; any failure leaves the pread path in place
   const char* pull_env = getenv("VNR_OOC_PULL");
   const uint64_t fsize = (uint64_t)lseek(q.fd, 0, SEEK_END);
-  if ((!pull_env || atoi(pull_env) != 0) && fsize <= ((uint64_t)64 << 30)) {
+  // (registering a private writable mapping may give the process its own pinned copy of the pages: files beyond 8 GiB -- or
+  // VNR_OOC_PULL_MAX_GB -- stay on the pread path)
+  uint64_t pull_max = (uint64_t)8 << 30;
+  if (const char* e = getenv("VNR_OOC_PULL_MAX_GB")) { const long g = atol(e); if (g > 0) pull_max = (uint64_t)g << 30; }
+  if ((!pull_env || atoi(pull_env) != 0) && fsize <= pull_max) {
     void* p = mmap(nullptr, (size_t)fsize, PROT_READ | PROT_WRITE, MAP_PRIVATE, q.fd, 0);
     if (p != MAP_FAILED) {
       void* dp = nullptr;
