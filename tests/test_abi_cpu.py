@@ -64,3 +64,17 @@ def test_compute_fails_loudly_without_device():
     with pytest.raises(vnr.VnrError) as e:
         vnr.NeuralVolume(vnr.example_model_json(), (8, 8, 8))
     assert e.value.code == -2 and "no CPU fallback" in str(e.value)
+
+
+def test_level_table_of_the_probe_matches_the_oracle():
+    """bench.py's level-structured gather probe (vnr_probe_levels) is sized by instantvnr_b200.hash_grid_level_entries: the same
+    per-level entry counts as the oracle's restatement of tcnn's grid layout (encodings/grid.h:591-611)"""
+    import numpy as np
+    import instantvnr_b200 as vnr
+    import oracle as O
+    for kw in (dict(), dict(n_levels=16, log2_hashmap=19, base_res=16), dict(n_levels=8, log2_hashmap=22, base_res=16), dict(n_levels=4, log2_hashmap=12, base_res=8)):
+        n_levels, log2, base = kw.get("n_levels", 8), kw.get("log2_hashmap", 19), kw.get("base_res", 16)
+        m = O.ModelCfg(n_levels, 8 if n_levels <= 8 else 2, log2, base, 2.0, 4)
+        want = np.diff(np.asarray(m.offsets[:n_levels + 1], dtype=np.int64))
+        got = np.asarray(vnr.hash_grid_level_entries(n_levels=n_levels, log2_hashmap=log2, base_res=base), dtype=np.int64)
+        assert np.array_equal(got, want), (kw, got, want)
