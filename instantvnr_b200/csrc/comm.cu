@@ -405,6 +405,7 @@ void comm_train_steps(Volume* v, int steps, size_t batch, bool update_macrocell,
   if (batch == 0) batch = 1 << 16;                                       // network.cu:183
   if (batch % kTile) throw InvalidError("Batch size must be a multiple of 128.");
   v->train_x.ensure(3 * batch); v->train_y.ensure(batch);
+  if (steps <= 0) return;                                                // nothing is drawn, nothing to merge
   const uint64_t ups = v->ooc ? 5 : 3;                                   // uniforms per sample of the sampler in use
   // rank r takes the r-th of `world` consecutive batches of the one sampler stream
   auto draw = [&](float* x, float* y, cudaStream_t st) {

@@ -1492,6 +1492,7 @@ void train_steps(Volume* v, int steps, size_t batch, bool update_macrocell, cuda
   if (!v->have_gt && !v->ooc) throw StateError("[error]: missing a reference volume.");
   if (batch == 0) batch = 1 << 16;                                       // network.cu:183
   if (batch % kTile) throw InvalidError("Batch size must be a multiple of 128.");
+  if (steps <= 0) return;                                                // nothing is drawn: the sampler stream stays where it is
   v->train_x.ensure(3 * batch); v->train_y.ensure(batch);
   apply_l2_policy(v, s);
   if (v->ooc || getenv("VNR_TRAIN_SERIAL")) {      // out-of-core batches come through pinned staging buffers in stream order
@@ -1548,7 +1549,7 @@ void train_steps(Volume* v, int steps, size_t batch, bool update_macrocell, cuda
     for (int i = 4; i < steps; ++i)
       for (int k = 0; k < 3; ++k) { float ms = 0; cudaEventElapsedTime(&ms, tev[4 * i + k], tev[4 * i + k + 1]); t[k] += ms; }
     float tot = 0; cudaEventElapsedTime(&tot, tev[16], tev[4 * (size_t)steps - 1]);
-    fprintf(stderr, "[vnr] train step (us): fused kernel + reduce %.1f, grid sweep %.1f, join wait %.1f; whole step %.1f\n", t[0] * 1e3 / (steps - 4),
+    fprintf(stderr, "[vnr] train step (us): fused kernel %.1f, grid sweep %.1f, join wait %.1f; whole step %.1f\n", t[0] * 1e3 / (steps - 4),
             t[1] * 1e3 / (steps - 4), t[2] * 1e3 / (steps - 4), tot * 1e3 / (steps - 4));
     for (auto& e : tev) cudaEventDestroy(e);
   }

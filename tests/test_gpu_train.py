@@ -33,6 +33,7 @@ def test_sampler_matches_oracle_bit_exact():
     s = torch.cuda.current_stream().cuda_stream
     for n in (1000, 128, 4096):           # consecutive batches share the pcg32 stream
         xyz = torch.empty(n, 3, device="cuda"); tgt = torch.empty(n, device="cuda")
+        vol.train(0, batch=1024)          # zero steps draw nothing: the stream stays where it is
         vol.sample(xyz, tgt, n, s)
         torch.cuda.synchronize()
         c, t = O.sample_batch(rng, n, gt, dims)
