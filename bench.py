@@ -1080,7 +1080,7 @@ def main():
     ap.add_argument("--out-of-core", action="store_true", help="train workload: the ground truth stays in a raw file, sampled through per-rank slab pools (configs[3])")
     ap.add_argument("--dp-mode", default="sharded", choices=["sharded", "allreduce"], help="train workload, N > 1: peer-memory optimizer or NCCL all-reduce")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
-    ap.add_argument("--pipeline", type=int, default=0, help="render workload, N = 1: renderers that take the frames in turn (device-resident timing)")
+    ap.add_argument("--pipeline", type=int, default=0, help="render workload: frame slots inside the renderer for the device-resident timing (0 = 2 on one or two GPUs, 3 on four, 4 on eight)")
     ap.add_argument("--gather", default="comm", choices=["comm", "nccl"],
                     help="N > 1: comm = the library's communicator (peer stores from the compositing kernels); nccl = torch.distributed gather of padded strips (comparison)")
     args = ap.parse_args()
