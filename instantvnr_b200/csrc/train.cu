@@ -35,13 +35,19 @@ __global__ void sampler_kernel(uint32_t n, Pcg32 base, uint32_t n_threads, const
                                float* __restrict__ coords, float* __restrict__ targets) {
   const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n) return;
+  // the three positions of a sample are 4 apart (consecutive generator threads) unless the thread index wraps: one full jump,
+  // then jumps of 3 from where the previous draw left the state -- the same stream positions, a third of the jump-ahead work
   float c[3];
+  Pcg32 r = base;
+  uint64_t at = 0;                                   // stream position of r, relative to base
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
     const uint32_t idx = 3u * s + (uint32_t)d;
-    Pcg32 r = base;
-    r.advance(4ull * (idx % n_threads) + idx / n_threads);
+    const uint64_t pos = 4ull * (idx % n_threads) + idx / n_threads;
+    if (d == 0 || pos < at) { r = base; r.advance(pos); }
+    else r.advance(pos - at);
     c[d] = r.next_float();
+    at = pos + 1;
   }
   coords[3 * (size_t)s] = c[0]; coords[3 * (size_t)s + 1] = c[1]; coords[3 * (size_t)s + 2] = c[2];
   if (targets) targets[s] = sample_volume_linear(vol, dims, c[0], c[1], c[2]);
